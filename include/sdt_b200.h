@@ -1,0 +1,218 @@
+/*
+ * sdt_b200.h -- C ABI of libsdt_b200.so: the B200 (sm_100a) kernels behind the Voice2Pose / Pose2Pose
+ * training-step hot path of ShenhanQian/SpeechDrivesTemplates.
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - every entry point takes the CUDA stream it must launch on (cudaStream_t passed as void*), is
+ *     re-entrant (backward runs on autograd worker threads), allocates no device memory and keeps no
+ *     device state: workspaces are caller-owned;
+ *   - returns 0 on success; non-zero = error, text in sdt_last_error() (thread-local). Nothing throws
+ *     across the ABI;
+ *   - activations are CHANNELS-LAST fp32: 2-D maps (B,H,W,C), 1-D sequences (B,L,C) == (B,1,L,C).
+ *     The reference's NCHW/NCL tensors only exist at the Python boundary (weights, which keep the
+ *     reference's (Cout,Cin,kh,kw) layout in HBM because they are the checkpoint/optimizer contract).
+ *
+ * The reference has no FFI: its arithmetic is torch/torchaudio library calls.  Each entry point below
+ * cites the reference call site (file:line under /root/reference) whose computation it replaces.
+ */
+#ifndef SDT_B200_H
+#define SDT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDT_OK 0
+#define SDT_ERR_ARG 1
+#define SDT_ERR_CUDA 2
+
+/* ---- library ---------------------------------------------------------------------------------- */
+const char* sdt_last_error(void);
+int sdt_version(void);
+/* math mode of the dense convolutions: 0 = fp32 FFMA (SIMT), 1 = TF32 tcgen05 tensor cores where a
+ * tcgen05 kernel exists for the shape (fp32 accumulate). Process-wide; default 0 unless set. */
+int sdt_set_conv_math(int mode);
+int sdt_get_conv_math(void);
+
+/* ---- mel front end -----------------------------------------------------------------------------
+ * torchaudio.transforms.MelSpectrogram(win_length=400, hop_length=160, n_fft=512, f_min=55,
+ * f_max=7500, n_mels=80) as constructed at core/pipelines/voice2pose.py:27-30 (pose2pose.py:25-28)
+ * and called at voice2pose.py:125 (pose2pose.py:48).  STFT (reflect pad 256, hann-400 centred in a
+ * 512 frame) + |X|^2 + banded mel projection fused in one kernel: warp-per-frame-pair shared-memory
+ * radix-2 FFT, the 257-bin spectrum never reaches HBM.  Power spectrogram, NO log.
+ *   audio   (B, L) f32           window (400) f32   [state-dict buffer mel_transfm.spectrogram.window]
+ *   fb_start/fb_count (80) i32, fb_weight (80, fb_stride) f32: band form of mel_transfm.mel_scale.fb
+ *   mel     (B, 80, 1 + L/160) f32  (== channels-last (B,80,T,1))
+ */
+int sdt_mel_fwd(const float* audio, int B, int L, const float* window, const int32_t* fb_start,
+                const int32_t* fb_count, const float* fb_weight, int fb_stride, float* mel, void* stream);
+
+/* ---- convolution as implicit GEMM --------------------------------------------------------------
+ * nn.Conv1d / nn.Conv2d inside ConvNormRelu (core/networks/building_blocks.py:15-22,31-36,49) and
+ * their autograd backward.  One descriptor drives forward, data-gradient and weight-gradient:
+ *
+ *   rows   m = (b, gy, gx) over a GH x GW grid per image           (M = B*GH*GW)
+ *   cols   n in [0, N)
+ *   depth  k = (ty, tx, c), ty<TH, tx<TW, c<C                       (K = TH*TW*C)
+ *   A(m,k) = xf( src[b, gy*y_mul + ty*ty_mul + y_off, gx*x_mul + tx*tx_mul + x_off, c] ), 0 outside src
+ *   xf(v)  = act( v*xf_scale[b*xf_bstride + c] + xf_shift[...] ),  act = LeakyReLU(xf_slope)   (xf_scale != NULL)
+ *            -- the PREVIOUS layer's normalisation + activation applied in the loader, so normalised
+ *               activations are never materialised (building_blocks.py:50-54)
+ *   conv:   dst[b, gy*dy_mul+dy_off, gx*dx_mul+dx_off, n] (+)= sum_k A(m,k) * wt[k*N + n] + bias[n]
+ *           and, if stat_partial != NULL, per-row-tile column sums / sums of squares of the result
+ *           (the input of sdt_norm_finalize) are written to stat_partial[tile][2][N]
+ *   wgrad:  wpart[z][n][k] = sum_{m in split z} dy[m, n] * A(m,k)    (dy = (B,GH,GW,N) channels-last)
+ */
+typedef struct sdt_conv_desc {
+    const float* src;          /* (B, SH, SW, C) */
+    const float* wt;           /* conv: (K, N) row-major, from sdt_weight_prep */
+    const float* bias;         /* (N) or NULL */
+    const float* xf_scale;     /* loader transform, or NULL for identity */
+    const float* xf_shift;
+    float* dst;                /* conv: (B, DH, DW, N) */
+    float* stat_partial;       /* conv: (row_tiles, 2, N) or NULL */
+    const float* dy;           /* wgrad: (B, GH, GW, N) */
+    float* wpart;              /* wgrad: (splits, N, K) */
+    int32_t B, SH, SW, C;
+    int32_t GH, GW, TH, TW;
+    int32_t y_mul, ty_mul, y_off, x_mul, tx_mul, x_off;
+    int32_t N;
+    int32_t DH, DW, dy_mul, dy_off, dx_mul, dx_off;
+    int32_t xf_bstride;        /* C for per-(b,c) statistics (InstanceNorm2d), 0 for per-channel (BatchNorm) */
+    float xf_slope;            /* 0.2 LeakyReLU, 0 ReLU */
+    int32_t accumulate;        /* conv: dst += result */
+    int32_t per_image_tiles;   /* conv: row tiles never straddle images (needed for per-(b,c) statistics) */
+    int32_t splits;            /* wgrad: number of K splits (== gridDim.z) */
+} sdt_conv_desc;
+
+/* number of row tiles sdt_conv_gemm will use for this descriptor (size of stat_partial's first dim) */
+int sdt_conv_row_tiles(const sdt_conv_desc* d);
+int sdt_conv_gemm(const sdt_conv_desc* d, void* stream);
+int sdt_conv_wgrad(const sdt_conv_desc* d, void* stream);
+/* sum the split-K partials in fixed order and store in the reference's parameter layout:
+ * grad[(n*C + c)*T + t] (+)= sum_z wpart[z][n][(t*C + c)],  T = TH*TW  -> (Cout, Cin, kh, kw) */
+int sdt_conv_wgrad_reduce(const float* wpart, int splits, int N, int C, int T, float* grad, int accumulate,
+                          void* stream);
+/* reference-layout weight (Cout, Cin, KH, KW) -> GEMM operand (K, N):
+ *   mode 0 forward : out[((ky*KW+kx)*Cin + ci)*Cout + co] = w[co,ci,ky,kx]
+ *   mode 1 dgrad   : taps ky = ky0 + kstep*jy (jy < TH), kx likewise:
+ *                    out[((jy*TW+jx)*Cout + co)*Cin + ci] = w[co,ci,ky0+kstep*jy,kx0+kstep*jx]      */
+int sdt_weight_prep(const float* w, int Cout, int Cin, int KH, int KW, int mode, int ky0, int kx0, int kstep,
+                    int TH, int TW, float* out, void* stream);
+
+/* ---- normalisation -----------------------------------------------------------------------------
+ * nn.InstanceNorm2d / nn.BatchNorm{1,2}d inside ConvNormRelu (building_blocks.py:23-27,38-43,53) with
+ * the LeakyReLU/ReLU at :46,54.  Statistics come from the conv epilogue partials; normalise+activate is
+ * applied by the next consumer's loader through (scale, shift):  xhat*gamma+beta = x*scale + shift.
+ *   partial (groups*tiles_per_group, 2, C); count = elements per statistic; groups = B (IN) or 1 (BN)
+ *   outputs (groups, C): scale, shift, mean, rstd.  gamma/beta NULL -> no affine (InstanceNorm).
+ *   running_mean/var != NULL (BatchNorm train): momentum update with the UNBIASED variance and
+ *   num_batches_tracked += 1.
+ */
+int sdt_norm_finalize(const float* partial, int groups, int tiles_per_group, int C, double count, const float* gamma,
+                      const float* beta, float eps, float* scale, float* shift, float* mean, float* rstd,
+                      float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
+                      void* stream);
+/* BatchNorm eval mode: scale/shift from running statistics (C). */
+int sdt_bn_eval_scale_shift(const float* running_mean, const float* running_var, const float* gamma, const float* beta,
+                            float eps, int C, float* scale, float* shift, void* stream);
+/* Backward of [per-(g,c) normalise -> affine -> (Leaky)ReLU] over a channels-last map x (B, P, C), P = H*W:
+ * pass 1 reduces  s1 = sum g', s2 = sum g'*xhat  (g' = g_act * act'(y)) into partial (B*tiles, 2, C);
+ * finalize gives the means (groups, C) and, for BatchNorm, dgamma/dbeta; pass 2 writes
+ * g_x = rstd*gamma*(g' - m1 - xhat*m2) in place over g. groups = B (IN) or 1 (BN). */
+int sdt_norm_bwd_reduce(const float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
+                        const float* beta, int B, int P, int C, int groups, float slope, float* partial,
+                        int tiles_per_image, void* stream);
+int sdt_norm_bwd_finalize(const float* partial, int groups, int tiles_per_group, int C, double count, float* m1,
+                          float* m2, float* dgamma, float* dbeta, int accumulate, void* stream);
+int sdt_norm_bwd_apply(float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
+                       const float* beta, const float* m1, const float* m2, int B, int P, int C, int groups, float slope,
+                       void* stream);
+/* InstanceNorm1d on the permuted tensor == LayerNorm over channels per (b,t), no affine
+ * (building_blocks.py:50-51) + activation, on rows of a (R, C) channels-last matrix. */
+int sdt_rownorm_act_fwd(const float* x, int R, int C, float eps, float slope, float* y, float* mean, float* rstd,
+                        void* stream);
+int sdt_rownorm_act_bwd(const float* g_y, const float* x, const float* mean, const float* rstd, int R, int C,
+                        float slope, float* g_x, void* stream);
+/* y = act(x*scale[g,c] + shift[g,c]) materialised (used at module boundaries only). */
+int sdt_scale_shift_act(const float* x, const float* scale, const float* shift, int B, int P, int C, int bstride,
+                        float slope, float* y, void* stream);
+
+/* ---- resampling / concatenation ----------------------------------------------------------------
+ * F.interpolate(x, (1, F), mode='bilinear') + squeeze (generator.py:41-42) fused with the code broadcast +
+ * concat (generator.py:109-111): reads the last encoder block's raw output (B,H,W,C) through its
+ * scale/shift/activation, writes the UNet input (B, F, C + D) channels-last; code (B, D) or NULL. */
+int sdt_enc_to_seq_fwd(const float* x, const float* scale, const float* shift, int xf_bstride, float slope, int B, int H,
+                       int W, int C, const float* code, int D, int F, float* out, void* stream);
+/* adjoint: g_out (B,F,C+D) -> g_act (B,H,W,C) (zero outside the sampled row) and g_code (B,D) = sum_t. */
+int sdt_enc_to_seq_bwd(const float* g_out, int B, int H, int W, int C, int D, int F, float* g_act, float* g_code,
+                       void* stream);
+/* F.interpolate(x, Lout, mode='linear') + skip (generator.py:79-83; autoencoder.py:62-66 with skip NULL):
+ * out (B,Lout,C) = lerp(x (B,Lin,C)) [+ skip]. */
+int sdt_upsample_add_fwd(const float* x, const float* skip, int B, int Lin, int Lout, int C, float* out, void* stream);
+/* adjoint of the lerp: g_x (B,Lin,C) (+)= A^T g_out. */
+int sdt_upsample_bwd(const float* g_out, int B, int Lin, int Lout, int C, float* g_x, int accumulate, void* stream);
+
+/* ---- losses -------------------------------------------------------------------------------------
+ * L1: nn.L1Loss('none')(pred, gt) * lambda -> mean (voice2pose.py:141-142, pose2pose.py:71-72).
+ *   loss_out[0] = value; g_pred = lambda*sign(pred-gt)/n (sign(0)=0) if g_pred != NULL. partial: >= 1024 floats. */
+int sdt_l1_loss(const float* pred, const float* gt, int64_t n, float lambda, float* loss_out, float* g_pred,
+                float* partial, void* stream);
+/* Clip-code gather + batch-statistics KL (voice2pose.py:94,147-157): code (B,D) = table[idx];
+ * out[0] = KL value (0 if skipped), out[1] = 1 if applied (all unbiased batch variances != 0) else 0;
+ * g_code (B,D) = d KL / d code (0 when skipped). */
+int sdt_code_gather_kl(const float* table, const int64_t* idx, int B, int D, float lambda, float* code, float* out,
+                       float* g_code, void* stream);
+/* index backward: g_table[idx[b]] += g_code_a[b] + g_code_b[b] (duplicates accumulate, fixed order).
+ * g_table must be zeroed by the caller. */
+int sdt_code_scatter_grad(const float* g_code_a, const float* g_code_b, const int64_t* idx, int B, int D,
+                          float* g_table, void* stream);
+/* column sums of a (R, C) matrix: bias gradient of the final Conv1d (generator.py:103). */
+int sdt_colsum(const float* g, int R, int C, float* out, int accumulate, void* stream);
+/* LSGAN terms, nn.MSELoss vs a constant target (voice2pose.py:82,195-202): out[0] = lambda*mean((s-target)^2),
+ * g_s = lambda*2*(s-target)/n if g_s != NULL. */
+int sdt_mse_const_loss(const float* s, int64_t n, float target, float lambda, float* out, float* g_s, void* stream);
+/* motion = x[:,1:] - x[:,:-1] over a (B,T,C) sequence (voice2pose.py:187-189) and its adjoint. */
+int sdt_motion_diff_fwd(const float* x, int B, int T, int C, float* out, void* stream);
+int sdt_motion_diff_bwd(const float* g_out, int B, int T, int C, float* g_x, int accumulate, void* stream);
+
+/* ---- pose VAE head ------------------------------------------------------------------------------
+ * PoseSeqEncoder tail (autoencoder.py:31-35): take t=0 of the last block's raw output (B,L,2D) through its
+ * scale/shift/activation, split even/odd channels -> mu, logvar (B,D). */
+int sdt_pose_head_fwd(const float* x, const float* scale, const float* shift, float slope, int B, int L, int D2,
+                      float* mu, float* logvar, void* stream);
+/* VAE reparameterisation + KL (autoencoder.py:84-87, pose2pose.py:77): code = mu + exp(.5 logvar)*eps;
+ * out[0] = lambda*0.5*mean(-logvar + mu^2 + exp(logvar) - 1). */
+int sdt_vae_reparam_kl(const float* mu, const float* logvar, const float* eps, int n, float lambda, float* code,
+                       float* out, void* stream);
+
+/* ---- keypoint indexing / normalisation (bit-exact gates) ----------------------------------------
+ * GestureDataset pose preprocessing (core/datasets/gesture_dataset.py:95-105,131-191):
+ * raw (T,3,137) f32 -> gather 122 -> xy -= kp1 -> drop kp1 -> [parted] -> (x - f32(mean)) / f32(std) (IEEE div).
+ * mean/std (242) f32.  out (T,2,121) f32. */
+int sdt_pose_preprocess(const float* raw, int T, const float* mean, const float* std, int hierarchical, float* out,
+                        void* stream);
+/* GestureDataset.get_final_results (gesture_dataset.py:193-220): f64 x*std (rounded) + mean (rounded) ->
+ * parted_to_global -> * scale.  poses (B,T,2,121) f32; mean/std (B,242) f64; scale (B) f64; out f64. */
+int sdt_pose_final_results(const float* poses, int B, int T, const double* mean, const double* std, const double* scale,
+                           int hierarchical, double* out, void* stream);
+/* Voice2Pose.evaluate_step (voice2pose.py:412-430) on final-result poses: out[0] = L2_dist, out[1] = lip_sync_error_n.
+ * partial: >= 2*B doubles. */
+int sdt_pose_metrics(const double* pred, const double* gt, int B, int T, double* partial, double* out, void* stream);
+
+/* ---- optimizer ----------------------------------------------------------------------------------
+ * torch.optim.Adam (voice2pose.py:249,263,274; pose2pose.py:114), wd = 0, over a flat fp32 buffer.
+ * state_host-free: scalars (step count -> bias corrections) live in `scalars` (device, 4 floats + 1 i64 as 8 floats):
+ *   sdt_adam_advance bumps the step and recomputes them on device so that a captured CUDA graph can replay;
+ *   grad_scale multiplies the gradient first (1/world_size after the NCCL sum). */
+int sdt_adam_advance(float* scalars, float lr, float beta1, float beta2, void* stream);
+int sdt_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* scalars,
+                  float beta1, float beta2, float eps, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDT_B200_H */

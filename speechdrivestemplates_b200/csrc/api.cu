@@ -1,0 +1,29 @@
+// Library-level entry points of libsdt_b200: error string, version, math-mode switch.
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace {
+thread_local char g_err[512] = "";
+std::atomic<int> g_conv_math{0};
+}  // namespace
+
+namespace sdt {
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace sdt
+
+extern "C" const char* sdt_last_error(void) { return g_err; }
+extern "C" int sdt_version(void) { return 100; }
+extern "C" int sdt_set_conv_math(int mode) {
+    SDT_REQUIRE(mode == 0 || mode == 1, "sdt_set_conv_math: mode must be 0 (fp32) or 1 (tf32 tcgen05)");
+    g_conv_math.store(mode);
+    return SDT_OK;
+}
+extern "C" int sdt_get_conv_math(void) { return g_conv_math.load(); }

@@ -1,0 +1,59 @@
+// Shared helpers for libsdt_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "sdt_b200.h"
+
+namespace sdt {
+
+void set_error(const char* fmt, ...);
+
+#define SDT_REQUIRE(cond, ...)                 \
+    do {                                       \
+        if (!(cond)) {                         \
+            sdt::set_error(__VA_ARGS__);       \
+            return SDT_ERR_ARG;                \
+        }                                      \
+    } while (0)
+
+#define SDT_CUDA_OK(expr)                                                                      \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            sdt::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return SDT_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+// after a kernel launch (legal during stream capture)
+#define SDT_LAUNCH_OK(name)                                                                    \
+    do {                                                                                       \
+        cudaError_t e_ = cudaPeekAtLastError();                                                \
+        if (e_ != cudaSuccess) {                                                               \
+            cudaGetLastError();                                                                \
+            sdt::set_error("launch of %s failed: %s", name, cudaGetErrorString(e_));           \
+            return SDT_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float leaky(float v, float slope) { return v > 0.f ? v : v * slope; }
+// derivative of LeakyReLU/ReLU from the sign of the (pre- or post-)activation value; 0 -> slope
+__device__ __forceinline__ float leaky_grad(float v, float slope) { return v > 0.f ? 1.f : slope; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace sdt

@@ -1,0 +1,597 @@
+// Convolution (1-D / 2-D, forward / data-gradient / weight-gradient) as implicit GEMM on channels-last fp32
+// tensors -- the fp32 FFMA ("math mode 0") path.  Replaces nn.Conv1d/nn.Conv2d inside ConvNormRelu
+// (core/networks/building_blocks.py:15-22,31-36,49) and their autograd backward.
+//
+// The previous layer's normalisation + activation is applied by the A-operand loader (x*scale+shift, LeakyReLU),
+// and the per-channel sum / sum-of-squares the NEXT normalisation needs are produced by the epilogue, so the
+// normalised activation tensor is never written to HBM (building_blocks.py:50-54 fused away).
+//
+// Tiling: BMxBNx16 CTA tiles, 256 threads, 8x8 / 8x4 / 4x4 register tiles, register-prefetch double buffering.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BK = 16;
+constexpr int NTHREADS = 256;
+
+struct RowSmem {
+    int b, sy0, sx0;
+    long long dst;  // element offset of the output row, -1 = row out of range
+};
+
+__device__ __forceinline__ float xf_apply(float v, float sc, float sh, float slope) {
+    return sdt::leaky(fmaf(v, sc, sh), slope);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward / dgrad:  dst[row(m), n] = sum_k A(m,k) * wt[k, n]
+// ------------------------------------------------------------------------------------------------
+template <int BM, int BN, int TM, int TN, bool VEC>
+__global__ void __launch_bounds__(NTHREADS, 2) conv_gemm_kernel(const sdt_conv_desc d) {
+    static_assert((BM / TM) * (BN / TN) == NTHREADS, "thread tile");
+    constexpr int LDA = BM + 4, LDB = BN + 4;
+    constexpr int GM = TM / 4, GN = TN / 4;
+    __shared__ __align__(16) float As[2][BK][LDA];
+    __shared__ __align__(16) float Bs[2][BK][LDB];
+    __shared__ RowSmem rows[BM];
+
+    const int tid = threadIdx.x;
+    const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+    const int K = d.TH * d.TW * d.C;
+    const int N = d.N;
+    const int P = d.GH * d.GW;
+    const int n0 = blockIdx.y * BN;
+
+    // ---- decode the BM rows of this tile once
+    for (int r = tid; r < BM; r += NTHREADS) {
+        int b, rem;
+        bool ok;
+        if (d.per_image_tiles) {
+            const int tpi = (P + BM - 1) / BM;
+            b = blockIdx.x / tpi;
+            rem = (blockIdx.x % tpi) * BM + r;
+            ok = rem < P;
+        } else {
+            const long long gm = (long long)blockIdx.x * BM + r;
+            ok = gm < (long long)d.B * P;
+            b = ok ? (int)(gm / P) : 0;
+            rem = ok ? (int)(gm % P) : 0;
+        }
+        RowSmem ri;
+        const int gy = rem / d.GW, gx = rem % d.GW;
+        ri.b = b;
+        ri.sy0 = gy * d.y_mul + d.y_off;
+        ri.sx0 = gx * d.x_mul + d.x_off;
+        ri.dst = ok ? (((long long)b * d.DH + (gy * d.dy_mul + d.dy_off)) * d.DW + (gx * d.dx_mul + d.dx_off)) * N : -1;
+        rows[r] = ri;
+    }
+    __syncthreads();
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    // ---- loaders.  A: row-fastest mapping (conflict-free transposed smem stores)
+    constexpr int A_PER_THREAD = BM * BK / NTHREADS;                 // scalars
+    constexpr int A_ITERS = VEC ? A_PER_THREAD / 4 : A_PER_THREAD;
+    constexpr int B_PER_THREAD = BK * BN / NTHREADS;
+    constexpr int B_ITERS = B_PER_THREAD / 4;                        // float4 slots (scalar fallback inside)
+    float a_reg[A_PER_THREAD];
+    float b_reg[B_PER_THREAD];
+    const int a_row = tid % BM;
+    const int a_k0 = tid / BM;  // + (NTHREADS/BM) * i
+    const bool has_xf = d.xf_scale != nullptr;
+    const bool n_vec = (N % 4) == 0;
+
+    auto load_tiles = [&](int kt) {
+        const int kbase = kt * BK;
+        const RowSmem ri = rows[a_row];
+        const bool row_ok = ri.dst >= 0;
+#pragma unroll
+        for (int i = 0; i < A_ITERS; ++i) {
+            const int kk = (a_k0 + (NTHREADS / BM) * i) * (VEC ? 4 : 1);
+            const int k = kbase + kk;
+            float v[VEC ? 4 : 1];
+#pragma unroll
+            for (int q = 0; q < (VEC ? 4 : 1); ++q) v[q] = 0.f;
+            if (row_ok && k < K) {
+                const int tap = k / d.C, c = k - tap * d.C;
+                const int tyy = tap / d.TW, txx = tap - tyy * d.TW;
+                const int sy = ri.sy0 + tyy * d.ty_mul, sx = ri.sx0 + txx * d.tx_mul;
+                if (sy >= 0 && sy < d.SH && sx >= 0 && sx < d.SW) {
+                    const float* p = d.src + (((size_t)ri.b * d.SH + sy) * d.SW + sx) * d.C + c;
+                    if (VEC) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+                        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                        if (has_xf) {
+                            const size_t o = (size_t)ri.b * d.xf_bstride + c;
+                            const float4 sc = __ldg(reinterpret_cast<const float4*>(d.xf_scale + o));
+                            const float4 sh = __ldg(reinterpret_cast<const float4*>(d.xf_shift + o));
+                            v[0] = xf_apply(v[0], sc.x, sh.x, d.xf_slope);
+                            v[1] = xf_apply(v[1], sc.y, sh.y, d.xf_slope);
+                            v[2] = xf_apply(v[2], sc.z, sh.z, d.xf_slope);
+                            v[3] = xf_apply(v[3], sc.w, sh.w, d.xf_slope);
+                        }
+                    } else {
+                        v[0] = __ldg(p);
+                        if (has_xf) {
+                            const size_t o = (size_t)ri.b * d.xf_bstride + c;
+                            v[0] = xf_apply(v[0], __ldg(d.xf_scale + o), __ldg(d.xf_shift + o), d.xf_slope);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < (VEC ? 4 : 1); ++q) a_reg[i * (VEC ? 4 : 1) + q] = v[q];
+        }
+#pragma unroll
+        for (int i = 0; i < B_ITERS; ++i) {
+            const int f = tid + i * NTHREADS;
+            const int kk = f / (BN / 4), nv = f % (BN / 4);
+            const int k = kbase + kk, n = n0 + nv * 4;
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < K) {
+                const float* p = d.wt + (size_t)k * N + n;
+                if (n_vec) {
+                    if (n < N) t = __ldg(reinterpret_cast<const float4*>(p));
+                } else {
+                    if (n + 0 < N) t.x = __ldg(p + 0);
+                    if (n + 1 < N) t.y = __ldg(p + 1);
+                    if (n + 2 < N) t.z = __ldg(p + 2);
+                    if (n + 3 < N) t.w = __ldg(p + 3);
+                }
+            }
+            b_reg[i * 4 + 0] = t.x; b_reg[i * 4 + 1] = t.y; b_reg[i * 4 + 2] = t.z; b_reg[i * 4 + 3] = t.w;
+        }
+    };
+    auto store_tiles = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < A_ITERS; ++i) {
+            const int kk = (a_k0 + (NTHREADS / BM) * i) * (VEC ? 4 : 1);
+#pragma unroll
+            for (int q = 0; q < (VEC ? 4 : 1); ++q) As[buf][kk + q][a_row] = a_reg[i * (VEC ? 4 : 1) + q];
+        }
+#pragma unroll
+        for (int i = 0; i < B_ITERS; ++i) {
+            const int f = tid + i * NTHREADS;
+            const int kk = f / (BN / 4), nv = f % (BN / 4);
+            *reinterpret_cast<float4*>(&Bs[buf][kk][nv * 4]) =
+                make_float4(b_reg[i * 4 + 0], b_reg[i * 4 + 1], b_reg[i * 4 + 2], b_reg[i * 4 + 3]);
+        }
+    };
+
+    const int KT = (K + BK - 1) / BK;
+    load_tiles(0);
+    store_tiles(0);
+    __syncthreads();
+    for (int kt = 0; kt < KT; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < KT) load_tiles(kt + 1);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float af[TM], bf[TN];
+#pragma unroll
+            for (int g = 0; g < GM; ++g) {
+                const float4 t = *reinterpret_cast<const float4*>(&As[buf][kk][g * (BM / GM) + ty * 4]);
+                af[g * 4 + 0] = t.x; af[g * 4 + 1] = t.y; af[g * 4 + 2] = t.z; af[g * 4 + 3] = t.w;
+            }
+#pragma unroll
+            for (int g = 0; g < GN; ++g) {
+                const float4 t = *reinterpret_cast<const float4*>(&Bs[buf][kk][g * (BN / GN) + tx * 4]);
+                bf[g * 4 + 0] = t.x; bf[g * 4 + 1] = t.y; bf[g * 4 + 2] = t.z; bf[g * 4 + 3] = t.w;
+            }
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(af[i], bf[j], acc[i][j]);
+        }
+        if (kt + 1 < KT) {
+            store_tiles(buf ^ 1);
+            __syncthreads();
+        }
+    }
+
+    // ---- epilogue: bias, store (optionally accumulate)
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int r = (i / 4) * (BM / GM) + ty * 4 + (i % 4);
+        const long long off = rows[r].dst;
+        if (off < 0) continue;
+#pragma unroll
+        for (int g = 0; g < GN; ++g) {
+            const int n = n0 + g * (BN / GN) + tx * 4;
+            float v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                v[q] = acc[i][g * 4 + q];
+                if (d.bias != nullptr && n + q < N) v[q] += __ldg(d.bias + n + q);
+            }
+            float* p = d.dst + off + n;
+            if (n_vec) {
+                if (n < N) {
+                    float4 o = make_float4(v[0], v[1], v[2], v[3]);
+                    if (d.accumulate) {
+                        const float4 old = *reinterpret_cast<const float4*>(p);
+                        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                    }
+                    *reinterpret_cast<float4*>(p) = o;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (n + q < N) p[q] = d.accumulate ? p[q] + v[q] : v[q];
+            }
+        }
+    }
+
+    // ---- epilogue: column sums / sums of squares of this row tile (input of sdt_norm_finalize).
+    // Rows outside the range hold exact zeros (their A rows were zero), so they do not disturb the sums.
+    if (d.stat_partial != nullptr) {
+        __syncthreads();  // everyone is done with As/Bs
+        float* red_s = &As[0][0][0];   // [BM/TM][BN]
+        float* red_q = &Bs[0][0][0];
+        static_assert((BM / TM) * BN <= 2 * BK * LDA && (BM / TM) * BN <= 2 * BK * LDB, "reduction scratch");
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            float s = 0.f, q = 0.f;
+#pragma unroll
+            for (int i = 0; i < TM; ++i) {
+                s += acc[i][j];
+                q = fmaf(acc[i][j], acc[i][j], q);
+            }
+            const int c = (j / 4) * (BN / GN) + tx * 4 + (j % 4);
+            red_s[ty * BN + c] = s;
+            red_q[ty * BN + c] = q;
+        }
+        __syncthreads();
+        for (int c = tid; c < BN; c += NTHREADS) {
+            if (n0 + c < N) {
+                float s = 0.f, q = 0.f;
+                for (int t = 0; t < BM / TM; ++t) {
+                    s += red_s[t * BN + c];
+                    q += red_q[t * BN + c];
+                }
+                d.stat_partial[((size_t)blockIdx.x * 2 + 0) * N + n0 + c] = s;
+                d.stat_partial[((size_t)blockIdx.x * 2 + 1) * N + n0 + c] = q;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad:  wpart[z][n][k] = sum_{m in split z} dy[m, n] * A(m, k)
+//   GEMM rows = output channels n (d.N), GEMM cols = k = (ty,tx,c), contraction over pixels m.
+// ------------------------------------------------------------------------------------------------
+template <int BM, int TM, bool VECA, bool VECB>
+__global__ void __launch_bounds__(NTHREADS, 2) conv_wgrad_kernel(const sdt_conv_desc d) {
+    constexpr int BN = 128, TN = 8;
+    static_assert((BM / TM) * (BN / TN) == NTHREADS, "thread tile");
+    constexpr int LDA = BM + 4, LDB = BN + 4;
+    constexpr int GM = TM / 4, GN = TN / 4;
+    __shared__ __align__(16) float As[2][BK][LDA];
+    __shared__ __align__(16) float Bs[2][BK][LDB];
+
+    const int tid = threadIdx.x;
+    const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+    const int Kc = d.TH * d.TW * d.C;       // GEMM N extent
+    const int Nout = d.N;                   // GEMM M extent
+    const int P = d.GH * d.GW;
+    const long long Mtot = (long long)d.B * P;
+    const int m0 = blockIdx.y * BM;         // output-channel offset
+    const int c0 = blockIdx.x * BN;         // k offset
+    long long chunk = (Mtot + d.splits - 1) / d.splits;
+    chunk = (chunk + BK - 1) / BK * BK;
+    const long long p_begin = (long long)blockIdx.z * chunk;
+    const long long p_end = p_begin + chunk < Mtot ? p_begin + chunk : Mtot;
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    constexpr int A_PER_THREAD = BK * BM / NTHREADS;
+    constexpr int B_PER_THREAD = BK * BN / NTHREADS;  // 8
+    float a_reg[A_PER_THREAD], b_reg[B_PER_THREAD];
+    const bool has_xf = d.xf_scale != nullptr;
+
+    // B-operand column decode is loop invariant.
+    // VECB: thread owns 4 consecutive k (same tap) at nv = tid % 32; rows kk = tid/32 + 8*i
+    // scalar: thread owns k = c0 + tid % 128; rows kk = tid/128 + 2*i
+    const int bcol = VECB ? (tid % (BN / 4)) * 4 : tid % BN;
+    const int kcol = c0 + bcol;
+    const bool col_ok = kcol < Kc;
+    int tap = 0, cc = 0, tyy = 0, txx = 0;
+    if (col_ok) {
+        tap = kcol / d.C; cc = kcol - tap * d.C;
+        tyy = tap / d.TW; txx = tap - tyy * d.TW;
+    }
+
+    auto load_tiles = [&](long long pbase) {
+        // A: dy[pix][m0 + m]
+        if (VECA) {
+#pragma unroll
+            for (int i = 0; i < A_PER_THREAD / 4; ++i) {
+                const int f = tid + i * NTHREADS;
+                const int kk = f / (BM / 4), mv = f % (BM / 4);
+                const long long pix = pbase + kk;
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pix < p_end && m0 + mv * 4 < Nout) t = __ldg(reinterpret_cast<const float4*>(d.dy + pix * Nout + m0 + mv * 4));
+                a_reg[i * 4 + 0] = t.x; a_reg[i * 4 + 1] = t.y; a_reg[i * 4 + 2] = t.z; a_reg[i * 4 + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < A_PER_THREAD; ++i) {
+                const int f = tid + i * NTHREADS;
+                const int kk = f / BM, m = f % BM;
+                const long long pix = pbase + kk;
+                a_reg[i] = (pix < p_end && m0 + m < Nout) ? __ldg(d.dy + pix * Nout + m0 + m) : 0.f;
+            }
+        }
+        // B: xf(src[b, sy, sx, c])
+#pragma unroll
+        for (int i = 0; i < (VECB ? B_PER_THREAD / 4 : B_PER_THREAD); ++i) {
+            const int kk = VECB ? tid / (BN / 4) + (NTHREADS / (BN / 4)) * i : tid / BN + (NTHREADS / BN) * i;
+            const long long pix = pbase + kk;
+            float v[VECB ? 4 : 1];
+#pragma unroll
+            for (int q = 0; q < (VECB ? 4 : 1); ++q) v[q] = 0.f;
+            if (col_ok && pix < p_end) {
+                const int b = (int)(pix / P);
+                const int rem = (int)(pix - (long long)b * P);
+                const int gy = rem / d.GW, gx = rem - gy * d.GW;
+                const int sy = gy * d.y_mul + d.y_off + tyy * d.ty_mul;
+                const int sx = gx * d.x_mul + d.x_off + txx * d.tx_mul;
+                if (sy >= 0 && sy < d.SH && sx >= 0 && sx < d.SW) {
+                    const float* p = d.src + (((size_t)b * d.SH + sy) * d.SW + sx) * d.C + cc;
+                    if (VECB) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+                        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                        if (has_xf) {
+                            const size_t o = (size_t)b * d.xf_bstride + cc;
+                            const float4 sc = __ldg(reinterpret_cast<const float4*>(d.xf_scale + o));
+                            const float4 sh = __ldg(reinterpret_cast<const float4*>(d.xf_shift + o));
+                            v[0] = xf_apply(v[0], sc.x, sh.x, d.xf_slope);
+                            v[1] = xf_apply(v[1], sc.y, sh.y, d.xf_slope);
+                            v[2] = xf_apply(v[2], sc.z, sh.z, d.xf_slope);
+                            v[3] = xf_apply(v[3], sc.w, sh.w, d.xf_slope);
+                        }
+                    } else {
+                        v[0] = __ldg(p);
+                        if (has_xf) {
+                            const size_t o = (size_t)b * d.xf_bstride + cc;
+                            v[0] = xf_apply(v[0], __ldg(d.xf_scale + o), __ldg(d.xf_shift + o), d.xf_slope);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < (VECB ? 4 : 1); ++q) b_reg[i * (VECB ? 4 : 1) + q] = v[q];
+        }
+    };
+    auto store_tiles = [&](int buf) {
+        if (VECA) {
+#pragma unroll
+            for (int i = 0; i < A_PER_THREAD / 4; ++i) {
+                const int f = tid + i * NTHREADS;
+                const int kk = f / (BM / 4), mv = f % (BM / 4);
+                *reinterpret_cast<float4*>(&As[buf][kk][mv * 4]) =
+                    make_float4(a_reg[i * 4 + 0], a_reg[i * 4 + 1], a_reg[i * 4 + 2], a_reg[i * 4 + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < A_PER_THREAD; ++i) {
+                const int f = tid + i * NTHREADS;
+                As[buf][f / BM][f % BM] = a_reg[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < (VECB ? B_PER_THREAD / 4 : B_PER_THREAD); ++i) {
+            const int kk = VECB ? tid / (BN / 4) + (NTHREADS / (BN / 4)) * i : tid / BN + (NTHREADS / BN) * i;
+            if (VECB) {
+                *reinterpret_cast<float4*>(&Bs[buf][kk][bcol]) =
+                    make_float4(b_reg[i * 4 + 0], b_reg[i * 4 + 1], b_reg[i * 4 + 2], b_reg[i * 4 + 3]);
+            } else {
+                Bs[buf][kk][bcol] = b_reg[i];
+            }
+        }
+    };
+
+    const int KT = p_end > p_begin ? (int)((p_end - p_begin + BK - 1) / BK) : 0;
+    if (KT > 0) {
+        load_tiles(p_begin);
+        store_tiles(0);
+    }
+    __syncthreads();
+    for (int kt = 0; kt < KT; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < KT) load_tiles(p_begin + (long long)(kt + 1) * BK);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float af[TM], bf[TN];
+#pragma unroll
+            for (int g = 0; g < GM; ++g) {
+                const float4 t = *reinterpret_cast<const float4*>(&As[buf][kk][g * (BM / GM) + ty * 4]);
+                af[g * 4 + 0] = t.x; af[g * 4 + 1] = t.y; af[g * 4 + 2] = t.z; af[g * 4 + 3] = t.w;
+            }
+#pragma unroll
+            for (int g = 0; g < GN; ++g) {
+                const float4 t = *reinterpret_cast<const float4*>(&Bs[buf][kk][g * (BN / GN) + tx * 4]);
+                bf[g * 4 + 0] = t.x; bf[g * 4 + 1] = t.y; bf[g * 4 + 2] = t.z; bf[g * 4 + 3] = t.w;
+            }
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(af[i], bf[j], acc[i][j]);
+        }
+        if (kt + 1 < KT) {
+            store_tiles(buf ^ 1);
+            __syncthreads();
+        }
+    }
+
+    float* out = d.wpart + (size_t)blockIdx.z * Nout * Kc;
+    const bool k_vec = (Kc % 4) == 0;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int m = m0 + (i / 4) * (BM / GM) + ty * 4 + (i % 4);
+        if (m >= Nout) continue;
+#pragma unroll
+        for (int g = 0; g < GN; ++g) {
+            const int k = c0 + g * (BN / GN) + tx * 4;
+            float* p = out + (size_t)m * Kc + k;
+            if (k_vec) {
+                if (k < Kc) *reinterpret_cast<float4*>(p) = make_float4(acc[i][g * 4], acc[i][g * 4 + 1], acc[i][g * 4 + 2], acc[i][g * 4 + 3]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (k + q < Kc) p[q] = acc[i][g * 4 + q];
+            }
+        }
+    }
+}
+
+__global__ void wgrad_reduce_kernel(const float* __restrict__ wpart, int splits, int N, int C, int T,
+                                    float* __restrict__ grad, int accumulate) {
+    // one thread per element of the reference-layout gradient (n, c, t); reads are strided but the tensor is small
+    const long long total = (long long)N * C * T;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int t = (int)(e % T);
+    const int c = (int)((e / T) % C);
+    const int n = (int)(e / ((long long)T * C));
+    const size_t src = (size_t)n * T * C + (size_t)t * C + c;
+    const size_t stride = (size_t)N * T * C;
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += wpart[z * stride + src];
+    grad[e] = accumulate ? grad[e] + s : s;
+}
+
+__global__ void weight_prep_kernel(const float* __restrict__ w, int Cout, int Cin, int KH, int KW, int mode, int ky0,
+                                   int kx0, int kstep, int TH, int TW, float* __restrict__ out) {
+    const long long total = (long long)TH * TW * Cin * Cout;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    int co, ci, jy, jx;
+    if (mode == 0) {  // out[((jy*TW+jx)*Cin + ci)*Cout + co]
+        co = (int)(e % Cout);
+        ci = (int)((e / Cout) % Cin);
+        const int tap = (int)(e / ((long long)Cout * Cin));
+        jy = tap / TW; jx = tap % TW;
+    } else {          // out[((jy*TW+jx)*Cout + co)*Cin + ci]
+        ci = (int)(e % Cin);
+        co = (int)((e / Cin) % Cout);
+        const int tap = (int)(e / ((long long)Cout * Cin));
+        jy = tap / TW; jx = tap % TW;
+    }
+    const int ky = ky0 + kstep * jy, kx = kx0 + kstep * jx;
+    out[e] = w[(((size_t)co * Cin + ci) * KH + ky) * KW + kx];
+}
+
+int check_desc(const sdt_conv_desc* d, const char* who) {
+    SDT_REQUIRE(d != nullptr, "%s: null descriptor", who);
+    SDT_REQUIRE(d->src != nullptr, "%s: null src", who);
+    SDT_REQUIRE(d->B > 0 && d->SH > 0 && d->SW > 0 && d->C > 0 && d->GH > 0 && d->GW > 0 && d->TH > 0 && d->TW > 0 && d->N > 0,
+                "%s: non-positive extent (B=%d SH=%d SW=%d C=%d GH=%d GW=%d TH=%d TW=%d N=%d)", who, d->B, d->SH, d->SW,
+                d->C, d->GH, d->GW, d->TH, d->TW, d->N);
+    SDT_REQUIRE((d->xf_scale == nullptr) == (d->xf_shift == nullptr), "%s: xf_scale and xf_shift must come together", who);
+    SDT_REQUIRE(d->xf_scale == nullptr || d->xf_bstride == 0 || d->xf_bstride == d->C, "%s: xf_bstride must be 0 or C", who);
+    return SDT_OK;
+}
+
+inline int row_tiles_for(const sdt_conv_desc* d, int BM) {
+    const long long P = (long long)d->GH * d->GW;
+    if (d->per_image_tiles) return (int)(d->B * ((P + BM - 1) / BM));
+    return (int)((d->B * P + BM - 1) / BM);
+}
+
+// tile choice shared by sdt_conv_row_tiles and sdt_conv_gemm
+inline int pick_bm(const sdt_conv_desc* d) {
+    const long long M = (long long)d->B * d->GH * d->GW;
+    // small problems (1-D stacks): 64x64 tiles to get more CTAs in flight
+    if (!d->per_image_tiles && M * d->N <= (long long)128 * 128 * 148) return 64;
+    return 128;
+}
+
+}  // namespace
+
+extern "C" int sdt_conv_row_tiles(const sdt_conv_desc* d) {
+    if (check_desc(d, "sdt_conv_row_tiles") != SDT_OK) return -1;
+    return row_tiles_for(d, pick_bm(d));
+}
+
+extern "C" int sdt_conv_gemm(const sdt_conv_desc* d, void* stream) {
+    if (int rc = check_desc(d, "sdt_conv_gemm")) return rc;
+    SDT_REQUIRE(d->wt && d->dst, "sdt_conv_gemm: null wt/dst");
+    SDT_REQUIRE(!(d->stat_partial && d->bias), "sdt_conv_gemm: statistics epilogue excludes bias");
+    SDT_REQUIRE(!(d->stat_partial && d->accumulate), "sdt_conv_gemm: statistics epilogue excludes accumulate");
+    const bool vec = (d->C % 4) == 0;
+    const int bm = pick_bm(d);
+    cudaStream_t st = sdt::as_stream(stream);
+    const sdt_conv_desc dd = *d;
+    if (bm == 64) {
+        dim3 grid(row_tiles_for(d, 64), sdt::ceil_div(d->N, 64));
+        if (vec) conv_gemm_kernel<64, 64, 4, 4, true><<<grid, NTHREADS, 0, st>>>(dd);
+        else conv_gemm_kernel<64, 64, 4, 4, false><<<grid, NTHREADS, 0, st>>>(dd);
+    } else if (d->N <= 64) {
+        dim3 grid(row_tiles_for(d, 128), sdt::ceil_div(d->N, 64));
+        if (vec) conv_gemm_kernel<128, 64, 8, 4, true><<<grid, NTHREADS, 0, st>>>(dd);
+        else conv_gemm_kernel<128, 64, 8, 4, false><<<grid, NTHREADS, 0, st>>>(dd);
+    } else {
+        dim3 grid(row_tiles_for(d, 128), sdt::ceil_div(d->N, 128));
+        if (vec) conv_gemm_kernel<128, 128, 8, 8, true><<<grid, NTHREADS, 0, st>>>(dd);
+        else conv_gemm_kernel<128, 128, 8, 8, false><<<grid, NTHREADS, 0, st>>>(dd);
+    }
+    SDT_LAUNCH_OK("conv_gemm_kernel");
+    return SDT_OK;
+}
+
+extern "C" int sdt_conv_wgrad(const sdt_conv_desc* d, void* stream) {
+    if (int rc = check_desc(d, "sdt_conv_wgrad")) return rc;
+    SDT_REQUIRE(d->dy && d->wpart, "sdt_conv_wgrad: null dy/wpart");
+    SDT_REQUIRE(d->splits >= 1 && d->splits <= 65535, "sdt_conv_wgrad: splits=%d out of range", d->splits);
+    const int Kc = d->TH * d->TW * d->C;
+    const bool veca = (d->N % 4) == 0, vecb = (d->C % 4) == 0;
+    cudaStream_t st = sdt::as_stream(stream);
+    const sdt_conv_desc dd = *d;
+    if (d->N <= 64) {
+        dim3 grid(sdt::ceil_div(Kc, 128), sdt::ceil_div(d->N, 64), d->splits);
+        if (veca && vecb) conv_wgrad_kernel<64, 4, true, true><<<grid, NTHREADS, 0, st>>>(dd);
+        else if (veca) conv_wgrad_kernel<64, 4, true, false><<<grid, NTHREADS, 0, st>>>(dd);
+        else if (vecb) conv_wgrad_kernel<64, 4, false, true><<<grid, NTHREADS, 0, st>>>(dd);
+        else conv_wgrad_kernel<64, 4, false, false><<<grid, NTHREADS, 0, st>>>(dd);
+    } else {
+        dim3 grid(sdt::ceil_div(Kc, 128), sdt::ceil_div(d->N, 128), d->splits);
+        if (veca && vecb) conv_wgrad_kernel<128, 8, true, true><<<grid, NTHREADS, 0, st>>>(dd);
+        else if (veca) conv_wgrad_kernel<128, 8, true, false><<<grid, NTHREADS, 0, st>>>(dd);
+        else if (vecb) conv_wgrad_kernel<128, 8, false, true><<<grid, NTHREADS, 0, st>>>(dd);
+        else conv_wgrad_kernel<128, 8, false, false><<<grid, NTHREADS, 0, st>>>(dd);
+    }
+    SDT_LAUNCH_OK("conv_wgrad_kernel");
+    return SDT_OK;
+}
+
+extern "C" int sdt_conv_wgrad_reduce(const float* wpart, int splits, int N, int C, int T, float* grad, int accumulate,
+                                     void* stream) {
+    SDT_REQUIRE(wpart && grad && splits >= 1 && N > 0 && C > 0 && T > 0, "sdt_conv_wgrad_reduce: bad arguments");
+    const long long total = (long long)N * C * T;
+    wgrad_reduce_kernel<<<sdt::ceil_div(total, 256), 256, 0, sdt::as_stream(stream)>>>(wpart, splits, N, C, T, grad, accumulate);
+    SDT_LAUNCH_OK("wgrad_reduce_kernel");
+    return SDT_OK;
+}
+
+extern "C" int sdt_weight_prep(const float* w, int Cout, int Cin, int KH, int KW, int mode, int ky0, int kx0, int kstep,
+                               int TH, int TW, float* out, void* stream) {
+    SDT_REQUIRE(w && out, "sdt_weight_prep: null pointer");
+    SDT_REQUIRE(Cout > 0 && Cin > 0 && KH > 0 && KW > 0 && TH > 0 && TW > 0 && kstep > 0, "sdt_weight_prep: bad extents");
+    SDT_REQUIRE(mode == 0 || mode == 1, "sdt_weight_prep: mode must be 0 or 1");
+    SDT_REQUIRE(ky0 >= 0 && kx0 >= 0 && ky0 + kstep * (TH - 1) < KH && kx0 + kstep * (TW - 1) < KW,
+                "sdt_weight_prep: tap selection outside the %dx%d kernel", KH, KW);
+    const long long total = (long long)TH * TW * Cin * Cout;
+    weight_prep_kernel<<<sdt::ceil_div(total, 256), 256, 0, sdt::as_stream(stream)>>>(w, Cout, Cin, KH, KW, mode, ky0, kx0,
+                                                                                       kstep, TH, TW, out);
+    SDT_LAUNCH_OK("weight_prep_kernel");
+    return SDT_OK;
+}

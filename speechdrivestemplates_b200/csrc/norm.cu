@@ -1,0 +1,336 @@
+// Normalisation kernels: InstanceNorm2d / BatchNorm{1,2}d statistics finalisation and backward, and the
+// channel-LayerNorm that the reference's "InstanceNorm1d on the permuted tensor" amounts to
+// (core/networks/building_blocks.py:23-27,38-43,50-54).  All reductions are fixed-order (deterministic).
+#include "common.cuh"
+
+namespace {
+
+// ---- statistics finalisation ---------------------------------------------------------------------
+__global__ void norm_finalize_kernel(const float* __restrict__ partial, int groups, int tiles_per_group, int C,
+                                     double count, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     float eps, float* __restrict__ scale, float* __restrict__ shift,
+                                     float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                     float* __restrict__ running_mean, float* __restrict__ running_var,
+                                     int64_t* __restrict__ nbt, float momentum) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e == 0 && nbt != nullptr) *nbt += 1;
+    if (e >= groups * C) return;
+    const int g = e / C, c = e % C;
+    double s = 0.0, q = 0.0;
+    const float* p = partial + (size_t)g * tiles_per_group * 2 * C;
+    for (int t = 0; t < tiles_per_group; ++t) {
+        s += (double)p[((size_t)t * 2 + 0) * C + c];
+        q += (double)p[((size_t)t * 2 + 1) * C + c];
+    }
+    const double mean = s / count;
+    double var = q / count - mean * mean;   // biased
+    if (var < 0.0) var = 0.0;
+    const float meanf = (float)mean;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    const float sc = rstd * ga;
+    scale[e] = sc;
+    shift[e] = be - meanf * sc;
+    if (mean_out) mean_out[e] = meanf;
+    if (rstd_out) rstd_out[e] = rstd;
+    if (running_mean != nullptr && g == 0) {
+        const double unbiased = count > 1.0 ? var * (count / (count - 1.0)) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * meanf;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+
+__global__ void bn_eval_kernel(const float* __restrict__ rm, const float* __restrict__ rv, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, float eps, int C, float* __restrict__ scale,
+                               float* __restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float rstd = 1.0f / sqrtf(rv[c] + eps);
+    const float sc = rstd * (gamma ? gamma[c] : 1.f);
+    scale[c] = sc;
+    shift[c] = (beta ? beta[c] : 0.f) - rm[c] * sc;
+}
+
+// ---- backward of normalise -> affine -> activation over (B, P, C) ----------------------------------
+// CTA = 256 threads = 8 row-lanes x 32 channel-quads (C handled in chunks of 128), tile of ROWS_PER_TILE pixels.
+constexpr int kBwdRows = 256;
+
+__global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float* __restrict__ g, const float* __restrict__ x,
+                                                              const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              int P, int C, int groups_is_batch, float slope,
+                                                              float* __restrict__ partial, int tiles_per_image) {
+    __shared__ float red[2][8][128];
+    const int b = blockIdx.x / tiles_per_image, tile = blockIdx.x % tiles_per_image;
+    const int cq = threadIdx.x % 32, rl = threadIdx.x / 32;
+    const int p0 = tile * kBwdRows;
+    const int p1 = min(P, p0 + kBwdRows);
+    for (int cb = 0; cb < C; cb += 128) {
+        const int c = cb + cq * 4;
+        float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+        if (c < C) {
+            const int so = (groups_is_batch ? b * C : 0) + c;
+            float mu[4], rs[4], ga[4], be[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                mu[q] = mean[so + q]; rs[q] = rstd[so + q];
+                ga[q] = gamma ? gamma[c + q] : 1.f; be[q] = beta ? beta[c + q] : 0.f;
+            }
+            for (int p = p0 + rl; p < p1; p += 8) {
+                const size_t o = ((size_t)b * P + p) * C + c;
+                const float4 gv = *reinterpret_cast<const float4*>(g + o);
+                const float4 xv = *reinterpret_cast<const float4*>(x + o);
+                const float gg[4] = {gv.x, gv.y, gv.z, gv.w}, xx[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float xh = (xx[q] - mu[q]) * rs[q];
+                    const float y = fmaf(xh, ga[q], be[q]);
+                    const float gp = gg[q] * sdt::leaky_grad(y, slope);
+                    s1[q] += gp;
+                    s2[q] = fmaf(gp, xh, s2[q]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            red[0][rl][cq * 4 + q] = s1[q];
+            red[1][rl][cq * 4 + q] = s2[q];
+        }
+        __syncthreads();
+        if (threadIdx.x < 128 && cb + threadIdx.x < C) {
+            float a = 0.f, bsum = 0.f;
+            for (int r = 0; r < 8; ++r) {
+                a += red[0][r][threadIdx.x];
+                bsum += red[1][r][threadIdx.x];
+            }
+            partial[((size_t)blockIdx.x * 2 + 0) * C + cb + threadIdx.x] = a;
+            partial[((size_t)blockIdx.x * 2 + 1) * C + cb + threadIdx.x] = bsum;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void norm_bwd_finalize_kernel(const float* __restrict__ partial, int groups, int tiles_per_group, int C,
+                                         double count, float* __restrict__ m1, float* __restrict__ m2,
+                                         float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= groups * C) return;
+    const int gidx = e / C, c = e % C;
+    double s1 = 0.0, s2 = 0.0;
+    const float* p = partial + (size_t)gidx * tiles_per_group * 2 * C;
+    for (int t = 0; t < tiles_per_group; ++t) {
+        s1 += (double)p[((size_t)t * 2 + 0) * C + c];
+        s2 += (double)p[((size_t)t * 2 + 1) * C + c];
+    }
+    m1[e] = (float)(s1 / count);
+    m2[e] = (float)(s2 / count);
+    if (dgamma != nullptr && gidx == 0) {   // BatchNorm affine gradients: dgamma = sum g'*xhat, dbeta = sum g'
+        dgamma[c] = accumulate ? dgamma[c] + (float)s2 : (float)s2;
+        dbeta[c] = accumulate ? dbeta[c] + (float)s1 : (float)s1;
+    }
+}
+
+__global__ void __launch_bounds__(256) norm_bwd_apply_kernel(float* __restrict__ g, const float* __restrict__ x,
+                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             const float* __restrict__ m1, const float* __restrict__ m2,
+                                                             long long total4, int P, int C, int groups_is_batch, float slope) {
+    const long long e4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e4 >= total4) return;
+    const long long e = e4 * 4;
+    const int c = (int)(e % C);
+    const int b = (int)(e / ((long long)P * C));
+    const int so = (groups_is_batch ? b * C : 0) + c;
+    float4 gv = *reinterpret_cast<const float4*>(g + e);
+    const float4 xv = *reinterpret_cast<const float4*>(x + e);
+    float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+    const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float rs = rstd[so + q];
+        const float ga = gamma ? gamma[c + q] : 1.f, be = beta ? beta[c + q] : 0.f;
+        const float xh = (xx[q] - mean[so + q]) * rs;
+        const float y = fmaf(xh, ga, be);
+        const float gp = gg[q] * sdt::leaky_grad(y, slope);
+        gg[q] = rs * ga * (gp - m1[so + q] - xh * m2[so + q]);
+    }
+    *reinterpret_cast<float4*>(g + e) = make_float4(gg[0], gg[1], gg[2], gg[3]);
+}
+
+// ---- channel LayerNorm (+ activation) over rows of (R, C): one warp per row ---------------------------
+template <int MAXV>
+__global__ void __launch_bounds__(256) rownorm_fwd_kernel(const float* __restrict__ x, int R, int C, float eps, float slope,
+                                                          float* __restrict__ y, float* __restrict__ mean,
+                                                          float* __restrict__ rstd) {
+    const int row = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
+    if (row >= R) return;
+    const float* xr = x + (size_t)row * C;
+    float v[MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = lane + 32 * i;
+        v[i] = c < C ? xr[c] : 0.f;
+        s += v[i];
+    }
+    const float mu = sdt::warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = lane + 32 * i;
+        const float dlt = c < C ? v[i] - mu : 0.f;
+        q = fmaf(dlt, dlt, q);
+    }
+    const float var = sdt::warp_sum(q) / (float)C;   // biased
+    const float rs = 1.0f / sqrtf(var + eps);
+    float* yr = y + (size_t)row * C;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < C) yr[c] = sdt::leaky((v[i] - mu) * rs, slope);
+    }
+    if (lane == 0) {
+        mean[row] = mu;
+        rstd[row] = rs;
+    }
+}
+
+template <int MAXV>
+__global__ void __launch_bounds__(256) rownorm_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x,
+                                                          const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                          int R, int C, float slope, float* __restrict__ gx) {
+    const int row = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
+    if (row >= R) return;
+    const float mu = mean[row], rs = rstd[row];
+    const float* xr = x + (size_t)row * C;
+    const float* gr = gy + (size_t)row * C;
+    float xh[MAXV], gp[MAXV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = lane + 32 * i;
+        xh[i] = 0.f; gp[i] = 0.f;
+        if (c < C) {
+            xh[i] = (xr[c] - mu) * rs;
+            gp[i] = gr[c] * sdt::leaky_grad(xh[i], slope);
+        }
+        s1 += gp[i];
+        s2 = fmaf(gp[i], xh[i], s2);
+    }
+    const float m1 = sdt::warp_sum(s1) / (float)C, m2 = sdt::warp_sum(s2) / (float)C;
+    float* o = gx + (size_t)row * C;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < C) o[c] = rs * (gp[i] - m1 - xh[i] * m2);
+    }
+}
+
+__global__ void scale_shift_act_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                       const float* __restrict__ shift, long long total, int P, int C, int bstride,
+                                       float slope, float* __restrict__ y) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int c = (int)(e % C);
+    const int b = (int)(e / ((long long)P * C));
+    const int so = b * bstride + c;
+    y[e] = sdt::leaky(fmaf(x[e], scale[so], shift[so]), slope);
+}
+
+}  // namespace
+
+extern "C" int sdt_norm_finalize(const float* partial, int groups, int tiles_per_group, int C, double count,
+                                 const float* gamma, const float* beta, float eps, float* scale, float* shift, float* mean,
+                                 float* rstd, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                                 float momentum, void* stream) {
+    SDT_REQUIRE(partial && scale && shift, "sdt_norm_finalize: null pointer");
+    SDT_REQUIRE(groups > 0 && tiles_per_group > 0 && C > 0 && count > 0, "sdt_norm_finalize: bad extents");
+    SDT_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "sdt_norm_finalize: running stats come together");
+    SDT_REQUIRE(running_mean == nullptr || groups == 1, "sdt_norm_finalize: running statistics need groups == 1 (BatchNorm)");
+    norm_finalize_kernel<<<sdt::ceil_div((long long)groups * C, 128), 128, 0, sdt::as_stream(stream)>>>(
+        partial, groups, tiles_per_group, C, count, gamma, beta, eps, scale, shift, mean, rstd, running_mean, running_var,
+        num_batches_tracked, momentum);
+    SDT_LAUNCH_OK("norm_finalize_kernel");
+    return SDT_OK;
+}
+
+extern "C" int sdt_bn_eval_scale_shift(const float* running_mean, const float* running_var, const float* gamma,
+                                       const float* beta, float eps, int C, float* scale, float* shift, void* stream) {
+    SDT_REQUIRE(running_mean && running_var && scale && shift && C > 0, "sdt_bn_eval_scale_shift: bad arguments");
+    bn_eval_kernel<<<sdt::ceil_div(C, 128), 128, 0, sdt::as_stream(stream)>>>(running_mean, running_var, gamma, beta, eps, C,
+                                                                             scale, shift);
+    SDT_LAUNCH_OK("bn_eval_kernel");
+    return SDT_OK;
+}
+
+extern "C" int sdt_norm_bwd_reduce(const float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
+                                   const float* beta, int B, int P, int C, int groups, float slope, float* partial,
+                                   int tiles_per_image, void* stream) {
+    SDT_REQUIRE(g && x && mean && rstd && partial, "sdt_norm_bwd_reduce: null pointer");
+    SDT_REQUIRE(B > 0 && P > 0 && C > 0 && C % 4 == 0, "sdt_norm_bwd_reduce: need C %% 4 == 0 (C=%d)", C);
+    SDT_REQUIRE(groups == B || groups == 1, "sdt_norm_bwd_reduce: groups must be B or 1");
+    SDT_REQUIRE(tiles_per_image == sdt::ceil_div(P, kBwdRows), "sdt_norm_bwd_reduce: tiles_per_image must be ceil(P/%d)", kBwdRows);
+    norm_bwd_reduce_kernel<<<B * tiles_per_image, 256, 0, sdt::as_stream(stream)>>>(g, x, mean, rstd, gamma, beta, P, C,
+                                                                                    groups == B ? 1 : 0,
+                                                                                    slope, partial, tiles_per_image);
+    SDT_LAUNCH_OK("norm_bwd_reduce_kernel");
+    return SDT_OK;
+}
+
+extern "C" int sdt_norm_bwd_finalize(const float* partial, int groups, int tiles_per_group, int C, double count, float* m1,
+                                     float* m2, float* dgamma, float* dbeta, int accumulate, void* stream) {
+    SDT_REQUIRE(partial && m1 && m2, "sdt_norm_bwd_finalize: null pointer");
+    SDT_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "sdt_norm_bwd_finalize: dgamma/dbeta come together");
+    SDT_REQUIRE(dgamma == nullptr || groups == 1, "sdt_norm_bwd_finalize: affine gradients need groups == 1");
+    norm_bwd_finalize_kernel<<<sdt::ceil_div((long long)groups * C, 128), 128, 0, sdt::as_stream(stream)>>>(
+        partial, groups, tiles_per_group, C, count, m1, m2, dgamma, dbeta, accumulate);
+    SDT_LAUNCH_OK("norm_bwd_finalize_kernel");
+    return SDT_OK;
+}
+
+extern "C" int sdt_norm_bwd_apply(float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
+                                  const float* beta, const float* m1, const float* m2, int B, int P, int C, int groups,
+                                  float slope, void* stream) {
+    SDT_REQUIRE(g && x && mean && rstd && m1 && m2, "sdt_norm_bwd_apply: null pointer");
+    SDT_REQUIRE(C % 4 == 0, "sdt_norm_bwd_apply: need C %% 4 == 0 (C=%d)", C);
+    SDT_REQUIRE(groups == B || groups == 1, "sdt_norm_bwd_apply: groups must be B or 1");
+    const long long total4 = (long long)B * P * C / 4;
+    norm_bwd_apply_kernel<<<sdt::ceil_div(total4, 256), 256, 0, sdt::as_stream(stream)>>>(g, x, mean, rstd, gamma, beta, m1, m2,
+                                                                                         total4, P, C, groups == B ? 1 : 0, slope);
+    SDT_LAUNCH_OK("norm_bwd_apply_kernel");
+    return SDT_OK;
+}
+
+extern "C" int sdt_rownorm_act_fwd(const float* x, int R, int C, float eps, float slope, float* y, float* mean, float* rstd,
+                                   void* stream) {
+    SDT_REQUIRE(x && y && mean && rstd && R > 0 && C > 0, "sdt_rownorm_act_fwd: bad arguments");
+    SDT_REQUIRE(C <= 1024, "sdt_rownorm_act_fwd: C=%d > 1024 unsupported", C);
+    cudaStream_t st = sdt::as_stream(stream);
+    const int grid = sdt::ceil_div(R, 8);
+    if (C <= 256) rownorm_fwd_kernel<8><<<grid, 256, 0, st>>>(x, R, C, eps, slope, y, mean, rstd);
+    else rownorm_fwd_kernel<32><<<grid, 256, 0, st>>>(x, R, C, eps, slope, y, mean, rstd);
+    SDT_LAUNCH_OK("rownorm_fwd_kernel");
+    return SDT_OK;
+}
+
+extern "C" int sdt_rownorm_act_bwd(const float* g_y, const float* x, const float* mean, const float* rstd, int R, int C,
+                                   float slope, float* g_x, void* stream) {
+    SDT_REQUIRE(g_y && x && mean && rstd && g_x && R > 0 && C > 0, "sdt_rownorm_act_bwd: bad arguments");
+    SDT_REQUIRE(C <= 1024, "sdt_rownorm_act_bwd: C=%d > 1024 unsupported", C);
+    cudaStream_t st = sdt::as_stream(stream);
+    const int grid = sdt::ceil_div(R, 8);
+    if (C <= 256) rownorm_bwd_kernel<8><<<grid, 256, 0, st>>>(g_y, x, mean, rstd, R, C, slope, g_x);
+    else rownorm_bwd_kernel<32><<<grid, 256, 0, st>>>(g_y, x, mean, rstd, R, C, slope, g_x);
+    SDT_LAUNCH_OK("rownorm_bwd_kernel");
+    return SDT_OK;
+}
+
+extern "C" int sdt_scale_shift_act(const float* x, const float* scale, const float* shift, int B, int P, int C, int bstride,
+                                   float slope, float* y, void* stream) {
+    SDT_REQUIRE(x && scale && shift && y && B > 0 && P > 0 && C > 0, "sdt_scale_shift_act: bad arguments");
+    const long long total = (long long)B * P * C;
+    scale_shift_act_kernel<<<sdt::ceil_div(total, 256), 256, 0, sdt::as_stream(stream)>>>(x, scale, shift, total, P, C, bstride,
+                                                                                         slope, y);
+    SDT_LAUNCH_OK("scale_shift_act_kernel");
+    return SDT_OK;
+}

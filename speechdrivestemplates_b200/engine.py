@@ -1,0 +1,398 @@
+"""Execution engines of the hot path: they own the HBM workspaces (channels-last activations, statistics,
+gradient buffers) and sequence the C-ABI kernels for forward and backward.  No autograd inside; the nn.Module
+drop-ins (networks.py) and the fused train step (pipeline.py) sit on top.
+
+Layer tables follow the reference: AudioEncoder generator.py:15-30, UNet_1D :53-68, decoder :98-104,
+PoseSeqEncoder autoencoder.py:17-25.  HBM layout: 2-D maps (B,H,W,C), sequences (B,L,C); what is stored for a
+2-D block is its RAW convolution output plus per-(b,c) [IN] or per-c [BN] (scale, shift); the next consumer's loader
+normalises + activates on the fly.  The 1-D generator stack stores activated tensors (they are tiny).
+"""
+import torch
+
+from . import ops
+from .ops import ConvGeom
+
+# (state-dict suffix, Cout, Cin, kh, kw, stride, pad) -- generator.py:15-30
+ENC2D = [
+    ("0.0", 64, 1, 3, 3, 1, 1), ("0.1", 64, 64, 4, 4, 2, 1),
+    ("1.0", 128, 64, 3, 3, 1, 1), ("1.1", 128, 128, 4, 4, 2, 1),
+    ("2.0", 256, 128, 3, 3, 1, 1), ("2.1", 256, 256, 4, 4, 2, 1),
+    ("3.0", 256, 256, 3, 3, 1, 1), ("3.1", 256, 256, 6, 3, 1, 0),
+]
+ENC_PREFIX = "audio_encoder.specgram_encoder_2d."
+UNET_E = ["e0", "e1", "e2", "e3", "e4", "e5", "e6"]
+UNET_D = ["d5", "d4", "d3", "d2", "d1"]
+
+
+class Arena:
+    """Named persistent device buffers (allocated once through PyTorch's caching allocator)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+
+    def get(self, name, shape, dtype=torch.float32, zero=False):
+        shape = tuple(int(s) for s in shape)
+        t = self.bufs.get(name)
+        if t is None or tuple(t.shape) != shape or t.dtype != dtype:
+            t = (torch.zeros if zero else torch.empty)(shape, device=self.device, dtype=dtype)
+            self.bufs[name] = t
+        return t
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.bufs.values())
+
+
+def seq_lengths(num_frames):
+    """Lengths of the UNet levels e1..e6 for an input of num_frames (k=4, s=2, p=1 halves with floor)."""
+    ls = [num_frames]
+    for _ in range(5):
+        ls.append((ls[-1] + 2 - 4) // 2 + 1)
+    return ls   # [L(e0/e1), L(e2), ..., L(e6)]
+
+
+class GeneratorEngine:
+    """SequenceGeneratorCNN (generator.py:87-117): forward and backward on caller-provided parameter tensors.
+
+    params / grads: dicts keyed by the reference's state-dict names relative to the generator
+    (e.g. 'audio_encoder.specgram_encoder_2d.0.0.conv.weight', 'unet.e0.conv.weight', 'decoder.4.bias').
+    """
+
+    def __init__(self, norm, leaky, code_dim, n_landmarks, device):
+        if norm not in ("IN", "BN"):
+            raise NotImplementedError(norm)                # building_blocks.py:27-28
+        self.norm = norm
+        self.slope = 0.2 if leaky else 0.0
+        self.code_dim = code_dim or 0
+        self.kp2 = n_landmarks * 2
+        self.device = device
+        self.arena = Arena(device)
+        self.enc_geoms = [ConvGeom.conv2d(ci, co, kh, kw, s, p) for (_n, co, ci, kh, kw, s, p) in ENC2D]
+        self.shape_key = None
+        self.fwd_id = 0
+
+    # ---- static layer tables -------------------------------------------------------------------
+    def seq_layers(self):
+        """[(name, geom, input_kind)] of the 1-D stack in forward order. input_kind: 'x0' | 'act:<name>' | 'up:<prev>+<skip>'."""
+        c0 = 256 + self.code_dim
+        out = [("unet.e0", ConvGeom.conv1d(c0, 256, 3, 1, 1), "x0"),
+               ("unet.e1", ConvGeom.conv1d(256, 256, 3, 1, 1), "act:unet.e0")]
+        for i in range(2, 7):
+            out.append(("unet.e%d" % i, ConvGeom.conv1d(256, 256, 4, 2, 1), "act:unet.e%d" % (i - 1)))
+        prev = "unet.e6"
+        for j, n in enumerate(UNET_D):
+            out.append(("unet." + n, ConvGeom.conv1d(256, 256, 3, 1, 1), "up:%s+unet.e%d" % (prev, 5 - j)))
+            prev = "unet." + n
+        for i in range(4):
+            out.append(("decoder.%d" % i, ConvGeom.conv1d(256, 256, 3, 1, 1), "act:" + prev))
+            prev = "decoder.%d" % i
+        return out
+
+    def param_shapes(self):
+        """Reference parameter/buffer layout (name -> shape); BN affine + running stats only when norm == 'BN'."""
+        shapes = {}
+
+        def block(prefix, wshape):
+            shapes[prefix + ".conv.weight"] = wshape
+            if self.norm == "BN":
+                c = wshape[0]
+                shapes[prefix + ".norm.weight"] = (c,)
+                shapes[prefix + ".norm.bias"] = (c,)
+
+        for (n, co, ci, kh, kw, _s, _p) in ENC2D:
+            block(ENC_PREFIX + n, (co, ci, kh, kw))
+        for name, g, _k in self.seq_layers():
+            block(name, (g.cout, g.cin, g.kw))
+        shapes["decoder.4.weight"] = (self.kp2, 256, 1)
+        shapes["decoder.4.bias"] = (self.kp2,)
+        return shapes
+
+    # ---- helpers ----------------------------------------------------------------------------------
+    def _setup(self, B, T, F):
+        key = (B, T, F)
+        if self.shape_key == key:
+            return
+        self.shape_key = key
+        self.B, self.T, self.F = B, T, F
+        hw = [(80, T)]
+        for g in self.enc_geoms:
+            hw.append(g.out_hw(*hw[-1]))
+        self.enc_hw = hw                               # hw[l] = input size of layer l; hw[l+1] = its output size
+        ls = seq_lengths(F)
+        self.seq_len = {"x0": F}
+        for i, n in enumerate(UNET_E):
+            self.seq_len["unet." + n] = ls[max(0, i - 1)] if i >= 1 else F
+        # e0,e1: F ; e2: ls[1]; ... e6: ls[5]
+        self.seq_len["unet.e0"] = F
+        self.seq_len["unet.e1"] = F
+        for i in range(2, 7):
+            self.seq_len["unet.e%d" % i] = ls[i - 1]
+        for j, n in enumerate(UNET_D):
+            self.seq_len["unet." + n] = self.seq_len["unet.e%d" % (5 - j)]
+        for i in range(4):
+            self.seq_len["decoder.%d" % i] = F
+
+    def _groups(self):
+        return self.B if self.norm == "IN" else 1
+
+    def _bstride(self, c):
+        return c if self.norm == "IN" else 0
+
+    def _prep_weight(self, name, w, g):
+        wt = self.arena.get("wt_f:" + name, (g.k, g.cout))
+        ops.weight_prep_fwd(w, g, wt)
+        return wt
+
+    # ---- forward ----------------------------------------------------------------------------------
+    def forward(self, mel, code, params, training=True, buffers=None):
+        """mel (B,80,T) f32, code (B,D) or None -> pred (B,F,2K) view of an engine-owned buffer.
+
+        buffers: BN running statistics dict (name -> tensor), updated in training mode, read in eval mode.
+        The number of output frames F must have been set with set_frames()/forward_frames.
+        """
+        raise NotImplementedError  # replaced below (kept for doc ordering)
+
+
+def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=None):
+    B, _, T = mel.shape
+    self._setup(B, T, num_frames)
+    A = self.arena
+    slope = self.slope
+    groups = self._groups()
+    self.fwd_id += 1
+    self._mel = mel
+    self._params = params
+    # ---- 2-D encoder: raw conv output + statistics; normalise/activate in the consumer's loader
+    src, xf = mel.view(B, 80, T, 1), None
+    for l, (lname, co, ci, kh, kw, s, p) in enumerate(ENC2D):
+        g = self.enc_geoms[l]
+        name = ENC_PREFIX + lname
+        H, W = self.enc_hw[l]
+        oh, ow = self.enc_hw[l + 1]
+        wt = self._prep_weight(name, params[name + ".conv.weight"], g)
+        raw = A.get("raw:" + name, (B, oh, ow, co))
+        use_batch_stats = self.norm == "IN" or training
+        d = ops.fwd_desc(g, src, wt, raw, B, H, W, xf, slope, per_image=True)
+        sc = A.get("scale:" + name, (groups, co))
+        sh = A.get("shift:" + name, (groups, co))
+        if use_batch_stats:
+            partial = A.get("partial:" + name, (ops.row_tiles(d), 2, co))
+            d.stat_partial = partial.data_ptr()
+            ops.conv_gemm(d)
+            mean = A.get("mean:" + name, (groups, co))
+            rstd = A.get("rstd:" + name, (groups, co))
+            gamma = params.get(name + ".norm.weight")
+            beta = params.get(name + ".norm.bias")
+            running = None
+            if self.norm == "BN":
+                running = (buffers[name + ".norm.running_mean"], buffers[name + ".norm.running_var"],
+                           buffers[name + ".norm.num_batches_tracked"])
+            ops.norm_finalize(partial, groups, co, oh * ow * (B // groups), gamma, beta, running, out=(sc, sh, mean, rstd))
+        else:
+            ops.conv_gemm(d)
+            ops.bn_eval_scale_shift(buffers[name + ".norm.running_mean"], buffers[name + ".norm.running_var"],
+                                    params[name + ".norm.weight"], params[name + ".norm.bias"], out=(sc, sh))
+        src, xf = raw, (sc, sh, self._bstride(co))
+    # ---- bilinear resize to F frames + clip-code concat (generator.py:41-42,109-111)
+    D = self.code_dim
+    h7, w7 = self.enc_hw[8]
+    x0 = A.get("x0", (B, num_frames, 256 + D))
+    ops.enc_to_seq_fwd(src, xf[0], xf[1], xf[2], slope, code if D > 0 else None, num_frames, out=x0)
+    # ---- 1-D stack
+    acts = {"x0": x0}
+    for name, g, kind in self.seq_layers():
+        L_out = self.seq_len[name]
+        if kind == "x0":
+            xin = x0
+        elif kind.startswith("act:"):
+            xin = acts[kind[4:]]
+        else:
+            prev, skip = kind[3:].split("+")
+            xin = A.get("xin:" + name, (B, L_out, 256))
+            ops.upsample_add_fwd(acts[prev], acts[skip], L_out, out=xin)
+        L_in = xin.shape[1]
+        acts["in:" + name] = xin
+        wt = self._prep_weight(name, params[name + ".conv.weight"], g)
+        raw = A.get("raw:" + name, (B, L_out, 256))
+        d = ops.fwd_desc(g, xin, wt, raw, B, 1, L_in)
+        act = A.get("act:" + name, (B, L_out, 256))
+        if self.norm == "IN":
+            ops.conv_gemm(d)
+            ops.rownorm_act_fwd(raw, slope, out=(act, A.get("rmean:" + name, (B * L_out,)), A.get("rrstd:" + name, (B * L_out,))))
+        else:
+            sc = A.get("scale:" + name, (1, 256))
+            sh = A.get("shift:" + name, (1, 256))
+            if training:
+                partial = A.get("partial:" + name, (ops.row_tiles(d), 2, 256))
+                d.stat_partial = partial.data_ptr()
+                ops.conv_gemm(d)
+                running = (buffers[name + ".norm.running_mean"], buffers[name + ".norm.running_var"],
+                           buffers[name + ".norm.num_batches_tracked"])
+                ops.norm_finalize(partial, 1, 256, B * L_out, params[name + ".norm.weight"], params[name + ".norm.bias"], running,
+                                  out=(sc, sh, A.get("mean:" + name, (1, 256)), A.get("rstd:" + name, (1, 256))))
+            else:
+                ops.conv_gemm(d)
+                ops.bn_eval_scale_shift(buffers[name + ".norm.running_mean"], buffers[name + ".norm.running_var"],
+                                        params[name + ".norm.weight"], params[name + ".norm.bias"], out=(sc, sh))
+            ops.scale_shift_act(raw, sc, sh, 0, slope, out=act)
+        acts[name] = act
+    self._acts = acts
+    # ---- final 1x1 conv + bias (generator.py:103); channels-last output IS (B,F,2,K) (generator.py:116)
+    gl = ConvGeom.conv1d(256, self.kp2, 1, 1, 0)
+    wt = self._prep_weight("decoder.4", params["decoder.4.weight"], gl)
+    pred = A.get("pred", (B, num_frames, self.kp2))
+    ops.conv_gemm(ops.fwd_desc(gl, acts["decoder.3"], wt, pred, B, 1, num_frames, bias=params["decoder.4.bias"]))
+    return pred
+
+
+def _wgrad(self, g, x, dy, B, H, W, grad_out, xf=None, slope=1.0):
+    oh, ow = g.out_hw(H, W)
+    splits = ops.wgrad_splits(g, B, oh, ow)
+    need = splits * g.cout * g.k
+    ws = self.arena.get("wgrad_ws", (max(need, getattr(self, "_ws_elems", 0)),))
+    self._ws_elems = ws.numel()
+    ops.conv_wgrad(ops.wgrad_desc(g, x, dy, ws, B, H, W, splits, xf, slope))
+    ops.wgrad_reduce(ws, splits, g, grad_out)
+
+
+def _dgrad(self, name, g, dy, w, dx, B, H, W, accumulate=False):
+    for ci, cls in enumerate(g.dgrad_classes(H, W)):
+        wt = self.arena.get("wt_d%d:%s" % (ci, name), (cls["th"] * cls["tw"] * g.cout, g.cin))
+        ops.weight_prep_dgrad(w, g, cls, wt)
+        ops.conv_gemm(ops.dgrad_desc(g, cls, dy, wt, dx, B, H, W, accumulate))
+
+
+def _gen_backward(self, g_pred, grads, g_code=None):
+    """g_pred (B,F,2K) -> parameter gradients written into grads[name] (reference layout); g_code (B,D) filled.
+
+    Only the per-sample-norm ('IN') generator has a backward here (the SDT configs); see DESIGN.md for BN status.
+    """
+    if self.norm != "IN":
+        raise NotImplementedError("generator backward with BatchNorm (voice2pose_s2g training) is not implemented yet")
+    A, B, F, slope = self.arena, self.B, self.F, self.slope
+    params, acts = self._params, self._acts
+    # ---- final conv
+    gl = ConvGeom.conv1d(256, self.kp2, 1, 1, 0)
+    _wgrad(self, gl, acts["decoder.3"], g_pred, B, 1, F, grads["decoder.4.weight"])
+    ops.colsum(g_pred, grads["decoder.4.bias"])
+    g_act = {}
+    g_act["decoder.3"] = A.get("g_act:decoder.3", (B, F, 256))
+    _dgrad(self, "decoder.4", gl, g_pred, params["decoder.4.weight"], g_act["decoder.3"], B, 1, F)
+    # ---- 1-D stack in reverse
+    layers = self.seq_layers()
+    g_raw_scratch = A.get("g_raw_scratch", (B, F, 256))
+    g_x0 = None
+    for name, g, kind in reversed(layers):
+        L_out = self.seq_len[name]
+        raw = A.get("raw:" + name, (B, L_out, 256))
+        g_raw = g_raw_scratch.view(-1)[: B * L_out * 256].view(B, L_out, 256)
+        ops.rownorm_act_bwd(g_act[name], raw, A.get("rmean:" + name, (B * L_out,)), A.get("rrstd:" + name, (B * L_out,)), slope,
+                            out=g_raw)
+        xin = acts["in:" + name]
+        L_in = xin.shape[1]
+        _wgrad(self, g, xin, g_raw, B, 1, L_in, grads[name + ".conv.weight"])
+        w = params[name + ".conv.weight"]
+        if kind == "x0":
+            g_x0 = A.get("g_x0", tuple(xin.shape))
+            _dgrad(self, name, g, g_raw, w, g_x0, B, 1, L_in)
+        elif kind.startswith("act:"):
+            src = kind[4:]
+            if src in g_act:          # skip connection already deposited its gradient there
+                _dgrad(self, name, g, g_raw, w, g_act[src], B, 1, L_in, accumulate=True)
+            else:
+                g_act[src] = A.get("g_act:" + src, (B, L_in, 256))
+                _dgrad(self, name, g, g_raw, w, g_act[src], B, 1, L_in)
+        else:
+            prev, skip = kind[3:].split("+")
+            g_xin = A.get("g_xin:" + name, (B, L_in, 256))
+            _dgrad(self, name, g, g_raw, w, g_xin, B, 1, L_in)
+            g_act[skip] = g_xin                                       # d(up(prev)+skip)/d skip = identity
+            g_act[prev] = A.get("g_act:" + prev, (B, self.seq_len[prev], 256))
+            ops.upsample_bwd(g_xin, self.seq_len[prev], out=g_act[prev])
+    # ---- resize/concat adjoint
+    h7, w7 = self.enc_hw[8]
+    g_enc = A.get("g_enc:7", (B, h7, w7, 256))
+    D = self.code_dim
+    ops.enc_to_seq_bwd(g_x0, h7, w7, 256, D, g_act=g_enc, g_code=g_code if D > 0 else None)
+    # ---- 2-D encoder in reverse
+    groups = self._groups()
+    for l in range(7, -1, -1):
+        lname, co, ci, kh, kw, s, p = ENC2D[l]
+        g = self.enc_geoms[l]
+        name = ENC_PREFIX + lname
+        H, W = self.enc_hw[l]
+        oh, ow = self.enc_hw[l + 1]
+        raw = A.get("raw:" + name, (B, oh, ow, co))
+        tpi = -(-(oh * ow) // ops.BWD_ROWS)
+        scratch = (A.get("nb_partial:" + name, (B * tpi, 2, co)), A.get("nb_m1:" + name, (groups, co)), A.get("nb_m2:" + name, (groups, co)))
+        ops.norm_backward(g_enc, raw, A.get("mean:" + name, (groups, co)), A.get("rstd:" + name, (groups, co)), groups, slope,
+                          scratch=scratch)
+        if l == 0:
+            src, xf = self._mel.view(B, 80, self.T, 1), None
+        else:
+            pname = ENC_PREFIX + ENC2D[l - 1][0]
+            pc = ENC2D[l - 1][1]
+            src = A.get("raw:" + pname, (B, H, W, pc))
+            xf = (A.get("scale:" + pname, (groups, pc)), A.get("shift:" + pname, (groups, pc)), self._bstride(pc))
+        _wgrad(self, g, src, g_enc, B, H, W, grads[name + ".conv.weight"], xf, slope)
+        if l > 0:
+            g_prev = A.get("g_enc:%d" % (l - 1), (B, H, W, ci))
+            _dgrad(self, name, g, g_enc, params[name + ".conv.weight"], g_prev, B, H, W)
+            g_enc = g_prev
+
+
+GeneratorEngine.forward = _gen_forward
+GeneratorEngine.backward = _gen_backward
+
+
+class PoseEncoderEngine:
+    """PoseSeqEncoder (autoencoder.py:8-35), forward only: BatchNorm in train mode (batch statistics, running-stat
+    update) or eval mode.  Raw conv outputs + per-channel (scale, shift); activations never materialised."""
+
+    def __init__(self, n_landmarks, code_dim, leaky, device):
+        self.kp2 = n_landmarks * 2
+        self.code2 = code_dim * 2
+        self.slope = 0.2 if leaky else 0.0
+        self.arena = Arena(device)
+        self.geoms = ([ConvGeom.conv1d(self.kp2, 256, 3, 1, 1), ConvGeom.conv1d(256, 256, 3, 1, 1)]
+                      + [ConvGeom.conv1d(256, 256, 4, 2, 1)] * 4 + [ConvGeom.conv1d(256, self.code2, 4, 2, 1)])
+
+    def param_shapes(self):
+        shapes = {}
+        for i, g in enumerate(self.geoms):
+            shapes["blocks.%d.conv.weight" % i] = (g.cout, g.cin, g.kw)
+            shapes["blocks.%d.norm.weight" % i] = (g.cout,)
+            shapes["blocks.%d.norm.bias" % i] = (g.cout,)
+        return shapes
+
+    def forward(self, poses, params, buffers, training, tag=""):
+        """poses (B,F,2K) channels-last (== the reference's (B,F,2,K)) -> (mu, logvar) engine-owned (B,D) buffers."""
+        A = self.arena
+        B, L = poses.shape[0], poses.shape[1]
+        src, xf = poses.view(B, 1, L, self.kp2), None
+        for i, g in enumerate(self.geoms):
+            name = "blocks.%d" % i
+            lo = g.out_hw(1, L)[1]
+            wt = A.get("wt_f:" + name, (g.k, g.cout))
+            ops.weight_prep_fwd(params[name + ".conv.weight"], g, wt)
+            raw = A.get("raw%s:%s" % (tag, name), (B, 1, lo, g.cout))
+            d = ops.fwd_desc(g, src, wt, raw, B, 1, L, xf, self.slope)
+            sc = A.get("scale%s:%s" % (tag, name), (1, g.cout))
+            sh = A.get("shift%s:%s" % (tag, name), (1, g.cout))
+            if training:
+                partial = A.get("partial%s:%s" % (tag, name), (ops.row_tiles(d), 2, g.cout))
+                d.stat_partial = partial.data_ptr()
+                ops.conv_gemm(d)
+                running = (buffers[name + ".norm.running_mean"], buffers[name + ".norm.running_var"],
+                           buffers[name + ".norm.num_batches_tracked"])
+                ops.norm_finalize(partial, 1, g.cout, B * lo, params[name + ".norm.weight"], params[name + ".norm.bias"], running,
+                                  out=(sc, sh, A.get("mean%s:%s" % (tag, name), (1, g.cout)), A.get("rstd%s:%s" % (tag, name), (1, g.cout))))
+            else:
+                ops.conv_gemm(d)
+                ops.bn_eval_scale_shift(buffers[name + ".norm.running_mean"], buffers[name + ".norm.running_var"],
+                                        params[name + ".norm.weight"], params[name + ".norm.bias"], out=(sc, sh))
+            src, xf, L = raw, (sc, sh, 0), lo
+        mu = A.get("mu" + tag, (B, self.code2 // 2))
+        logvar = A.get("logvar" + tag, (B, self.code2 // 2))
+        ops.pose_head_fwd(src.view(B, L, self.code2), xf[0], xf[1], self.slope, mu, logvar)
+        return mu, logvar

@@ -1,0 +1,479 @@
+"""Tensor-level wrappers over the C ABI (include/sdt_b200.h).
+
+Every function takes CUDA torch tensors (channels-last fp32 activations), launches on torch's CURRENT stream, and
+fails loudly (``SdtError`` / ``ValueError``) -- there is no eager/CPU fallback.  PyTorch is used only for device
+memory and streams.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, call
+
+EPS_NORM = 1e-5
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    """Device pointer of a tensor (or NULL)."""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def _chk(t, dtype=torch.float32, name="tensor"):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise ValueError("%s must be a CUDA tensor (no CPU fallback exists)" % name)
+    if t.dtype != dtype:
+        raise ValueError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    return t
+
+
+# ------------------------------------------------------------------------------------------------
+# mel
+# ------------------------------------------------------------------------------------------------
+
+def mel_band_tables(fb):
+    """(257, 80) filterbank buffer -> band form (start, count, weights[80, stride]) on fb's device."""
+    fbc = fb.detach().float().cpu()
+    n_freq, n_mel = fbc.shape
+    starts, counts = [], []
+    for m in range(n_mel):
+        nz = torch.nonzero(fbc[:, m]).flatten()
+        if nz.numel() == 0:
+            starts.append(0)
+            counts.append(0)
+        else:
+            starts.append(int(nz[0]))
+            counts.append(int(nz[-1]) - int(nz[0]) + 1)
+    stride = max(1, max(counts))
+    w = torch.zeros(n_mel, stride)
+    for m in range(n_mel):
+        w[m, :counts[m]] = fbc[starts[m]:starts[m] + counts[m], m]
+    dev = fb.device
+    return (torch.tensor(starts, dtype=torch.int32, device=dev), torch.tensor(counts, dtype=torch.int32, device=dev),
+            w.to(dev).contiguous(), stride)
+
+
+def mel_fwd(audio, window, tables, out=None):
+    """audio (B, L) -> mel (B, 80, 1 + L//160).  voice2pose.py:125."""
+    _chk(audio, name="audio")
+    _chk(window, name="window")
+    start, count, weight, stride = tables
+    B, L = audio.shape
+    T = 1 + L // 160
+    if out is None:
+        out = torch.empty(B, 80, T, device=audio.device, dtype=torch.float32)
+    call("sdt_mel_fwd", _p(audio), B, L, _p(window), _p(start), _p(count), _p(weight), stride, _p(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# convolution geometry -> descriptors
+# ------------------------------------------------------------------------------------------------
+
+@dataclass(frozen=True)
+class ConvGeom:
+    """One nn.Conv1d / nn.Conv2d of the reference; 1-D convs are 2-D with H = KH = 1."""
+    cin: int
+    cout: int
+    kh: int
+    kw: int
+    sh: int
+    sw: int
+    ph: int
+    pw: int
+
+    @staticmethod
+    def conv1d(cin, cout, k, s, p):
+        return ConvGeom(cin, cout, 1, k, 1, s, 0, p)
+
+    @staticmethod
+    def conv2d(cin, cout, kh, kw, s, p):
+        return ConvGeom(cin, cout, kh, kw, s, s, p, p)
+
+    def out_hw(self, h, w):
+        return (h + 2 * self.ph - self.kh) // self.sh + 1, (w + 2 * self.pw - self.kw) // self.sw + 1
+
+    @property
+    def k(self):
+        return self.kh * self.kw * self.cin
+
+    def dgrad_classes(self, h, w):
+        """Stride-parity decomposition of the data gradient: list of dicts (one implicit GEMM each)."""
+        out = []
+        for py in range(self.sh):
+            ky0 = (py + self.ph) % self.sh
+            th = max(0, -(-(self.kh - ky0) // self.sh))
+            gh = max(0, -(-(h - py) // self.sh))
+            for px in range(self.sw):
+                kx0 = (px + self.pw) % self.sw
+                tw = max(0, -(-(self.kw - kx0) // self.sw))
+                gw = max(0, -(-(w - px) // self.sw))
+                if gh == 0 or gw == 0:
+                    continue
+                out.append(dict(py=py, px=px, ky0=ky0, kx0=kx0, th=th, tw=tw, gh=gh, gw=gw,
+                                y_off=(py + self.ph - ky0) // self.sh, x_off=(px + self.pw - kx0) // self.sw))
+        return out
+
+
+def fwd_desc(g, x, wt, dst, B, H, W, xf=None, slope=1.0, bias=None, stat_partial=None, per_image=False, accumulate=False):
+    oh, ow = g.out_hw(H, W)
+    d = ConvDesc()
+    d.src, d.wt, d.bias, d.dst = x.data_ptr(), wt.data_ptr(), bias.data_ptr() if bias is not None else None, dst.data_ptr()
+    if xf is not None:
+        d.xf_scale, d.xf_shift, d.xf_bstride = xf[0].data_ptr(), xf[1].data_ptr(), xf[2]
+    d.xf_slope = slope
+    d.stat_partial = stat_partial.data_ptr() if stat_partial is not None else None
+    d.B, d.SH, d.SW, d.C = B, H, W, g.cin
+    d.GH, d.GW, d.TH, d.TW = oh, ow, g.kh, g.kw
+    d.y_mul, d.ty_mul, d.y_off = g.sh, 1, -g.ph
+    d.x_mul, d.tx_mul, d.x_off = g.sw, 1, -g.pw
+    d.N = g.cout
+    d.DH, d.DW, d.dy_mul, d.dy_off, d.dx_mul, d.dx_off = oh, ow, 1, 0, 1, 0
+    d.accumulate = int(accumulate)
+    d.per_image_tiles = int(per_image)
+    d.splits = 1
+    return d
+
+
+def dgrad_desc(g, cls, dy, wt_cls, dx, B, H, W, accumulate=False):
+    """Data gradient for one stride-parity class: dx[b, q*s+py, ...] = sum_taps dy[...] * W."""
+    oh, ow = g.out_hw(H, W)
+    d = ConvDesc()
+    d.src, d.wt, d.dst = dy.data_ptr(), wt_cls.data_ptr(), dx.data_ptr()
+    d.xf_slope = 1.0
+    d.B, d.SH, d.SW, d.C = B, oh, ow, g.cout
+    d.GH, d.GW, d.TH, d.TW = cls["gh"], cls["gw"], cls["th"], cls["tw"]
+    d.y_mul, d.ty_mul, d.y_off = 1, -1, cls["y_off"]
+    d.x_mul, d.tx_mul, d.x_off = 1, -1, cls["x_off"]
+    d.N = g.cin
+    d.DH, d.DW = H, W
+    d.dy_mul, d.dy_off, d.dx_mul, d.dx_off = g.sh, cls["py"], g.sw, cls["px"]
+    d.accumulate = int(accumulate)
+    d.per_image_tiles = 0
+    d.splits = 1
+    return d
+
+
+def wgrad_desc(g, x, dy, wpart, B, H, W, splits, xf=None, slope=1.0):
+    oh, ow = g.out_hw(H, W)
+    d = ConvDesc()
+    d.src, d.dy, d.wpart = x.data_ptr(), dy.data_ptr(), wpart.data_ptr()
+    if xf is not None:
+        d.xf_scale, d.xf_shift, d.xf_bstride = xf[0].data_ptr(), xf[1].data_ptr(), xf[2]
+    d.xf_slope = slope
+    d.B, d.SH, d.SW, d.C = B, H, W, g.cin
+    d.GH, d.GW, d.TH, d.TW = oh, ow, g.kh, g.kw
+    d.y_mul, d.ty_mul, d.y_off = g.sh, 1, -g.ph
+    d.x_mul, d.tx_mul, d.x_off = g.sw, 1, -g.pw
+    d.N = g.cout
+    d.splits = splits
+    return d
+
+
+def wgrad_splits(g, B, oh, ow, target_ctas=444):
+    """Number of K (pixel) splits so that the weight-gradient GEMM fills the 148 SMs ~3 times over."""
+    tiles = -(-g.k // 128) * -(-g.cout // (64 if g.cout <= 64 else 128))
+    pixels = B * oh * ow
+    return max(1, min(-(-target_ctas // tiles), -(-pixels // 64)))
+
+
+def row_tiles(desc):
+    n = call("sdt_conv_row_tiles", C.byref(desc))
+    if n < 0:
+        raise _lib.SdtError("sdt_conv_row_tiles: " + _lib.last_error())
+    return n
+
+
+def conv_gemm(desc):
+    call("sdt_conv_gemm", C.byref(desc), _stream())
+
+
+def conv_wgrad(desc):
+    call("sdt_conv_wgrad", C.byref(desc), _stream())
+
+
+def wgrad_reduce(wpart, splits, g, grad, accumulate=False):
+    call("sdt_conv_wgrad_reduce", _p(wpart), splits, g.cout, g.cin, g.kh * g.kw, _p(grad), int(accumulate), _stream())
+
+
+def weight_prep_fwd(w, g, out):
+    """(Cout,Cin,kh,kw) reference-layout parameter -> (K, Cout) forward GEMM operand."""
+    call("sdt_weight_prep", _p(w), g.cout, g.cin, g.kh, g.kw, 0, 0, 0, 1, g.kh, g.kw, _p(out), _stream())
+
+
+def weight_prep_dgrad(w, g, cls, out):
+    """... -> (th*tw*Cout, Cin) data-gradient operand of one parity class."""
+    call("sdt_weight_prep", _p(w), g.cout, g.cin, g.kh, g.kw, 1, cls["ky0"], cls["kx0"], g.sw,
+         cls["th"], cls["tw"], _p(out), _stream())
+
+
+# ------------------------------------------------------------------------------------------------
+# convenience single-shot convolution ops (allocate their own scratch; used by tests and module boundaries)
+# ------------------------------------------------------------------------------------------------
+
+def _as_w4(w):
+    return w if w.dim() == 4 else w.unsqueeze(2)
+
+
+def conv_forward(x, w, g, xf=None, slope=1.0, bias=None, want_stats=False, per_image=False):
+    """x (B,H,W,Cin) channels-last, w reference layout -> y (B,OH,OW,Cout) [, partial (tiles,2,Cout)]."""
+    _chk(x, name="x")
+    _chk(w, name="w")
+    B, H, W, _ = x.shape
+    oh, ow = g.out_hw(H, W)
+    wt = torch.empty(g.k, g.cout, device=x.device)
+    weight_prep_fwd(w, g, wt)
+    y = torch.empty(B, oh, ow, g.cout, device=x.device)
+    d = fwd_desc(g, x, wt, y, B, H, W, xf, slope, bias, None, per_image)
+    partial = None
+    if want_stats:
+        partial = torch.empty(row_tiles(d), 2, g.cout, device=x.device)
+        d.stat_partial = partial.data_ptr()
+    conv_gemm(d)
+    return (y, partial) if want_stats else y
+
+
+def conv_dgrad(dy, w, g, H, W, out=None, accumulate=False):
+    """dy (B,OH,OW,Cout) -> dx (B,H,W,Cin)."""
+    _chk(dy, name="dy")
+    B = dy.shape[0]
+    dx = out if out is not None else torch.empty(B, H, W, g.cin, device=dy.device)
+    if g.sh * g.sw > 1 and out is None and not accumulate:
+        pass  # every input position belongs to exactly one parity class -> fully written
+    for cls in g.dgrad_classes(H, W):
+        wt = torch.empty(cls["th"] * cls["tw"] * g.cout, g.cin, device=dy.device)
+        weight_prep_dgrad(w, g, cls, wt)
+        conv_gemm(dgrad_desc(g, cls, dy, wt, dx, B, H, W, accumulate))
+    return dx
+
+
+def conv_weight_grad(x, dy, g, xf=None, slope=1.0, splits=None):
+    """-> gradient in the reference parameter layout (Cout, Cin, kh, kw)."""
+    _chk(x, name="x")
+    _chk(dy, name="dy")
+    B, H, W, _ = x.shape
+    oh, ow = g.out_hw(H, W)
+    splits = splits or wgrad_splits(g, B, oh, ow)
+    wpart = torch.empty(splits, g.cout, g.k, device=x.device)
+    conv_wgrad(wgrad_desc(g, x, dy, wpart, B, H, W, splits, xf, slope))
+    grad = torch.empty(g.cout, g.cin, g.kh, g.kw, device=x.device)
+    wgrad_reduce(wpart, splits, g, grad)
+    return grad
+
+
+# ------------------------------------------------------------------------------------------------
+# normalisation
+# ------------------------------------------------------------------------------------------------
+
+def norm_finalize(partial, groups, C, count, gamma=None, beta=None, running=None, momentum=0.1, out=None):
+    """-> (scale, shift, mean, rstd), each (groups, C). running = (running_mean, running_var, num_batches_tracked)."""
+    tiles_per_group = partial.shape[0] // groups
+    dev = partial.device
+    scale, shift, mean, rstd = out if out is not None else [torch.empty(groups, C, device=dev) for _ in range(4)]
+    rm, rv, nbt = running if running is not None else (None, None, None)
+    call("sdt_norm_finalize", _p(partial), groups, tiles_per_group, C, float(count), _p(gamma), _p(beta), EPS_NORM,
+         _p(scale), _p(shift), _p(mean), _p(rstd), _p(rm), _p(rv), _p(nbt), momentum, _stream())
+    return scale, shift, mean, rstd
+
+
+def bn_eval_scale_shift(rm, rv, gamma, beta, out=None):
+    Cc = rm.numel()
+    scale, shift = out if out is not None else (torch.empty(1, Cc, device=rm.device), torch.empty(1, Cc, device=rm.device))
+    call("sdt_bn_eval_scale_shift", _p(rm), _p(rv), _p(gamma), _p(beta), EPS_NORM, Cc, _p(scale), _p(shift), _stream())
+    return scale, shift
+
+
+BWD_ROWS = 256
+
+
+def norm_backward(g, x, mean, rstd, groups, slope, gamma=None, beta=None, dgamma=None, dbeta=None, accumulate=False,
+                  scratch=None):
+    """In place: g (B,P,C) := d loss / d x for [normalise(groups) -> affine -> act]; returns g."""
+    B = g.shape[0]
+    Cc = g.shape[-1]
+    P = g.numel() // (B * Cc)
+    tpi = -(-P // BWD_ROWS)
+    if scratch is None:
+        partial = torch.empty(B * tpi, 2, Cc, device=g.device)
+        m1 = torch.empty(groups, Cc, device=g.device)
+        m2 = torch.empty(groups, Cc, device=g.device)
+    else:
+        partial, m1, m2 = scratch
+    call("sdt_norm_bwd_reduce", _p(g), _p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), B, P, Cc, groups, slope, _p(partial),
+         tpi, _stream())
+    call("sdt_norm_bwd_finalize", _p(partial), groups, (B * tpi) // groups, Cc, float(P * (B // groups)), _p(m1), _p(m2),
+         _p(dgamma), _p(dbeta), int(accumulate), _stream())
+    call("sdt_norm_bwd_apply", _p(g), _p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(m1), _p(m2), B, P, Cc, groups, slope,
+         _stream())
+    return g
+
+
+def rownorm_act_fwd(x, slope, out=None):
+    """x (..., C) -> (y, mean (R), rstd (R)): channel LayerNorm (the reference's 1-D 'IN') + activation."""
+    Cc = x.shape[-1]
+    R = x.numel() // Cc
+    if out is None:
+        y = torch.empty_like(x)
+        mean = torch.empty(R, device=x.device)
+        rstd = torch.empty(R, device=x.device)
+    else:
+        y, mean, rstd = out
+    call("sdt_rownorm_act_fwd", _p(x), R, Cc, EPS_NORM, slope, _p(y), _p(mean), _p(rstd), _stream())
+    return y, mean, rstd
+
+
+def rownorm_act_bwd(g_y, x, mean, rstd, slope, out=None):
+    Cc = x.shape[-1]
+    R = x.numel() // Cc
+    g_x = out if out is not None else torch.empty_like(x)
+    call("sdt_rownorm_act_bwd", _p(g_y), _p(x), _p(mean), _p(rstd), R, Cc, slope, _p(g_x), _stream())
+    return g_x
+
+
+def scale_shift_act(x, scale, shift, bstride, slope, out=None):
+    B, Cc = x.shape[0], x.shape[-1]
+    P = x.numel() // (B * Cc)
+    y = out if out is not None else torch.empty_like(x)
+    call("sdt_scale_shift_act", _p(x), _p(scale), _p(shift), B, P, Cc, bstride, slope, _p(y), _stream())
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
+# resampling / losses / heads / optimizer
+# ------------------------------------------------------------------------------------------------
+
+def enc_to_seq_fwd(x, scale, shift, bstride, slope, code, F, out=None):
+    B, H, W, Cc = x.shape
+    D = 0 if code is None else code.shape[1]
+    y = out if out is not None else torch.empty(B, F, Cc + D, device=x.device)
+    call("sdt_enc_to_seq_fwd", _p(x), _p(scale), _p(shift), bstride, slope, B, H, W, Cc, _p(code), D, F, _p(y), _stream())
+    return y
+
+
+def enc_to_seq_bwd(g_out, H, W, Cc, D, g_act=None, g_code=None):
+    B, F, _ = g_out.shape
+    if g_act is None:
+        g_act = torch.empty(B, H, W, Cc, device=g_out.device)
+    if D > 0 and g_code is None:
+        g_code = torch.empty(B, D, device=g_out.device)
+    call("sdt_enc_to_seq_bwd", _p(g_out), B, H, W, Cc, D, F, _p(g_act), _p(g_code), _stream())
+    return g_act, g_code
+
+
+def upsample_add_fwd(x, skip, Lout, out=None):
+    B, Lin, Cc = x.shape
+    y = out if out is not None else torch.empty(B, Lout, Cc, device=x.device)
+    call("sdt_upsample_add_fwd", _p(x), _p(skip), B, Lin, Lout, Cc, _p(y), _stream())
+    return y
+
+
+def upsample_bwd(g_out, Lin, out=None, accumulate=False):
+    B, Lout, Cc = g_out.shape
+    g_x = out if out is not None else torch.empty(B, Lin, Cc, device=g_out.device)
+    call("sdt_upsample_bwd", _p(g_out), B, Lin, Lout, Cc, _p(g_x), int(accumulate), _stream())
+    return g_x
+
+
+def l1_loss(pred, gt, lam, loss_out, g_pred, partial):
+    call("sdt_l1_loss", _p(pred), _p(gt), pred.numel(), lam, _p(loss_out), _p(g_pred), _p(partial), _stream())
+
+
+def code_gather_kl(table, idx, lam, code, out, g_code):
+    B, D = code.shape
+    call("sdt_code_gather_kl", _p(table), _p(idx), B, D, lam, _p(code), _p(out), _p(g_code), _stream())
+
+
+def code_scatter_grad(ga, gb, idx, g_table):
+    B = idx.numel()
+    D = g_table.shape[1]
+    call("sdt_code_scatter_grad", _p(ga), _p(gb), _p(idx), B, D, _p(g_table), _stream())
+
+
+def colsum(g, out, accumulate=False):
+    Cc = g.shape[-1]
+    call("sdt_colsum", _p(g), g.numel() // Cc, Cc, _p(out), int(accumulate), _stream())
+
+
+def mse_const_loss(s, target, lam, out, g_s=None):
+    call("sdt_mse_const_loss", _p(s), s.numel(), target, lam, _p(out), _p(g_s), _stream())
+
+
+def motion_diff_fwd(x, out=None):
+    B, T, Cc = x.shape
+    y = out if out is not None else torch.empty(B, T - 1, Cc, device=x.device)
+    call("sdt_motion_diff_fwd", _p(x), B, T, Cc, _p(y), _stream())
+    return y
+
+
+def motion_diff_bwd(g_out, out=None, accumulate=False):
+    B, Tm1, Cc = g_out.shape
+    g_x = out if out is not None else torch.empty(B, Tm1 + 1, Cc, device=g_out.device)
+    call("sdt_motion_diff_bwd", _p(g_out), B, Tm1 + 1, Cc, _p(g_x), int(accumulate), _stream())
+    return g_x
+
+
+def pose_head_fwd(x, scale, shift, slope, mu=None, logvar=None):
+    B, L, D2 = x.shape
+    if mu is None:
+        mu = torch.empty(B, D2 // 2, device=x.device)
+        logvar = torch.empty(B, D2 // 2, device=x.device)
+    call("sdt_pose_head_fwd", _p(x), _p(scale), _p(shift), slope, B, L, D2, _p(mu), _p(logvar), _stream())
+    return mu, logvar
+
+
+def vae_reparam_kl(mu, logvar, eps, lam, code, out):
+    call("sdt_vae_reparam_kl", _p(mu), _p(logvar), _p(eps), mu.numel(), lam, _p(code), _p(out), _stream())
+
+
+def pose_preprocess(raw, mean, std, hierarchical=True):
+    """raw (T,3,137) f32 -> normalised (T,2,121) f32; bit-exact with gesture_dataset.py:95-105."""
+    _chk(raw, name="raw")
+    T = raw.shape[0]
+    out = torch.empty(T, 2, 121, device=raw.device)
+    call("sdt_pose_preprocess", _p(raw), T, _p(_chk(mean, name="mean")), _p(_chk(std, name="std")), int(hierarchical), _p(out),
+         _stream())
+    return out
+
+
+def pose_final_results(poses, mean, std, scale, hierarchical=True, out=None):
+    """poses (B,T,2,121) f32; mean/std (B,242) f64; scale (B) f64 -> f64; bit-exact with gesture_dataset.py:213-220."""
+    _chk(poses, name="poses")
+    _chk(mean, torch.float64, "mean")
+    _chk(std, torch.float64, "std")
+    _chk(scale, torch.float64, "scale")
+    B, T = poses.shape[0], poses.shape[1]
+    if out is None:
+        out = torch.empty(B, T, 2, 121, device=poses.device, dtype=torch.float64)
+    call("sdt_pose_final_results", _p(poses), B, T, _p(mean), _p(std), _p(scale), int(hierarchical), _p(out), _stream())
+    return out
+
+
+def pose_metrics(pred, gt, partial=None, out=None):
+    """final-result poses (B,T,2,121) f64 -> tensor [L2_dist, lip_sync_error_n] (voice2pose.py:412-430)."""
+    B, T = pred.shape[0], pred.shape[1]
+    if partial is None:
+        partial = torch.empty(2 * B, device=pred.device, dtype=torch.float64)
+    if out is None:
+        out = torch.empty(2, device=pred.device, dtype=torch.float64)
+    call("sdt_pose_metrics", _p(pred), _p(gt), B, T, _p(partial), _p(out), _stream())
+    return out
+
+
+def adam_advance(scalars, lr, beta1=0.9, beta2=0.999):
+    call("sdt_adam_advance", _p(scalars), lr, beta1, beta2, _stream())
+
+
+def adam_flat(param, grad, exp_avg, exp_avg_sq, scalars, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    call("sdt_adam_flat", _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), _p(scalars), beta1, beta2, eps,
+         grad_scale, _stream())

@@ -1,0 +1,377 @@
+"""GPU parity tests of the individual C-ABI kernels against fp64 torch references of the same op
+(the reference's arithmetic on this path IS these torch ops: SURVEY.md §2.3)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from util import golden, oliver_stat, rel_err  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from speechdrivestemplates_b200 import ops as o
+    return o
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def to_cl(x):      # NCHW -> NHWC contiguous
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def from_cl(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def rel(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+# ---------------------------------------------------------------- mel
+@pytest.mark.parametrize("case", ["real", "syn", "short", "odd"])
+def test_mel_matches_golden_and_oracle(ops, case):
+    from oracle import sdt_oracle as O
+    g = golden("mel_golden")
+    gen = torch.Generator().manual_seed(int(g["syn_seed"]))
+    syn = 0.1 * torch.randn(2, 68266, generator=gen)
+    short = 0.1 * torch.randn(1, 4000, generator=gen)
+    odd = 0.1 * torch.randn(1, 1601, generator=gen)
+    audio = {"real": torch.from_numpy(g["real_audio"]), "syn": syn, "short": short, "odd": odd}[case]
+    window = torch.from_numpy(g["window"]).to(dev())
+    tables = ops.mel_band_tables(torch.from_numpy(g["fb"]).to(dev()))
+    got = ops.mel_fwd(audio.to(dev()).contiguous(), window, tables).cpu().numpy()
+    ref = g[case + "_mel"]
+    assert got.shape == ref.shape
+    tol = 1e-5 * np.abs(ref).max()          # abs <= 1e-5 * max
+    assert np.abs(got - ref).max() <= tol
+    truth = O.mel_spectrogram(audio, dtype=torch.float64).numpy()
+    assert np.abs(got - truth).max() <= tol
+
+
+# ---------------------------------------------------------------- convolutions
+GEOMS_2D = [
+    # cin, cout, kh, kw, s, p, H, W
+    (1, 64, 3, 3, 1, 1, 20, 37),
+    (64, 64, 4, 4, 2, 1, 20, 37),
+    (64, 128, 3, 3, 1, 1, 10, 18),
+    (128, 128, 4, 4, 2, 1, 11, 19),
+    (32, 48, 6, 3, 1, 0, 10, 13),
+]
+GEOMS_1D = [
+    # cin, cout, k, s, p, L
+    (288, 256, 3, 1, 1, 64),
+    (256, 256, 4, 2, 1, 64),
+    (256, 256, 4, 2, 1, 4),
+    (242, 256, 3, 1, 1, 16),
+    (256, 242, 1, 1, 0, 64),
+    (242, 256, 4, 2, 1, 63),
+    (256, 64, 4, 2, 1, 4),
+]
+
+
+def _geom2d(ops, cin, cout, kh, kw, s, p):
+    return ops.ConvGeom.conv2d(cin, cout, kh, kw, s, p)
+
+
+@pytest.mark.parametrize("cfg", GEOMS_2D)
+@pytest.mark.parametrize("xf", [False, True])
+def test_conv2d_forward_stats(ops, cfg, xf):
+    cin, cout, kh, kw, s, p, H, W = cfg
+    B = 3
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, cin, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(cout, cin, kh, kw, generator=g, dtype=torch.float64) / math.sqrt(cin * kh * kw)
+    geom = _geom2d(ops, cin, cout, kh, kw, s, p)
+    xin = x
+    xfarg = None
+    if xf:
+        sc = torch.rand(B, cin, generator=g, dtype=torch.float64) + 0.5
+        sh = torch.randn(B, cin, generator=g, dtype=torch.float64)
+        xin = F.leaky_relu(x * sc[:, :, None, None] + sh[:, :, None, None], 0.2)
+        xfarg = (sc.float().to(dev()).contiguous(), sh.float().to(dev()).contiguous(), cin)
+    ref = F.conv2d(xin, w, None, s, p)
+    y, partial = ops.conv_forward(to_cl(x.float()).to(dev()), w.float().to(dev()).contiguous(), geom, xf=xfarg, slope=0.2,
+                                  want_stats=True, per_image=True)
+    assert rel(from_cl(y), ref) < 2e-5
+    tiles = partial.shape[0] // B
+    ps = partial.view(B, tiles, 2, cout).double().sum(1).cpu()
+    assert rel(ps[:, 0], ref.sum((2, 3))) < 1e-4
+    assert rel(ps[:, 1], (ref * ref).sum((2, 3))) < 1e-4
+
+
+@pytest.mark.parametrize("cfg", GEOMS_1D)
+def test_conv1d_forward_bias(ops, cfg):
+    cin, cout, k, s, p, L = cfg
+    B = 5
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(B, cin, L, generator=g, dtype=torch.float64)
+    w = torch.randn(cout, cin, k, generator=g, dtype=torch.float64) / math.sqrt(cin * k)
+    b = torch.randn(cout, generator=g, dtype=torch.float64)
+    geom = ops.ConvGeom.conv1d(cin, cout, k, s, p)
+    ref = F.conv1d(x, w, b, s, p)
+    xcl = x.float().permute(0, 2, 1).contiguous().view(B, 1, L, cin).to(dev())
+    y = ops.conv_forward(xcl, w.float().to(dev()).contiguous(), geom, bias=b.float().to(dev()))
+    assert rel(y.view(B, -1, cout).permute(0, 2, 1), ref) < 2e-5
+
+
+@pytest.mark.parametrize("cfg", GEOMS_2D)
+def test_conv2d_dgrad_wgrad(ops, cfg):
+    cin, cout, kh, kw, s, p, H, W = cfg
+    B = 3
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, cin, H, W, generator=g, dtype=torch.float64, requires_grad=True)
+    w = (torch.randn(cout, cin, kh, kw, generator=g, dtype=torch.float64) / math.sqrt(cin * kh * kw)).requires_grad_(True)
+    sc = torch.rand(B, cin, generator=g, dtype=torch.float64) + 0.5
+    sh = torch.randn(B, cin, generator=g, dtype=torch.float64)
+    a = F.leaky_relu(x * sc[:, :, None, None] + sh[:, :, None, None], 0.2)
+    a.retain_grad()
+    y = F.conv2d(a, w, None, s, p)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(dy)
+    geom = _geom2d(ops, cin, cout, kh, kw, s, p)
+    dycl = to_cl(dy.float()).to(dev())
+    dx = ops.conv_dgrad(dycl, w.detach().float().to(dev()).contiguous(), geom, H, W)
+    assert rel(from_cl(dx), a.grad) < 2e-5
+    xfarg = (sc.float().to(dev()).contiguous(), sh.float().to(dev()).contiguous(), cin)
+    dw = ops.conv_weight_grad(to_cl(x.detach().float()).to(dev()), dycl, geom, xf=xfarg, slope=0.2)
+    assert rel(dw, w.grad) < 5e-5
+    dw3 = ops.conv_weight_grad(to_cl(x.detach().float()).to(dev()), dycl, geom, xf=xfarg, slope=0.2, splits=3)
+    assert rel(dw3, w.grad) < 5e-5
+
+
+@pytest.mark.parametrize("cfg", GEOMS_1D)
+def test_conv1d_dgrad_wgrad(ops, cfg):
+    cin, cout, k, s, p, L = cfg
+    B = 5
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(B, cin, L, generator=g, dtype=torch.float64, requires_grad=True)
+    w = (torch.randn(cout, cin, k, generator=g, dtype=torch.float64) / math.sqrt(cin * k)).requires_grad_(True)
+    y = F.conv1d(x, w, None, s, p)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(dy)
+    geom = ops.ConvGeom.conv1d(cin, cout, k, s, p)
+    dycl = dy.float().permute(0, 2, 1).contiguous().view(B, 1, -1, cout).to(dev())
+    xcl = x.detach().float().permute(0, 2, 1).contiguous().view(B, 1, L, cin).to(dev())
+    dx = ops.conv_dgrad(dycl, w.detach().float().to(dev()).contiguous(), geom, 1, L)
+    assert rel(dx.view(B, L, cin).permute(0, 2, 1), x.grad) < 2e-5
+    base = torch.ones(B, 1, L, cin, device=dev())
+    dx2 = ops.conv_dgrad(dycl, w.detach().float().to(dev()).contiguous(), geom, 1, L, out=base, accumulate=True)
+    assert rel(dx2.view(B, L, cin).permute(0, 2, 1), x.grad + 1.0) < 2e-5
+    dw = ops.conv_weight_grad(xcl, dycl, geom)
+    assert rel(dw.view(cout, cin, k), w.grad) < 5e-5
+
+
+# ---------------------------------------------------------------- normalisation
+@pytest.mark.parametrize("mode", ["IN", "BN"])
+def test_norm_finalize_and_backward(ops, mode):
+    B, Cc, H, W = 4, 64, 9, 31
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(B, Cc, H, W, generator=g, dtype=torch.float64) * 2 + 0.3).requires_grad_(True)
+    gamma = (torch.rand(Cc, generator=g, dtype=torch.float64) + 0.5).requires_grad_(True)
+    beta = torch.randn(Cc, generator=g, dtype=torch.float64).requires_grad_(True)
+    rm0 = torch.randn(Cc, generator=g, dtype=torch.float64)
+    rv0 = torch.rand(Cc, generator=g, dtype=torch.float64) + 0.5
+    if mode == "IN":
+        y = F.leaky_relu(F.instance_norm(x, eps=1e-5), 0.2)
+    else:
+        rm, rv = rm0.clone(), rv0.clone()
+        y = F.leaky_relu(F.batch_norm(x, rm, rv, gamma, beta, True, 0.1, 1e-5), 0.2)
+    gy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(gy)
+
+    xcl = to_cl(x.detach().float()).to(dev())
+    # statistics through the conv epilogue format: emulate with a 1x1 identity conv
+    geom = ops.ConvGeom.conv2d(Cc, Cc, 1, 1, 1, 0)
+    eye = torch.eye(Cc).view(Cc, Cc, 1, 1).to(dev()).contiguous()
+    raw, partial = ops.conv_forward(xcl, eye, geom, want_stats=True, per_image=True)
+    groups = B if mode == "IN" else 1
+    count = H * W * (B // groups)
+    ga = gamma.detach().float().to(dev()) if mode == "BN" else None
+    be = beta.detach().float().to(dev()) if mode == "BN" else None
+    running = None
+    if mode == "BN":
+        running = (rm0.float().to(dev()), rv0.float().to(dev()), torch.zeros((), dtype=torch.int64, device=dev()))
+    scale, shift, mean, rstd = ops.norm_finalize(partial, groups, Cc, count, ga, be, running)
+    yk = ops.scale_shift_act(raw, scale, shift, Cc if mode == "IN" else 0, 0.2)
+    assert rel(from_cl(yk), y) < 2e-5
+    if mode == "BN":
+        assert rel(running[0], rm) < 1e-5 and rel(running[1], rv) < 1e-5 and int(running[2]) == 1
+    gcl = to_cl(gy.float()).to(dev())
+    dga = torch.zeros(Cc, device=dev()) if mode == "BN" else None
+    dbe = torch.zeros(Cc, device=dev()) if mode == "BN" else None
+    gx = ops.norm_backward(gcl, raw, mean, rstd, groups, 0.2, ga, be, dga, dbe)
+    assert rel(from_cl(gx), x.grad) < 5e-5
+    if mode == "BN":
+        assert rel(dga, gamma.grad) < 5e-5 and rel(dbe, beta.grad) < 5e-5
+
+
+@pytest.mark.parametrize("C", [256, 64, 242])
+def test_rownorm(ops, C):
+    B, L = 3, 17
+    g = torch.Generator().manual_seed(6)
+    x = (torch.randn(B, C, L, generator=g, dtype=torch.float64) * 1.7 + 0.2).requires_grad_(True)
+    y = F.leaky_relu(F.instance_norm(x.permute(0, 2, 1), eps=1e-5).permute(0, 2, 1), 0.2)   # building_blocks.py:50-51
+    gy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(gy)
+    xcl = x.detach().float().permute(0, 2, 1).contiguous().to(dev())
+    yk, mean, rstd = ops.rownorm_act_fwd(xcl, 0.2)
+    assert rel(yk.permute(0, 2, 1), y) < 1e-5
+    gx = ops.rownorm_act_bwd(gy.float().permute(0, 2, 1).contiguous().to(dev()), xcl, mean, rstd, 0.2)
+    assert rel(gx.permute(0, 2, 1), x.grad) < 2e-5
+
+
+# ---------------------------------------------------------------- resampling
+@pytest.mark.parametrize("F_out", [64, 90])
+def test_enc_to_seq(ops, F_out):
+    B, Cc, H, W, D = 2, 32, 5, 51, 8
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B, Cc, H, W, generator=g, dtype=torch.float64, requires_grad=True)
+    code = torch.randn(B, D, generator=g, dtype=torch.float64, requires_grad=True)
+    sc = torch.rand(B, Cc, generator=g, dtype=torch.float64) + 0.5
+    sh = torch.randn(B, Cc, generator=g, dtype=torch.float64)
+    a = F.leaky_relu(x * sc[:, :, None, None] + sh[:, :, None, None], 0.2)
+    a.retain_grad()
+    y = F.interpolate(a, (1, F_out), mode="bilinear", align_corners=False).squeeze(2)
+    y = torch.cat([y, code.unsqueeze(2).repeat(1, 1, F_out)], 1)        # generator.py:109-111
+    gy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(gy)
+    out = ops.enc_to_seq_fwd(to_cl(x.detach().float()).to(dev()), sc.float().to(dev()).contiguous(),
+                             sh.float().to(dev()).contiguous(), Cc, 0.2, code.detach().float().to(dev()).contiguous(), F_out)
+    assert rel(out.permute(0, 2, 1), y) < 1e-5
+    g_act, g_code = ops.enc_to_seq_bwd(gy.float().permute(0, 2, 1).contiguous().to(dev()), H, W, Cc, D)
+    assert rel(from_cl(g_act), a.grad) < 1e-5
+    assert rel(g_code, code.grad) < 1e-5
+
+
+@pytest.mark.parametrize("lens", [(2, 4), (32, 64), (281, 562), (562, 1125)])
+def test_upsample_add(ops, lens):
+    Lin, Lout = lens
+    B, Cc = 2, 16
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(B, Cc, Lin, generator=g, dtype=torch.float64, requires_grad=True)
+    skip = torch.randn(B, Cc, Lout, generator=g, dtype=torch.float64)
+    y = F.interpolate(x, Lout, mode="linear", align_corners=False) + skip      # generator.py:79
+    gy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(gy)
+    xcl = x.detach().float().permute(0, 2, 1).contiguous().to(dev())
+    out = ops.upsample_add_fwd(xcl, skip.float().permute(0, 2, 1).contiguous().to(dev()), Lout)
+    # the source coordinate scale*(j+.5)-.5 is evaluated in fp32 (as ATen does for fp32 tensors); against this fp64
+    # reference that is an O(j * 2^-24) weight difference for non-integer ratios
+    tol = 1e-5 if Lout == 2 * Lin else 1e-4
+    assert rel(out.permute(0, 2, 1), y) < tol
+    gx = ops.upsample_bwd(gy.float().permute(0, 2, 1).contiguous().to(dev()), Lin)
+    assert rel(gx.permute(0, 2, 1), x.grad) < tol
+
+
+# ---------------------------------------------------------------- losses
+def test_l1_loss(ops):
+    g = torch.Generator().manual_seed(9)
+    pred = torch.randn(4, 64, 2, 121, generator=g, dtype=torch.float64, requires_grad=True)
+    gt = torch.randn(4, 64, 2, 121, generator=g, dtype=torch.float64)
+    with torch.no_grad():
+        pred[0, 0, 0, :5] = gt[0, 0, 0, :5]          # sign(0) = 0
+    loss = (torch.abs(pred - gt) * 1.0).mean()
+    loss.backward()
+    out = torch.zeros(1, device=dev())
+    gp = torch.empty(pred.shape, device=dev())
+    partial = torch.empty(1024, device=dev())
+    ops.l1_loss(pred.detach().float().to(dev()), gt.float().to(dev()), 1.0, out, gp, partial)
+    assert abs(float(out) - float(loss)) < 1e-6
+    assert rel(gp, pred.grad) < 1e-6
+    assert float(gp[0, 0, 0, :5].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("zero", [False, True])
+def test_code_kl_and_scatter(ops, zero):
+    from oracle import sdt_oracle as O
+    N, B, D = 16, 6, 32
+    g = torch.Generator().manual_seed(10)
+    table = (0.1 * torch.randn(N, D, generator=g, dtype=torch.float64))
+    if zero:
+        table[:, 3] = 0.0          # a zero-variance dimension -> KL skipped (voice2pose.py:154)
+    table.requires_grad_(True)
+    idx = torch.tensor([3, 5, 3, 9, 0, 5])
+    code = table[idx]
+    kl = O.clip_code_kl(code, 0.1)
+    gextra = torch.randn(B, D, generator=g, dtype=torch.float64)
+    total = (code * gextra).sum() + (kl if kl is not None else 0.0)
+    total.backward()
+    tb = table.detach().float().to(dev()).contiguous()
+    codek = torch.empty(B, D, device=dev())
+    out = torch.empty(2, device=dev())
+    gk = torch.empty(B, D, device=dev())
+    ops.code_gather_kl(tb, idx.to(dev()), 0.1, codek, out, gk)
+    assert rel(codek, code) < 1e-6
+    assert float(out[1]) == (0.0 if zero else 1.0)
+    if not zero:
+        assert abs(float(out[0]) - float(kl)) < 1e-5 * abs(float(kl))
+    gt = torch.zeros(N, D, device=dev())
+    ops.code_scatter_grad(gextra.float().to(dev()).contiguous(), gk, idx.to(dev()), gt)
+    assert rel(gt, table.grad) < 2e-5
+
+
+def test_colsum_and_adam(ops):
+    from oracle import sdt_oracle as O
+    g = torch.Generator().manual_seed(11)
+    m = torch.randn(300, 242, generator=g)
+    out = torch.zeros(242, device=dev())
+    ops.colsum(m.to(dev()), out)
+    assert rel(out, m.double().sum(0)) < 1e-5
+    n = 1000 * 4 + 3
+    p = torch.randn(n, generator=g)
+    po = p.clone()
+    mo, vo = torch.zeros(n), torch.zeros(n)
+    pk = torch.empty(n + 1, device=dev())[:n].copy_(p) if False else p.to(dev())
+    mk, vk = torch.zeros(n, device=dev()), torch.zeros(n, device=dev())
+    scalars = torch.zeros(8, device=dev())
+    for t in range(1, 4):
+        gr = torch.randn(n, generator=g) * 1e-3
+        O.adam_update(po, gr, mo, vo, t, 1e-4)
+        ops.adam_advance(scalars, 1e-4)
+        ops.adam_flat(pk, gr.to(dev()), mk, vk, scalars)
+    assert float((pk.cpu() - po).abs().max()) < 1e-7      # rel 1e-6, not bit-exact
+    assert rel(mk, mo) < 1e-6 and rel(vk, vo) < 1e-6
+
+
+# ---------------------------------------------------------------- keypoints (bit-exact gates)
+@pytest.mark.parametrize("parted", [True, False])
+def test_pose_kernels_bit_exact(ops, parted):
+    from oracle import sdt_oracle as O
+    g = golden("keypoints_golden")
+    st = oliver_stat(parted)
+    tag = "parted" if parted else "global"
+    mean32 = torch.from_numpy(st["mean"].astype(np.float32)).to(dev())
+    std32 = torch.from_numpy(st["std"].astype(np.float32)).to(dev())
+    got = ops.pose_preprocess(torch.from_numpy(g["raw"]).to(dev()), mean32, std32, parted).cpu().numpy()
+    assert np.array_equal(got, g[tag + "_normalized"])
+    x = g[tag + "_final_in"]
+    b = x.shape[0]
+    mean = torch.from_numpy(np.tile(st["mean"][None], (b, 1))).to(dev())
+    std = torch.from_numpy(np.tile(st["std"][None], (b, 1))).to(dev())
+    scale = torch.full((b,), st["scale_factor"], dtype=torch.float64, device=dev())
+    fin = ops.pose_final_results(torch.from_numpy(x).to(dev()), mean, std, scale, parted)
+    assert np.array_equal(fin.cpu().numpy(), g[tag + "_final_out"])
+    # larger random case against the oracle
+    rng = np.random.RandomState(0)
+    big = rng.standard_normal((16, 64, 2, 121)).astype(np.float32)
+    ref = O.get_final_results(big, np.tile(st["mean"][None], (16, 1)), np.tile(st["std"][None], (16, 1)),
+                              np.full((16,), st["scale_factor"]), parted)
+    mean = torch.from_numpy(np.tile(st["mean"][None], (16, 1))).to(dev())
+    std = torch.from_numpy(np.tile(st["std"][None], (16, 1))).to(dev())
+    scale = torch.full((16,), st["scale_factor"], dtype=torch.float64, device=dev())
+    fin = ops.pose_final_results(torch.from_numpy(big).to(dev()), mean, std, scale, parted)
+    assert np.array_equal(fin.cpu().numpy(), ref)
+    other = ref + rng.standard_normal(ref.shape)
+    met = ops.pose_metrics(fin, torch.from_numpy(other).to(dev())).cpu().numpy()
+    om = O.evaluate_step(ref, other)
+    assert abs(met[0] - om["L2_dist"]) < 1e-12 * om["L2_dist"]
+    assert abs(met[1] - om["lip_sync_error_n"]) < 1e-12 * max(1.0, om["lip_sync_error_n"])

@@ -283,6 +283,10 @@ def crop_pad_audio(wav, audio_length):
 # --------------------------------------------------------------------------------------------
 
 def _act(x, leaky):
+    """LeakyReLU(0.2) / ReLU (building_blocks.py:46).  A float selects an arbitrary negative slope: the tests use
+    slope 1.0 (identity) to compare gradients without the activation's derivative discontinuity."""
+    if isinstance(leaky, float):
+        return F.leaky_relu(x, leaky)
     return F.leaky_relu(x, 0.2) if leaky else F.relu(x)
 
 

@@ -312,14 +312,15 @@ __global__ void __launch_bounds__(1024) vae_reparam_kl_kernel(const float* __res
 }
 
 // ---- Adam: torch.optim.Adam single-tensor form, flat buffer -------------------------------------------
-// scalars: [0] step_size = lr / (1 - beta1^t), [1] 1/sqrt(1 - beta2^t), [2] t (as float, informational);
-//          8 bytes at scalars+4 hold t as int64.
-__global__ void adam_advance_kernel(float* scalars, float lr, float beta1, float beta2) {
+// scalars: [0] step_size = lr / (1 - beta1^t), [1] 1/sqrt(1 - beta2^t), [2] t (as float, informational),
+//          [3] learning rate used when the lr argument is negative; 8 bytes at scalars+4 hold t as int64.
+__global__ void adam_advance_kernel(float* scalars, float lr, double beta1, double beta2) {
     long long* tptr = reinterpret_cast<long long*>(scalars + 4);
     const long long t = *tptr + 1;
     *tptr = t;
-    const double bc1 = 1.0 - pow((double)beta1, (double)t);
-    const double bc2 = 1.0 - pow((double)beta2, (double)t);
+    if (lr < 0.f) lr = scalars[3];   // learning rate kept on the device (a captured CUDA graph can then follow MultiStepLR)
+    const double bc1 = 1.0 - pow(beta1, (double)t);
+    const double bc2 = 1.0 - pow(beta2, (double)t);
     scalars[0] = (float)((double)lr / bc1);
     scalars[1] = (float)(1.0 / sqrt(bc2));
     scalars[2] = (float)t;
@@ -327,8 +328,9 @@ __global__ void adam_advance_kernel(float* scalars, float lr, float beta1, float
 
 __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                         float* __restrict__ m, float* __restrict__ v, long long n,
-                                                        const float* __restrict__ scalars, float beta1, float beta2, float eps,
-                                                        float grad_scale) {
+                                                        const float* __restrict__ scalars, float beta1, float beta2,
+                                                        float omb1, float omb2, float eps, float grad_scale) {
+    // omb1/omb2 = (float)(1 - beta) evaluated in double on the host, as torch does for add_(alpha=1-beta1)
     const float step_size = scalars[0], inv_sqrt_bc2 = scalars[1];
     const long long n4 = n / 4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -340,8 +342,8 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const float gq = gg[q] * grad_scale;
-            mm[q] = beta1 * mm[q] + (1.f - beta1) * gq;
-            vq[q] = beta2 * vq[q] + (1.f - beta2) * gq * gq;
+            mm[q] = beta1 * mm[q] + omb1 * gq;
+            vq[q] = beta2 * vq[q] + omb2 * gq * gq;
             const float denom = sqrtf(vq[q]) * inv_sqrt_bc2 + eps;
             pp[q] -= step_size * (mm[q] / denom);
         }
@@ -353,8 +355,8 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
     if (blockIdx.x == 0) {
         for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
             const float gq = g[i] * grad_scale;
-            const float mq = beta1 * m[i] + (1.f - beta1) * gq;
-            const float vq = beta2 * v[i] + (1.f - beta2) * gq * gq;
+            const float mq = beta1 * m[i] + omb1 * gq;
+            const float vq = beta2 * v[i] + omb2 * gq * gq;
             m[i] = mq; v[i] = vq;
             p[i] -= step_size * (mq / (sqrtf(vq) * inv_sqrt_bc2 + eps));
         }
@@ -475,7 +477,7 @@ extern "C" int sdt_vae_reparam_kl(const float* mu, const float* logvar, const fl
     return SDT_OK;
 }
 
-extern "C" int sdt_adam_advance(float* scalars, float lr, float beta1, float beta2, void* stream) {
+extern "C" int sdt_adam_advance(float* scalars, float lr, double beta1, double beta2, void* stream) {
     SDT_REQUIRE(scalars, "sdt_adam_advance: null pointer");
     adam_advance_kernel<<<1, 1, 0, sdt::as_stream(stream)>>>(scalars, lr, beta1, beta2);
     SDT_LAUNCH_OK("adam_advance_kernel");
@@ -483,14 +485,15 @@ extern "C" int sdt_adam_advance(float* scalars, float lr, float beta1, float bet
 }
 
 extern "C" int sdt_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
-                             const float* scalars, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+                             const float* scalars, double beta1, double beta2, double eps, float grad_scale, void* stream) {
     SDT_REQUIRE(param && grad && exp_avg && exp_avg_sq && scalars && n > 0, "sdt_adam_flat: bad arguments");
     SDT_REQUIRE((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0,
                 "sdt_adam_flat: buffers must be 16-byte aligned");
     int blocks = sdt::ceil_div(n / 4 + 1, 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    adam_flat_kernel<<<blocks, 256, 0, sdt::as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, scalars, beta1, beta2, eps,
-                                                                 grad_scale);
+    adam_flat_kernel<<<blocks, 256, 0, sdt::as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, scalars, (float)beta1,
+                                                                 (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2),
+                                                                 (float)eps, grad_scale);
     SDT_LAUNCH_OK("adam_flat_kernel");
     return SDT_OK;
 }

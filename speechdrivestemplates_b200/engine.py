@@ -62,7 +62,7 @@ class GeneratorEngine:
         if norm not in ("IN", "BN"):
             raise NotImplementedError(norm)                # building_blocks.py:27-28
         self.norm = norm
-        self.slope = 0.2 if leaky else 0.0
+        self.slope = float(leaky) if isinstance(leaky, float) else (0.2 if leaky else 0.0)   # building_blocks.py:46
         self.code_dim = code_dim or 0
         self.kp2 = n_landmarks * 2
         self.device = device
@@ -119,10 +119,7 @@ class GeneratorEngine:
             hw.append(g.out_hw(*hw[-1]))
         self.enc_hw = hw                               # hw[l] = input size of layer l; hw[l+1] = its output size
         ls = seq_lengths(F)
-        self.seq_len = {"x0": F}
-        for i, n in enumerate(UNET_E):
-            self.seq_len["unet." + n] = ls[max(0, i - 1)] if i >= 1 else F
-        # e0,e1: F ; e2: ls[1]; ... e6: ls[5]
+        self.seq_len = {"x0": F}          # e0,e1: F ; e2: ls[1]; ... e6: ls[5]
         self.seq_len["unet.e0"] = F
         self.seq_len["unet.e1"] = F
         for i in range(2, 7):

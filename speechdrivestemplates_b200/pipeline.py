@@ -1,0 +1,485 @@
+"""Voice2Pose step model and train step on the B200 kernels.
+
+``Voice2PoseModel`` mirrors core/pipelines/voice2pose.py:22-210 (constructor signature, attribute / parameter /
+buffer names, ``forward(batch, dataset) -> (losses_dict, results_dict)`` with an autograd-connected ``G_loss``), so
+the reference's ``Voice2Pose`` trainer can hold it unchanged.  ``Voice2PoseTrainer.train_step`` is the numeric part
+of core/pipelines/voice2pose.py:281-312 as ONE fused device program: host batch -> H2D -> mel -> generator -> losses
+-> FGD encoder x2 -> f64 final results + metrics -> backward -> (NCCL all-reduce) -> Adam, replayable as a CUDA graph.
+"""
+import math
+from collections import OrderedDict
+
+import torch
+from torch import nn
+
+from . import _lib, ops
+from .networks import PoseSeqEncoder, SequenceGeneratorCNN, get_model
+
+
+# ------------------------------------------------------------------------------------------------
+# mel front end module (state-dict compatible with torchaudio.transforms.MelSpectrogram)
+# ------------------------------------------------------------------------------------------------
+def melscale_fbanks_htk(n_freqs=257, f_min=55.0, f_max=7500.0, n_mels=80, sample_rate=16000):
+    """HTK triangular filterbank, no normalisation, evaluated in fp32 as torchaudio does -> (n_freqs, n_mels)."""
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_min = 2595.0 * math.log10(1.0 + f_min / 700.0)
+    m_max = 2595.0 * math.log10(1.0 + f_max / 700.0)
+    m_pts = torch.linspace(m_min, m_max, n_mels + 2)
+    f_pts = 700.0 * (10.0 ** (m_pts / 2595.0) - 1.0)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    down = -slopes[:, :-2] / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    return torch.clamp(torch.minimum(down, up), min=0.0)
+
+
+class _Buffer(nn.Module):
+    def __init__(self, name, value):
+        super().__init__()
+        self.register_buffer(name, value)
+
+
+class MelSpectrogram(nn.Module):
+    """Buffers ``spectrogram.window`` (400) and ``mel_scale.fb`` (257, 80) like the torchaudio module built at
+    voice2pose.py:27-30; forward(audio (B, L)) -> (B, 80, 1 + L//160) power mel spectrogram via sdt_mel_fwd."""
+
+    def __init__(self):
+        super().__init__()
+        self.spectrogram = _Buffer("window", torch.hann_window(400))
+        self.mel_scale = _Buffer("fb", melscale_fbanks_htk())
+        self._tables = None
+        self._tables_key = None
+
+    def tables(self):
+        fb = self.mel_scale.fb
+        key = (fb.data_ptr(), fb._version, fb.device)
+        if self._tables_key != key:
+            self._tables = ops.mel_band_tables(fb)
+            self._tables_key = key
+        return self._tables
+
+    def forward(self, audio, out=None):
+        if not audio.is_cuda:
+            raise RuntimeError("MelSpectrogram runs only on CUDA tensors (libsdt_b200 has no CPU fallback)")
+        lead = audio.shape[:-1]
+        a2 = audio.detach().reshape(-1, audio.shape[-1]).contiguous().float()
+        mel = ops.mel_fwd(a2, self.spectrogram.window, self.tables(), out=out)
+        return mel.view(*lead, 80, mel.shape[-1])
+
+
+# ------------------------------------------------------------------------------------------------
+# step engine (no autograd): forward of the whole loss graph + backward into caller-provided gradient tensors
+# ------------------------------------------------------------------------------------------------
+class Voice2PoseStepEngine:
+    """Sequences the kernels of Voice2PoseModel.forward (training branch) and its backward."""
+
+    def __init__(self, model):
+        self.model = model
+        self.arena = None
+
+    def _arena(self, device):
+        from .engine import Arena
+        if self.arena is None or self.arena.device != device:
+            self.arena = Arena(device)
+        return self.arena
+
+    def forward(self, audio, poses, clip_index, stat=None, code_table=None):
+        """audio (B,L) f32, poses (B,F,2,K) f32, clip_index (B) i64 on device; stat = (mean, std, scale) f64 or None.
+
+        Returns a dict of engine-owned device tensors (valid until the next forward).
+        """
+        m = self.model
+        cfg = m.cfg
+        dev = audio.device
+        A = self._arena(dev)
+        B, F = poses.shape[0], poses.shape[1]
+        K2 = poses.shape[2] * poses.shape[3]
+        gcfg = cfg.VOICE2POSE.GENERATOR
+        out = OrderedDict()
+        mel = m.mel_transfm(audio, out=A.get("mel", (audio.shape[0], 80, 1 + audio.shape[1] // 160)))
+        D = gcfg.CLIP_CODE.DIMENSION
+        code = None
+        self._code_live = False
+        if D is not None:
+            table = code_table if code_table is not None else m.clips_code
+            code = A.get("code", (B, D))
+            kl = A.get("kl_out", (2,))
+            ops.code_gather_kl(table.detach(), clip_index, float(gcfg.LAMBDA_CLIP_KL), code, kl, A.get("g_code_kl", (B, D)))
+            out["G_clipcode_kl_loss"] = kl[0:1]
+            out["kl_applied"] = kl[1:2]
+            self._code_live = True
+        gparams = {n: p.detach() for n, p in m.netG.named_parameters()}
+        pred = m.netG.engine().forward(mel, F, code, gparams, m.netG.training, m.netG._buffers_dict())
+        reg = A.get("reg_out", (1,))
+        self._g_pred = A.get("g_pred", (B, F, K2))
+        ops.l1_loss(pred, poses, float(gcfg.LAMBDA_REG), reg, self._g_pred, A.get("l1_partial", (1024,)))
+        out["G_reg_loss"] = reg
+        g_loss = A.get("g_loss", (1,))
+        if D is not None:
+            torch.add(reg, out["G_clipcode_kl_loss"], out=g_loss)       # the KL slot holds 0 when the guard skipped it
+        else:
+            g_loss.copy_(reg)
+        out["G_loss"] = g_loss
+        out["poses_pred_batch"] = pred.view(B, F, 2, -1)
+        out["condition_code"] = code
+        # FGD feature extractor on prediction and ground truth (voice2pose.py:162-176), no gradient
+        if cfg.VOICE2POSE.POSE_ENCODER.NAME is not None:
+            if not cfg.DATASET.HIERARCHICAL_POSE:
+                raise NotImplementedError("POSE_ENCODER with HIERARCHICAL_POSE=False (transform_normalized_parted2global)")
+            pe = m.pose_encoder
+            pparams = {n: p.detach() for n, p in pe.named_parameters()}
+            pbuf = pe._buffers_dict()
+            out["mu_pred"], out["logvar_pred"] = pe.engine().forward(pred, pparams, pbuf, pe.training, tag="/pred")
+            out["mu_gt"], out["logvar_gt"] = pe.engine().forward(poses.view(B, F, K2), pparams, pbuf, pe.training, tag="/gt")
+        if stat is not None:          # dataset.get_final_results x2 + evaluate_step (voice2pose.py:289-292)
+            mean, std, scale = stat
+            hier = bool(cfg.DATASET.HIERARCHICAL_POSE)
+            fp = ops.pose_final_results(pred.view(B, F, 2, -1), mean, std, scale, hier, out=A.get("final_pred", (B, F, 2, K2 // 2), torch.float64))
+            fg = ops.pose_final_results(poses, mean, std, scale, hier, out=A.get("final_gt", (B, F, 2, K2 // 2), torch.float64))
+            met = ops.pose_metrics(fp, fg, A.get("met_partial", (2 * B,), torch.float64), A.get("met_out", (2,), torch.float64))
+            out["final_pred"], out["final_gt"] = fp, fg
+            out["L2_dist"], out["lip_sync_error_n"] = met[0:1], met[1:2]
+        self._clip_index = clip_index
+        self._B, self._F = B, F
+        return out
+
+    def backward(self, g_grads, g_table=None, g_pred=None):
+        """d G_loss: generator parameter gradients into g_grads[name]; dense clip-code gradient added into g_table
+        (which the caller has zeroed).  g_pred overrides the stored L1 gradient (B,F,2K)."""
+        m = self.model
+        D = m.cfg.VOICE2POSE.GENERATOR.CLIP_CODE.DIMENSION
+        A = self.arena
+        g_code = A.get("g_code_e0", (self._B, D)) if D is not None else None
+        m.netG.engine().backward(self._g_pred if g_pred is None else g_pred, g_grads, g_code)
+        if D is not None and g_table is not None:
+            ops.code_scatter_grad(g_code, A.get("g_code_kl", (self._B, D)), self._clip_index, g_table)
+        return g_code
+
+
+class _V2PLossFn(torch.autograd.Function):
+    """Autograd bridge for the drop-in model: (pred, G_reg_loss, KL) as one node over the step engine."""
+
+    @staticmethod
+    def forward(ctx, model, audio, poses, clip_index, clips_code, *gparams):
+        eng = model.step_engine()
+        out = eng.forward(audio, poses, clip_index, None, clips_code)
+        ctx.model, ctx.eng = model, eng
+        ctx.fwd_id = model.netG.engine().fwd_id
+        ctx.names = [n for n, _ in model.netG.named_parameters()]
+        ctx.shapes = [p.shape for p in gparams]
+        ctx.table_shape = clips_code.shape if clips_code is not None else None
+        ctx.code_needs_grad = clips_code is not None and clips_code.requires_grad
+        ctx.set_materialize_grads(False)
+        ctx.results = out
+        kl = out.get("G_clipcode_kl_loss")
+        return (out["poses_pred_batch"].clone(), out["G_reg_loss"].clone().squeeze(0),
+                kl.clone().squeeze(0) if kl is not None else torch.zeros((), device=audio.device))
+
+    @staticmethod
+    def backward(ctx, g_pred_ext, g_reg, g_kl):
+        model, eng = ctx.model, ctx.eng
+        if model.netG.engine().fwd_id != ctx.fwd_id:
+            raise RuntimeError("Voice2PoseModel.backward: saved activations were overwritten by a later forward")
+        dev = eng._g_pred.device
+        gp = eng._g_pred
+        if g_reg is None:
+            gp = torch.zeros_like(gp)
+        elif float(g_reg) != 1.0:
+            gp = gp * g_reg
+        if g_pred_ext is not None:
+            gp = gp + g_pred_ext.reshape(gp.shape)
+        grads = {n: torch.empty(s, device=dev) for n, s in zip(ctx.names, ctx.shapes)}
+        g_table = None
+        if ctx.code_needs_grad:
+            g_table = torch.zeros(ctx.table_shape, device=dev)
+            if g_kl is None or float(g_kl) != 1.0:
+                eng.arena.bufs["g_code_kl"].mul_(0.0 if g_kl is None else float(g_kl))
+        eng.backward(grads, g_table, gp.contiguous())
+        return (None, None, None, None, g_table) + tuple(grads[n] for n in ctx.names)
+
+
+# ------------------------------------------------------------------------------------------------
+# drop-in step model
+# ------------------------------------------------------------------------------------------------
+class Voice2PoseModel(nn.Module):
+    """core/pipelines/voice2pose.py:22-210 on libsdt_b200.  State-dict groups: ``clips_code``,
+    ``mel_transfm.spectrogram.window``, ``mel_transfm.mel_scale.fb``, ``netG.*``, ``pose_encoder.*``."""
+
+    def __init__(self, cfg, state_dict=None, num_train_samples=None, rank=0):
+        super().__init__()
+        self.cfg = cfg
+        self.mel_transfm = MelSpectrogram()
+        self.netG = get_model(cfg.VOICE2POSE.GENERATOR.NAME)(cfg)
+        ccfg = cfg.VOICE2POSE.GENERATOR.CLIP_CODE
+        if ccfg.DIMENSION is not None:
+            if ccfg.EXTERNAL_CODE:
+                path = ccfg.EXTERNAL_CODE_PTH or cfg.VOICE2POSE.POSE_ENCODER.AE_CHECKPOINT
+                if path is None:
+                    raise RuntimeError("External code not provide.")             # voice2pose.py:48
+                ckpt = torch.load(path, map_location={"cuda:0": "cuda:%d" % rank})
+                codes = {k.replace("module.", ""): v for k, v in ckpt["model_state_dict"].items() if "clip_code" in k}
+                self.clips_code = codes["clip_code_mu"]                              # plain tensor, not trained (:50-55)
+            else:
+                if num_train_samples is None:
+                    assert state_dict is not None, "No state_dict available, while no dataset is configured."
+                    num_train_samples = state_dict["module.clips_code"].shape[0]
+                if ccfg.FRAME_VARIANT:
+                    raise NotImplementedError("CLIP_CODE.FRAME_VARIANT")
+                self.clips_code = nn.Parameter(torch.zeros(num_train_samples, ccfg.DIMENSION), requires_grad=bool(ccfg.TRAIN))
+        else:
+            self.clips_code = None
+        if cfg.VOICE2POSE.POSE_ENCODER.NAME is not None:
+            self.pose_encoder = get_model(cfg.VOICE2POSE.POSE_ENCODER.NAME)(cfg)
+            self.pose_encoder.eval()                                                 # voice2pose.py:77
+        if cfg.VOICE2POSE.POSE_DISCRIMINATOR.NAME is not None:
+            raise NotImplementedError("POSE_DISCRIMINATOR (voice2pose_s2g training) is not implemented yet on the B200 path")
+        self._step_engine = None
+
+    def step_engine(self):
+        if self._step_engine is None:
+            self._step_engine = Voice2PoseStepEngine(self)
+        return self._step_engine
+
+    def _condition_code(self, batch, clip_indices, audio, poses_gt, return_loss, interpolation_coeff):
+        """Eval-time code selection (voice2pose.py:96-120)."""
+        cfg = self.cfg
+        ccfg = cfg.VOICE2POSE.GENERATOR.CLIP_CODE
+        dev = audio.device
+        if ccfg.SAMPLE_FROM_NORMAL:
+            return torch.randn([len(clip_indices), ccfg.DIMENSION]).to(dev)
+        if ccfg.TEST_WITH_GT_CODE:
+            assert cfg.VOICE2POSE.POSE_ENCODER.NAME is not None
+            with torch.no_grad():
+                mu_gt, _ = self.pose_encoder(poses_gt)
+            return mu_gt
+        table = self.clips_code.to(dev)
+        if cfg.DEMO.CODE_INDEX is not None:
+            assert not return_loss, 'WARNING: Do not set "DEMO.CODE_INDEX" in train or test mode!'
+            assert 0 <= cfg.DEMO.CODE_INDEX < table.size(0)
+            code = table[torch.full((len(audio),), cfg.DEMO.CODE_INDEX, dtype=torch.long, device=dev)]
+            if interpolation_coeff is not None:
+                assert cfg.DEMO.CODE_INDEX_B < table.size(0)
+                code_b = table[torch.full((len(audio),), cfg.DEMO.CODE_INDEX_B, dtype=torch.long, device=dev)]
+                code = code * (1 - interpolation_coeff) + code_b * interpolation_coeff
+            return code
+        return table[torch.randint(table.size(0), (len(audio),)).to(dev)]
+
+    def forward(self, batch, dataset=None, return_loss=True, interpolation_coeff=None):
+        cfg = self.cfg
+        audio = batch["audio"].cuda()
+        clip_indices = batch["clip_index"].cuda()
+        num_frames = int(batch["num_frames"][0].item())
+        poses_gt = batch["poses"].cuda() if return_loss else None
+        D = cfg.VOICE2POSE.GENERATOR.CLIP_CODE.DIMENSION
+
+        if self.training and return_loss:
+            gparams = [p for _, p in self.netG.named_parameters()]
+            pred, reg, kl = _V2PLossFn.apply(self, audio.contiguous().float(), poses_gt.contiguous().float(),
+                                             clip_indices.contiguous(), self.clips_code if D is not None else None, *gparams)
+            res = _V2PLossFn_last_results(self)
+            losses = OrderedDict()
+            losses["G_reg_loss"] = reg
+            g_loss = reg.clone()
+            if D is not None and float(res["kl_applied"]) != 0.0:          # the reference's host-side guard (voice2pose.py:154)
+                losses["G_clipcode_kl_loss"] = kl
+                g_loss = g_loss + kl
+            losses["G_loss"] = g_loss
+            results = {"poses_pred_batch": pred, "condition_code": res["condition_code"], "poses_gt_batch": poses_gt}
+            for k in ("mu_pred", "mu_gt", "logvar_pred", "logvar_gt"):
+                if k in res:
+                    results[k] = res[k].clone()
+            return losses, results
+
+        # eval / demo: code selection then a plain generator forward
+        code = None
+        if D is not None:
+            code = self._condition_code(batch, clip_indices, audio, poses_gt, return_loss, interpolation_coeff)
+        with torch.no_grad():
+            mel = self.mel_transfm(audio)
+            pred = self.netG(mel, num_frames, code)
+        results = {"poses_pred_batch": pred, "condition_code": code}
+        if not return_loss:
+            return results
+        results["poses_gt_batch"] = poses_gt
+        losses = OrderedDict()
+        reg = (torch.abs(pred - poses_gt) * cfg.VOICE2POSE.GENERATOR.LAMBDA_REG).mean()   # eval-time logging only
+        losses["G_reg_loss"] = reg
+        losses["G_loss"] = reg.clone()
+        if cfg.VOICE2POSE.POSE_ENCODER.NAME is not None:
+            with torch.no_grad():
+                results["mu_pred"], results["logvar_pred"] = self.pose_encoder(pred)
+                results["mu_gt"], results["logvar_gt"] = self.pose_encoder(poses_gt)
+        return losses, results
+
+
+def _V2PLossFn_last_results(model):
+    eng = model.step_engine()
+    A = eng.arena
+    out = {"kl_applied": A.bufs["kl_out"][1] if "kl_out" in A.bufs else torch.zeros(()),
+           "condition_code": A.bufs["code"].clone() if "code" in A.bufs else None}
+    pe = getattr(model, "pose_encoder", None)
+    if pe is not None and pe._eng is not None:
+        b = pe._eng.arena.bufs
+        out.update(mu_pred=b["mu/pred"], logvar_pred=b["logvar/pred"], mu_gt=b["mu/gt"], logvar_gt=b["logvar/gt"])
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# fused train step
+# ------------------------------------------------------------------------------------------------
+class Voice2PoseTrainer:
+    """The numeric part of Voice2Pose.train_step (voice2pose.py:281-312) for the SDT configs as a fused device program.
+
+    * parameters of netG (and the dense clips_code table) live in ONE flat fp32 buffer; the nn.Parameters of
+      ``self.model`` are views into it, so ``state_dict()`` keeps the reference layout;
+    * gradients are written by the backward kernels straight into a flat gradient buffer (no autograd), all-reduced
+      with a single NCCL call when world_size > 1, then consumed by a flat fused Adam (K18);
+    * after one eager warm-up step the whole step is captured into CUDA graphs and replayed.
+    """
+
+    def __init__(self, cfg, num_train_samples, device, use_cuda_graph=True, process_group=None, seed=0):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        torch.manual_seed(seed)                                       # main.py:37
+        self.model = Voice2PoseModel(cfg, num_train_samples=num_train_samples).to(self.device)
+        self.model.train()                                            # trainer.py:382
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.use_graph = use_cuda_graph
+        self.lr = float(cfg.TRAIN.LR)
+        self.code_lr = self.lr * float(cfg.VOICE2POSE.GENERATOR.CLIP_CODE.LR_SCALING)
+        m = self.model
+        self.g_names = [n for n, _ in m.netG.named_parameters()]
+        g_params = [p for _, p in m.netG.named_parameters()]
+        self.train_code = isinstance(m.clips_code, nn.Parameter) and m.clips_code.requires_grad
+        # flat layout: [netG parameters | pad to a multiple of 4 | clips_code (N*D) | pad]
+        self.n_g = sum(p.numel() for p in g_params)
+        self.n_g_pad = self.n_g + ((-self.n_g) % 4)
+        self.n_code = m.clips_code.numel() if self.train_code else 0
+        self.flat_p = torch.zeros(self.n_g_pad + self.n_code + ((-self.n_code) % 4), device=self.device)
+        off = 0
+        for p in g_params:
+            v = self.flat_p[off:off + p.numel()].view(p.shape)
+            v.copy_(p.data)
+            p.data = v
+            off += p.numel()
+        if self.train_code:
+            v = self.flat_p[self.n_g_pad:self.n_g_pad + self.n_code].view(m.clips_code.shape)
+            v.copy_(m.clips_code.data)
+            m.clips_code.data = v
+        self.flat_g = torch.zeros_like(self.flat_p)
+        self.exp_avg = torch.zeros_like(self.flat_p)
+        self.exp_avg_sq = torch.zeros_like(self.flat_p)
+        self.grads = {}
+        off = 0
+        for n, p in zip(self.g_names, g_params):
+            self.grads[n] = self.flat_g[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+        self.g_table = self.flat_g[self.n_g_pad:self.n_g_pad + self.n_code].view(-1, m.clips_code.shape[1]) if self.train_code else None
+        self.adam_g = torch.zeros(8, device=self.device)
+        self.adam_c = torch.zeros(8, device=self.device)
+        self.set_lr(self.lr)
+        self.engine = m.step_engine()
+        self._staging = None
+        self._graphs = None
+        self._warm = 0
+        self.kernels_per_step = 0
+        self.steps_done = 0
+
+    # ---- schedule hook (MultiStepLR steps per epoch in the reference, voice2pose.py:251-257)
+    def set_lr(self, lr):
+        self.lr = float(lr)
+        self.code_lr = self.lr * float(self.cfg.VOICE2POSE.GENERATOR.CLIP_CODE.LR_SCALING)
+        self.adam_g[3] = self.lr
+        self.adam_c[3] = self.code_lr
+
+    # ---- host -> device staging
+    def _stage(self, batch):
+        dev = self.device
+        audio, poses, idx = batch["audio"], batch["poses"], batch["clip_index"]
+        st = batch["speaker_stat"]
+        if self._staging is None or self._staging["audio"].shape != audio.shape or self._staging["poses"].shape != poses.shape:
+            self._staging = dict(
+                audio=torch.empty(audio.shape, device=dev), poses=torch.empty(poses.shape, device=dev),
+                idx=torch.empty(idx.shape, device=dev, dtype=torch.long),
+                mean=torch.empty(tuple(st["mean"].shape), device=dev, dtype=torch.float64),
+                std=torch.empty(tuple(st["std"].shape), device=dev, dtype=torch.float64),
+                scale=torch.empty(tuple(st["scale_factor"].shape), device=dev, dtype=torch.float64))
+            self._graphs = None
+        s = self._staging
+        s["audio"].copy_(audio, non_blocking=True)
+        s["poses"].copy_(poses, non_blocking=True)
+        s["idx"].copy_(idx, non_blocking=True)
+        s["mean"].copy_(torch.as_tensor(st["mean"]), non_blocking=True)
+        s["std"].copy_(torch.as_tensor(st["std"]), non_blocking=True)
+        s["scale"].copy_(torch.as_tensor(st["scale_factor"]), non_blocking=True)
+        return s
+
+    # ---- the device program, in two halves around the all-reduce
+    def _fwd_bwd(self):
+        s = self._staging
+        if self.train_code:
+            self.g_table.zero_()                                       # optimizerClipCode.zero_grad(); dense grad (K12)
+        self.out = self.engine.forward(s["audio"], s["poses"], s["idx"], (s["mean"], s["std"], s["scale"]))
+        self.engine.backward(self.grads, self.g_table)
+
+    def _optim(self):
+        gs = 1.0 / self.world
+        ops.adam_advance(self.adam_g, -1.0)
+        ops.adam_flat(self.flat_p[:self.n_g_pad], self.flat_g[:self.n_g_pad], self.exp_avg[:self.n_g_pad],
+                      self.exp_avg_sq[:self.n_g_pad], self.adam_g, grad_scale=gs)
+        if self.train_code:
+            ops.adam_advance(self.adam_c, -1.0)
+            sl = slice(self.n_g_pad, self.flat_p.numel())
+            ops.adam_flat(self.flat_p[sl], self.flat_g[sl], self.exp_avg[sl], self.exp_avg_sq[sl], self.adam_c, grad_scale=gs)
+
+    def _allreduce(self):
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_g, group=self.pg)   # ONE flat NCCL all-reduce per step
+
+    def run_staged(self):
+        """Run one step on the already-staged device batch (bench.py's device-resident timing)."""
+        if self.use_graph and self._graphs is None and self._warm >= 2:
+            self._capture()
+        if self._graphs is not None:
+            self._graphs[0].replay()
+            self._allreduce()
+            self._graphs[1].replay()
+        else:
+            n0 = _lib.launch_count
+            self._fwd_bwd()
+            self._allreduce()
+            self._optim()
+            self.kernels_per_step = _lib.launch_count - n0
+            self._warm += 1
+        self.steps_done += 1
+        return self.out
+
+    def _capture(self):
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g1, stream=side):
+                self._fwd_bwd()
+            with torch.cuda.graph(g2, stream=side):
+                self._optim()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graphs = (g1, g2)
+
+    def train_step(self, batch):
+        """batch: the reference's batch dict (host tensors; pinned memory recommended). Returns a dict of device
+        tensors: G_reg_loss, [G_clipcode_kl_loss], G_loss, L2_dist, lip_sync_error_n, poses_pred_batch, mu_*/logvar_*."""
+        self._stage(batch)
+        return self.run_staged()
+
+    def losses_to_host(self, out):
+        """One small D2H read of the step's scalars (the reference logs these every LOG_INTERVAL steps)."""
+        keys = ["G_reg_loss", "G_loss", "L2_dist", "lip_sync_error_n"] + (["G_clipcode_kl_loss", "kl_applied"] if "kl_applied" in out else [])
+        vals = torch.cat([out[k].double().view(1) for k in keys]).cpu().tolist()
+        d = dict(zip(keys, vals))
+        if "kl_applied" in d and d.pop("kl_applied") == 0.0:
+            d.pop("G_clipcode_kl_loss")
+        return d

@@ -75,7 +75,11 @@ _RESTYPES = {"sdt_last_error": C.c_char_p}
 _NOT_STATUS = {"sdt_last_error", "sdt_version", "sdt_get_conv_math", "sdt_conv_row_tiles"}
 
 _lib = None
-launch_count = 0     # number of kernel-launching C-ABI calls made through this binding (bench.py's gpu_launches)
+launch_count = 0     # number of CUDA kernels launched through this binding (bench.py's gpu_launches)
+# entry points that launch more than one kernel
+_KERNELS_PER_CALL = {"sdt_l1_loss": 2, "sdt_pose_metrics": 2, "sdt_enc_to_seq_bwd": 2}
+# optional (pre, post) callables invoked around every kernel-launching call: bench.py brackets calls with CUDA events
+hooks = None
 
 
 class SdtError(RuntimeError):
@@ -108,10 +112,15 @@ def call(name, *args):
     """Call a status-returning entry point; raise SdtError with sdt_last_error() on failure."""
     global launch_count
     fn = getattr(load(), name)
-    rc = fn(*args)
     if name in _NOT_STATUS:
-        return rc
+        return fn(*args)
+    if hooks is not None:
+        token = hooks[0](name, args)
+        rc = fn(*args)
+        hooks[1](token)
+    else:
+        rc = fn(*args)
     if rc != 0:
         raise SdtError("%s failed (%d): %s" % (name, rc, last_error()))
-    launch_count += 1
+    launch_count += _KERNELS_PER_CALL.get(name, 1)
     return 0

@@ -12,7 +12,7 @@ from collections import OrderedDict
 import torch
 from torch import nn
 
-from . import _lib, ops
+from . import _lib, ops, parallel
 from .networks import PoseSeqEncoder, SequenceGeneratorCNN, get_model
 
 
@@ -435,7 +435,7 @@ class Voice2PoseTrainer:
 
     def _allreduce(self):
         if self.world > 1:
-            torch.distributed.all_reduce(self.flat_g, group=self.pg)   # ONE flat NCCL all-reduce per step
+            parallel.allreduce_flat_(self.flat_g, self.pg)             # ONE flat NCCL all-reduce per step
 
     def run_staged(self):
         """Run one step on the already-staged device batch (bench.py's device-resident timing)."""

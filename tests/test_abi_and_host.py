@@ -1,0 +1,111 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/sdt_b200.h declares (no compute calls
+without a GPU), the ctypes mirror of sdt_conv_desc matches the header, host-side geometry logic, drop-in state-dict
+layout, loud failure without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header():
+    with open(os.path.join(ROOT, "include", "sdt_b200.h")) as f:
+        return f.read()
+
+
+def _built():
+    import __graft_entry__ as ge
+    ge.build()
+
+
+def test_library_exports_every_declared_symbol():
+    _built()
+    from speechdrivestemplates_b200 import _lib
+    lib = _lib.load()
+    declared = set(re.findall(r"^(?:const char\*|int)\s+(sdt_\w+)\s*\(", _header(), re.M))
+    assert len(declared) >= 35
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.sdt_version() >= 100
+    assert lib.sdt_get_conv_math() in (0, 1)
+
+
+def test_conv_desc_mirror_matches_header():
+    from speechdrivestemplates_b200._lib import ConvDesc
+    body = re.search(r"typedef struct sdt_conv_desc \{(.*?)\} sdt_conv_desc;", _header(), re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        decl = re.sub(r"^(const\s+)?(float\*|int32_t|float)\s*", "", decl)
+        names += [n.strip().lstrip("*") for n in decl.split(",")]
+    assert names == [f[0] for f in ConvDesc._fields_]
+    assert ctypes.sizeof(ConvDesc) == 9 * 8 + 26 * 4
+
+
+def test_argument_errors_are_reported_not_thrown():
+    _built()
+    from speechdrivestemplates_b200 import _lib
+    with pytest.raises(_lib.SdtError, match="null pointer"):
+        _lib.call("sdt_mel_fwd", None, 1, 1000, None, None, None, None, 1, None, None)
+    with pytest.raises(_lib.SdtError, match="mode must be"):
+        _lib.call("sdt_set_conv_math", 7)
+
+
+def test_dgrad_parity_classes_cover_every_input_once():
+    from speechdrivestemplates_b200.ops import ConvGeom
+    for g, h, w in [(ConvGeom.conv2d(64, 64, 4, 4, 2, 1), 80, 427), (ConvGeom.conv2d(8, 8, 3, 3, 1, 1), 5, 7),
+                    (ConvGeom.conv1d(256, 256, 4, 2, 1), 1, 63), (ConvGeom.conv2d(4, 4, 6, 3, 1, 0), 10, 53)]:
+        seen = torch.zeros(h, w, dtype=torch.int32)
+        taps = 0
+        for c in g.dgrad_classes(h, w):
+            ys = torch.arange(c["gh"]) * g.sh + c["py"]
+            xs = torch.arange(c["gw"]) * g.sw + c["px"]
+            assert ys.max() < h and xs.max() < w
+            seen[ys[:, None], xs[None, :]] += 1
+            taps += c["th"] * c["tw"]
+        assert bool((seen == 1).all())
+        assert taps == g.kh * g.kw                 # every kernel tap belongs to exactly one class
+
+
+def test_dropin_state_dict_layout_and_cpu_refusal():
+    from speechdrivestemplates_b200 import config, pipeline
+    from util import golden
+    cfg = config.get_cfg("voice2pose_sdt_bp")
+    torch.manual_seed(0)
+    m = pipeline.Voice2PoseModel(cfg, num_train_samples=16)
+    g = golden("sdt_bp_zero_code_golden")
+    ref_keys = sorted(k[len("init/"):-len("/digest")] for k in g.files if k.startswith("init/") and k.endswith("/digest"))
+    assert sorted(m.state_dict().keys()) == ref_keys
+    assert m.pose_encoder.training is False                 # voice2pose.py:77
+    with pytest.raises(RuntimeError):                       # no CPU fallback: fails loudly
+        m.netG(torch.zeros(1, 80, 427), 64, torch.zeros(1, 32))
+    with pytest.raises(KeyError, match="Unknown model"):
+        from speechdrivestemplates_b200 import networks
+        networks.get_model("NoSuchNet")
+
+
+def test_config_overlays_match_reference_yaml_when_available():
+    ref = "/root/reference/configs"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present")
+    import yaml
+    from speechdrivestemplates_b200 import config
+    for name in config.OVERLAYS:
+        with open(os.path.join(ref, name + ".yaml")) as f:
+            y = yaml.safe_load(f)
+        cfg = config.get_cfg(name)
+
+        def walk(node, d):
+            for k, v in d.items():
+                if isinstance(v, dict):
+                    walk(node[k], v)
+                else:
+                    assert float(node[k]) == float(v) if isinstance(v, str) and k == "LR" else node[k] == v, (name, k)
+        walk(cfg, y)

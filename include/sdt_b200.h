@@ -36,6 +36,8 @@ int sdt_version(void);
  * tcgen05 kernel exists for the shape (fp32 accumulate). Process-wide; default 0 unless set. */
 int sdt_set_conv_math(int mode);
 int sdt_get_conv_math(void);
+/* number of tcgen05 kernel launches made by this process so far (lets callers/tests verify which path ran) */
+int64_t sdt_tc_launches(void);
 
 /* ---- mel front end -----------------------------------------------------------------------------
  * torchaudio.transforms.MelSpectrogram(win_length=400, hop_length=160, n_fft=512, f_min=55,
@@ -68,7 +70,8 @@ int sdt_mel_fwd(const float* audio, int B, int L, const float* window, const int
  */
 typedef struct sdt_conv_desc {
     const float* src;          /* (B, SH, SW, C) */
-    const float* wt;           /* conv: (K, N) row-major, from sdt_weight_prep */
+    const float* wt;           /* conv: (K, N) row-major, from sdt_weight_prep mode 0/1 (FFMA path) */
+    const float* wt_nk;        /* conv: (N, K) row-major (K-major rows), mode 2/3; enables the tcgen05 path, may be NULL */
     const float* bias;         /* (N) or NULL */
     const float* xf_scale;     /* loader transform, or NULL for identity */
     const float* xf_shift;
@@ -99,7 +102,9 @@ int sdt_conv_wgrad_reduce(const float* wpart, int splits, int N, int C, int T, f
 /* reference-layout weight (Cout, Cin, KH, KW) -> GEMM operand (K, N):
  *   mode 0 forward : out[((ky*KW+kx)*Cin + ci)*Cout + co] = w[co,ci,ky,kx]
  *   mode 1 dgrad   : taps ky = ky0 + kstep*jy (jy < TH), kx likewise:
- *                    out[((jy*TW+jx)*Cout + co)*Cin + ci] = w[co,ci,ky0+kstep*jy,kx0+kstep*jx]      */
+ *                    out[((jy*TW+jx)*Cout + co)*Cin + ci] = w[co,ci,ky0+kstep*jy,kx0+kstep*jx]
+ *   mode 2 / 3     : the transposes of mode 0 / 1, i.e. (N, K) with K contiguous -- the K-major tensor-core operand:
+ *                    mode 2 out[co*K + (ky*KW+kx)*Cin + ci], mode 3 out[ci*K' + (jy*TW+jx)*Cout + co]           */
 int sdt_weight_prep(const float* w, int Cout, int Cin, int KH, int KW, int mode, int ky0, int kx0, int kstep,
                     int TH, int TW, float* out, void* stream);
 

@@ -17,7 +17,7 @@ i32, i64, f32, f64 = C.c_int32, C.c_int64, C.c_float, C.c_double
 class ConvDesc(C.Structure):
     """Mirror of ``sdt_conv_desc`` (include/sdt_b200.h)."""
     _fields_ = [
-        ("src", c_ptr), ("wt", c_ptr), ("bias", c_ptr), ("xf_scale", c_ptr), ("xf_shift", c_ptr),
+        ("src", c_ptr), ("wt", c_ptr), ("wt_nk", c_ptr), ("bias", c_ptr), ("xf_scale", c_ptr), ("xf_shift", c_ptr),
         ("dst", c_ptr), ("stat_partial", c_ptr), ("dy", c_ptr), ("wpart", c_ptr),
         ("B", i32), ("SH", i32), ("SW", i32), ("C", i32),
         ("GH", i32), ("GW", i32), ("TH", i32), ("TW", i32),
@@ -37,6 +37,7 @@ SIGNATURES = {
     "sdt_version": [],
     "sdt_set_conv_math": [i32],
     "sdt_get_conv_math": [],
+    "sdt_tc_launches": [],
     "sdt_mel_fwd": [c_ptr, i32, i32, c_ptr, c_ptr, c_ptr, c_ptr, i32, c_ptr, c_ptr],
     "sdt_conv_row_tiles": [_P],
     "sdt_conv_gemm": [_P, c_ptr],
@@ -70,9 +71,9 @@ SIGNATURES = {
     "sdt_adam_advance": [c_ptr, f32, f64, f64, c_ptr],
     "sdt_adam_flat": [c_ptr, c_ptr, c_ptr, c_ptr, i64, c_ptr, f64, f64, f64, f32, c_ptr],
 }
-_RESTYPES = {"sdt_last_error": C.c_char_p}
+_RESTYPES = {"sdt_last_error": C.c_char_p, "sdt_tc_launches": C.c_int64}
 # entry points whose int return value is a result, not a status
-_NOT_STATUS = {"sdt_last_error", "sdt_version", "sdt_get_conv_math", "sdt_conv_row_tiles"}
+_NOT_STATUS = {"sdt_last_error", "sdt_version", "sdt_get_conv_math", "sdt_conv_row_tiles", "sdt_tc_launches"}
 
 _lib = None
 launch_count = 0     # number of CUDA kernels launched through this binding (bench.py's gpu_launches)

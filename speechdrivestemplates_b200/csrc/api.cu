@@ -8,7 +8,10 @@
 namespace {
 thread_local char g_err[512] = "";
 std::atomic<int> g_conv_math{0};
+std::atomic<long long> g_tc_launches{0};
 }  // namespace
+
+void sdt_note_tc_launch() { g_tc_launches.fetch_add(1); }
 
 namespace sdt {
 void set_error(const char* fmt, ...) {
@@ -27,3 +30,4 @@ extern "C" int sdt_set_conv_math(int mode) {
     return SDT_OK;
 }
 extern "C" int sdt_get_conv_math(void) { return g_conv_math.load(); }
+extern "C" int64_t sdt_tc_launches(void) { return g_tc_launches.load(); }

@@ -8,6 +8,7 @@
 //
 // Tiling: BMxBNx16 CTA tiles, 256 threads, 8x8 / 8x4 / 4x4 register tiles, register-prefetch double buffering.
 #include "common.cuh"
+#include "tc_api.h"
 
 namespace {
 
@@ -475,7 +476,17 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, int Cout, int Ci
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
     int co, ci, jy, jx;
-    if (mode == 0) {  // out[((jy*TW+jx)*Cin + ci)*Cout + co]
+    if (mode == 2) {  // out[co*K + (jy*TW+jx)*Cin + ci]
+        ci = (int)(e % Cin);
+        const int tap = (int)((e / Cin) % (TH * TW));
+        co = (int)(e / ((long long)Cin * TH * TW));
+        jy = tap / TW; jx = tap % TW;
+    } else if (mode == 3) {  // out[ci*K' + (jy*TW+jx)*Cout + co]
+        co = (int)(e % Cout);
+        const int tap = (int)((e / Cout) % (TH * TW));
+        ci = (int)(e / ((long long)Cout * TH * TW));
+        jy = tap / TW; jx = tap % TW;
+    } else if (mode == 0) {  // out[((jy*TW+jx)*Cin + ci)*Cout + co]
         co = (int)(e % Cout);
         ci = (int)((e / Cout) % Cin);
         const int tap = (int)(e / ((long long)Cout * Cin));
@@ -517,9 +528,11 @@ inline int pick_bm(const sdt_conv_desc* d) {
 
 }  // namespace
 
+inline bool use_tc(const sdt_conv_desc* d) { return sdt_get_conv_math() == 1 && sdt_tc_conv_eligible(d); }
+
 extern "C" int sdt_conv_row_tiles(const sdt_conv_desc* d) {
     if (check_desc(d, "sdt_conv_row_tiles") != SDT_OK) return -1;
-    return row_tiles_for(d, pick_bm(d));
+    return row_tiles_for(d, use_tc(d) ? 128 : pick_bm(d));
 }
 
 extern "C" int sdt_conv_gemm(const sdt_conv_desc* d, void* stream) {
@@ -527,9 +540,10 @@ extern "C" int sdt_conv_gemm(const sdt_conv_desc* d, void* stream) {
     SDT_REQUIRE(d->wt && d->dst, "sdt_conv_gemm: null wt/dst");
     SDT_REQUIRE(!(d->stat_partial && d->bias), "sdt_conv_gemm: statistics epilogue excludes bias");
     SDT_REQUIRE(!(d->stat_partial && d->accumulate), "sdt_conv_gemm: statistics epilogue excludes accumulate");
+    cudaStream_t st = sdt::as_stream(stream);
+    if (use_tc(d)) return sdt_tc_conv_launch(d, row_tiles_for(d, 128), st);   // math mode 1: tcgen05 TF32
     const bool vec = (d->C % 4) == 0;
     const int bm = pick_bm(d);
-    cudaStream_t st = sdt::as_stream(stream);
     const sdt_conv_desc dd = *d;
     if (bm == 64) {
         dim3 grid(row_tiles_for(d, 64), sdt::ceil_div(d->N, 64));
@@ -555,6 +569,7 @@ extern "C" int sdt_conv_wgrad(const sdt_conv_desc* d, void* stream) {
     const int Kc = d->TH * d->TW * d->C;
     const bool veca = (d->N % 4) == 0, vecb = (d->C % 4) == 0;
     cudaStream_t st = sdt::as_stream(stream);
+    if (sdt_get_conv_math() == 1 && sdt_tc_wgrad_eligible(d)) return sdt_tc_wgrad_launch(d, st);   // tcgen05 TF32
     const sdt_conv_desc dd = *d;
     if (d->N <= 64) {
         dim3 grid(sdt::ceil_div(Kc, 128), sdt::ceil_div(d->N, 64), d->splits);
@@ -586,7 +601,7 @@ extern "C" int sdt_weight_prep(const float* w, int Cout, int Cin, int KH, int KW
                                int TH, int TW, float* out, void* stream) {
     SDT_REQUIRE(w && out, "sdt_weight_prep: null pointer");
     SDT_REQUIRE(Cout > 0 && Cin > 0 && KH > 0 && KW > 0 && TH > 0 && TW > 0 && kstep > 0, "sdt_weight_prep: bad extents");
-    SDT_REQUIRE(mode == 0 || mode == 1, "sdt_weight_prep: mode must be 0 or 1");
+    SDT_REQUIRE(mode >= 0 && mode <= 3, "sdt_weight_prep: mode must be 0..3");
     SDT_REQUIRE(ky0 >= 0 && kx0 >= 0 && ky0 + kstep * (TH - 1) < KH && kx0 + kstep * (TW - 1) < KW,
                 "sdt_weight_prep: tap selection outside the %dx%d kernel", KH, KW);
     const long long total = (long long)TH * TW * Cin * Cout;

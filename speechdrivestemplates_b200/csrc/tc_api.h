@@ -1,0 +1,11 @@
+// Internal interface between the FFMA dispatchers (conv_gemm.cu) and the tcgen05 kernels (tc_conv.cu, tc_wgrad.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "sdt_b200.h"
+
+bool sdt_tc_conv_eligible(const sdt_conv_desc* d);
+int sdt_tc_conv_launch(const sdt_conv_desc* d, int row_tiles, cudaStream_t st);
+bool sdt_tc_wgrad_eligible(const sdt_conv_desc* d);
+int sdt_tc_wgrad_launch(const sdt_conv_desc* d, cudaStream_t st);
+void sdt_note_tc_launch();

@@ -126,10 +126,26 @@ class ConvGeom:
         return out
 
 
-def fwd_desc(g, x, wt, dst, B, H, W, xf=None, slope=1.0, bias=None, stat_partial=None, per_image=False, accumulate=False):
+def set_conv_math(mode):
+    """0 = fp32 FFMA kernels, 1 = tcgen05 TF32 tensor-core kernels where a layer is eligible (process-wide)."""
+    call("sdt_set_conv_math", int(mode))
+
+
+def get_conv_math():
+    return call("sdt_get_conv_math")
+
+
+def tc_eligible(cin, cout):
+    """Static part of the tcgen05 path's eligibility (csrc/tc_conv.cu): K-block = 32 channels, N tile = 64/128/256."""
+    return cin % 32 == 0 and cout in (64, 128, 256)
+
+
+def fwd_desc(g, x, wt, dst, B, H, W, xf=None, slope=1.0, bias=None, stat_partial=None, per_image=False, accumulate=False,
+             wt_nk=None):
     oh, ow = g.out_hw(H, W)
     d = ConvDesc()
     d.src, d.wt, d.bias, d.dst = x.data_ptr(), wt.data_ptr(), bias.data_ptr() if bias is not None else None, dst.data_ptr()
+    d.wt_nk = wt_nk.data_ptr() if wt_nk is not None else None
     if xf is not None:
         d.xf_scale, d.xf_shift, d.xf_bstride = xf[0].data_ptr(), xf[1].data_ptr(), xf[2]
     d.xf_slope = slope
@@ -146,11 +162,12 @@ def fwd_desc(g, x, wt, dst, B, H, W, xf=None, slope=1.0, bias=None, stat_partial
     return d
 
 
-def dgrad_desc(g, cls, dy, wt_cls, dx, B, H, W, accumulate=False):
+def dgrad_desc(g, cls, dy, wt_cls, dx, B, H, W, accumulate=False, wt_nk=None):
     """Data gradient for one stride-parity class: dx[b, q*s+py, ...] = sum_taps dy[...] * W."""
     oh, ow = g.out_hw(H, W)
     d = ConvDesc()
     d.src, d.wt, d.dst = dy.data_ptr(), wt_cls.data_ptr(), dx.data_ptr()
+    d.wt_nk = wt_nk.data_ptr() if wt_nk is not None else None
     d.xf_slope = 1.0
     d.B, d.SH, d.SW, d.C = B, oh, ow, g.cout
     d.GH, d.GW, d.TH, d.TW = cls["gh"], cls["gw"], cls["th"], cls["tw"]
@@ -218,6 +235,17 @@ def weight_prep_dgrad(w, g, cls, out):
          cls["th"], cls["tw"], _p(out), _stream())
 
 
+def weight_prep_fwd_nk(w, g, out):
+    """... -> (Cout, K) K-major tensor-core operand of the forward GEMM."""
+    call("sdt_weight_prep", _p(w), g.cout, g.cin, g.kh, g.kw, 2, 0, 0, 1, g.kh, g.kw, _p(out), _stream())
+
+
+def weight_prep_dgrad_nk(w, g, cls, out):
+    """... -> (Cin, th*tw*Cout) K-major tensor-core operand of one data-gradient parity class."""
+    call("sdt_weight_prep", _p(w), g.cout, g.cin, g.kh, g.kw, 3, cls["ky0"], cls["kx0"], g.sw,
+         cls["th"], cls["tw"], _p(out), _stream())
+
+
 # ------------------------------------------------------------------------------------------------
 # convenience single-shot convolution ops (allocate their own scratch; used by tests and module boundaries)
 # ------------------------------------------------------------------------------------------------
@@ -234,8 +262,12 @@ def conv_forward(x, w, g, xf=None, slope=1.0, bias=None, want_stats=False, per_i
     oh, ow = g.out_hw(H, W)
     wt = torch.empty(g.k, g.cout, device=x.device)
     weight_prep_fwd(w, g, wt)
+    wt_nk = None
+    if get_conv_math() == 1 and tc_eligible(g.cin, g.cout):
+        wt_nk = torch.empty(g.cout, g.k, device=x.device)
+        weight_prep_fwd_nk(w, g, wt_nk)
     y = torch.empty(B, oh, ow, g.cout, device=x.device)
-    d = fwd_desc(g, x, wt, y, B, H, W, xf, slope, bias, None, per_image)
+    d = fwd_desc(g, x, wt, y, B, H, W, xf, slope, bias, None, per_image, wt_nk=wt_nk)
     partial = None
     if want_stats:
         partial = torch.empty(row_tiles(d), 2, g.cout, device=x.device)
@@ -254,7 +286,11 @@ def conv_dgrad(dy, w, g, H, W, out=None, accumulate=False):
     for cls in g.dgrad_classes(H, W):
         wt = torch.empty(cls["th"] * cls["tw"] * g.cout, g.cin, device=dy.device)
         weight_prep_dgrad(w, g, cls, wt)
-        conv_gemm(dgrad_desc(g, cls, dy, wt, dx, B, H, W, accumulate))
+        wt_nk = None
+        if get_conv_math() == 1 and tc_eligible(g.cout, g.cin):
+            wt_nk = torch.empty(g.cin, cls["th"] * cls["tw"] * g.cout, device=dy.device)
+            weight_prep_dgrad_nk(w, g, cls, wt_nk)
+        conv_gemm(dgrad_desc(g, cls, dy, wt, dx, B, H, W, accumulate, wt_nk=wt_nk))
     return dx
 
 

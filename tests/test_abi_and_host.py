@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     _built()
     from speechdrivestemplates_b200 import _lib
     lib = _lib.load()
-    declared = set(re.findall(r"^(?:const char\*|int)\s+(sdt_\w+)\s*\(", _header(), re.M))
+    declared = set(re.findall(r"^(?:const char\*|int|int64_t)\s+(sdt_\w+)\s*\(", _header(), re.M))
     assert len(declared) >= 35
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
@@ -46,7 +46,7 @@ def test_conv_desc_mirror_matches_header():
         decl = re.sub(r"^(const\s+)?(float\*|int32_t|float)\s*", "", decl)
         names += [n.strip().lstrip("*") for n in decl.split(",")]
     assert names == [f[0] for f in ConvDesc._fields_]
-    assert ctypes.sizeof(ConvDesc) == 9 * 8 + 26 * 4
+    assert ctypes.sizeof(ConvDesc) == 10 * 8 + 26 * 4
 
 
 def test_argument_errors_are_reported_not_thrown():

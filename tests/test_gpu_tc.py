@@ -1,0 +1,155 @@
+"""tcgen05 (TF32 tensor-core) convolution kernels against the fp32 FFMA kernels and fp64 references.
+Tolerance: TF32 keeps 10 mantissa bits of each operand (fp32 accumulate) -> ~1e-3 relative to the output scale."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TF32_TOL = 2e-3
+
+
+@pytest.fixture()
+def ops():
+    from speechdrivestemplates_b200 import ops as o
+    o.set_conv_math(1)
+    yield o
+    o.set_conv_math(0)
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def tc_launches():
+    from speechdrivestemplates_b200 import _lib
+    return _lib.call("sdt_tc_launches")
+
+
+def to_cl(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def from_cl(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+# encoder layer geometries 0.1 .. 3.1 on reduced spatial sizes (odd widths, partial tiles) + one full-size layer
+GEOMS = [
+    # cin, cout, kh, kw, s, p, H, W, B
+    (64, 64, 4, 4, 2, 1, 20, 37, 3),
+    (64, 128, 3, 3, 1, 1, 10, 18, 3),
+    (128, 128, 4, 4, 2, 1, 11, 19, 2),
+    (128, 256, 3, 3, 1, 1, 10, 13, 2),
+    (256, 256, 4, 4, 2, 1, 20, 27, 2),
+    (256, 256, 3, 3, 1, 1, 10, 53, 2),
+    (256, 256, 6, 3, 1, 0, 10, 53, 2),
+    (64, 64, 4, 4, 2, 1, 80, 427, 2),
+]
+
+
+@pytest.mark.parametrize("cfg", GEOMS)
+def test_tc_forward_with_loader_transform_and_stats(ops, cfg):
+    cin, cout, kh, kw, s, p, H, W, B = cfg
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(B, cin, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(cout, cin, kh, kw, generator=g, dtype=torch.float64) / math.sqrt(cin * kh * kw)
+    sc = torch.rand(B, cin, generator=g, dtype=torch.float64) + 0.5
+    sh = torch.randn(B, cin, generator=g, dtype=torch.float64)
+    a = F.leaky_relu(x * sc[:, :, None, None] + sh[:, :, None, None], 0.2)
+    ref = F.conv2d(a, w, None, s, p)
+    geom = ops.ConvGeom.conv2d(cin, cout, kh, kw, s, p)
+    xf = (sc.float().to(dev()).contiguous(), sh.float().to(dev()).contiguous(), cin)
+    n0 = tc_launches()
+    y, partial = ops.conv_forward(to_cl(x.float()).to(dev()), w.float().to(dev()).contiguous(), geom, xf=xf, slope=0.2,
+                                  want_stats=True, per_image=True)
+    torch.cuda.synchronize()
+    assert rel(from_cl(y), ref) < TF32_TOL
+    assert tc_launches() == n0 + 1                       # the tcgen05 kernel ran (no silent FFMA fallback)
+    tiles = partial.shape[0] // B
+    ps = partial.view(B, tiles, 2, cout).double().sum(1).cpu()
+    got = from_cl(y).double().cpu()
+    assert rel(ps[:, 0], got.sum((2, 3))) < 1e-4          # the statistics describe the tensor that was stored
+    assert rel(ps[:, 1], (got * got).sum((2, 3))) < 1e-4
+
+
+@pytest.mark.parametrize("cfg", GEOMS[:7])
+def test_tc_dgrad(ops, cfg):
+    cin, cout, kh, kw, s, p, H, W, B = cfg
+    g = torch.Generator().manual_seed(22)
+    x = torch.randn(B, cin, H, W, generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(cout, cin, kh, kw, generator=g, dtype=torch.float64) / math.sqrt(cin * kh * kw)
+    y = F.conv2d(x, w, None, s, p)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(dy)
+    geom = ops.ConvGeom.conv2d(cin, cout, kh, kw, s, p)
+    n0 = tc_launches()
+    dx = ops.conv_dgrad(to_cl(dy.float()).to(dev()), w.float().to(dev()).contiguous(), geom, H, W)
+    torch.cuda.synchronize()
+    assert rel(from_cl(dx), x.grad) < TF32_TOL
+    assert tc_launches() == n0 + s * s                   # one tcgen05 launch per stride-parity class
+
+
+def test_tc_conv1d_forward_bias_and_accumulating_dgrad(ops):
+    B, L, cin, cout = 8, 64, 256, 256
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(B, cin, L, generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(cout, cin, 3, generator=g, dtype=torch.float64) / math.sqrt(cin * 3)
+    b = torch.randn(cout, generator=g, dtype=torch.float64)
+    y = F.conv1d(x, w, b, 1, 1)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(dy)
+    geom = ops.ConvGeom.conv1d(cin, cout, 3, 1, 1)
+    xcl = x.detach().float().permute(0, 2, 1).contiguous().view(B, 1, L, cin).to(dev())
+    yk = ops.conv_forward(xcl, w.float().to(dev()).contiguous(), geom, bias=b.float().to(dev()))
+    assert rel(yk.view(B, L, cout).permute(0, 2, 1), y) < TF32_TOL
+    base = torch.ones(B, 1, L, cin, device=dev())
+    dx = ops.conv_dgrad(dy.float().permute(0, 2, 1).contiguous().view(B, 1, L, cout).to(dev()), w.float().to(dev()).contiguous(),
+                        geom, 1, L, out=base, accumulate=True)
+    assert rel(dx.view(B, L, cin).permute(0, 2, 1), x.grad + 1.0) < TF32_TOL
+
+
+@pytest.mark.parametrize("cfg", GEOMS)
+@pytest.mark.parametrize("splits", [None, 1, 5])
+def test_tc_wgrad(ops, cfg, splits):
+    cin, cout, kh, kw, s, p, H, W, B = cfg
+    if splits is not None and H * W > 2000:
+        pytest.skip("one split setting is enough for the large case")
+    g = torch.Generator().manual_seed(24)
+    x = torch.randn(B, cin, H, W, generator=g, dtype=torch.float64)
+    w = (torch.randn(cout, cin, kh, kw, generator=g, dtype=torch.float64) / math.sqrt(cin * kh * kw)).requires_grad_(True)
+    sc = torch.rand(B, cin, generator=g, dtype=torch.float64) + 0.5
+    sh = torch.randn(B, cin, generator=g, dtype=torch.float64)
+    a = F.leaky_relu(x * sc[:, :, None, None] + sh[:, :, None, None], 0.2)
+    y = F.conv2d(a, w, None, s, p)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(dy)
+    geom = ops.ConvGeom.conv2d(cin, cout, kh, kw, s, p)
+    xf = (sc.float().to(dev()).contiguous(), sh.float().to(dev()).contiguous(), cin)
+    n0 = tc_launches()
+    dw = ops.conv_weight_grad(to_cl(x.float()).to(dev()), to_cl(dy.float()).to(dev()), geom, xf=xf, slope=0.2, splits=splits)
+    torch.cuda.synchronize()
+    assert tc_launches() == n0 + 1
+    assert rel(dw, w.grad) < TF32_TOL
+
+
+def test_tc_wgrad_conv1d(ops):
+    B, L, cin, cout = 8, 64, 256, 256
+    g = torch.Generator().manual_seed(25)
+    x = torch.randn(B, cin, L, generator=g, dtype=torch.float64)
+    w = (torch.randn(cout, cin, 4, generator=g, dtype=torch.float64) / math.sqrt(cin * 4)).requires_grad_(True)
+    y = F.conv1d(x, w, None, 2, 1)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(dy)
+    geom = ops.ConvGeom.conv1d(cin, cout, 4, 2, 1)
+    xcl = x.float().permute(0, 2, 1).contiguous().view(B, 1, L, cin).to(dev())
+    dycl = dy.float().permute(0, 2, 1).contiguous().view(B, 1, -1, cout).to(dev())
+    dw = ops.conv_weight_grad(xcl, dycl, geom)
+    assert rel(dw.view(cout, cin, 4), w.grad) < TF32_TOL

@@ -204,8 +204,9 @@ def run_own(args):
         pg = dist.group.WORLD
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
 
+    conv_math = {"fp32": 0, "tf32": 1}[args.math]
     tr = pipeline.Voice2PoseTrainer(config.get_cfg("voice2pose_sdt_bp"), N_TRAIN, dev, use_cuda_graph=not args.no_graph,
-                                    process_group=pg, seed=0)
+                                    process_group=pg, seed=0, conv_math=conv_math)
     tr.model.clips_code.data.copy_(0.1 * torch.randn(N_TRAIN, 32, generator=torch.Generator().manual_seed(11)))
     host_batches = make_batches(B, rank)
     dev_batches = []
@@ -287,7 +288,8 @@ def run_own(args):
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
         "frac": achieved / pk["tf_sustained"], "traffic": None,
-        "kernel": "conv_gemm_kernel + conv_wgrad_kernel (implicit-GEMM convolutions, fp32 FFMA path)",
+        "kernel": "implicit-GEMM convolutions: " + ("conv_gemm_kernel + conv_wgrad_kernel (fp32 FFMA)" if conv_math == 0
+                                                      else "tc_conv_kernel + tc_wgrad_kernel (tcgen05 TF32) + FFMA kernels for ineligible layers"),
         "share_of_step": conv_ms / total_ms if total_ms else None,
         "launches_per_step": conv_n // reps, "avg_launch_ms": conv_ms / max(conv_n, 1),
         "peak_source": pk["src"] + " bf16 dense, sustained (kernel timed inside a long step)",
@@ -313,12 +315,12 @@ def run_own(args):
     clips = B * world * K
     line = {
         "metric": METRIC, "value": clips / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if conv_math == 0 else "tf32",
         "data": "synthetic",
         "config": {"workload": workload_name(B), "per_gpu_batch": B, "global_batch": B * world, "parallelism": "dp%d" % world,
                    "n_train_clips": N_TRAIN, "cuda_graph": tr._graphs is not None,
                    "l2": "no explicit flush: each step streams ~%.1f GB of activations/gradients (>> 126 MB L2) and rotates over 4 distinct input batches" % (tr.model.netG.engine().arena.nbytes() / 1e9),
-                   "conv_math": "fp32 FFMA"},
+                   "conv_math": "fp32 FFMA" if conv_math == 0 else "tcgen05 TF32 operands, fp32 accumulate (FFMA for ineligible layers)"},
         "e2e": {"value": clips / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / K, "wall_s": wall_e2e},
         "gpu_launches": launches_per_step * K * 2,
@@ -338,6 +340,8 @@ def main():
     ap.add_argument("--impl", default="own")
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU (BASELINE configs[1]: 32)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--math", default="fp32", choices=["fp32", "tf32"],
+                    help="convolution math: fp32 FFMA kernels or tcgen05 TF32 tensor-core kernels (fp32 accumulate)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

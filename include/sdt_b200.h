@@ -94,6 +94,8 @@ typedef struct sdt_conv_desc {
 /* number of row tiles sdt_conv_gemm will use for this descriptor (size of stat_partial's first dim) */
 int sdt_conv_row_tiles(const sdt_conv_desc* d);
 int sdt_conv_gemm(const sdt_conv_desc* d, void* stream);
+/* wgrad: contractions with K = TH*TW*C <= 16 and N <= 64 (first encoder layer) use a streaming kernel whose CTA count
+ * equals `splits`; otherwise split-K GEMM tiles (FFMA, or tcgen05 in math mode 1 when C % 32 == 0, N in {64,128,256}). */
 int sdt_conv_wgrad(const sdt_conv_desc* d, void* stream);
 /* sum the split-K partials in fixed order and store in the reference's parameter layout:
  * grad[(n*C + c)*T + t] (+)= sum_z wpart[z][n][(t*C + c)],  T = TH*TW  -> (Cout, Cin, kh, kw) */
@@ -107,6 +109,15 @@ int sdt_conv_wgrad_reduce(const float* wpart, int splits, int N, int C, int T, f
  *                    mode 2 out[co*K + (ky*KW+kx)*Cin + ci], mode 3 out[ci*K' + (jy*TW+jx)*Cout + co]           */
 int sdt_weight_prep(const float* w, int Cout, int Cin, int KH, int KW, int mode, int ky0, int kx0, int kstep,
                     int TH, int TW, float* out, void* stream);
+
+/* All weight operands of a network in ONE launch: items_device is a device array of n_items records (pointers are
+ * static across steps, so the table is uploaded once); max_elems = the largest TH*TW*Cin*Cout among them. */
+typedef struct sdt_prep_item {
+    const float* w;            /* (Cout, Cin, KH, KW) parameter */
+    float* out;                /* operand buffer */
+    int32_t Cout, Cin, KH, KW, mode, ky0, kx0, kstep, TH, TW, pad0, pad1;
+} sdt_prep_item;
+int sdt_weight_prep_batch(const sdt_prep_item* items_device, int n_items, long long max_elems, void* stream);
 
 /* ---- normalisation -----------------------------------------------------------------------------
  * nn.InstanceNorm2d / nn.BatchNorm{1,2}d inside ConvNormRelu (building_blocks.py:23-27,38-43,53) with

@@ -501,6 +501,105 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, int Cout, int Ci
     out[e] = w[(((size_t)co * Cin + ci) * KH + ky) * KW + kx];
 }
 
+// ------------------------------------------------------------------------------------------------
+// wgrad for tiny contractions (K = TH*TW*C <= 16, e.g. the 1->64 3x3 first encoder layer, K = 9): a 128-wide GEMM tile
+// would be >90 % padding, so this is a streaming kernel instead: each CTA walks a contiguous pixel range, stages 64
+// pixels of dy (64 x N) and of the im2col patch (64 x 16) in shared memory, thread (q, n) accumulates the 16 taps of
+// output channel n over a quarter of the pixels; one partial (N x K) per CTA, reduced by wgrad_reduce_kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int SK_PIX = 64;
+__global__ void __launch_bounds__(256) conv_wgrad_smallk_kernel(const sdt_conv_desc d) {
+    __shared__ __align__(16) float dy_s[SK_PIX][64 + 1];
+    __shared__ __align__(16) float a_s[SK_PIX][16];
+    __shared__ float red[4][64][16 + 1];
+    const int tid = threadIdx.x;
+    const int Kc = d.TH * d.TW * d.C, N = d.N, P = d.GH * d.GW;
+    const long long Mtot = (long long)d.B * P;
+    long long chunk = (Mtot + gridDim.x - 1) / gridDim.x;
+    chunk = (chunk + SK_PIX - 1) / SK_PIX * SK_PIX;
+    const long long p_begin = (long long)blockIdx.x * chunk;
+    const long long p_end = p_begin + chunk < Mtot ? p_begin + chunk : Mtot;
+    const int n = tid & 63, q = tid >> 6;
+    const bool has_xf = d.xf_scale != nullptr;
+    float acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+    for (long long pb = p_begin; pb < p_end; pb += SK_PIX) {
+        // stage dy: 64 pixels x N (N <= 64), coalesced
+        for (int e = tid; e < SK_PIX * 64; e += 256) {
+            const int pp = e >> 6, nn = e & 63;
+            const long long pix = pb + pp;
+            dy_s[pp][nn] = (pix < p_end && nn < N) ? __ldg(d.dy + pix * N + nn) : 0.f;
+        }
+        // stage the patches: 64 pixels x 16 (k >= Kc -> 0)
+        for (int e = tid; e < SK_PIX * 16; e += 256) {
+            const int pp = e >> 4, k = e & 15;
+            const long long pix = pb + pp;
+            float v = 0.f;
+            if (pix < p_end && k < Kc) {
+                const int b = (int)(pix / P);
+                const int rem = (int)(pix - (long long)b * P);
+                const int gy = rem / d.GW, gx = rem - gy * d.GW;
+                const int tap = k / d.C, c = k - tap * d.C;
+                const int tyy = tap / d.TW, txx = tap - tyy * d.TW;
+                const int sy = gy * d.y_mul + d.y_off + tyy * d.ty_mul, sx = gx * d.x_mul + d.x_off + txx * d.tx_mul;
+                if (sy >= 0 && sy < d.SH && sx >= 0 && sx < d.SW) {
+                    v = __ldg(d.src + (((size_t)b * d.SH + sy) * d.SW + sx) * d.C + c);
+                    if (has_xf) {
+                        const size_t o = (size_t)b * d.xf_bstride + c;
+                        v = xf_apply(v, __ldg(d.xf_scale + o), __ldg(d.xf_shift + o), d.xf_slope);
+                    }
+                }
+            }
+            a_s[pp][k] = v;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int pp = q; pp < SK_PIX; pp += 4) {
+            const float g = dy_s[pp][n];
+            const float4 a0 = *reinterpret_cast<const float4*>(&a_s[pp][0]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&a_s[pp][4]);
+            const float4 a2 = *reinterpret_cast<const float4*>(&a_s[pp][8]);
+            const float4 a3 = *reinterpret_cast<const float4*>(&a_s[pp][12]);
+            acc[0] = fmaf(g, a0.x, acc[0]); acc[1] = fmaf(g, a0.y, acc[1]); acc[2] = fmaf(g, a0.z, acc[2]); acc[3] = fmaf(g, a0.w, acc[3]);
+            acc[4] = fmaf(g, a1.x, acc[4]); acc[5] = fmaf(g, a1.y, acc[5]); acc[6] = fmaf(g, a1.z, acc[6]); acc[7] = fmaf(g, a1.w, acc[7]);
+            acc[8] = fmaf(g, a2.x, acc[8]); acc[9] = fmaf(g, a2.y, acc[9]); acc[10] = fmaf(g, a2.z, acc[10]); acc[11] = fmaf(g, a2.w, acc[11]);
+            acc[12] = fmaf(g, a3.x, acc[12]); acc[13] = fmaf(g, a3.y, acc[13]); acc[14] = fmaf(g, a3.z, acc[14]); acc[15] = fmaf(g, a3.w, acc[15]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) red[q][n][k] = acc[k];
+    __syncthreads();
+    float* out = d.wpart + (size_t)blockIdx.x * N * Kc;
+    for (int e = tid; e < N * Kc; e += 256) {
+        const int nn = e / Kc, k = e - nn * Kc;
+        out[e] = ((red[0][nn][k] + red[1][nn][k]) + red[2][nn][k]) + red[3][nn][k];
+    }
+}
+
+struct PrepItem {     // mirrors sdt_prep_item
+    const float* w;
+    float* out;
+    int32_t Cout, Cin, KH, KW, mode, ky0, kx0, kstep, TH, TW, pad0, pad1;
+};
+
+__global__ void weight_prep_batch_kernel(const PrepItem* __restrict__ items) {
+    const PrepItem it = items[blockIdx.y];
+    const long long total = (long long)it.TH * it.TW * it.Cin * it.Cout;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        int co, ci, tap;
+        const int T = it.TH * it.TW;
+        if (it.mode == 2) { ci = (int)(e % it.Cin); tap = (int)((e / it.Cin) % T); co = (int)(e / ((long long)it.Cin * T)); }
+        else if (it.mode == 3) { co = (int)(e % it.Cout); tap = (int)((e / it.Cout) % T); ci = (int)(e / ((long long)it.Cout * T)); }
+        else if (it.mode == 0) { co = (int)(e % it.Cout); ci = (int)((e / it.Cout) % it.Cin); tap = (int)(e / ((long long)it.Cout * it.Cin)); }
+        else { ci = (int)(e % it.Cin); co = (int)((e / it.Cin) % it.Cout); tap = (int)(e / ((long long)it.Cout * it.Cin)); }
+        const int jy = tap / it.TW, jx = tap % it.TW;
+        const int ky = it.ky0 + it.kstep * jy, kx = it.kx0 + it.kstep * jx;
+        it.out[e] = it.w[(((size_t)co * it.Cin + ci) * it.KH + ky) * it.KW + kx];
+    }
+}
+
 int check_desc(const sdt_conv_desc* d, const char* who) {
     SDT_REQUIRE(d != nullptr, "%s: null descriptor", who);
     SDT_REQUIRE(d->src != nullptr, "%s: null src", who);
@@ -537,11 +636,12 @@ extern "C" int sdt_conv_row_tiles(const sdt_conv_desc* d) {
 
 extern "C" int sdt_conv_gemm(const sdt_conv_desc* d, void* stream) {
     if (int rc = check_desc(d, "sdt_conv_gemm")) return rc;
-    SDT_REQUIRE(d->wt && d->dst, "sdt_conv_gemm: null wt/dst");
+    SDT_REQUIRE(d->dst && (d->wt || d->wt_nk), "sdt_conv_gemm: null dst or no weight operand");
     SDT_REQUIRE(!(d->stat_partial && d->bias), "sdt_conv_gemm: statistics epilogue excludes bias");
     SDT_REQUIRE(!(d->stat_partial && d->accumulate), "sdt_conv_gemm: statistics epilogue excludes accumulate");
     cudaStream_t st = sdt::as_stream(stream);
     if (use_tc(d)) return sdt_tc_conv_launch(d, row_tiles_for(d, 128), st);   // math mode 1: tcgen05 TF32
+    SDT_REQUIRE(d->wt != nullptr, "sdt_conv_gemm: the FFMA path needs the (K,N) operand `wt` (tcgen05 path not eligible here)");
     const bool vec = (d->C % 4) == 0;
     const int bm = pick_bm(d);
     const sdt_conv_desc dd = *d;
@@ -570,6 +670,11 @@ extern "C" int sdt_conv_wgrad(const sdt_conv_desc* d, void* stream) {
     const bool veca = (d->N % 4) == 0, vecb = (d->C % 4) == 0;
     cudaStream_t st = sdt::as_stream(stream);
     if (sdt_get_conv_math() == 1 && sdt_tc_wgrad_eligible(d)) return sdt_tc_wgrad_launch(d, st);   // tcgen05 TF32
+    if (Kc <= 16 && d->N <= 64) {       // tiny contraction: streaming kernel, one partial per CTA (gridDim.x == splits)
+        conv_wgrad_smallk_kernel<<<d->splits, 256, 0, st>>>(*d);
+        SDT_LAUNCH_OK("conv_wgrad_smallk_kernel");
+        return SDT_OK;
+    }
     const sdt_conv_desc dd = *d;
     if (d->N <= 64) {
         dim3 grid(sdt::ceil_div(Kc, 128), sdt::ceil_div(d->N, 64), d->splits);
@@ -608,5 +713,15 @@ extern "C" int sdt_weight_prep(const float* w, int Cout, int Cin, int KH, int KW
     weight_prep_kernel<<<sdt::ceil_div(total, 256), 256, 0, sdt::as_stream(stream)>>>(w, Cout, Cin, KH, KW, mode, ky0, kx0,
                                                                                        kstep, TH, TW, out);
     SDT_LAUNCH_OK("weight_prep_kernel");
+    return SDT_OK;
+}
+
+extern "C" int sdt_weight_prep_batch(const sdt_prep_item* items_device, int n_items, long long max_elems, void* stream) {
+    SDT_REQUIRE(items_device && n_items > 0 && max_elems > 0, "sdt_weight_prep_batch: bad arguments");
+    static_assert(sizeof(PrepItem) == sizeof(sdt_prep_item), "sdt_prep_item layout");
+    int gx = sdt::ceil_div(max_elems, 256 * 4);
+    if (gx > 1024) gx = 1024;
+    weight_prep_batch_kernel<<<dim3(gx, n_items), 256, 0, sdt::as_stream(stream)>>>(reinterpret_cast<const PrepItem*>(items_device));
+    SDT_LAUNCH_OK("weight_prep_batch_kernel");
     return SDT_OK;
 }

@@ -13,6 +13,8 @@
 //                 back to the producers; a final commit signals the epilogue.
 //   epilogue    : the 12 producer warps read the accumulator with tcgen05.ld (warp w owns TMEM lanes 32*(w%4)..+31),
 //                 add bias, store 128-byte row segments, and reduce the column statistics with a shuffle transpose.
+#include <limits.h>
+
 #include "tc_api.h"
 #include "tc_common.cuh"
 
@@ -26,6 +28,11 @@ constexpr int GROUPS = 3;
 constexpr int PRODUCERS = GROUPS * 128;
 constexpr int THREADS = PRODUCERS + 32;
 
+struct __align__(16) RowInfo {
+    long long base;     // element offset of src[b, sy0, sx0, 0] (may point outside the tensor; guarded by sy0/sx0)
+    int sy0, sx0;       // sy0 = INT_MIN/2 marks a row outside the problem
+};
+
 template <int BN>
 struct TcCfg {
     static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
@@ -35,7 +42,8 @@ struct TcCfg {
     static_assert((2 * STAGES + 1) * 8 + 16 <= BAR_BYTES, "barrier block");
     static constexpr int XF_BYTES = 2 * 256 * 4;
     static constexpr int RED_BYTES = 2 * 4 * BN * 4;
-    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + XF_BYTES + RED_BYTES + 1024;
+    static constexpr int ROW_BYTES = BM * 16 + BM * 8;           // {base, sy0, sx0} per row + dst offset per row
+    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + XF_BYTES + RED_BYTES + ROW_BYTES + 1024;
 };
 
 template <int BN>
@@ -54,6 +62,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(const sdt_conv_desc
     float* s_scale = reinterpret_cast<float*>(after + Cfg::BAR_BYTES);
     float* s_shift = s_scale + 256;
     float* s_red = s_shift + 256;                                 // [2][4][BN]
+    RowInfo* s_rows = reinterpret_cast<RowInfo*>(s_red + 2 * 4 * BN);
+    long long* s_dst = reinterpret_cast<long long*>(s_rows + BM);
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
     const uint32_t tmem_full_bar = bars + 8u * (2 * STAGES);
@@ -88,12 +98,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(const sdt_conv_desc
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // ---- row owned by this thread (producers and epilogue use the same row <-> thread map: r = tid % 128)
-    const int r = tid & 127;
-    int row_b = 0, sy0 = 0, sx0 = 0;
-    long long dst_off = -1;
-    if (tid < PRODUCERS) {
-        int rem;
+    // ---- decode the 128 rows of the tile once into shared memory
+    if (tid < BM) {
+        const int r = tid;
+        int row_b, rem;
         bool ok;
         if (d.per_image_tiles) {
             const int tpi = (P + BM - 1) / BM;
@@ -107,67 +115,70 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(const sdt_conv_desc
             rem = ok ? (int)(gm % P) : 0;
         }
         const int gy = rem / d.GW, gx = rem % d.GW;
-        sy0 = gy * d.y_mul + d.y_off;
-        sx0 = gx * d.x_mul + d.x_off;
-        if (ok) dst_off = (((long long)row_b * d.DH + (gy * d.dy_mul + d.dy_off)) * d.DW + (gx * d.dx_mul + d.dx_off)) * N;
+        RowInfo ri;
+        ri.sy0 = ok ? gy * d.y_mul + d.y_off : INT_MIN / 2;
+        ri.sx0 = gx * d.x_mul + d.x_off;
+        ri.base = (((long long)row_b * d.SH + ri.sy0) * d.SW + ri.sx0) * d.C;
+        s_rows[r] = ri;
+        s_dst[r] = ok ? (((long long)row_b * d.DH + (gy * d.dy_mul + d.dy_off)) * d.DW + (gx * d.dx_mul + d.dx_off)) * N : -1;
     }
+    __syncthreads();
+    const long long dst_off = tid < PRODUCERS ? s_dst[tid & 127] : -1;
 
     if (tid < PRODUCERS) {
         // ================= producers =================
-        const int g = tid >> 7;
-        const bool row_ok = dst_off >= 0;
-        constexpr int B_ROWS = BN >= 128 ? BN / 128 : 1;
-        const bool loads_b = BN >= 128 || r < BN;
+        // piece map: 16-byte chunk `ch` (fixed per thread) of rows rsub, rsub+16, ...: the 8 lanes of a row read its
+        // 128 bytes contiguously (4 cache lines per warp instruction) and write one swizzled 128-byte smem row.
+        const int g = tid >> 7, t = tid & 127;
+        const int ch = t & 7, rsub = t >> 3;
+        const uint32_t sw_off = (uint32_t)((ch ^ (rsub & 7)) << 4);      // (r & 7) == (rsub & 7) for r = rsub + 16*i
+        constexpr int B_PIECES = BN / 16;
         for (int kb = g; kb < KB; kb += GROUPS) {
             const int s = kb % STAGES, round = kb / STAGES;
             const int k = kb * BKF;
             const int tap = k / d.C, c0 = k - tap * d.C;
             const int tyy = tap / d.TW, txx = tap - tyy * d.TW;
-            const int sy = sy0 + tyy * d.ty_mul, sx = sx0 + txx * d.tx_mul;
-            const bool valid = row_ok && sy >= 0 && sy < d.SH && sx >= 0 && sx < d.SW;
+            const int dy_ = tyy * d.ty_mul, dx_ = txx * d.tx_mul;
+            const long long delta = ((long long)dy_ * d.SW + dx_) * d.C + c0 + ch * 4;
             float4 a[8];
-            if (valid) {
-                const float4* p = reinterpret_cast<const float4*>(d.src + (((size_t)row_b * d.SH + sy) * d.SW + sx) * d.C + c0);
+            unsigned vmask = 0;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) a[j] = __ldg(p + j);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            float4 bw[B_ROWS][8];
-            if (loads_b) {
-#pragma unroll
-                for (int q = 0; q < B_ROWS; ++q) {
-                    const float4* p = reinterpret_cast<const float4*>(d.wt_nk + (size_t)(n0 + r + q * 128) * K + k);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) bw[q][j] = __ldg(p + j);
+            for (int i = 0; i < 8; ++i) {
+                const RowInfo ri = s_rows[rsub + 16 * i];
+                const int sy = ri.sy0 + dy_, sx = ri.sx0 + dx_;
+                if (sy >= 0 && sy < d.SH && sx >= 0 && sx < d.SW) {
+                    a[i] = __ldg(reinterpret_cast<const float4*>(d.src + ri.base + delta));
+                    vmask |= 1u << i;
+                } else {
+                    a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
-            if (has_xf && valid) {
-                const float4* sc = reinterpret_cast<const float4*>(s_scale + c0);
-                const float4* sh = reinterpret_cast<const float4*>(s_shift + c0);
+            float4 bw[B_PIECES];
+            {
+                const float* wp = d.wt_nk + (size_t)(n0 + rsub) * K + k + ch * 4;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 c = sc[j], h = sh[j];
-                    a[j].x = sdt::leaky(fmaf(a[j].x, c.x, h.x), d.xf_slope);
-                    a[j].y = sdt::leaky(fmaf(a[j].y, c.y, h.y), d.xf_slope);
-                    a[j].z = sdt::leaky(fmaf(a[j].z, c.z, h.z), d.xf_slope);
-                    a[j].w = sdt::leaky(fmaf(a[j].w, c.w, h.w), d.xf_slope);
+                for (int i = 0; i < B_PIECES; ++i) bw[i] = __ldg(reinterpret_cast<const float4*>(wp + (size_t)(16 * i) * K));
+            }
+            if (has_xf) {
+                const float4 c = *reinterpret_cast<const float4*>(s_scale + c0 + ch * 4);
+                const float4 h = *reinterpret_cast<const float4*>(s_shift + c0 + ch * 4);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (vmask & (1u << i)) {
+                        a[i].x = sdt::leaky(fmaf(a[i].x, c.x, h.x), d.xf_slope);
+                        a[i].y = sdt::leaky(fmaf(a[i].y, c.y, h.y), d.xf_slope);
+                        a[i].z = sdt::leaky(fmaf(a[i].z, c.z, h.z), d.xf_slope);
+                        a[i].w = sdt::leaky(fmaf(a[i].w, c.w, h.w), d.xf_slope);
+                    }
                 }
             }
             mbar_wait(empty_bar(s), (uint32_t)((round & 1) ^ 1));
-            const uint32_t arow = smA + s * Cfg::A_BYTES + r * 128;
+            const uint32_t abase = smA + s * Cfg::A_BYTES + rsub * 128 + sw_off;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) st_shared_v4(arow + ((j ^ (r & 7)) << 4), a[j]);
-            if (loads_b) {
+            for (int i = 0; i < 8; ++i) st_shared_v4(abase + i * 16 * 128, a[i]);
+            const uint32_t bbase = smB + s * Cfg::B_BYTES + rsub * 128 + sw_off;
 #pragma unroll
-                for (int q = 0; q < B_ROWS; ++q) {
-                    const int n = r + q * 128;
-                    const uint32_t brow = smB + s * Cfg::B_BYTES + n * 128;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) st_shared_v4(brow + ((j ^ (n & 7)) << 4), bw[q][j]);
-                }
-            }
+            for (int i = 0; i < B_PIECES; ++i) st_shared_v4(bbase + i * 16 * 128, bw[i]);
             fence_proxy_async_smem();
             mbar_arrive(full_bar(s));
         }
@@ -277,7 +288,10 @@ bool sdt_tc_conv_eligible(const sdt_conv_desc* d) {
 }
 
 int sdt_tc_conv_launch(const sdt_conv_desc* d, int row_tiles, cudaStream_t st) {
-    if (d->N == 256) return launch_tc<256>(d, row_tiles, st);
-    if (d->N == 128) return launch_tc<128>(d, row_tiles, st);
+    // widest N tile that still gives every SM a CTA; small problems (the 1-D stacks) split N to fill the chip
+    int bn = d->N;
+    while (bn > 64 && (long long)row_tiles * (d->N / bn) < 148) bn /= 2;
+    if (bn == 256) return launch_tc<256>(d, row_tiles, st);
+    if (bn == 128) return launch_tc<128>(d, row_tiles, st);
     return launch_tc<64>(d, row_tiles, st);
 }

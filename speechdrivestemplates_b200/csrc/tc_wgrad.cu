@@ -86,9 +86,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_wgrad_kernel(const sdt_conv_des
 
     if (tid < PRODUCERS) {
         // ================= producers =================
+        // piece map: 16-byte piece `w` (fixed per thread) of (pixel, 32-channel chunk) pairs pr, pr+16, ...: the 8 lanes
+        // of a pair read its 128 bytes contiguously (4 cache lines per warp instruction).
         const int g = tid >> 7, t = tid & 127;
-        // A: thread -> (pixel kk, 32-channel chunk ja); the tap / channel offset of the chunk is loop invariant
-        const int kk = t >> 2, ja = t & 3;
+        const int w = t & 7, pr0 = t >> 3;                  // pair index = pr0 + 16*i
+        // A pairs: (pixel kk = pair >> 2, chunk ja = pair & 3); ja = pr0 & 3 is loop invariant
+        const int ja = pr0 & 3;
         const int kidx = kidx0 + ja * 32;
         const bool chunk_ok = kidx < Kc;
         int c0 = 0, tyy = 0, txx = 0;
@@ -98,77 +101,63 @@ __global__ void __launch_bounds__(THREADS, 1) tc_wgrad_kernel(const sdt_conv_des
             tyy = tap / d.TW;
             txx = tap - tyy * d.TW;
         }
-        const uint32_t a_off = (uint32_t)(((kk >> 2) * 4 + ja) * 512 + (kk & 3) * 128);
-        constexpr int B_PER = BN >= 128 ? BN / 128 : 1;
-        const bool loads_b = BN >= 128 || t < BN;
+        const int dy_ = tyy * d.ty_mul, dx_ = txx * d.tx_mul;
+        constexpr int B_PIECES = 2 * NCH;                   // 32 pixels x NCH chunks x 8 pieces / 128 threads
         for (int kb = g; kb < KB; kb += GROUPS) {
             const int s = kb % STAGES, round = kb / STAGES;
             const long long pbase = p_begin + (long long)kb * PIX;
-            // ---- A: im2col segment of pixel pbase+kk through the loader transform
+            // ---- A: im2col segments through the loader transform
             float4 a[8];
-            bool valid = false;
-            int b = 0;
-            const long long pix = pbase + kk;
-            if (chunk_ok && pix < p_end) {
-                b = (int)(pix / P);
-                const int rem = (int)(pix - (long long)b * P);
-                const int gy = rem / d.GW, gx = rem - gy * d.GW;
-                const int sy = gy * d.y_mul + d.y_off + tyy * d.ty_mul;
-                const int sx = gx * d.x_mul + d.x_off + txx * d.tx_mul;
-                if (sy >= 0 && sy < d.SH && sx >= 0 && sx < d.SW) {
-                    valid = true;
-                    const float4* p = reinterpret_cast<const float4*>(d.src + (((size_t)b * d.SH + sy) * d.SW + sx) * d.C + c0);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) a[j] = __ldg(p + j);
-                }
-            }
-            if (!valid) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            // ---- B: dy rows
-            float4 bw[B_PER][8];
-            if (loads_b) {
-#pragma unroll
-                for (int q = 0; q < B_PER; ++q) {
-                    const int u = t + q * 128;
-                    const int kb_pix = u / NCH, jb = u % NCH;
-                    const long long pb = pbase + kb_pix;
-                    if (pb < p_end) {
-                        const float4* p = reinterpret_cast<const float4*>(d.dy + pb * BN + jb * 32);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) bw[q][j] = __ldg(p + j);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) bw[q][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < 8; ++i) {
+                const int kk = (pr0 + 16 * i) >> 2;
+                const long long pix = pbase + kk;
+                a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (chunk_ok && pix < p_end) {
+                    const int b = (int)(pix / P);
+                    const int rem = (int)(pix - (long long)b * P);
+                    const int gy = rem / d.GW, gx = rem - gy * d.GW;
+                    const int sy = gy * d.y_mul + d.y_off + dy_;
+                    const int sx = gx * d.x_mul + d.x_off + dx_;
+                    if (sy >= 0 && sy < d.SH && sx >= 0 && sx < d.SW) {
+                        float4 v = __ldg(reinterpret_cast<const float4*>(d.src + (((size_t)b * d.SH + sy) * d.SW + sx) * d.C + c0 + w * 4));
+                        if (has_xf) {
+                            const size_t o = (size_t)b * d.xf_bstride + c0 + w * 4;
+                            const float4 c = __ldg(reinterpret_cast<const float4*>(d.xf_scale + o));
+                            const float4 h = __ldg(reinterpret_cast<const float4*>(d.xf_shift + o));
+                            v.x = sdt::leaky(fmaf(v.x, c.x, h.x), d.xf_slope);
+                            v.y = sdt::leaky(fmaf(v.y, c.y, h.y), d.xf_slope);
+                            v.z = sdt::leaky(fmaf(v.z, c.z, h.z), d.xf_slope);
+                            v.w = sdt::leaky(fmaf(v.w, c.w, h.w), d.xf_slope);
+                        }
+                        a[i] = v;
                     }
                 }
             }
-            if (has_xf && valid) {
-                const float4* sc = reinterpret_cast<const float4*>(d.xf_scale + (size_t)b * d.xf_bstride + c0);
-                const float4* sh = reinterpret_cast<const float4*>(d.xf_shift + (size_t)b * d.xf_bstride + c0);
+            // ---- B: dy rows, pairs (pixel = pair / NCH, chunk jb = pair % NCH)
+            float4 bw[B_PIECES];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 c = __ldg(sc + j), h = __ldg(sh + j);
-                    a[j].x = sdt::leaky(fmaf(a[j].x, c.x, h.x), d.xf_slope);
-                    a[j].y = sdt::leaky(fmaf(a[j].y, c.y, h.y), d.xf_slope);
-                    a[j].z = sdt::leaky(fmaf(a[j].z, c.z, h.z), d.xf_slope);
-                    a[j].w = sdt::leaky(fmaf(a[j].w, c.w, h.w), d.xf_slope);
-                }
+            for (int i = 0; i < B_PIECES; ++i) {
+                const int pair = pr0 + 16 * i;
+                const int kp = pair / NCH, jb = pair % NCH;
+                const long long pb = pbase + kp;
+                bw[i] = pb < p_end ? __ldg(reinterpret_cast<const float4*>(d.dy + pb * BN + jb * 32 + w * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             mbar_wait(empty_bar(s), (uint32_t)((round & 1) ^ 1));
-            const uint32_t arow = smA + s * Cfg::A_BYTES + a_off;
+            const uint32_t abase = smA + s * Cfg::A_BYTES;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) st_shared_v4(arow + ((((j >> 1) ^ (kk & 3)) << 5) | ((j & 1) << 4)), a[j]);
-            if (loads_b) {
+            for (int i = 0; i < 8; ++i) {
+                const int kk = (pr0 + 16 * i) >> 2;
+                const uint32_t off = (uint32_t)(((kk >> 2) * 4 + ja) * 512 + (kk & 3) * 128 + ((((w >> 1) ^ (kk & 3)) << 5) | ((w & 1) << 4)));
+                st_shared_v4(abase + off, a[i]);
+            }
+            const uint32_t bbase = smB + s * Cfg::B_BYTES;
 #pragma unroll
-                for (int q = 0; q < B_PER; ++q) {
-                    const int u = t + q * 128;
-                    const int kb_pix = u / NCH, jb = u % NCH;
-                    const uint32_t brow = smB + s * Cfg::B_BYTES + (uint32_t)(((kb_pix >> 2) * NCH + jb) * 512 + (kb_pix & 3) * 128);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) st_shared_v4(brow + ((((j >> 1) ^ (kb_pix & 3)) << 5) | ((j & 1) << 4)), bw[q][j]);
-                }
+            for (int i = 0; i < B_PIECES; ++i) {
+                const int pair = pr0 + 16 * i;
+                const int kp = pair / NCH, jb = pair % NCH;
+                const uint32_t off = (uint32_t)(((kp >> 2) * NCH + jb) * 512 + (kp & 3) * 128 + ((((w >> 1) ^ (kp & 3)) << 5) | ((w & 1) << 4)));
+                st_shared_v4(bbase + off, bw[i]);
             }
             fence_proxy_async_smem();
             mbar_arrive(full_bar(s));

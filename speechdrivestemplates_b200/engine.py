@@ -43,6 +43,80 @@ class Arena:
         return sum(t.numel() * t.element_size() for t in self.bufs.values())
 
 
+class WeightPrep:
+    """All GEMM weight operands of a network, refreshed by ONE kernel launch per step (sdt_weight_prep_batch).
+
+    The parameters keep the reference layout (Cout,Cin,kh,kw); the kernels want (K,N) [FFMA] or K-major (N,K)
+    [tcgen05] copies, per stride-parity class for the data gradient.  Pointers are static across steps, so the item
+    table is built and uploaded once and rebuilt only if a parameter moved or the math mode changed.
+    """
+
+    def __init__(self, arena):
+        self.arena = arena
+        self.key = None
+        self.fwd = {}       # name -> (wt or None, wt_nk or None)
+        self.dgrad = {}     # name -> [(cls, wt or None, wt_nk or None)]
+
+    def ensure(self, layers, params, with_dgrad):
+        """layers: [(name, weight key, geom, (H, W) of the layer input, needs_dgrad[, tc_ok])].
+
+        tc_ok=False keeps a layer on the FFMA operands even in math mode 1 (the tcgen05 kernel stages one image's
+        scale/shift per CTA, so layers whose loader transform spans a batch-wide statistic stay on the FFMA kernel)."""
+        import numpy as np
+        tc = ops.get_conv_math() == 1
+        key = (tc, with_dgrad) + tuple(params[l[1]].data_ptr() for l in layers)
+        if key == self.key:
+            return
+        self.key = key
+        A = self.arena
+        dt = np.dtype([("w", "<u8"), ("out", "<u8"), ("i", "<i4", (12,))])
+        items, max_elems = [], 1
+        self.fwd, self.dgrad = {}, {}
+
+        def add(w, out, g, mode, ky0, kx0, th, tw):
+            nonlocal max_elems
+            kstep = g.sw if mode in (1, 3) else 1          # forward operands take every tap; dgrad classes every s-th
+            items.append((w.data_ptr(), out.data_ptr(), (g.cout, g.cin, g.kh, g.kw, mode, ky0, kx0, kstep, th, tw, 0, 0)))
+            max_elems = max(max_elems, th * tw * g.cin * g.cout)
+
+        for layer in layers:
+            name, wkey, g, (H, W), needs_dgrad = layer[:5]
+            tc_ok = layer[5] if len(layer) > 5 else True
+            w = params[wkey]
+            if tc and tc_ok and ops.tc_eligible(g.cin, g.cout):
+                nk = A.get("wt_fnk:" + name, (g.cout, g.k))
+                add(w, nk, g, 2, 0, 0, g.kh, g.kw)
+                self.fwd[name] = (None, nk)
+            else:
+                kn = A.get("wt_f:" + name, (g.k, g.cout))
+                add(w, kn, g, 0, 0, 0, g.kh, g.kw)
+                self.fwd[name] = (kn, None)
+            if with_dgrad and needs_dgrad:
+                lst = []
+                dtc = tc and tc_ok and ops.tc_eligible(g.cout, g.cin)
+                for ci, cls in enumerate(g.dgrad_classes(H, W)):
+                    kd = cls["th"] * cls["tw"] * g.cout
+                    if dtc:
+                        nk = A.get("wt_dnk%d:%s" % (ci, name), (g.cin, kd))
+                        add(w, nk, g, 3, cls["ky0"], cls["kx0"], cls["th"], cls["tw"])
+                        lst.append((cls, None, nk))
+                    else:
+                        kn = A.get("wt_d%d:%s" % (ci, name), (kd, g.cin))
+                        add(w, kn, g, 1, cls["ky0"], cls["kx0"], cls["th"], cls["tw"])
+                        lst.append((cls, kn, None))
+                self.dgrad[name] = lst
+        arr = np.zeros(len(items), dtype=dt)
+        for i, (wp, op, ints) in enumerate(items):
+            arr[i] = (wp, op, ints)
+        self.table = torch.from_numpy(arr.view(np.uint8).copy()).to(A.device)
+        self.n_items, self.max_elems = len(items), max_elems
+
+    def run(self):
+        import ctypes as C
+        from ._lib import call
+        call("sdt_weight_prep_batch", C.c_void_p(self.table.data_ptr()), self.n_items, self.max_elems, ops._stream())
+
+
 def seq_lengths(num_frames):
     """Lengths of the UNet levels e1..e6 for an input of num_frames (k=4, s=2, p=1 halves with floor)."""
     ls = [num_frames]
@@ -70,6 +144,7 @@ class GeneratorEngine:
         self.enc_geoms = [ConvGeom.conv2d(ci, co, kh, kw, s, p) for (_n, co, ci, kh, kw, s, p) in ENC2D]
         self.shape_key = None
         self.fwd_id = 0
+        self.wprep = WeightPrep(self.arena)
 
     # ---- static layer tables -------------------------------------------------------------------
     def seq_layers(self):
@@ -136,9 +211,24 @@ class GeneratorEngine:
         return c if self.norm == "IN" else 0
 
     def _prep_weight(self, name, w, g):
-        wt = self.arena.get("wt_f:" + name, (g.k, g.cout))
-        ops.weight_prep_fwd(w, g, wt)
-        return wt
+        """-> (FFMA operand (K,N) or None, tensor-core operand (N,K) or None); filled by the batched prep launch."""
+        return self.wprep.fwd[name]
+
+    def _all_layers(self):
+        """[(name, geom, input (H, W), needs_dgrad)] of every convolution of the generator."""
+        out = []
+        for l, (lname, *_r) in enumerate(ENC2D):
+            out.append((ENC_PREFIX + lname, ENC_PREFIX + lname + ".conv.weight", self.enc_geoms[l], self.enc_hw[l], l > 0))  # mel needs no gradient
+        for name, g, kind in self.seq_layers():
+            if kind == "x0":
+                lin = self.F
+            elif kind.startswith("act:"):
+                lin = self.seq_len[kind[4:]]
+            else:                                   # up(prev)+skip: resampled to the skip's (== this layer's) length
+                lin = self.seq_len[name]
+            out.append((name, name + ".conv.weight", g, (1, lin), True))
+        out.append(("decoder.4", "decoder.4.weight", ConvGeom.conv1d(256, self.kp2, 1, 1, 0), (1, self.F), True))
+        return out
 
     # ---- forward ----------------------------------------------------------------------------------
     def forward(self, mel, code, params, training=True, buffers=None):
@@ -159,6 +249,8 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
     self.fwd_id += 1
     self._mel = mel
     self._params = params
+    self.wprep.ensure(self._all_layers(), params, with_dgrad=self.norm == "IN" and training)
+    self.wprep.run()
     # ---- 2-D encoder: raw conv output + statistics; normalise/activate in the consumer's loader
     src, xf = mel.view(B, 80, T, 1), None
     for l, (lname, co, ci, kh, kw, s, p) in enumerate(ENC2D):
@@ -166,10 +258,10 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
         name = ENC_PREFIX + lname
         H, W = self.enc_hw[l]
         oh, ow = self.enc_hw[l + 1]
-        wt = self._prep_weight(name, params[name + ".conv.weight"], g)
+        wt, wt_nk = self._prep_weight(name, params[name + ".conv.weight"], g)
         raw = A.get("raw:" + name, (B, oh, ow, co))
         use_batch_stats = self.norm == "IN" or training
-        d = ops.fwd_desc(g, src, wt, raw, B, H, W, xf, slope, per_image=True)
+        d = ops.fwd_desc(g, src, wt, raw, B, H, W, xf, slope, per_image=True, wt_nk=wt_nk)
         sc = A.get("scale:" + name, (groups, co))
         sh = A.get("shift:" + name, (groups, co))
         if use_batch_stats:
@@ -209,9 +301,9 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
             ops.upsample_add_fwd(acts[prev], acts[skip], L_out, out=xin)
         L_in = xin.shape[1]
         acts["in:" + name] = xin
-        wt = self._prep_weight(name, params[name + ".conv.weight"], g)
+        wt, wt_nk = self._prep_weight(name, params[name + ".conv.weight"], g)
         raw = A.get("raw:" + name, (B, L_out, 256))
-        d = ops.fwd_desc(g, xin, wt, raw, B, 1, L_in)
+        d = ops.fwd_desc(g, xin, wt, raw, B, 1, L_in, wt_nk=wt_nk)
         act = A.get("act:" + name, (B, L_out, 256))
         if self.norm == "IN":
             ops.conv_gemm(d)
@@ -236,9 +328,9 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
     self._acts = acts
     # ---- final 1x1 conv + bias (generator.py:103); channels-last output IS (B,F,2,K) (generator.py:116)
     gl = ConvGeom.conv1d(256, self.kp2, 1, 1, 0)
-    wt = self._prep_weight("decoder.4", params["decoder.4.weight"], gl)
+    wt, wt_nk = self._prep_weight("decoder.4", params["decoder.4.weight"], gl)
     pred = A.get("pred", (B, num_frames, self.kp2))
-    ops.conv_gemm(ops.fwd_desc(gl, acts["decoder.3"], wt, pred, B, 1, num_frames, bias=params["decoder.4.bias"]))
+    ops.conv_gemm(ops.fwd_desc(gl, acts["decoder.3"], wt, pred, B, 1, num_frames, bias=params["decoder.4.bias"], wt_nk=wt_nk))
     return pred
 
 
@@ -253,10 +345,9 @@ def _wgrad(self, g, x, dy, B, H, W, grad_out, xf=None, slope=1.0):
 
 
 def _dgrad(self, name, g, dy, w, dx, B, H, W, accumulate=False):
-    for ci, cls in enumerate(g.dgrad_classes(H, W)):
-        wt = self.arena.get("wt_d%d:%s" % (ci, name), (cls["th"] * cls["tw"] * g.cout, g.cin))
-        ops.weight_prep_dgrad(w, g, cls, wt)
-        ops.conv_gemm(ops.dgrad_desc(g, cls, dy, wt, dx, B, H, W, accumulate))
+    # stride-parity classes with their weight operands, prepared at the start of the step by the batched launch
+    for cls, wt, wt_nk in self.wprep.dgrad[name]:
+        ops.conv_gemm(ops.dgrad_desc(g, cls, dy, wt, dx, B, H, W, accumulate, wt_nk=wt_nk))
 
 
 def _gen_backward(self, g_pred, grads, g_code=None):
@@ -353,6 +444,7 @@ class PoseEncoderEngine:
         self.arena = Arena(device)
         self.geoms = ([ConvGeom.conv1d(self.kp2, 256, 3, 1, 1), ConvGeom.conv1d(256, 256, 3, 1, 1)]
                       + [ConvGeom.conv1d(256, 256, 4, 2, 1)] * 4 + [ConvGeom.conv1d(256, self.code2, 4, 2, 1)])
+        self.wprep = WeightPrep(self.arena)
 
     def param_shapes(self):
         shapes = {}
@@ -367,13 +459,18 @@ class PoseEncoderEngine:
         A = self.arena
         B, L = poses.shape[0], poses.shape[1]
         src, xf = poses.view(B, 1, L, self.kp2), None
+        if tag in ("", "/pred"):        # the two FGD passes of a step share one weight refresh
+            self.wprep.ensure([("blocks.%d" % i, "blocks.%d.conv.weight" % i, g, (1, 1), False, False)
+                               for i, g in enumerate(self.geoms)], params, False)
+            self.wprep.run()
         for i, g in enumerate(self.geoms):
             name = "blocks.%d" % i
             lo = g.out_hw(1, L)[1]
-            wt = A.get("wt_f:" + name, (g.k, g.cout))
-            ops.weight_prep_fwd(params[name + ".conv.weight"], g, wt)
+            wt, wt_nk = self.wprep.fwd[name]
             raw = A.get("raw%s:%s" % (tag, name), (B, 1, lo, g.cout))
-            d = ops.fwd_desc(g, src, wt, raw, B, 1, L, xf, self.slope)
+            # BN statistics span the batch, so row tiles may straddle clips; the tcgen05 kernel stages one image's
+            # scale/shift per CTA and therefore only takes the layers whose loader has no transform (the first one)
+            d = ops.fwd_desc(g, src, wt, raw, B, 1, L, xf, self.slope, wt_nk=wt_nk)
             sc = A.get("scale%s:%s" % (tag, name), (1, g.cout))
             sh = A.get("shift%s:%s" % (tag, name), (1, g.cout))
             if training:

@@ -144,7 +144,8 @@ def fwd_desc(g, x, wt, dst, B, H, W, xf=None, slope=1.0, bias=None, stat_partial
              wt_nk=None):
     oh, ow = g.out_hw(H, W)
     d = ConvDesc()
-    d.src, d.wt, d.bias, d.dst = x.data_ptr(), wt.data_ptr(), bias.data_ptr() if bias is not None else None, dst.data_ptr()
+    d.src, d.bias, d.dst = x.data_ptr(), bias.data_ptr() if bias is not None else None, dst.data_ptr()
+    d.wt = wt.data_ptr() if wt is not None else None
     d.wt_nk = wt_nk.data_ptr() if wt_nk is not None else None
     if xf is not None:
         d.xf_scale, d.xf_shift, d.xf_bstride = xf[0].data_ptr(), xf[1].data_ptr(), xf[2]
@@ -166,7 +167,8 @@ def dgrad_desc(g, cls, dy, wt_cls, dx, B, H, W, accumulate=False, wt_nk=None):
     """Data gradient for one stride-parity class: dx[b, q*s+py, ...] = sum_taps dy[...] * W."""
     oh, ow = g.out_hw(H, W)
     d = ConvDesc()
-    d.src, d.wt, d.dst = dy.data_ptr(), wt_cls.data_ptr(), dx.data_ptr()
+    d.src, d.dst = dy.data_ptr(), dx.data_ptr()
+    d.wt = wt_cls.data_ptr() if wt_cls is not None else None
     d.wt_nk = wt_nk.data_ptr() if wt_nk is not None else None
     d.xf_slope = 1.0
     d.B, d.SH, d.SW, d.C = B, oh, ow, g.cout
@@ -200,6 +202,8 @@ def wgrad_desc(g, x, dy, wpart, B, H, W, splits, xf=None, slope=1.0):
 
 def wgrad_splits(g, B, oh, ow, target_ctas=444):
     """Number of K (pixel) splits so that the weight-gradient GEMM fills the 148 SMs ~3 times over."""
+    if g.k <= 16 and g.cout <= 64:          # streaming small-K kernel: one partial per CTA, 4 CTAs per SM
+        return min(148 * 4, max(1, -(-(B * oh * ow) // 64)))
     tiles = -(-g.k // 128) * -(-g.cout // (64 if g.cout <= 64 else 128))
     pixels = B * oh * ow
     return max(1, min(-(-target_ctas // tiles), -(-pixels // 64)))

@@ -337,9 +337,11 @@ class Voice2PoseTrainer:
     * after one eager warm-up step the whole step is captured into CUDA graphs and replayed.
     """
 
-    def __init__(self, cfg, num_train_samples, device, use_cuda_graph=True, process_group=None, seed=0):
+    def __init__(self, cfg, num_train_samples, device, use_cuda_graph=True, process_group=None, seed=0, conv_math=None):
         self.cfg = cfg
         self.device = torch.device(device)
+        if conv_math is not None:          # 0 = fp32 FFMA, 1 = tcgen05 TF32 (the reference's own GPU default: cudnn.allow_tf32)
+            ops.set_conv_math(conv_math)
         torch.manual_seed(seed)                                       # main.py:37
         self.model = Voice2PoseModel(cfg, num_train_samples=num_train_samples).to(self.device)
         self.model.train()                                            # trainer.py:382

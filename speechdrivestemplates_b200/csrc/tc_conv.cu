@@ -288,7 +288,9 @@ bool sdt_tc_conv_eligible(const sdt_conv_desc* d) {
     if (d->wt_nk == nullptr) return false;
     if (d->C % 32 != 0 || (d->C > 256 && d->xf_scale != nullptr)) return false;
     if (!(d->N == 64 || d->N == 128 || d->N == 256)) return false;
-    if (d->xf_scale != nullptr && !d->per_image_tiles) return false;   // one image per CTA for the staged scale/shift
+    // the loader transform's scale/shift are staged once per CTA: either one image per CTA (per-(b,c) statistics) or
+    // statistics that do not depend on the image at all (BatchNorm, xf_bstride == 0)
+    if (d->xf_scale != nullptr && !d->per_image_tiles && d->xf_bstride != 0) return false;
     if ((((uintptr_t)d->src | (uintptr_t)d->wt_nk | (uintptr_t)d->dst | (uintptr_t)d->bias) & 15) != 0) return false;
     return true;
 }

@@ -460,7 +460,7 @@ class PoseEncoderEngine:
         B, L = poses.shape[0], poses.shape[1]
         src, xf = poses.view(B, 1, L, self.kp2), None
         if tag in ("", "/pred"):        # the two FGD passes of a step share one weight refresh
-            self.wprep.ensure([("blocks.%d" % i, "blocks.%d.conv.weight" % i, g, (1, 1), False, False)
+            self.wprep.ensure([("blocks.%d" % i, "blocks.%d.conv.weight" % i, g, (1, 1), False)
                                for i, g in enumerate(self.geoms)], params, False)
             self.wprep.run()
         for i, g in enumerate(self.geoms):
@@ -468,8 +468,7 @@ class PoseEncoderEngine:
             lo = g.out_hw(1, L)[1]
             wt, wt_nk = self.wprep.fwd[name]
             raw = A.get("raw%s:%s" % (tag, name), (B, 1, lo, g.cout))
-            # BN statistics span the batch, so row tiles may straddle clips; the tcgen05 kernel stages one image's
-            # scale/shift per CTA and therefore only takes the layers whose loader has no transform (the first one)
+            # BN statistics span the batch (row tiles may straddle clips); scale/shift are per channel (bstride 0)
             d = ops.fwd_desc(g, src, wt, raw, B, 1, L, xf, self.slope, wt_nk=wt_nk)
             sc = A.get("scale%s:%s" % (tag, name), (1, g.cout))
             sh = A.get("shift%s:%s" % (tag, name), (1, g.cout))

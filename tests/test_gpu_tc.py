@@ -153,3 +153,40 @@ def test_tc_wgrad_conv1d(ops):
     dycl = dy.float().permute(0, 2, 1).contiguous().view(B, 1, -1, cout).to(dev())
     dw = ops.conv_weight_grad(xcl, dycl, geom)
     assert rel(dw.view(cout, cin, 4), w.grad) < TF32_TOL
+
+
+def test_sdt_bp_train_step_tf32_mode_vs_reference_fixture():
+    """Whole fused train step with the tcgen05 TF32 convolutions against the reference's recorded fp32 step.
+    Stated TF32 tolerance: losses 1e-3, prediction 5e-3 of its range, final f64 results 5e-3; gradients agree in
+    direction and size (relative L2 error < 0.25 per tensor: TF32 operand rounding moves ~0.1 % of the LeakyReLU units
+    across zero, see tests/diag_grad_noise.py), the fp32 FFMA mode carries the tight gradient checks."""
+    import numpy as np
+    from oracle import sdt_oracle as O
+    from speechdrivestemplates_b200 import _lib, config, ops as o, pipeline
+    from test_gpu_step import _to_host_batch
+    from util import golden, oliver_stat, rel_err
+    g = golden("sdt_bp_step_golden")
+    try:
+        tr = pipeline.Voice2PoseTrainer(config.get_cfg("voice2pose_sdt_bp"), 16, dev(), use_cuda_graph=False, seed=0, conv_math=1)
+        tr.model.clips_code.data.copy_(0.1 * torch.randn(16, 32, generator=torch.Generator().manual_seed(11)))
+        n0 = tc_launches()
+        out = tr.train_step(_to_host_batch(O.synthetic_batch(2, 16, oliver_stat(True), seed=100)))
+        host = tr.losses_to_host(out)
+        assert tc_launches() - n0 >= 60                    # encoder + 1-D stacks ran on the tensor cores
+        for k in ("G_reg_loss", "G_loss", "G_clipcode_kl_loss", "L2_dist", "lip_sync_error_n"):
+            ref = float(g["step0/loss/" + k])
+            assert abs(host[k] - ref) <= 1e-3 * max(1.0, abs(ref)), (k, host[k], ref)
+        assert rel_err(out["poses_pred_batch"].cpu().numpy(), g["step0/pred"]) < 5e-3
+        assert rel_err(out["final_pred"].cpu().numpy(), g["step0/final_pred"]) < 5e-3
+        assert np.array_equal(out["final_gt"].cpu().numpy()[0, 0, 0, :4], out["final_gt"].cpu().numpy()[0, 0, 0, :4])
+        # gradients: compare against the fp32 FFMA trainer on the same inputs
+        tr0 = pipeline.Voice2PoseTrainer(config.get_cfg("voice2pose_sdt_bp"), 16, dev(), use_cuda_graph=False, seed=0, conv_math=0)
+        tr0.model.clips_code.data.copy_(0.1 * torch.randn(16, 32, generator=torch.Generator().manual_seed(11)))
+        tr0.train_step(_to_host_batch(O.synthetic_batch(2, 16, oliver_stat(True), seed=100)))
+        for n in tr.grads:
+            a, b = tr.grads[n].double().flatten(), tr0.grads[n].double().flatten()
+            err = float((a - b).norm() / (b.norm() + 1e-30))
+            cos = float((a * b).sum() / (a.norm() * b.norm() + 1e-30))
+            assert err < 0.25 and cos > 0.97, (n, err, cos)
+    finally:
+        o.set_conv_math(0)

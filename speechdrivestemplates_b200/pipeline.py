@@ -102,6 +102,10 @@ class Voice2PoseStepEngine:
         self._code_live = False
         if D is not None:
             table = code_table if code_table is not None else m.clips_code
+            if table.device != dev:                      # external (frozen) code table loaded from a checkpoint (voice2pose.py:40-55)
+                table = table.to(dev).contiguous().float()
+                if code_table is None:
+                    m.clips_code = table
             code = A.get("code", (B, D))
             kl = A.get("kl_out", (2,))
             ops.code_gather_kl(table.detach(), clip_index, float(gcfg.LAMBDA_CLIP_KL), code, kl, A.get("g_code_kl", (B, D)))
@@ -344,6 +348,11 @@ class Voice2PoseTrainer:
             ops.set_conv_math(conv_math)
         torch.manual_seed(seed)                                       # main.py:37
         self.model = Voice2PoseModel(cfg, num_train_samples=num_train_samples).to(self.device)
+        ae_ckpt = cfg.VOICE2POSE.POSE_ENCODER.AE_CHECKPOINT
+        if cfg.VOICE2POSE.POSE_ENCODER.NAME is not None and ae_ckpt is not None:      # voice2pose.py:234-242
+            ckpt = torch.load(ae_ckpt, map_location="cpu")
+            enc = OrderedDict((k.replace("module.ae.encoder.", ""), v) for k, v in ckpt["model_state_dict"].items() if "encoder" in k)
+            self.model.pose_encoder.load_state_dict(enc)
         self.model.train()                                            # trainer.py:382
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1

@@ -242,3 +242,62 @@ def test_full_size_properties():
     touched[batch["clip_index"]] = True
     assert float(g_table[~touched.to(dev())].abs().max()) == 0.0
     assert float(g_table[touched.to(dev())].abs().min()) >= 0.0 and float(g_table.abs().max()) > 0.0
+
+
+def test_sdt_vae_step_external_frozen_code(tmp_path):
+    """BASELINE configs[2] (voice2pose_sdt_vae): the clip code is a frozen lookup into clip_code_mu of a pose2pose
+    checkpoint (voice2pose.py:40-55); the KL term is computed but constant; FGD encoder weights come from the same file."""
+    from speechdrivestemplates_b200 import pipeline
+    from oracle import sdt_oracle as O
+    n_train, bs = 16, 3
+    ocfg = O.make_cfg("voice2pose_sdt_vae")
+    p2p = O.init_pose2pose(O.make_cfg("pose2pose"), n_train, seed=3)
+    table = 0.3 * torch.randn(n_train, 32, generator=torch.Generator().manual_seed(4))
+    ck = {"module." + k: v.clone() for k, v in p2p.items()}
+    ck["module.clip_code_mu"] = table.clone()
+    path = str(tmp_path / "p2p.pth")
+    torch.save({"epoch": 1, "step": 1, "model_state_dict": ck}, path)
+    orc = O.Voice2PoseOracle(ocfg, n_train, seed=0)
+    for k, v in p2p.items():
+        if k.startswith("ae.encoder."):
+            orc.sd["pose_encoder." + k[len("ae.encoder."):]] = v.clone()
+    batch = O.synthetic_batch(bs, n_train, oliver_stat(True), seed=77)
+    batch["external_code_table"] = table
+    losses, results, grads = orc.train_step(batch)
+    cfg = _cfg("voice2pose_sdt_vae", ["VOICE2POSE.POSE_ENCODER.AE_CHECKPOINT", path])
+    tr = pipeline.Voice2PoseTrainer(cfg, n_train, dev(), use_cuda_graph=False, seed=0)
+    assert not tr.train_code and "clips_code" not in tr.model.state_dict()        # SURVEY App. C
+    out = tr.train_step(_to_host_batch(batch))
+    host = tr.losses_to_host(out)
+    assert abs(host["G_loss"] - float(losses["G_loss"])) < 1e-5
+    assert abs(host["G_clipcode_kl_loss"] - float(losses["G_clipcode_kl_loss"])) < 1e-6
+    assert rel_err(out["poses_pred_batch"].cpu().numpy(), results["poses_pred_batch"].detach().numpy()) < 1e-4
+    assert rel_err(out["mu_gt"].cpu().numpy(), results["mu_gt"].numpy()) < 1e-4
+    for n, t in tr.grads.items():
+        ref = grads["netG." + n].numpy()
+        err = np.linalg.norm(t.cpu().numpy().ravel() - ref.ravel()) / (np.linalg.norm(ref.ravel()) + 1e-30)
+        assert err <= 0.15, (n, err)
+
+
+@pytest.mark.parametrize("seconds", [12, 60])
+def test_demo_inference_long_audio(seconds):
+    """BASELINE configs[4] (demo): one fully-convolutional forward over a long wav: mel + generator in
+    eval mode with a fixed clip code, num_frames = int(len / (sr / fps)); odd UNet lengths exercise the general lerp."""
+    from speechdrivestemplates_b200 import networks, pipeline
+    from oracle import sdt_oracle as O
+    sr, fps = 16000, 15
+    n = seconds * sr + 37
+    alen, nf = O.parse_audio_length(n, sr, fps)
+    g = torch.Generator().manual_seed(8)
+    audio = 0.1 * torch.randn(1, alen, generator=g)
+    code = 0.1 * torch.randn(1, 32, generator=g)
+    ocfg = O.make_cfg("voice2pose_sdt_bp")
+    torch.manual_seed(0)
+    sd = O.init_generator(ocfg)
+    ref = O.generator_forward(O.mel_spectrogram(audio), nf, code, sd, ocfg, False, "netG.")
+    torch.manual_seed(0)
+    net = networks.SequenceGeneratorCNN(_cfg("voice2pose_sdt_bp")).to(dev()).eval()
+    with torch.no_grad():
+        pred = net(pipeline.MelSpectrogram().to(dev())(audio.to(dev())), nf, code.to(dev()))
+    assert pred.shape == (1, nf, 2, 121) and nf == seconds * fps
+    assert rel_err(pred.cpu().numpy(), ref.numpy()) < 2e-4

@@ -205,6 +205,12 @@ int sdt_pose_head_fwd(const float* x, const float* scale, const float* shift, fl
 int sdt_vae_reparam_kl(const float* mu, const float* logvar, const float* eps, int n, float lambda, float* code,
                        float* out, void* stream);
 
+/* adjoints of the two entry points above: g_act (B,L,2D) is zero except t = 0;
+ * d mu = g_code + lambda*mu/n, d logvar = g_code*0.5*exp(0.5 logvar)*eps + lambda*0.5*(exp(logvar)-1)/n. */
+int sdt_pose_head_bwd(const float* g_mu, const float* g_logvar, int B, int L, int D2, float* g_act, void* stream);
+int sdt_vae_reparam_kl_bwd(const float* mu, const float* logvar, const float* eps, const float* g_code, int n, float lambda,
+                           float* g_mu, float* g_logvar, void* stream);
+
 /* ---- keypoint indexing / normalisation (bit-exact gates) ----------------------------------------
  * GestureDataset pose preprocessing (core/datasets/gesture_dataset.py:95-105,131-191):
  * raw (T,3,137) f32 -> gather 122 -> xy -= kp1 -> drop kp1 -> [parted] -> (x - f32(mean)) / f32(std) (IEEE div).

@@ -66,6 +66,8 @@ SIGNATURES = {
     "sdt_motion_diff_bwd": [c_ptr, i32, i32, i32, c_ptr, i32, c_ptr],
     "sdt_pose_head_fwd": [c_ptr, c_ptr, c_ptr, f32, i32, i32, i32, c_ptr, c_ptr, c_ptr],
     "sdt_vae_reparam_kl": [c_ptr, c_ptr, c_ptr, i32, f32, c_ptr, c_ptr, c_ptr],
+    "sdt_pose_head_bwd": [c_ptr, c_ptr, i32, i32, i32, c_ptr, c_ptr],
+    "sdt_vae_reparam_kl_bwd": [c_ptr, c_ptr, c_ptr, c_ptr, i32, f32, c_ptr, c_ptr, c_ptr],
     "sdt_pose_preprocess": [c_ptr, i32, c_ptr, c_ptr, i32, c_ptr, c_ptr],
     "sdt_pose_final_results": [c_ptr, i32, i32, c_ptr, c_ptr, c_ptr, i32, c_ptr, c_ptr],
     "sdt_pose_metrics": [c_ptr, c_ptr, i32, i32, c_ptr, c_ptr, c_ptr],

@@ -311,6 +311,30 @@ __global__ void __launch_bounds__(1024) vae_reparam_kl_kernel(const float* __res
     }
 }
 
+// backward of the reparameterisation + KL:
+//   d mu = g_code + lambda*mu/n ;  d logvar = g_code*0.5*exp(0.5 logvar)*eps + lambda*0.5*(exp(logvar) - 1)/n
+__global__ void vae_reparam_kl_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ logvar,
+                                          const float* __restrict__ eps, const float* __restrict__ g_code, int n, float lambda,
+                                          float* __restrict__ g_mu, float* __restrict__ g_logvar) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const float m = mu[e], lv = logvar[e], gc = g_code[e];
+    g_mu[e] = gc + lambda * m / (float)n;
+    g_logvar[e] = gc * 0.5f * expf(0.5f * lv) * eps[e] + lambda * 0.5f * (expf(lv) - 1.f) / (float)n;
+}
+
+// adjoint of the PoseSeqEncoder tail (autoencoder.py:31-35): g_act (B,L,2D) = 0 except t = 0, where even channels get
+// g_mu and odd channels g_logvar
+__global__ void pose_head_bwd_kernel(const float* __restrict__ g_mu, const float* __restrict__ g_logvar, int B, int L, int D2,
+                                     float* __restrict__ g_act) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B * L * D2) return;
+    const int ch = e % D2, t = (e / D2) % L, b = e / (D2 * L);
+    float v = 0.f;
+    if (t == 0) v = (ch & 1) ? g_logvar[b * (D2 / 2) + ch / 2] : g_mu[b * (D2 / 2) + ch / 2];
+    g_act[e] = v;
+}
+
 // ---- Adam: torch.optim.Adam single-tensor form, flat buffer -------------------------------------------
 // scalars: [0] step_size = lr / (1 - beta1^t), [1] 1/sqrt(1 - beta2^t), [2] t (as float, informational),
 //          [3] learning rate used when the lr argument is negative; 8 bytes at scalars+4 hold t as int64.
@@ -495,5 +519,20 @@ extern "C" int sdt_adam_flat(float* param, const float* grad, float* exp_avg, fl
                                                                  (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2),
                                                                  (float)eps, grad_scale);
     SDT_LAUNCH_OK("adam_flat_kernel");
+    return SDT_OK;
+}
+
+extern "C" int sdt_vae_reparam_kl_bwd(const float* mu, const float* logvar, const float* eps, const float* g_code, int n,
+                                      float lambda, float* g_mu, float* g_logvar, void* stream) {
+    SDT_REQUIRE(mu && logvar && eps && g_code && g_mu && g_logvar && n > 0, "sdt_vae_reparam_kl_bwd: bad arguments");
+    vae_reparam_kl_bwd_kernel<<<GRID1D(n)>>>(mu, logvar, eps, g_code, n, lambda, g_mu, g_logvar);
+    SDT_LAUNCH_OK("vae_reparam_kl_bwd_kernel");
+    return SDT_OK;
+}
+
+extern "C" int sdt_pose_head_bwd(const float* g_mu, const float* g_logvar, int B, int L, int D2, float* g_act, void* stream) {
+    SDT_REQUIRE(g_mu && g_logvar && g_act && B > 0 && L > 0 && D2 > 0 && D2 % 2 == 0, "sdt_pose_head_bwd: bad arguments");
+    pose_head_bwd_kernel<<<GRID1D(B * L * D2)>>>(g_mu, g_logvar, B, L, D2, g_act);
+    SDT_LAUNCH_OK("pose_head_bwd_kernel");
     return SDT_OK;
 }

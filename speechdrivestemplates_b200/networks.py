@@ -213,9 +213,156 @@ class PoseSeqEncoder(_EngineModule):
         return mu.clone(), logvar.clone()
 
 
+class _PoseSeqDecoder(nn.Module):
+    """Parameter container with the attribute names of autoencoder.PoseSeqDecoder (autoencoder.py:37-57)."""
+
+    def __init__(self, code_dim, kp2):
+        super().__init__()
+        self.d5 = ConvNormRelu((256, code_dim, 3), "BN")
+        for n in ("d4", "d3", "d2", "d1"):
+            setattr(self, n, ConvNormRelu((256, 256, 3), "BN"))
+        self.blocks = _seq(*[ConvNormRelu((256, 256, 3), "BN") for _ in range(4)],
+                           ConvWeights((kp2, 256, 1), bias=True, kaiming_normal=False))
+
+
+class Autoencoder(_EngineModule):
+    """core/networks/poses_reconstruction/autoencoder.py:71-92 (pose VAE).
+
+    forward(x: (B,F,2,K), num_frames, mel=None, external_code=None) -> (pred (B,F,2,K), mu, logvar), autograd-connected.
+    The N(0,1) draw uses ``torch.randn(logvar.shape, device=...)`` exactly like autoencoder.py:86, i.e. the same
+    generator stream as the reference on the same device."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        acfg = cfg.POSE2POSE.AUTOENCODER
+        if acfg.NORM != "BN":
+            raise NotImplementedError("Autoencoder with NORM=%s" % acfg.NORM)
+        self.leaky = bool(acfg.LEAKY_RELU)
+        self.code_dim = acfg.CODE_DIM
+        self.n_landmarks = cfg.DATASET.NUM_LANDMARKS
+        self.encoder = PoseSeqEncoder(cfg)
+        self.decoder = _PoseSeqDecoder(self.code_dim, self.n_landmarks * 2)
+        self._ae_eng = None
+        self.lambda_kl_fused = 0.0          # the drop-in leaves the KL term to the caller's torch expression (pose2pose.py:77)
+
+    def engine(self):
+        from .engine_seq import AutoencoderEngine
+        dev = self._device()
+        if self._ae_eng is None or self._ae_eng.device != dev:
+            self._ae_eng = AutoencoderEngine(self.n_landmarks, self.code_dim, self.leaky, dev)
+        return self._ae_eng
+
+    def forward(self, x, num_frames, mel=None, external_code=None):
+        self._require_cuda(x if x is not None else external_code)
+        names, params = self._named()
+        if external_code is not None:                                   # autoencoder.py:80-83
+            pdict = {n: p.detach() for n, p in zip(names, params)}
+            eng = self.engine()
+            eng._prep(pdict, eng._lengths(num_frames), with_dgrad=False)
+            with torch.no_grad():
+                pred = eng.decode(external_code.detach().contiguous().float(), pdict, self._buffers_dict(), self.training)
+            B = external_code.shape[0]
+            return pred.view(B, num_frames, 2, self.n_landmarks).clone(), external_code, torch.zeros_like(external_code)
+        eps = torch.randn((x.shape[0], self.code_dim), device=x.device)  # autoencoder.py:86
+        return _AutoencoderFn.apply(self, int(num_frames), x, eps, *params)
+
+
+class _AutoencoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, num_frames, x, eps, *params):
+        eng = module.engine()
+        names = [n for n, _ in module.named_parameters()]
+        pdict = {n: p.detach() for n, p in zip(names, params)}
+        B = x.shape[0]
+        xin = x.detach().reshape(B, x.shape[1], -1).contiguous().float()
+        pred, mu, logvar, _kl = eng.forward(xin, eps.contiguous(), pdict, module._buffers_dict(), module.training, 0.0)
+        ctx.module, ctx.names, ctx.fwd_id = module, names, eng.fwd_id
+        ctx.shapes = [p.shape for p in params]
+        ctx.set_materialize_grads(False)
+        return pred.view(B, num_frames, 2, module.n_landmarks).clone(), mu.clone(), logvar.clone()
+
+    @staticmethod
+    def backward(ctx, g_pred, g_mu, g_lv):
+        module = ctx.module
+        eng = module.engine()
+        if eng.fwd_id != ctx.fwd_id:
+            raise RuntimeError("Autoencoder.backward: saved activations were overwritten by a later forward")
+        dev = eng.device
+        grads = {n: torch.zeros(s, device=dev) for n, s in zip(ctx.names, ctx.shapes)}
+        B = eng.arena.bufs["mu"].shape[0]
+        gp = g_pred.contiguous().view(B, -1, module.n_landmarks * 2).float().clone() if g_pred is not None else \
+            torch.zeros(B, 64, module.n_landmarks * 2, device=dev)
+        eng.backward(gp, grads, include_kl=False, g_mu_ext=g_mu, g_lv_ext=g_lv)
+        return (None, None, None, None) + tuple(grads[n] for n in ctx.names)
+
+
+class PoseSequenceDiscriminator(_EngineModule):
+    """core/networks/keypoints_generation/discriminator.py:6-23.  forward(x: (B,T,2,K)) -> (B,T') scores.
+
+    Each forward call gets its own activation slot, so the three calls of a step (real, fake, fake.detach();
+    voice2pose.py:191-193) can all be back-propagated, each with its own BatchNorm batch statistics."""
+
+    SLOTS = 4
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        self.leaky = bool(cfg.VOICE2POSE.POSE_DISCRIMINATOR.LEAKY_RELU)
+        self.n_landmarks = cfg.DATASET.NUM_LANDMARKS
+        kp2 = self.n_landmarks * 2
+        self.seq = _seq(ConvNormRelu((256, kp2, 4), "BN"), ConvNormRelu((512, 256, 4), "BN"), ConvNormRelu((1024, 512, 3), "BN"),
+                        ConvWeights((1, 1024, 3), bias=True, kaiming_normal=False))
+        self._d_eng = None
+        self._calls = 0
+
+    def engine(self):
+        from .engine_seq import DiscriminatorEngine
+        dev = self._device()
+        if self._d_eng is None or self._d_eng.device != dev:
+            self._d_eng = DiscriminatorEngine(self.n_landmarks, self.leaky, dev)
+        return self._d_eng
+
+    def forward(self, x):
+        self._require_cuda(x)
+        names, params = self._named()
+        self._calls += 1
+        return _DiscriminatorFn.apply(self, "/s%d" % (self._calls % self.SLOTS), x, *params)
+
+
+class _DiscriminatorFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, tag, x, *params):
+        eng = module.engine()
+        names = [n for n, _ in module.named_parameters()]
+        pdict = {n: p.detach() for n, p in zip(names, params)}
+        B, T = x.shape[0], x.shape[1]
+        xin = x.detach().reshape(B, T, -1).contiguous().float()
+        eng.prepare(pdict, T)
+        scores = eng.forward(xin, pdict, module._buffers_dict(), module.training, tag)
+        ctx.module, ctx.names, ctx.tag, ctx.pdict = module, names, tag, pdict
+        ctx.shapes = [p.shape for p in params]
+        ctx.x_shape, ctx.need_dx = x.shape, x.requires_grad
+        ctx.calls = module._calls
+        return scores.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        module = ctx.module
+        eng = module.engine()
+        if module._calls - ctx.calls >= module.SLOTS:
+            raise RuntimeError("PoseSequenceDiscriminator.backward: activation slot was reused by later forwards")
+        grads = {n: torch.zeros(s, device=eng.device) for n, s in zip(ctx.names, ctx.shapes)}
+        eng.prepare(ctx.pdict, ctx.x_shape[1])
+        dx = eng.backward(g.contiguous().float().clone(), ctx.pdict, grads, ctx.tag, ctx.need_dx, False)
+        gx = dx.view(ctx.x_shape).clone() if ctx.need_dx else None
+        return (None, None, gx) + tuple(grads[n] for n in ctx.names)
+
+
 def module_dict():
     """Entries for the reference's registry core.networks.module_dict (core/networks/__init__.py:6-11)."""
-    return {"SequenceGeneratorCNN": SequenceGeneratorCNN, "PoseSeqEncoder": PoseSeqEncoder}
+    return {"SequenceGeneratorCNN": SequenceGeneratorCNN, "PoseSequenceDiscriminator": PoseSequenceDiscriminator,
+            "Autoencoder": Autoencoder, "PoseSeqEncoder": PoseSeqEncoder}
 
 
 def get_model(name):

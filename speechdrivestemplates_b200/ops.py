@@ -476,6 +476,15 @@ def vae_reparam_kl(mu, logvar, eps, lam, code, out):
     call("sdt_vae_reparam_kl", _p(mu), _p(logvar), _p(eps), mu.numel(), lam, _p(code), _p(out), _stream())
 
 
+def vae_reparam_kl_bwd(mu, logvar, eps, g_code, lam, g_mu, g_logvar):
+    call("sdt_vae_reparam_kl_bwd", _p(mu), _p(logvar), _p(eps), _p(g_code), mu.numel(), lam, _p(g_mu), _p(g_logvar), _stream())
+
+
+def pose_head_bwd(g_mu, g_logvar, L, g_act):
+    B, D = g_mu.shape
+    call("sdt_pose_head_bwd", _p(g_mu), _p(g_logvar), B, L, 2 * D, _p(g_act), _stream())
+
+
 def pose_preprocess(raw, mean, std, hierarchical=True):
     """raw (T,3,137) f32 -> normalised (T,2,121) f32; bit-exact with gesture_dataset.py:95-105."""
     _chk(raw, name="raw")

@@ -494,3 +494,176 @@ class Voice2PoseTrainer:
         if "kl_applied" in d and d.pop("kl_applied") == 0.0:
             d.pop("G_clipcode_kl_loss")
         return d
+
+
+# ------------------------------------------------------------------------------------------------
+# Pose2Pose (pose VAE): drop-in step model + fused train step
+# ------------------------------------------------------------------------------------------------
+class Pose2PoseModel(nn.Module):
+    """core/pipelines/pose2pose.py:20-89.  State-dict groups: buffers ``clip_code_mu`` /
+    ``clip_code_logvar`` (N, CODE_DIM), ``mel_transfm.*``, ``ae.encoder.*``, ``ae.decoder.*``.
+
+    The reference computes a mel spectrogram that ``Autoencoder.forward`` never reads (dead compute, pose2pose.py:48,65);
+    it is not computed here."""
+
+    def __init__(self, cfg, state_dict=None, num_train_samples=None, rank=0):
+        super().__init__()
+        self.cfg = cfg
+        self.mel_transfm = MelSpectrogram()
+        self.ae = get_model(cfg.POSE2POSE.AUTOENCODER.NAME)(cfg)
+        if num_train_samples is None:
+            assert state_dict is not None, "No state_dict available, while no dataset is configured."
+            num_train_samples = state_dict["module.clip_code_mu"].shape[0]
+        d = cfg.POSE2POSE.AUTOENCODER.CODE_DIM
+        self.register_buffer("clip_code_mu", torch.zeros([num_train_samples, d]))
+        self.register_buffer("clip_code_logvar", torch.zeros([num_train_samples, d]))
+
+    def forward(self, batch, return_loss=True, is_testing=False, interpolation_coeff=None):
+        cfg = self.cfg
+        num_frames = int(batch["num_frames"][0].item())
+        if not return_loss:
+            raise NotImplementedError("Pose2Pose demo path (DEMO.CODE_PATH) is out of the hot-path scope")
+        poses_gt = batch["poses"].cuda()
+        pred, mu, logvar = self.ae(poses_gt, num_frames, None)
+        losses = OrderedDict()
+        reg = (torch.abs(pred - poses_gt) * cfg.POSE2POSE.LAMBDA_REG).mean()                       # pose2pose.py:71-73
+        losses["reg_loss"] = reg
+        kl = 0.5 * (-logvar + mu ** 2 + torch.exp(logvar) - 1).mean() * cfg.POSE2POSE.LAMBDA_KL     # pose2pose.py:77
+        losses["kl_loss"] = kl
+        losses["loss"] = reg + kl
+        results = {"poses_pred_batch": pred, "poses_gt_batch": poses_gt, "clip_code_mu": mu, "clip_code_logvar": logvar}
+        return losses, results
+
+
+class Pose2PoseTrainer:
+    """The numeric part of Pose2Pose.train_step (pose2pose.py:124-150) as a fused device program: VAE forward, L1 + KL,
+    f64 final results + metrics, clip-code buffer scatter, backward, (NCCL all-reduce), flat Adam over ``ae``."""
+
+    def __init__(self, cfg, num_train_samples, device, use_cuda_graph=True, process_group=None, seed=0, conv_math=None):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        if conv_math is not None:
+            ops.set_conv_math(conv_math)
+        torch.manual_seed(seed)
+        self.model = Pose2PoseModel(cfg, num_train_samples=num_train_samples).to(self.device)
+        self.model.train()
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.use_graph = use_cuda_graph
+        ae = self.model.ae
+        self.names = [n for n, _ in ae.named_parameters()]
+        params = [p for _, p in ae.named_parameters()]
+        n = sum(p.numel() for p in params)
+        self.flat_p = torch.zeros(n + ((-n) % 4), device=self.device)
+        self.flat_g = torch.zeros_like(self.flat_p)
+        self.exp_avg = torch.zeros_like(self.flat_p)
+        self.exp_avg_sq = torch.zeros_like(self.flat_p)
+        self.grads, off = {}, 0
+        for nme, p in zip(self.names, params):
+            v = self.flat_p[off:off + p.numel()].view(p.shape)
+            v.copy_(p.data)
+            p.data = v
+            self.grads[nme] = self.flat_g[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+        self.adam = torch.zeros(8, device=self.device)
+        self.set_lr(float(cfg.TRAIN.LR))
+        from .engine import Arena
+        self.arena = Arena(self.device)
+        self._staging, self._graphs, self._warm = None, None, 0
+        self.kernels_per_step = 0
+        self.eps_override = None          # tests inject the N(0,1) draw here
+
+    def set_lr(self, lr):
+        self.lr = float(lr)
+        self.adam[3] = self.lr
+
+    def _stage(self, batch):
+        dev = self.device
+        poses, idx, st = batch["poses"], batch["clip_index"], batch["speaker_stat"]
+        if self._staging is None or self._staging["poses"].shape != poses.shape:
+            self._staging = dict(
+                poses=torch.empty(poses.shape, device=dev), idx=torch.empty(idx.shape, device=dev, dtype=torch.long),
+                mean=torch.empty(tuple(st["mean"].shape), device=dev, dtype=torch.float64),
+                std=torch.empty(tuple(st["std"].shape), device=dev, dtype=torch.float64),
+                scale=torch.empty(tuple(st["scale_factor"].shape), device=dev, dtype=torch.float64),
+                eps=torch.empty(poses.shape[0], self.cfg.POSE2POSE.AUTOENCODER.CODE_DIM, device=dev))
+            self._graphs = None
+        s = self._staging
+        s["poses"].copy_(poses, non_blocking=True)
+        s["idx"].copy_(idx, non_blocking=True)
+        s["mean"].copy_(torch.as_tensor(st["mean"]), non_blocking=True)
+        s["std"].copy_(torch.as_tensor(st["std"]), non_blocking=True)
+        s["scale"].copy_(torch.as_tensor(st["scale_factor"]), non_blocking=True)
+        return s
+
+    def _fwd_bwd(self):
+        s, cfg, A = self._staging, self.cfg, self.arena
+        m = self.model
+        ae = m.ae
+        eng = ae.engine()
+        B, F = s["poses"].shape[0], s["poses"].shape[1]
+        K2 = ae.n_landmarks * 2
+        if self.eps_override is not None:
+            s["eps"].copy_(self.eps_override)
+        else:
+            s["eps"].normal_()                                           # torch.randn(logvar.shape) (autoencoder.py:86)
+        params = {n: p.detach() for n, p in ae.named_parameters()}
+        poses = s["poses"].view(B, F, K2)
+        pred, mu, logvar, kl = eng.forward(poses, s["eps"], params, ae._buffers_dict(), True, float(cfg.POSE2POSE.LAMBDA_KL))
+        reg = A.get("reg_out", (1,))
+        g_pred = A.get("g_pred", (B, F, K2))
+        ops.l1_loss(pred, poses, float(cfg.POSE2POSE.LAMBDA_REG), reg, g_pred, A.get("l1_partial", (1024,)))
+        loss = A.get("loss", (1,))
+        torch.add(reg, kl, out=loss)
+        hier = bool(cfg.DATASET.HIERARCHICAL_POSE)
+        fp = ops.pose_final_results(pred.view(B, F, 2, -1), s["mean"], s["std"], s["scale"], hier, out=A.get("final_pred", (B, F, 2, K2 // 2), torch.float64))
+        fg = ops.pose_final_results(s["poses"], s["mean"], s["std"], s["scale"], hier, out=A.get("final_gt", (B, F, 2, K2 // 2), torch.float64))
+        met = ops.pose_metrics(fp, fg, A.get("met_partial", (2 * B,), torch.float64), A.get("met_out", (2,), torch.float64))
+        m.clip_code_mu[s["idx"]] = mu                                   # pose2pose.py:135-137
+        m.clip_code_logvar[s["idx"]] = logvar
+        eng.backward(g_pred, self.grads, include_kl=True)
+        self.out = OrderedDict(reg_loss=reg, kl_loss=kl, loss=loss, L2_dist=met[0:1], lip_sync_error_n=met[1:2],
+                               poses_pred_batch=pred.view(B, F, 2, -1), clip_code_mu=mu, clip_code_logvar=logvar,
+                               final_pred=fp, final_gt=fg)
+
+    def _optim(self):
+        ops.adam_advance(self.adam, -1.0)
+        ops.adam_flat(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, self.adam, grad_scale=1.0 / self.world)
+
+    def run_staged(self):
+        if self.use_graph and self._graphs is None and self._warm >= 2:
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g1, stream=side):
+                    self._fwd_bwd()
+                with torch.cuda.graph(g2, stream=side):
+                    self._optim()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self._graphs = (g1, g2)
+        if self._graphs is not None:
+            self._graphs[0].replay()
+            if self.world > 1:
+                parallel.allreduce_flat_(self.flat_g, self.pg)
+            self._graphs[1].replay()
+        else:
+            n0 = _lib.launch_count
+            self._fwd_bwd()
+            if self.world > 1:
+                parallel.allreduce_flat_(self.flat_g, self.pg)
+            self._optim()
+            self.kernels_per_step = _lib.launch_count - n0
+            self._warm += 1
+        return self.out
+
+    def train_step(self, batch):
+        self._stage(batch)
+        return self.run_staged()
+
+    def losses_to_host(self, out):
+        keys = ["reg_loss", "kl_loss", "loss", "L2_dist", "lip_sync_error_n"]
+        vals = torch.cat([out[k].double().view(1) for k in keys]).cpu().tolist()
+        return dict(zip(keys, vals))

@@ -25,8 +25,10 @@ def _to_host_batch(b):
     return out
 
 
-def _check_against_fixture(g, prefix, tensors, rtol, what):
-    n = 0
+def _check_against_fixture(g, prefix, tensors, rtol, what, outlier_frac=0.0):
+    """Sampled elements of each tensor vs the fixture, error relative to the tensor's rms.  outlier_frac > 0 tolerates
+    the few entries moved by a flipped LeakyReLU unit (BatchNorm nets at batch 4, see tests/diag_grad_noise.py)."""
+    n = bad = tot = 0
     for k, v in tensors.items():
         key = "%s/%s/samples" % (prefix, k)
         if key not in g.files:
@@ -34,10 +36,14 @@ def _check_against_fixture(g, prefix, tensors, rtol, what):
         ref = g[key].astype(np.float64)
         numel = v.numel()
         rms = float(np.sqrt(g["%s/%s/digest" % (prefix, k)][1] / numel)) + 1e-30
-        err = np.abs(samples_of(v).astype(np.float64) - ref).max()
-        assert err <= rtol * rms, "%s %s: err %.3e vs rms %.3e" % (what, k, err, rms)
+        errs = np.abs(samples_of(v).astype(np.float64) - ref)
+        if outlier_frac == 0.0:
+            assert errs.max() <= rtol * rms, "%s %s: err %.3e vs rms %.3e" % (what, k, errs.max(), rms)
+        assert errs.max() <= 0.5 * rms, "%s %s: err %.3e vs rms %.3e" % (what, k, errs.max(), rms)
+        bad += int((errs > rtol * rms).sum())
+        tot += errs.size
         n += 1
-    assert n > 0
+    assert n > 0 and bad <= outlier_frac * tot, "%s: %d of %d samples beyond %.0e rms" % (what, bad, tot, rtol)
 
 
 def test_s2g_generator_forward_parity_gate():
@@ -301,3 +307,110 @@ def test_demo_inference_long_audio(seconds):
         pred = net(pipeline.MelSpectrogram().to(dev())(audio.to(dev())), nf, code.to(dev()))
     assert pred.shape == (1, nf, 2, 121) and nf == seconds * fps
     assert rel_err(pred.cpu().numpy(), ref.numpy()) < 2e-4
+
+
+def test_pose2pose_train_step_vs_reference_fixture():
+    """BASELINE configs[3] (pose2pose VAE): fused train step vs the reference's recorded steps with the same injected
+    N(0,1) draw: losses, reconstruction, mu/logvar, every gradient (incl. BatchNorm affine), state after Adam."""
+    from speechdrivestemplates_b200 import pipeline
+    from oracle import sdt_oracle as O
+    g = golden("pose2pose_step_golden")
+    n_train, bs = int(g["n_train"]), int(g["batch_size"])
+    tr = pipeline.Pose2PoseTrainer(_cfg("pose2pose"), n_train, dev(), use_cuda_graph=False, seed=0)
+    stat = oliver_stat(True)
+    for s in range(int(g["steps"])):
+        batch = _to_host_batch(O.synthetic_batch(bs, n_train, stat, seed=200 + s))
+        tr.eps_override = torch.from_numpy(g["step%d/eps" % s]).to(dev())
+        out = tr.train_step(batch)
+        host = tr.losses_to_host(out)
+        p = "step%d" % s
+        ftol = 1e-4 if s == 0 else 5e-3
+        for k in ("reg_loss", "kl_loss", "loss"):
+            ref = float(g["%s/loss/%s" % (p, k)])
+            assert abs(host[k] - ref) <= ftol * max(1.0, abs(ref)), (k, host[k], ref)
+        assert rel_err(out["poses_pred_batch"].cpu().numpy(), g[p + "/pred"]) < ftol
+        assert rel_err(out["clip_code_mu"].cpu().numpy(), g[p + "/mu"]) < 10 * ftol
+        assert rel_err(out["clip_code_logvar"].cpu().numpy(), g[p + "/logvar"]) < 10 * ftol
+        if s == 0:
+            # BatchNorm over a batch of 4: the fp32 noise floor of the first layers' gradients is a few 1e-2 of rms
+            # (same measurement as for voice2pose_s2g in test_oracle_golden); the tight backward check is the
+            # identity-activation test below
+            _check_against_fixture(g, p + "/grad", {"ae." + n: t for n, t in tr.grads.items()}, 5e-2, "grad", outlier_frac=0.03)
+        for k, v in tr.model.state_dict().items():
+            ref = g["%s/state/%s/samples" % (p, k)].astype(np.float64)
+            err = np.abs(samples_of(v).astype(np.float64) - ref).max()
+            # parameters move by <= lr per Adam step; the clip_code buffers hold network outputs (ftol of their range)
+            assert err <= ftol * np.abs(ref).max() + 2.5e-4 * (s + 1), (k, err)
+
+
+def test_autoencoder_and_discriminator_dropin_autograd():
+    """Module-level drop-ins driven by autograd exactly as the reference's pipelines do: Autoencoder (loss terms as torch
+    expressions, pose2pose.py:71-80) and PoseSequenceDiscriminator (three forwards, LSGAN losses, voice2pose.py:191-202)
+    against the fp64 oracle with identity activations (no LeakyReLU derivative discontinuity)."""
+    from speechdrivestemplates_b200 import networks
+    from oracle import sdt_oracle as O
+    B = 4
+    g = torch.Generator().manual_seed(12)
+    poses = torch.randn(B, 64, 2, 121, generator=g)
+    # ---- discriminator
+    cfg = _cfg("voice2pose_s2g")
+    cfg.VOICE2POSE.POSE_DISCRIMINATOR.LEAKY_RELU = True
+    torch.manual_seed(0)
+    D = networks.PoseSequenceDiscriminator(cfg).to(dev()).train()
+    ocfg = O.make_cfg("voice2pose_s2g", d_leaky=1.0)
+    D.engine().slope = 1.0
+    for b_ in D.engine().seq:
+        b_.slope = 1.0 if b_.norm else b_.slope
+    torch.manual_seed(0)
+    sd = O.init_discriminator(ocfg)
+    sd64 = {k: (v.double().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd.items()}
+    real = (poses[:, 1:] - poses[:, :-1])
+    fake = torch.randn(real.shape, generator=g)
+    fake64 = fake.double().requires_grad_(True)
+    s_real = O.discriminator_forward(real.double(), sd64, ocfg, True)
+    s_fake = O.discriminator_forward(fake64, sd64, ocfg, True)
+    loss_ref = ((s_real - 1) ** 2).mean() + (s_fake ** 2).mean() * 0.5
+    names = [k for k in sd64 if sd64[k].requires_grad]
+    gref = torch.autograd.grad(loss_ref, [sd64[k] for k in names] + [fake64])
+    fk = fake.to(dev()).requires_grad_(True)
+    sr = D(real.to(dev()))
+    sf = D(fk)
+    assert sr.shape == (B, 15)
+    loss = ((sr - 1) ** 2).mean() + (sf ** 2).mean() * 0.5
+    loss.backward()
+    assert abs(float(loss) - float(loss_ref)) < 1e-4 * max(1.0, abs(float(loss_ref)))
+    for k, ref in zip(names, gref[:-1]):
+        got = dict(D.named_parameters())[k[len("netD_pose."):]].grad
+        ref = ref.numpy()
+        rms = float(np.sqrt((ref ** 2).mean())) + 1e-30
+        assert np.abs(got.cpu().numpy() - ref).max() / rms < 5e-3, k
+    assert rel_err(fk.grad.cpu().numpy(), gref[-1].numpy()) < 2e-3
+    assert int(D.seq[0].norm.num_batches_tracked) == 2
+    # ---- autoencoder
+    cfg2 = _cfg("pose2pose")
+    torch.manual_seed(0)
+    ae = networks.Autoencoder(cfg2).to(dev()).train()
+    eng = ae.engine()
+    for b_ in eng.blocks:
+        b_.slope = 1.0
+    ocfg2 = O.make_cfg("pose2pose", ae_leaky=1.0)
+    sd2 = O.init_pose2pose(ocfg2, 8, seed=0)
+    sd2_64 = {k: (v.double().requires_grad_(True) if k.startswith("ae.") and v.is_floating_point() and "running" not in k else v.clone())
+              for k, v in sd2.items()}
+    torch.manual_seed(123)
+    eps = torch.randn((B, 32), device=dev())
+    pred64, mu64, lv64 = O.autoencoder_forward(poses.double(), 64, sd2_64, ocfg2, eps.cpu().double(), True, "ae.")
+    loss_ref = torch.abs(pred64 - poses.double()).mean() + 0.5 * (-lv64 + mu64 ** 2 + torch.exp(lv64) - 1).mean() * 0.1
+    names2 = [k for k in sd2_64 if sd2_64[k].requires_grad]
+    gref2 = torch.autograd.grad(loss_ref, [sd2_64[k] for k in names2])
+    torch.manual_seed(123)                   # the module draws eps with torch.randn on the device, like the reference
+    pgpu = poses.to(dev())
+    pred, mu, lv = ae(pgpu, 64, None)
+    loss = torch.abs(pred - pgpu).mean() + 0.5 * (-lv + mu ** 2 + torch.exp(lv) - 1).mean() * 0.1
+    loss.backward()
+    assert abs(float(loss) - float(loss_ref)) < 1e-4
+    for k, ref in zip(names2, gref2):
+        got = dict(ae.named_parameters())[k[len("ae."):]].grad
+        ref = ref.numpy()
+        rms = float(np.sqrt((ref ** 2).mean())) + 1e-30
+        assert np.abs(got.cpu().numpy() - ref).max() / rms < 5e-3, k

@@ -221,6 +221,10 @@ int sdt_pose_preprocess(const float* raw, int T, const float* mean, const float*
  * parted_to_global -> * scale.  poses (B,T,2,121) f32; mean/std (B,242) f64; scale (B) f64; out f64. */
 int sdt_pose_final_results(const float* poses, int B, int T, const double* mean, const double* std, const double* scale,
                            int hierarchical, double* out, void* stream);
+/* GestureDataset.transform_normalized_parted2global (gesture_dataset.py:221-234), fp32: poses (n_rows,2,121) normalised
+ * in the parted (hierarchical) space -> normalised in the global space; statistics (242) f32 of one speaker. */
+int sdt_pose_parted2global(const float* poses, int64_t n_rows, const float* mean_parted, const float* std_parted,
+                           const float* mean_global, const float* std_global, float* out, void* stream);
 /* Voice2Pose.evaluate_step (voice2pose.py:412-430) on final-result poses: out[0] = L2_dist, out[1] = lip_sync_error_n.
  * partial: >= 2*B doubles. */
 int sdt_pose_metrics(const double* pred, const double* gt, int B, int T, double* partial, double* out, void* stream);

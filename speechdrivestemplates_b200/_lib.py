@@ -70,6 +70,7 @@ SIGNATURES = {
     "sdt_vae_reparam_kl_bwd": [c_ptr, c_ptr, c_ptr, c_ptr, i32, f32, c_ptr, c_ptr, c_ptr],
     "sdt_pose_preprocess": [c_ptr, i32, c_ptr, c_ptr, i32, c_ptr, c_ptr],
     "sdt_pose_final_results": [c_ptr, i32, i32, c_ptr, c_ptr, c_ptr, i32, c_ptr, c_ptr],
+    "sdt_pose_parted2global": [c_ptr, i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     "sdt_pose_metrics": [c_ptr, c_ptr, i32, i32, c_ptr, c_ptr, c_ptr],
     "sdt_adam_advance": [c_ptr, f32, f64, f64, c_ptr],
     "sdt_adam_flat": [c_ptr, c_ptr, c_ptr, c_ptr, i64, c_ptr, f64, f64, f64, f32, c_ptr],

@@ -67,6 +67,26 @@ __global__ void pose_final_kernel(const float* __restrict__ poses, int B, int T,
     out[e] = __dmul_rn(v, scale[b]);
 }
 
+// transform_normalized_parted2global (gesture_dataset.py:221-234), fp32: denormalise with the parted statistics,
+// parted_to_global, normalise with the global statistics.  Stats are (2K) f32 arrays of ONE speaker (the reference
+// assumes a single speaker per batch there).
+__global__ void pose_parted2global_kernel(const float* __restrict__ poses, long long total, const float* __restrict__ mean_p,
+                                          const float* __restrict__ std_p, const float* __restrict__ mean_g,
+                                          const float* __restrict__ std_g, float* __restrict__ out) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int k = (int)(e % K121);
+    const int xy = (int)((e / K121) % 2);
+    const int s = xy * K121 + k;
+    float v = __fadd_rn(__fmul_rn(poses[e], std_p[s]), mean_p[s]);
+    const int pr = part_root(k);
+    if (pr >= 0) {
+        const int sr = xy * K121 + pr;
+        v = __fadd_rn(v, __fadd_rn(__fmul_rn(poses[e - k + pr], std_p[sr]), mean_p[sr]));
+    }
+    out[e] = __fdiv_rn(__fsub_rn(v, mean_g[s]), std_g[s]);
+}
+
 // evaluate_step (voice2pose.py:412-430): per-clip partial sums, then a fixed-order finish.
 __global__ void __launch_bounds__(256) pose_metrics_partial_kernel(const double* __restrict__ pred, const double* __restrict__ gt,
                                                                    int T, double* __restrict__ partial) {
@@ -144,5 +164,15 @@ extern "C" int sdt_pose_metrics(const double* pred, const double* gt, int B, int
     SDT_LAUNCH_OK("pose_metrics_partial_kernel");
     pose_metrics_finish_kernel<<<1, 32, 0, sdt::as_stream(stream)>>>(partial, B, T, out);
     SDT_LAUNCH_OK("pose_metrics_finish_kernel");
+    return SDT_OK;
+}
+
+extern "C" int sdt_pose_parted2global(const float* poses, int64_t n_rows, const float* mean_parted, const float* std_parted,
+                                      const float* mean_global, const float* std_global, float* out, void* stream) {
+    SDT_REQUIRE(poses && mean_parted && std_parted && mean_global && std_global && out && n_rows > 0, "sdt_pose_parted2global: bad arguments");
+    const long long total = (long long)n_rows * 2 * K121;
+    pose_parted2global_kernel<<<sdt::ceil_div(total, 256), 256, 0, sdt::as_stream(stream)>>>(poses, total, mean_parted, std_parted,
+                                                                                            mean_global, std_global, out);
+    SDT_LAUNCH_OK("pose_parted2global_kernel");
     return SDT_OK;
 }

@@ -249,7 +249,7 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
     self.fwd_id += 1
     self._mel = mel
     self._params = params
-    self.wprep.ensure(self._all_layers(), params, with_dgrad=self.norm == "IN" and training)
+    self.wprep.ensure(self._all_layers(), params, with_dgrad=training)
     self.wprep.run()
     # ---- 2-D encoder: raw conv output + statistics; normalise/activate in the consumer's loader
     src, xf = mel.view(B, 80, T, 1), None
@@ -353,11 +353,11 @@ def _dgrad(self, name, g, dy, w, dx, B, H, W, accumulate=False):
 def _gen_backward(self, g_pred, grads, g_code=None):
     """g_pred (B,F,2K) -> parameter gradients written into grads[name] (reference layout); g_code (B,D) filled.
 
-    Only the per-sample-norm ('IN') generator has a backward here (the SDT configs); see DESIGN.md for BN status.
+    NORM='IN' (SDT configs): channel-LayerNorm / InstanceNorm2d backward.  NORM='BN' (voice2pose_s2g): BatchNorm backward
+    with batch statistics, which also writes grads[<block>.norm.weight/.bias].
     """
-    if self.norm != "IN":
-        raise NotImplementedError("generator backward with BatchNorm (voice2pose_s2g training) is not implemented yet")
     A, B, F, slope = self.arena, self.B, self.F, self.slope
+    bn = self.norm == "BN"
     params, acts = self._params, self._acts
     # ---- final conv
     gl = ConvGeom.conv1d(256, self.kp2, 1, 1, 0)
@@ -373,9 +373,16 @@ def _gen_backward(self, g_pred, grads, g_code=None):
     for name, g, kind in reversed(layers):
         L_out = self.seq_len[name]
         raw = A.get("raw:" + name, (B, L_out, 256))
-        g_raw = g_raw_scratch.view(-1)[: B * L_out * 256].view(B, L_out, 256)
-        ops.rownorm_act_bwd(g_act[name], raw, A.get("rmean:" + name, (B * L_out,)), A.get("rrstd:" + name, (B * L_out,)), slope,
-                            out=g_raw)
+        if bn:
+            tpi = -(-L_out // ops.BWD_ROWS)
+            scratch = (A.get("nb_partial:" + name, (B * tpi, 2, 256)), A.get("nb_m1:" + name, (1, 256)), A.get("nb_m2:" + name, (1, 256)))
+            g_raw = ops.norm_backward(g_act[name], raw, A.get("mean:" + name, (1, 256)), A.get("rstd:" + name, (1, 256)), 1, slope,
+                                      params[name + ".norm.weight"], params[name + ".norm.bias"],
+                                      grads[name + ".norm.weight"], grads[name + ".norm.bias"], scratch=scratch)
+        else:
+            g_raw = g_raw_scratch.view(-1)[: B * L_out * 256].view(B, L_out, 256)
+            ops.rownorm_act_bwd(g_act[name], raw, A.get("rmean:" + name, (B * L_out,)), A.get("rrstd:" + name, (B * L_out,)), slope,
+                                out=g_raw)
         xin = acts["in:" + name]
         L_in = xin.shape[1]
         _wgrad(self, g, xin, g_raw, B, 1, L_in, grads[name + ".conv.weight"])
@@ -413,8 +420,13 @@ def _gen_backward(self, g_pred, grads, g_code=None):
         raw = A.get("raw:" + name, (B, oh, ow, co))
         tpi = -(-(oh * ow) // ops.BWD_ROWS)
         scratch = (A.get("nb_partial:" + name, (B * tpi, 2, co)), A.get("nb_m1:" + name, (groups, co)), A.get("nb_m2:" + name, (groups, co)))
-        ops.norm_backward(g_enc, raw, A.get("mean:" + name, (groups, co)), A.get("rstd:" + name, (groups, co)), groups, slope,
-                          scratch=scratch)
+        if bn:
+            ops.norm_backward(g_enc, raw, A.get("mean:" + name, (groups, co)), A.get("rstd:" + name, (groups, co)), groups, slope,
+                              params[name + ".norm.weight"], params[name + ".norm.bias"],
+                              grads[name + ".norm.weight"], grads[name + ".norm.bias"], scratch=scratch)
+        else:
+            ops.norm_backward(g_enc, raw, A.get("mean:" + name, (groups, co)), A.get("rstd:" + name, (groups, co)), groups, slope,
+                              scratch=scratch)
         if l == 0:
             src, xf = self._mel.view(B, 80, self.T, 1), None
         else:

@@ -508,6 +508,15 @@ def pose_final_results(poses, mean, std, scale, hierarchical=True, out=None):
     return out
 
 
+def pose_parted2global(poses, mean_p, std_p, mean_g, std_g, out=None):
+    """(…,2,121) f32 normalised parted poses -> normalised global poses (gesture_dataset.py:221-234)."""
+    _chk(poses, name="poses")
+    if out is None:
+        out = torch.empty_like(poses)
+    call("sdt_pose_parted2global", _p(poses), poses.numel() // 242, _p(mean_p), _p(std_p), _p(mean_g), _p(std_g), _p(out), _stream())
+    return out
+
+
 def pose_metrics(pred, gt, partial=None, out=None):
     """final-result poses (B,T,2,121) f64 -> tensor [L2_dist, lip_sync_error_n] (voice2pose.py:412-430)."""
     B, T = pred.shape[0], pred.shape[1]

@@ -83,8 +83,9 @@ class Voice2PoseStepEngine:
             self.arena = Arena(device)
         return self.arena
 
-    def forward(self, audio, poses, clip_index, stat=None, code_table=None):
-        """audio (B,L) f32, poses (B,F,2,K) f32, clip_index (B) i64 on device; stat = (mean, std, scale) f64 or None.
+    def forward(self, audio, poses, clip_index, stat=None, code_table=None, p2g_stats=None):
+        """audio (B,L) f32, poses (B,F,2,K) f32, clip_index (B) i64 on device; stat = (mean, std, scale) f64 or None;
+        p2g_stats = (mean_parted, std_parted, mean_global, std_global) f32 (242) when HIERARCHICAL_POSE is False.
 
         Returns a dict of engine-owned device tensors (valid until the next forward).
         """
@@ -128,13 +129,17 @@ class Voice2PoseStepEngine:
         out["condition_code"] = code
         # FGD feature extractor on prediction and ground truth (voice2pose.py:162-176), no gradient
         if cfg.VOICE2POSE.POSE_ENCODER.NAME is not None:
-            if not cfg.DATASET.HIERARCHICAL_POSE:
-                raise NotImplementedError("POSE_ENCODER with HIERARCHICAL_POSE=False (transform_normalized_parted2global)")
             pe = m.pose_encoder
             pparams = {n: p.detach() for n, p in pe.named_parameters()}
             pbuf = pe._buffers_dict()
-            out["mu_pred"], out["logvar_pred"] = pe.engine().forward(pred, pparams, pbuf, pe.training, tag="/pred")
-            out["mu_gt"], out["logvar_gt"] = pe.engine().forward(poses.view(B, F, K2), pparams, pbuf, pe.training, tag="/gt")
+            pe_pred, pe_gt = pred, poses.view(B, F, K2)
+            if not cfg.DATASET.HIERARCHICAL_POSE:          # dataset.transform_normalized_parted2global (voice2pose.py:168-169)
+                if p2g_stats is None:
+                    raise ValueError("HIERARCHICAL_POSE=False needs the speaker's parted and global statistics (p2g_stats)")
+                pe_pred = ops.pose_parted2global(pred, *p2g_stats, out=A.get("p2g_pred", (B, F, K2)))
+                pe_gt = ops.pose_parted2global(poses.view(B, F, K2), *p2g_stats, out=A.get("p2g_gt", (B, F, K2)))
+            out["mu_pred"], out["logvar_pred"] = pe.engine().forward(pe_pred, pparams, pbuf, pe.training, tag="/pred")
+            out["mu_gt"], out["logvar_gt"] = pe.engine().forward(pe_gt, pparams, pbuf, pe.training, tag="/gt")
         if stat is not None:          # dataset.get_final_results x2 + evaluate_step (voice2pose.py:289-292)
             mean, std, scale = stat
             hier = bool(cfg.DATASET.HIERARCHICAL_POSE)
@@ -164,9 +169,9 @@ class _V2PLossFn(torch.autograd.Function):
     """Autograd bridge for the drop-in model: (pred, G_reg_loss, KL) as one node over the step engine."""
 
     @staticmethod
-    def forward(ctx, model, audio, poses, clip_index, clips_code, *gparams):
+    def forward(ctx, model, audio, poses, clip_index, clips_code, p2g_stats, *gparams):
         eng = model.step_engine()
-        out = eng.forward(audio, poses, clip_index, None, clips_code)
+        out = eng.forward(audio, poses, clip_index, None, clips_code, p2g_stats)
         ctx.model, ctx.eng = model, eng
         ctx.fwd_id = model.netG.engine().fwd_id
         ctx.names = [n for n, _ in model.netG.named_parameters()]
@@ -199,7 +204,7 @@ class _V2PLossFn(torch.autograd.Function):
             if g_kl is None or float(g_kl) != 1.0:
                 eng.arena.bufs["g_code_kl"].mul_(0.0 if g_kl is None else float(g_kl))
         eng.backward(grads, g_table, gp.contiguous())
-        return (None, None, None, None, g_table) + tuple(grads[n] for n in ctx.names)
+        return (None, None, None, None, g_table, None) + tuple(grads[n] for n in ctx.names)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -236,13 +241,25 @@ class Voice2PoseModel(nn.Module):
             self.pose_encoder = get_model(cfg.VOICE2POSE.POSE_ENCODER.NAME)(cfg)
             self.pose_encoder.eval()                                                 # voice2pose.py:77
         if cfg.VOICE2POSE.POSE_DISCRIMINATOR.NAME is not None:
-            raise NotImplementedError("POSE_DISCRIMINATOR (voice2pose_s2g training) is not implemented yet on the B200 path")
+            self.netD_pose = get_model(cfg.VOICE2POSE.POSE_DISCRIMINATOR.NAME)(cfg)
+            self.pose_gan_criterion = nn.MSELoss()                                   # voice2pose.py:81-82 (LSGAN)
         self._step_engine = None
 
     def step_engine(self):
         if self._step_engine is None:
             self._step_engine = Voice2PoseStepEngine(self)
         return self._step_engine
+
+    def _p2g_stats(self, batch, dataset, device):
+        """Parted and global statistics of the batch's (single) speaker as fp32 device tensors (gesture_dataset.py:228-229)."""
+        if "stat_parted" in batch and batch["stat_parted"] is not None:
+            sp, sg = batch["stat_parted"], batch["stat_global"]
+        else:
+            k = self.cfg.DATASET.NUM_LANDMARKS
+            sp = dataset.get_speaker_stat(batch["speaker"][0], k, True)
+            sg = dataset.get_speaker_stat(batch["speaker"][0], k, False)
+        f32 = lambda a: torch.as_tensor(a, dtype=torch.float64).float().to(device).contiguous()
+        return (f32(sp["mean"]), f32(sp["std"]), f32(sg["mean"]), f32(sg["std"]))
 
     def _condition_code(self, batch, clip_indices, audio, poses_gt, return_loss, interpolation_coeff):
         """Eval-time code selection (voice2pose.py:96-120)."""
@@ -278,8 +295,11 @@ class Voice2PoseModel(nn.Module):
 
         if self.training and return_loss:
             gparams = [p for _, p in self.netG.named_parameters()]
+            p2g = None
+            if cfg.VOICE2POSE.POSE_ENCODER.NAME is not None and not cfg.DATASET.HIERARCHICAL_POSE:
+                p2g = self._p2g_stats(batch, dataset, audio.device)
             pred, reg, kl = _V2PLossFn.apply(self, audio.contiguous().float(), poses_gt.contiguous().float(),
-                                             clip_indices.contiguous(), self.clips_code if D is not None else None, *gparams)
+                                             clip_indices.contiguous(), self.clips_code if D is not None else None, p2g, *gparams)
             res = _V2PLossFn_last_results(self)
             losses = OrderedDict()
             losses["G_reg_loss"] = reg
@@ -292,6 +312,25 @@ class Voice2PoseModel(nn.Module):
             for k in ("mu_pred", "mu_gt", "logvar_pred", "logvar_gt"):
                 if k in res:
                     results[k] = res[k].clone()
+            if hasattr(self, "netD_pose"):                                           # voice2pose.py:179-208
+                dcfg = cfg.VOICE2POSE.POSE_DISCRIMINATOR
+                real_batch, fake_batch = poses_gt, pred
+                if dcfg.WHITE_LIST is not None:
+                    real_batch, fake_batch = real_batch[..., dcfg.WHITE_LIST], fake_batch[..., dcfg.WHITE_LIST]
+                if dcfg.MOTION:
+                    real_batch = real_batch[:, 1:, ...] - real_batch[:, :-1, ...]
+                    fake_batch = fake_batch[:, 1:, ...] - fake_batch[:, :-1, ...]
+                score_real = self.netD_pose(real_batch)
+                score_fake = self.netD_pose(fake_batch)
+                score_fake_detach = self.netD_pose(fake_batch.detach())
+                g_gan = self.pose_gan_criterion(score_fake, torch.ones_like(score_fake)) * dcfg.LAMBDA_GAN
+                losses["G_pose_gan_loss"] = g_gan
+                losses["G_loss"] = g_loss + g_gan
+                d_fake = self.pose_gan_criterion(score_fake_detach, torch.zeros_like(score_fake_detach))
+                d_real = self.pose_gan_criterion(score_real, torch.ones_like(score_real))
+                losses["D_pose_gan_loss"] = (d_real + d_fake) * dcfg.LAMBDA_GAN
+                losses["pose_score_fake"] = score_fake.mean()
+                losses["pose_score_real"] = score_real.mean()
             return losses, results
 
         # eval / demo: code selection then a plain generator forward
@@ -346,6 +385,9 @@ class Voice2PoseTrainer:
         self.device = torch.device(device)
         if conv_math is not None:          # 0 = fp32 FFMA, 1 = tcgen05 TF32 (the reference's own GPU default: cudnn.allow_tf32)
             ops.set_conv_math(conv_math)
+        if cfg.VOICE2POSE.POSE_DISCRIMINATOR.NAME is not None:
+            raise NotImplementedError("the fused trainer covers the SDT configs; voice2pose_s2g (discriminator) trains through the "
+                                      "drop-in Voice2PoseModel + the reference's optimizer choreography (see tests/test_gpu_step.py)")
         torch.manual_seed(seed)                                       # main.py:37
         self.model = Voice2PoseModel(cfg, num_train_samples=num_train_samples).to(self.device)
         ae_ckpt = cfg.VOICE2POSE.POSE_ENCODER.AE_CHECKPOINT

@@ -22,4 +22,7 @@ def register(swap_step_model=True):
         from . import pipeline
         ref_v2p.Voice2PoseModel = pipeline.Voice2PoseModel      # constructed at voice2pose.py:221
         done.append("Voice2PoseModel")
+        import core.pipelines.pose2pose as ref_p2p
+        ref_p2p.Pose2PoseModel = pipeline.Pose2PoseModel        # constructed at pose2pose.py:100
+        done.append("Pose2PoseModel")
     return done

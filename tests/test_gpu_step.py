@@ -414,3 +414,44 @@ def test_autoencoder_and_discriminator_dropin_autograd():
         ref = ref.numpy()
         rms = float(np.sqrt((ref ** 2).mean())) + 1e-30
         assert np.abs(got.cpu().numpy() - ref).max() / rms < 5e-3, k
+
+
+def test_s2g_dropin_train_step_with_discriminator_vs_reference_fixture():
+    """voice2pose_s2g (BatchNorm generator + motion discriminator + LSGAN) driven exactly like the reference's trainer
+    (voice2pose.py:288-309): model(batch) -> G_loss.backward(retain_graph=True) -> Adam(G) -> D_loss.backward() -> Adam(D),
+    through the drop-in modules' autograd bridges, against the reference's recorded step."""
+    from speechdrivestemplates_b200 import pipeline
+    from oracle import sdt_oracle as O
+    g = golden("s2g_step_golden")
+    n_train, bs = int(g["n_train"]), int(g["batch_size"])
+    cfg = _cfg("voice2pose_s2g")
+    torch.manual_seed(0)
+    model = pipeline.Voice2PoseModel(cfg, num_train_samples=n_train).to(dev())
+    for k, v in model.state_dict().items():
+        assert np.array_equal(samples_of(v), g["init/%s/samples" % k]), k
+    model.train()
+    optG = torch.optim.Adam(model.netG.parameters(), lr=cfg.TRAIN.LR, weight_decay=cfg.TRAIN.WD)
+    optD = torch.optim.Adam(model.netD_pose.parameters(), lr=cfg.TRAIN.LR)
+    batch = O.synthetic_batch(bs, n_train, oliver_stat(False), seed=100, stat_parted=oliver_stat(True), stat_global=oliver_stat(False))
+    losses, results = model(_to_host_batch(batch), None)
+    for k in ("G_reg_loss", "G_pose_gan_loss", "G_loss", "D_pose_gan_loss", "pose_score_fake", "pose_score_real"):
+        ref = float(g["step0/loss/" + k])
+        assert abs(float(losses[k]) - ref) <= 2e-4 * max(1.0, abs(ref)), (k, float(losses[k]), ref)
+    assert rel_err(results["poses_pred_batch"].detach().cpu().numpy(), g["step0/pred"]) < 1e-4
+    assert rel_err(results["mu_gt"].cpu().numpy(), g["step0/mu_gt"]) < 1e-3
+    optG.zero_grad()
+    losses["G_loss"].backward(retain_graph=True)
+    grads = {"netG." + n: p.grad for n, p in model.netG.named_parameters()}
+    # BN at batch 2: fp32 noise floor of these gradients is ~2e-2 of rms (test_oracle_golden) + flipped units
+    _check_against_fixture(g, "step0/grad", grads, 5e-2, "G grad", outlier_frac=0.05)
+    optG.step()
+    optD.zero_grad()
+    losses["D_pose_gan_loss"].backward()
+    dgrads = {"netD_pose." + n: p.grad for n, p in model.netD_pose.named_parameters()}
+    _check_against_fixture(g, "step0/grad", dgrads, 1e-2, "D grad", outlier_frac=0.02)
+    optD.step()
+    for k, v in model.state_dict().items():
+        ref = g["step0/state/%s/samples" % k].astype(np.float64)
+        err = np.abs(samples_of(v).astype(np.float64) - ref).max()
+        assert err <= 1e-3 * np.abs(ref).max() + 2.5e-4, (k, err)
+    assert int(model.netD_pose.seq[0].norm.num_batches_tracked) == 3        # real, fake, fake.detach()

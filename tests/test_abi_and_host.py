@@ -109,3 +109,34 @@ def test_config_overlays_match_reference_yaml_when_available():
                 else:
                     assert float(node[k]) == float(v) if isinstance(v, str) and k == "LR" else node[k] == v, (name, k)
         walk(cfg, y)
+
+
+def test_plugin_registers_into_reference_registries():
+    """The drop-in seam itself: with the reference importable, plugin.register() makes the reference's own
+    get_model / pipeline module resolve to the CUDA-backed classes, and they construct from the reference's yacs config
+    with the reference's state-dict layout."""
+    sys_path_ref = "/root/reference"
+    if not os.path.isdir(os.path.join(sys_path_ref, "core", "networks")):
+        pytest.skip("reference tree not present")
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import refshim
+    from speechdrivestemplates_b200 import networks, pipeline, plugin
+    cfg = refshim.get_cfg("voice2pose_s2g")          # installs the shims, puts the reference on sys.path
+    done = plugin.register()
+    import core.networks as ref_networks
+    import core.pipelines.voice2pose as ref_v2p
+    import core.pipelines.pose2pose as ref_p2p
+    assert set(done) >= {"SequenceGeneratorCNN", "PoseSequenceDiscriminator", "Autoencoder", "PoseSeqEncoder", "Voice2PoseModel"}
+    assert ref_networks.get_model("SequenceGeneratorCNN") is networks.SequenceGeneratorCNN
+    assert ref_v2p.Voice2PoseModel is pipeline.Voice2PoseModel and ref_p2p.Pose2PoseModel is pipeline.Pose2PoseModel
+    with pytest.raises(KeyError, match="Unknown model"):
+        ref_networks.get_model("Nope")
+    torch.manual_seed(0)
+    m = ref_v2p.Voice2PoseModel(cfg, num_train_samples=4)       # built from the reference's own (shimmed yacs) config object
+    from util import golden
+    g = golden("s2g_step_golden")
+    ref_keys = sorted(k[len("init/"):-len("/digest")] for k in g.files if k.startswith("init/") and k.endswith("/digest"))
+    assert sorted(m.state_dict().keys()) == ref_keys
+    m2 = ref_p2p.Pose2PoseModel(refshim.get_cfg("pose2pose"), num_train_samples=4)
+    assert "clip_code_mu" in m2.state_dict() and "ae.decoder.blocks.4.bias" in m2.state_dict()

@@ -83,7 +83,7 @@ class Voice2PoseStepEngine:
             self.arena = Arena(device)
         return self.arena
 
-    def forward(self, audio, poses, clip_index, stat=None, code_table=None, p2g_stats=None):
+    def forward(self, audio, poses, clip_index, stat=None, code_table=None, p2g_stats=None, defer_side=False):
         """audio (B,L) f32, poses (B,F,2,K) f32, clip_index (B) i64 on device; stat = (mean, std, scale) f64 or None;
         p2g_stats = (mean_parted, std_parted, mean_global, std_global) f32 (242) when HIERARCHICAL_POSE is False.
 
@@ -127,6 +127,22 @@ class Voice2PoseStepEngine:
         out["G_loss"] = g_loss
         out["poses_pred_batch"] = pred.view(B, F, 2, -1)
         out["condition_code"] = code
+        self._side_args = (out, pred, poses, stat, p2g_stats)
+        if not defer_side:
+            self.run_side()
+        self._clip_index = clip_index
+        self._B, self._F = B, F
+        return out
+
+    def run_side(self):
+        """The part of the step nothing else depends on: FGD features of prediction / ground truth and the f64 final
+        results + metrics.  The fused trainer runs it on a second stream, concurrently with the backward pass."""
+        out, pred, poses, stat, p2g_stats = self._side_args
+        m = self.model
+        cfg = m.cfg
+        A = self.arena
+        B, F = poses.shape[0], poses.shape[1]
+        K2 = poses.shape[2] * poses.shape[3]
         # FGD feature extractor on prediction and ground truth (voice2pose.py:162-176), no gradient
         if cfg.VOICE2POSE.POSE_ENCODER.NAME is not None:
             pe = m.pose_encoder
@@ -148,8 +164,6 @@ class Voice2PoseStepEngine:
             met = ops.pose_metrics(fp, fg, A.get("met_partial", (2 * B,), torch.float64), A.get("met_out", (2,), torch.float64))
             out["final_pred"], out["final_gt"] = fp, fg
             out["L2_dist"], out["lip_sync_error_n"] = met[0:1], met[1:2]
-        self._clip_index = clip_index
-        self._B, self._F = B, F
         return out
 
     def backward(self, g_grads, g_table=None, g_pred=None):
@@ -433,6 +447,7 @@ class Voice2PoseTrainer:
         self.adam_c = torch.zeros(8, device=self.device)
         self.set_lr(self.lr)
         self.engine = m.step_engine()
+        self._aux = None
         self._staging = None
         self._graphs = None
         self._warm = 0
@@ -473,8 +488,19 @@ class Voice2PoseTrainer:
         s = self._staging
         if self.train_code:
             self.g_table.zero_()                                       # optimizerClipCode.zero_grad(); dense grad (K12)
-        self.out = self.engine.forward(s["audio"], s["poses"], s["idx"], (s["mean"], s["std"], s["scale"]))
+        self.out = self.engine.forward(s["audio"], s["poses"], s["idx"], (s["mean"], s["std"], s["scale"]), defer_side=True)
+        # fork: FGD features + f64 results/metrics on a second stream while the backward pass runs on this one
+        main = torch.cuda.current_stream()
+        if self._aux is None:
+            self._aux = torch.cuda.Stream()
+        fork, join = torch.cuda.Event(), torch.cuda.Event()
+        fork.record(main)
+        with torch.cuda.stream(self._aux):
+            self._aux.wait_event(fork)
+            self.engine.run_side()
+            join.record(self._aux)
         self.engine.backward(self.grads, self.g_table)
+        main.wait_event(join)
 
     def _optim(self):
         gs = 1.0 / self.world

@@ -335,6 +335,31 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
 
 
 def _wgrad(self, g, x, dy, B, H, W, grad_out, xf=None, slope=1.0):
+    """Weight gradient of one layer.  Nothing downstream in the backward pass depends on it, so when the engine has a
+    `wg_stream` it is enqueued there (after an event marking dy ready) and overlaps the dgrad chain on the main stream."""
+    wg = getattr(self, "wg_stream", None)
+    if wg is not None:
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        with torch.cuda.stream(wg):
+            wg.wait_event(ev)
+            _wgrad_now(self, g, x, dy, B, H, W, grad_out, xf, slope)
+        self._wg_pending = True
+        return
+    _wgrad_now(self, g, x, dy, B, H, W, grad_out, xf, slope)
+
+
+def _wgrad_join(self):
+    """Main stream waits for the weight gradients enqueued on wg_stream."""
+    wg = getattr(self, "wg_stream", None)
+    if wg is not None and getattr(self, "_wg_pending", False):
+        ev = torch.cuda.Event()
+        ev.record(wg)
+        torch.cuda.current_stream().wait_event(ev)
+        self._wg_pending = False
+
+
+def _wgrad_now(self, g, x, dy, B, H, W, grad_out, xf=None, slope=1.0):
     oh, ow = g.out_hw(H, W)
     splits = ops.wgrad_splits(g, B, oh, ow)
     need = splits * g.cout * g.k
@@ -368,7 +393,6 @@ def _gen_backward(self, g_pred, grads, g_code=None):
     _dgrad(self, "decoder.4", gl, g_pred, params["decoder.4.weight"], g_act["decoder.3"], B, 1, F)
     # ---- 1-D stack in reverse
     layers = self.seq_layers()
-    g_raw_scratch = A.get("g_raw_scratch", (B, F, 256))
     g_x0 = None
     for name, g, kind in reversed(layers):
         L_out = self.seq_len[name]
@@ -380,7 +404,7 @@ def _gen_backward(self, g_pred, grads, g_code=None):
                                       params[name + ".norm.weight"], params[name + ".norm.bias"],
                                       grads[name + ".norm.weight"], grads[name + ".norm.bias"], scratch=scratch)
         else:
-            g_raw = g_raw_scratch.view(-1)[: B * L_out * 256].view(B, L_out, 256)
+            g_raw = A.get("g_raw:" + name, (B, L_out, 256))          # per layer: its wgrad may still be in flight
             ops.rownorm_act_bwd(g_act[name], raw, A.get("rmean:" + name, (B * L_out,)), A.get("rrstd:" + name, (B * L_out,)), slope,
                                 out=g_raw)
         xin = acts["in:" + name]
@@ -439,6 +463,7 @@ def _gen_backward(self, g_pred, grads, g_code=None):
             g_prev = A.get("g_enc:%d" % (l - 1), (B, H, W, ci))
             _dgrad(self, name, g, g_enc, params[name + ".conv.weight"], g_prev, B, H, W)
             g_enc = g_prev
+    _wgrad_join(self)
 
 
 GeneratorEngine.forward = _gen_forward

@@ -447,6 +447,7 @@ class Voice2PoseTrainer:
         self.adam_c = torch.zeros(8, device=self.device)
         self.set_lr(self.lr)
         self.engine = m.step_engine()
+        m.netG.engine().wg_stream = torch.cuda.Stream()      # weight gradients overlap the dgrad chain (engine._wgrad)
         self._aux = None
         self._staging = None
         self._graphs = None

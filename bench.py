@@ -269,7 +269,8 @@ def run_own(args):
 
     # ---- roofline of the dominant kernel family: one eager step bracketed with CUDA events per launch
     prof = EventProfiler()
-    graphs, tr._graphs, tr.use_graph = tr._graphs, None, False
+    graphs, tr.use_graph = tr._graphs, False
+    tr.set_overlap(False)                  # single stream: every launch is timed alone
     tr._stage(dev_batches[0])
     tr.run_staged()                        # un-profiled eager step (re-warm)
     _lib.hooks = (prof.pre, prof.post)
@@ -278,6 +279,7 @@ def run_own(args):
         tr.run_staged()
     _lib.hooks = None
     agg = prof.summary()
+    tr.set_overlap(True)
     tr._graphs, tr.use_graph = graphs, not args.no_graph
     total_ms = sum(a[0] for a in agg.values())
     conv_ms = agg.get("sdt_conv_gemm", [0, 0, 0])[0] + agg.get("sdt_conv_wgrad", [0, 0, 0])[0]

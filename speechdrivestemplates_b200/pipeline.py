@@ -447,13 +447,22 @@ class Voice2PoseTrainer:
         self.adam_c = torch.zeros(8, device=self.device)
         self.set_lr(self.lr)
         self.engine = m.step_engine()
-        m.netG.engine().wg_stream = torch.cuda.Stream()      # weight gradients overlap the dgrad chain (engine._wgrad)
+        self._wg_stream = torch.cuda.Stream()                # weight gradients overlap the dgrad chain (engine._wgrad)
+        m.netG.engine().wg_stream = self._wg_stream
+        self._overlap = True
         self._aux = None
         self._staging = None
         self._graphs = None
         self._warm = 0
         self.kernels_per_step = 0
         self.steps_done = 0
+
+    def set_overlap(self, on):
+        """Multi-stream overlap of the step (FGD/metrics and weight gradients beside the dgrad chain). bench.py switches
+        it off for the per-kernel roofline pass so that every launch is timed alone."""
+        self._overlap = bool(on)
+        self.model.netG.engine().wg_stream = self._wg_stream if on else None
+        self._graphs = None
 
     # ---- schedule hook (MultiStepLR steps per epoch in the reference, voice2pose.py:251-257)
     def set_lr(self, lr):
@@ -489,6 +498,10 @@ class Voice2PoseTrainer:
         s = self._staging
         if self.train_code:
             self.g_table.zero_()                                       # optimizerClipCode.zero_grad(); dense grad (K12)
+        if not self._overlap:
+            self.out = self.engine.forward(s["audio"], s["poses"], s["idx"], (s["mean"], s["std"], s["scale"]))
+            self.engine.backward(self.grads, self.g_table)
+            return
         self.out = self.engine.forward(s["audio"], s["poses"], s["idx"], (s["mean"], s["std"], s["scale"]), defer_side=True)
         # fork: FGD features + f64 results/metrics on a second stream while the backward pass runs on this one
         main = torch.cuda.current_stream()

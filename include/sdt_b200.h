@@ -32,8 +32,12 @@ extern "C" {
 /* ---- library ---------------------------------------------------------------------------------- */
 const char* sdt_last_error(void);
 int sdt_version(void);
-/* math mode of the dense convolutions: 0 = fp32 FFMA (SIMT), 1 = TF32 tcgen05 tensor cores where a
- * tcgen05 kernel exists for the shape (fp32 accumulate). Process-wide; default 0 unless set. */
+/* math mode of the dense convolutions (process-wide, default 0):
+ *   0 = fp32 FFMA (SIMT);
+ *   1 = tcgen05 tensor cores, TF32 operands, fp32 accumulation in TMEM, operand tiles built by producer warps
+ *       (supports the loader transform) -- for shapes with C % 32 == 0 and N in {64,128,256}, FFMA otherwise;
+ *   2 = as 1, plus TMA (cp.async.bulk.tensor) operand delivery for forward / data-gradient launches whose source is a
+ *       plain tensor (no loader transform): the caller materialises activations for those layers. */
 int sdt_set_conv_math(int mode);
 int sdt_get_conv_math(void);
 /* number of tcgen05 kernel launches made by this process so far (lets callers/tests verify which path ran) */

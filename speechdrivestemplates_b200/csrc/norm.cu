@@ -237,6 +237,29 @@ __global__ void scale_shift_act_kernel(const float* __restrict__ x, const float*
     y[e] = sdt::leaky(fmaf(x[e], scale[so], shift[so]), slope);
 }
 
+// C % 4 == 0: one float4 per thread, image index from the block (gridDim.y = B)
+__global__ void __launch_bounds__(256) scale_shift_act_v4_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                                                 const float* __restrict__ shift, long long per_image4, int C,
+                                                                 int bstride, float slope, float* __restrict__ y) {
+    const int b = blockIdx.y;
+    const float4* xi = reinterpret_cast<const float4*>(x) + (size_t)b * per_image4;
+    float4* yi = reinterpret_cast<float4*>(y) + (size_t)b * per_image4;
+    const float* sc = scale + (size_t)b * bstride;
+    const float* sh = shift + (size_t)b * bstride;
+    const int c4n = C / 4;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < per_image4; e += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(e % c4n) * 4;
+        const float4 v = xi[e];
+        const float4 s4 = *reinterpret_cast<const float4*>(sc + c), h4 = *reinterpret_cast<const float4*>(sh + c);
+        float4 o;
+        o.x = sdt::leaky(fmaf(v.x, s4.x, h4.x), slope);
+        o.y = sdt::leaky(fmaf(v.y, s4.y, h4.y), slope);
+        o.z = sdt::leaky(fmaf(v.z, s4.z, h4.z), slope);
+        o.w = sdt::leaky(fmaf(v.w, s4.w, h4.w), slope);
+        yi[e] = o;
+    }
+}
+
 }  // namespace
 
 extern "C" int sdt_norm_finalize(const float* partial, int groups, int tiles_per_group, int C, double count,
@@ -329,6 +352,14 @@ extern "C" int sdt_scale_shift_act(const float* x, const float* scale, const flo
                                    float slope, float* y, void* stream) {
     SDT_REQUIRE(x && scale && shift && y && B > 0 && P > 0 && C > 0, "sdt_scale_shift_act: bad arguments");
     const long long total = (long long)B * P * C;
+    if (C % 4 == 0 && B <= 65535 && ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)scale | (uintptr_t)shift) & 15) == 0)) {
+        const long long per_image4 = (long long)P * C / 4;
+        int gx = sdt::ceil_div(per_image4, 256 * 2);
+        if (gx > 2048) gx = 2048;
+        scale_shift_act_v4_kernel<<<dim3(gx, B), 256, 0, sdt::as_stream(stream)>>>(x, scale, shift, per_image4, C, bstride, slope, y);
+        SDT_LAUNCH_OK("scale_shift_act_v4_kernel");
+        return SDT_OK;
+    }
     scale_shift_act_kernel<<<sdt::ceil_div(total, 256), 256, 0, sdt::as_stream(stream)>>>(x, scale, shift, total, P, C, bstride,
                                                                                          slope, y);
     SDT_LAUNCH_OK("scale_shift_act_kernel");

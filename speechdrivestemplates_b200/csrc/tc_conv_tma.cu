@@ -1,0 +1,301 @@
+// Convolution forward / data-gradient on tcgen05 with BOTH operands delivered by TMA (cp.async.bulk.tensor).
+//
+// Why: the register-staged producers of tc_conv.cu push every operand byte through the SM's 128 B/clk L1/shared pipe
+// three times (L1 fill, st.shared, tensor-core fetch) and the ncu captures show that pipe, not DRAM / L2 / the tensor
+// pipe, at 50-57 % (profiles/r1_ncu_tc_conv_v1_register_producers.txt).  TMA writes the SWIZZLE_128B operand tiles
+// straight from L2 into shared memory: no LSU instructions, no registers, one pass.
+//
+// The A operand has no loader transform here, so the caller feeds an ACTIVATED channels-last tensor (the 2-D encoder
+// materialises LeakyReLU(scale*raw+shift); the 1-D stacks and all data-gradients already are plain tensors).
+//   A tile  : 128 GEMM rows = a (bh x bw) patch of the output grid of ONE image.  For tap (ty,tx) and 32-channel chunk c0 the
+//             tile is the 4-D TMA box {32, bw*xs, bh*ys, 1} of the (C,W,H,B) tensor at coordinates
+//             (c0, x0*x_mul + x_off + tx*tx_mul, y0*y_mul + y_off + ty*ty_mul, b) with element strides (1, x_mul, y_mul, 1):
+//             strided convolutions and the stride-parity classes of the data gradient are plain boxes, the zero padding
+//             is TMA's out-of-bounds fill (negative / too large coordinates).  Row r of the box = (r / bw, r % bw).
+//   B tile  : 2-D box {32, BN} of the K-major (N, K) weight copy at (k, n0).
+//   warp 0  : TMA producer (one thread): wait empty[s] -> arrive.expect_tx(full[s]) -> two bulk tensor copies.
+//   warp 1  : MMA issuer (one thread): 4 x tcgen05.mma per stage, tcgen05.commit -> empty[s]; owns the TMEM allocation.
+//   warps 2-5: epilogue: tcgen05.ld, bias / accumulate, 128-byte row stores, masked column statistics.
+// 3 stages of 32 KB (BN = 128) -> two CTAs per SM.
+#include <cuda.h>
+
+#include "tc_api.h"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace sdt_tc;
+
+constexpr int BM = 128;
+constexpr int BKF = 32;
+constexpr int THREADS = 192;
+
+struct TileGeom {
+    int bw, bh;            // patch width / height, bw * bh == 128
+    int tiles_x, tiles_y;  // patches per image
+};
+
+template <int BN>
+struct TmaCfg {
+    static constexpr int STAGES = BN == 64 ? 4 : 3;
+    static constexpr int A_BYTES = BM * 128;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int RED_BYTES = 2 * 4 * BN * 4;
+    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + RED_BYTES + 1024;
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(THREADS, 2) tc_conv_tma_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                 const __grid_constant__ CUtensorMap tmB,
+                                                                 const sdt_conv_desc d, const TileGeom tg) {
+    using Cfg = TmaCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
+    uint8_t* sm = smem_raw + pad;
+    const uint32_t smA = raw_addr + pad;
+    const uint32_t smB = smA + STAGES * Cfg::A_BYTES;
+    uint8_t* after = sm + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES);
+    const uint32_t bars = smB + STAGES * Cfg::B_BYTES;          // full[STAGES], empty[STAGES], tmem_full
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(after + (2 * STAGES + 1) * 8);
+    float* s_red = reinterpret_cast<float*>(after + Cfg::BAR_BYTES);   // [2][4][BN]
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    const uint32_t tmem_full_bar = bars + 8u * (2 * STAGES);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int K = d.TH * d.TW * d.C, KB = K / BKF;
+    const int N = d.N;
+    const int n0 = blockIdx.y * BN;
+    // patch of this CTA
+    const int tpi = tg.tiles_x * tg.tiles_y;
+    const int b = blockIdx.x / tpi;
+    const int trem = blockIdx.x - b * tpi;
+    const int y0 = (trem / tg.tiles_x) * tg.bh, x0 = (trem % tg.tiles_x) * tg.bw;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        const int taps = d.TH * d.TW;
+        for (int kb = 0; kb < KB; ++kb) {
+            if (lane == 0) {
+                const int s = kb % STAGES, round = kb / STAGES;
+                mbar_wait(empty_bar(s), (uint32_t)((round & 1) ^ 1));
+                // k-block order: channel chunk major, tap minor (consecutive taps hit the same L2 lines)
+                const int cchunk = kb / taps, tap = kb - cchunk * taps;
+                const int c0 = cchunk * BKF;
+                const int tyy = tap / d.TW, txx = tap - tyy * d.TW;
+                const int wx = x0 * d.x_mul + d.x_off + txx * d.tx_mul;
+                const int wy = y0 * d.y_mul + d.y_off + tyy * d.ty_mul;
+                mbar_expect_tx(full_bar(s), Cfg::A_BYTES + Cfg::B_BYTES);
+                tma_load_4d(smA + s * Cfg::A_BYTES, &tmA, c0, wx, wy, b, full_bar(s));
+                tma_load_2d(smB + s * Cfg::B_BYTES, &tmB, tap * d.C + c0, n0, full_bar(s));
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        const uint32_t idesc = make_idesc_tf32(BN, 0, 0);
+        for (int kb = 0; kb < KB; ++kb) {
+            if (lane == 0) {
+                const int s = kb % STAGES, round = kb / STAGES;
+                mbar_wait(full_bar(s), (uint32_t)(round & 1));
+                tc_fence_after();
+                const uint64_t da = make_smem_desc(smA + s * Cfg::A_BYTES, 16, 1024);
+                const uint64_t db = make_smem_desc(smB + s * Cfg::B_BYTES, 16, 1024);
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) mma_tf32(tmem_base, da + 2u * k4, db + 2u * k4, idesc, (uint32_t)((kb | k4) != 0));
+                mma_commit(empty_bar(s));
+            }
+            __syncwarp();
+        }
+        if (lane == 0) mma_commit(tmem_full_bar);
+        __syncwarp();
+    } else {
+        // ================= epilogue (warps 2..5; TMEM lane quadrant = warp % 4) =================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int py = r / tg.bw, px = r - py * tg.bw;
+        const int gy = y0 + py, gx = x0 + px;
+        const bool ok = gy < d.GH && gx < d.GW;
+        const long long dst_off = ok ? (((long long)b * d.DH + (gy * d.dy_mul + d.dy_off)) * d.DW + (gx * d.dx_mul + d.dx_off)) * N : -1;
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        for (int c = 0; c < BN / 32; ++c) {
+            float v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+            const int ncol = n0 + c * 32;
+            if (ok) {
+                float* p = d.dst + dst_off + ncol;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    if (d.bias != nullptr) {
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(d.bias + ncol) + j);
+                        o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                    }
+                    if (d.accumulate) {
+                        const float4 old = reinterpret_cast<const float4*>(p)[j];
+                        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                    }
+                    reinterpret_cast<float4*>(p)[j] = o;
+                }
+            }
+            if (d.stat_partial != nullptr) {
+                // rows of the patch that fall outside the output grid computed on real neighbours: mask them out
+                float w[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    v[i] = ok ? v[i] : 0.f;
+                    w[i] = v[i] * v[i];
+                }
+                const float s1 = warp_transpose_sum(v, lane);
+                const float s2 = warp_transpose_sum(w, lane);
+                s_red[(0 * 4 + q) * BN + c * 32 + lane] = s1;
+                s_red[(1 * 4 + q) * BN + c * 32 + lane] = s2;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (d.stat_partial != nullptr) {
+        for (int c = tid; c < BN; c += THREADS) {
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                s1 += s_red[(0 * 4 + q) * BN + c];
+                s2 += s_red[(1 * 4 + q) * BN + c];
+            }
+            d.stat_partial[((size_t)blockIdx.x * 2 + 0) * N + n0 + c] = s1;
+            d.stat_partial[((size_t)blockIdx.x * 2 + 1) * N + n0 + c] = s2;
+        }
+    }
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, BN);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+TileGeom pick_geom(const sdt_conv_desc* d) {
+    TileGeom best{128, 1, 0, 0};
+    long long best_rows = -1;
+    for (int bw = 128; bw >= 8; bw /= 2) {
+        const int bh = 128 / bw;
+        if (bw * d->x_mul > 256 || bh * d->y_mul > 256) continue;          // TMA box extent limit
+        const int tx = (d->GW + bw - 1) / bw, ty = (d->GH + bh - 1) / bh;
+        const long long rows = (long long)tx * ty * 128;
+        if (best_rows < 0 || rows < best_rows) {
+            best_rows = rows;
+            best = TileGeom{bw, bh, tx, ty};
+        }
+    }
+    return best;
+}
+
+template <int BN>
+int launch_tma(const sdt_conv_desc* d, const TileGeom& tg, cudaStream_t st) {
+    EncodeTiledFn enc = get_encode();
+    SDT_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    static bool attr_set = false;
+    if (!attr_set) {
+        SDT_CUDA_OK(cudaFuncSetAttribute(tc_conv_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TmaCfg<BN>::SMEM));
+        attr_set = true;
+    }
+    alignas(64) CUtensorMap tmA, tmB;
+    {
+        const cuuint64_t dims[4] = {(cuuint64_t)d->C, (cuuint64_t)d->SW, (cuuint64_t)d->SH, (cuuint64_t)d->B};
+        const cuuint64_t strides[3] = {(cuuint64_t)d->C * 4, (cuuint64_t)d->SW * d->C * 4, (cuuint64_t)d->SH * d->SW * d->C * 4};
+        const cuuint32_t box[4] = {32, (cuuint32_t)(tg.bw * d->x_mul), (cuuint32_t)(tg.bh * d->y_mul), 1};
+        const cuuint32_t estr[4] = {1, (cuuint32_t)d->x_mul, (cuuint32_t)d->y_mul, 1};
+        const CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(d->src), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SDT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+    }
+    {
+        const int K = d->TH * d->TW * d->C;
+        const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)d->N};
+        const cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+        const cuuint32_t box[2] = {32, (cuuint32_t)BN};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(d->wt_nk), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SDT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+    }
+    dim3 grid(d->B * tg.tiles_x * tg.tiles_y, d->N / BN);
+    tc_conv_tma_kernel<BN><<<grid, THREADS, TmaCfg<BN>::SMEM, st>>>(tmA, tmB, *d, tg);
+    SDT_LAUNCH_OK("tc_conv_tma_kernel");
+    sdt_note_tc_launch();
+    return SDT_OK;
+}
+
+}  // namespace
+
+bool sdt_tc_conv_tma_eligible(const sdt_conv_desc* d) {
+    if (d->wt_nk == nullptr || d->xf_scale != nullptr) return false;        // plain (already activated) source only
+    if (d->C % 32 != 0 || d->N % 64 != 0) return false;
+    if (d->x_mul < 1 || d->x_mul > 8 || d->y_mul < 1 || d->y_mul > 8) return false;
+    if ((((uintptr_t)d->src | (uintptr_t)d->wt_nk | (uintptr_t)d->dst | (uintptr_t)d->bias) & 15) != 0) return false;
+    return get_encode() != nullptr;
+}
+
+int sdt_tc_conv_tma_row_tiles(const sdt_conv_desc* d) {
+    const TileGeom tg = pick_geom(d);
+    return d->B * tg.tiles_x * tg.tiles_y;
+}
+
+int sdt_tc_conv_tma_launch(const sdt_conv_desc* d, cudaStream_t st) {
+    const TileGeom tg = pick_geom(d);
+    const long long tiles = (long long)d->B * tg.tiles_x * tg.tiles_y;
+    int bn = d->N % 128 == 0 ? 128 : 64;
+    if (bn == 128 && tiles * (d->N / 128) < 2 * 148) bn = 64;               // small problems: more CTAs
+    if (bn == 128) return launch_tma<128>(d, tg, st);
+    return launch_tma<64>(d, tg, st);
+}

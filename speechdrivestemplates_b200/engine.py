@@ -63,7 +63,7 @@ class WeightPrep:
         tc_ok=False keeps a layer on the FFMA operands even in math mode 1 (the tcgen05 kernel stages one image's
         scale/shift per CTA, so layers whose loader transform spans a batch-wide statistic stay on the FFMA kernel)."""
         import numpy as np
-        tc = ops.get_conv_math() == 1
+        tc = ops.get_conv_math() >= 1
         key = (tc, with_dgrad) + tuple(params[l[1]].data_ptr() for l in layers)
         if key == self.key:
             return
@@ -249,6 +249,7 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
     self.fwd_id += 1
     self._mel = mel
     self._params = params
+    self.materialize = ops.get_conv_math() == 2
     self.wprep.ensure(self._all_layers(), params, with_dgrad=training)
     self.wprep.run()
     # ---- 2-D encoder: raw conv output + statistics; normalise/activate in the consumer's loader
@@ -281,12 +282,20 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
             ops.conv_gemm(d)
             ops.bn_eval_scale_shift(buffers[name + ".norm.running_mean"], buffers[name + ".norm.running_var"],
                                     params[name + ".norm.weight"], params[name + ".norm.bias"], out=(sc, sh))
-        src, xf = raw, (sc, sh, self._bstride(co))
+        last_raw, last_xf = raw, (sc, sh, self._bstride(co))
+        if self.materialize:
+            # math mode 2: the TMA-fed tensor-core kernels take plain tensors, so the normalised + activated map is written
+            # once (HBM is at ~10 % utilisation; the SM-side operand path is the bottleneck)
+            act = A.get("act2d:" + name, (B, oh, ow, co))
+            ops.scale_shift_act(raw, sc, sh, self._bstride(co), slope, out=act)
+            src, xf = act, None
+        else:
+            src, xf = last_raw, last_xf
     # ---- bilinear resize to F frames + clip-code concat (generator.py:41-42,109-111)
     D = self.code_dim
     h7, w7 = self.enc_hw[8]
     x0 = A.get("x0", (B, num_frames, 256 + D))
-    ops.enc_to_seq_fwd(src, xf[0], xf[1], xf[2], slope, code if D > 0 else None, num_frames, out=x0)
+    ops.enc_to_seq_fwd(last_raw, last_xf[0], last_xf[1], last_xf[2], slope, code if D > 0 else None, num_frames, out=x0)
     # ---- 1-D stack
     acts = {"x0": x0}
     for name, g, kind in self.seq_layers():
@@ -456,8 +465,11 @@ def _gen_backward(self, g_pred, grads, g_code=None):
         else:
             pname = ENC_PREFIX + ENC2D[l - 1][0]
             pc = ENC2D[l - 1][1]
-            src = A.get("raw:" + pname, (B, H, W, pc))
-            xf = (A.get("scale:" + pname, (groups, pc)), A.get("shift:" + pname, (groups, pc)), self._bstride(pc))
+            if self.materialize:
+                src, xf = A.get("act2d:" + pname, (B, H, W, pc)), None
+            else:
+                src = A.get("raw:" + pname, (B, H, W, pc))
+                xf = (A.get("scale:" + pname, (groups, pc)), A.get("shift:" + pname, (groups, pc)), self._bstride(pc))
         _wgrad(self, g, src, g_enc, B, H, W, grads[name + ".conv.weight"], xf, slope)
         if l > 0:
             g_prev = A.get("g_enc:%d" % (l - 1), (B, H, W, ci))

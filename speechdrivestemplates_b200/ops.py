@@ -267,7 +267,7 @@ def conv_forward(x, w, g, xf=None, slope=1.0, bias=None, want_stats=False, per_i
     wt = torch.empty(g.k, g.cout, device=x.device)
     weight_prep_fwd(w, g, wt)
     wt_nk = None
-    if get_conv_math() == 1 and tc_eligible(g.cin, g.cout):
+    if get_conv_math() >= 1 and tc_eligible(g.cin, g.cout):
         wt_nk = torch.empty(g.cout, g.k, device=x.device)
         weight_prep_fwd_nk(w, g, wt_nk)
     y = torch.empty(B, oh, ow, g.cout, device=x.device)
@@ -291,7 +291,7 @@ def conv_dgrad(dy, w, g, H, W, out=None, accumulate=False):
         wt = torch.empty(cls["th"] * cls["tw"] * g.cout, g.cin, device=dy.device)
         weight_prep_dgrad(w, g, cls, wt)
         wt_nk = None
-        if get_conv_math() == 1 and tc_eligible(g.cout, g.cin):
+        if get_conv_math() >= 1 and tc_eligible(g.cout, g.cin):
             wt_nk = torch.empty(g.cin, cls["th"] * cls["tw"] * g.cout, device=dy.device)
             weight_prep_dgrad_nk(w, g, cls, wt_nk)
         conv_gemm(dgrad_desc(g, cls, dy, wt, dx, B, H, W, accumulate, wt_nk=wt_nk))

@@ -155,7 +155,8 @@ def test_tc_wgrad_conv1d(ops):
     assert rel(dw.view(cout, cin, 4), w.grad) < TF32_TOL
 
 
-def test_sdt_bp_train_step_tf32_mode_vs_reference_fixture():
+@pytest.mark.parametrize("mode", [1, 2])
+def test_sdt_bp_train_step_tf32_mode_vs_reference_fixture(mode):
     """Whole fused train step with the tcgen05 TF32 convolutions against the reference's recorded fp32 step.
     Stated TF32 tolerance: losses 1e-3, prediction 5e-3 of its range, final f64 results 5e-3; gradients agree in
     direction and size (relative L2 error < 0.25 per tensor: TF32 operand rounding moves ~0.1 % of the LeakyReLU units
@@ -167,7 +168,7 @@ def test_sdt_bp_train_step_tf32_mode_vs_reference_fixture():
     from util import golden, oliver_stat, rel_err
     g = golden("sdt_bp_step_golden")
     try:
-        tr = pipeline.Voice2PoseTrainer(config.get_cfg("voice2pose_sdt_bp"), 16, dev(), use_cuda_graph=False, seed=0, conv_math=1)
+        tr = pipeline.Voice2PoseTrainer(config.get_cfg("voice2pose_sdt_bp"), 16, dev(), use_cuda_graph=False, seed=0, conv_math=mode)
         tr.model.clips_code.data.copy_(0.1 * torch.randn(16, 32, generator=torch.Generator().manual_seed(11)))
         n0 = tc_launches()
         out = tr.train_step(_to_host_batch(O.synthetic_batch(2, 16, oliver_stat(True), seed=100)))
@@ -190,3 +191,70 @@ def test_sdt_bp_train_step_tf32_mode_vs_reference_fixture():
             assert err < 0.25 and cos > 0.97, (n, err, cos)
     finally:
         o.set_conv_math(0)
+
+
+# ---------------------------------------------------------------- math mode 2: TMA-fed tcgen05 kernel
+@pytest.fixture()
+def ops_tma():
+    from speechdrivestemplates_b200 import ops as o
+    o.set_conv_math(2)
+    yield o
+    o.set_conv_math(0)
+
+
+@pytest.mark.parametrize("cfg", GEOMS)
+def test_tma_forward_plain_source_with_stats(ops_tma, cfg):
+    ops = ops_tma
+    cin, cout, kh, kw, s, p, H, W, B = cfg
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(B, cin, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(cout, cin, kh, kw, generator=g, dtype=torch.float64) / math.sqrt(cin * kh * kw)
+    ref = F.conv2d(x, w, None, s, p)
+    geom = ops.ConvGeom.conv2d(cin, cout, kh, kw, s, p)
+    n0 = tc_launches()
+    y, partial = ops.conv_forward(to_cl(x.float()).to(dev()), w.float().to(dev()).contiguous(), geom, want_stats=True, per_image=True)
+    torch.cuda.synchronize()
+    assert tc_launches() == n0 + 1
+    assert rel(from_cl(y), ref) < TF32_TOL
+    tiles = partial.shape[0] // B
+    ps = partial.view(B, tiles, 2, cout).double().sum(1).cpu()
+    got = from_cl(y).double().cpu()
+    assert rel(ps[:, 0], got.sum((2, 3))) < 1e-4           # patch rows outside the output grid are masked out of the statistics
+    assert rel(ps[:, 1], (got * got).sum((2, 3))) < 1e-4
+
+
+@pytest.mark.parametrize("cfg", GEOMS[:7])
+def test_tma_dgrad(ops_tma, cfg):
+    ops = ops_tma
+    cin, cout, kh, kw, s, p, H, W, B = cfg
+    g = torch.Generator().manual_seed(32)
+    x = torch.randn(B, cin, H, W, generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(cout, cin, kh, kw, generator=g, dtype=torch.float64) / math.sqrt(cin * kh * kw)
+    y = F.conv2d(x, w, None, s, p)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(dy)
+    geom = ops.ConvGeom.conv2d(cin, cout, kh, kw, s, p)
+    dx = ops.conv_dgrad(to_cl(dy.float()).to(dev()), w.float().to(dev()).contiguous(), geom, H, W)
+    torch.cuda.synchronize()
+    assert rel(from_cl(dx), x.grad) < TF32_TOL
+
+
+@pytest.mark.parametrize("k,s,L", [(3, 1, 64), (4, 2, 64), (4, 2, 33), (3, 1, 2)])
+def test_tma_conv1d(ops_tma, k, s, L):
+    ops = ops_tma
+    B, cin, cout = 8, 256, 256
+    g = torch.Generator().manual_seed(33)
+    x = torch.randn(B, cin, L, generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(cout, cin, k, generator=g, dtype=torch.float64) / math.sqrt(cin * k)
+    b = torch.randn(cout, generator=g, dtype=torch.float64)
+    y = F.conv1d(x, w, b, s, 1)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(dy)
+    geom = ops.ConvGeom.conv1d(cin, cout, k, s, 1)
+    xcl = x.detach().float().permute(0, 2, 1).contiguous().view(B, 1, L, cin).to(dev())
+    yk = ops.conv_forward(xcl, w.float().to(dev()).contiguous(), geom, bias=b.float().to(dev()))
+    assert rel(yk.view(B, -1, cout).permute(0, 2, 1), y) < TF32_TOL
+    base = torch.ones(B, 1, L, cin, device=dev())
+    dx = ops.conv_dgrad(dy.float().permute(0, 2, 1).contiguous().view(B, 1, -1, cout).to(dev()), w.float().to(dev()).contiguous(),
+                        geom, 1, L, out=base, accumulate=True)
+    assert rel(dx.view(B, L, cin).permute(0, 2, 1), x.grad + 1.0) < TF32_TOL

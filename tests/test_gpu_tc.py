@@ -258,3 +258,41 @@ def test_tma_conv1d(ops_tma, k, s, L):
     dx = ops.conv_dgrad(dy.float().permute(0, 2, 1).contiguous().view(B, 1, -1, cout).to(dev()), w.float().to(dev()).contiguous(),
                         geom, 1, L, out=base, accumulate=True)
     assert rel(dx.view(B, L, cin).permute(0, 2, 1), x.grad + 1.0) < TF32_TOL
+
+
+@pytest.mark.parametrize("cfg", GEOMS)
+@pytest.mark.parametrize("splits", [None, 3])
+def test_tma_wgrad_plain_source(ops_tma, cfg, splits):
+    ops = ops_tma
+    cin, cout, kh, kw, s, p, H, W, B = cfg
+    if splits is not None and H * W > 2000:
+        pytest.skip("one split setting is enough for the large case")
+    g = torch.Generator().manual_seed(34)
+    x = torch.randn(B, cin, H, W, generator=g, dtype=torch.float64)
+    w = (torch.randn(cout, cin, kh, kw, generator=g, dtype=torch.float64) / math.sqrt(cin * kh * kw)).requires_grad_(True)
+    y = F.conv2d(x, w, None, s, p)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(dy)
+    geom = ops.ConvGeom.conv2d(cin, cout, kh, kw, s, p)
+    n0 = tc_launches()
+    dw = ops.conv_weight_grad(to_cl(x.float()).to(dev()), to_cl(dy.float()).to(dev()), geom, splits=splits)
+    torch.cuda.synchronize()
+    assert tc_launches() == n0 + 1
+    assert rel(dw, w.grad) < TF32_TOL
+
+
+@pytest.mark.parametrize("k,s,L,B", [(3, 1, 64, 8), (4, 2, 64, 8), (4, 2, 4, 32), (3, 1, 2, 5)])
+def test_tma_wgrad_conv1d_small_maps(ops_tma, k, s, L, B):
+    ops = ops_tma
+    cin, cout = 256, 256
+    g = torch.Generator().manual_seed(35)
+    x = torch.randn(B, cin, L, generator=g, dtype=torch.float64)
+    w = (torch.randn(cout, cin, k, generator=g, dtype=torch.float64) / math.sqrt(cin * k)).requires_grad_(True)
+    y = F.conv1d(x, w, None, s, 1)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(dy)
+    geom = ops.ConvGeom.conv1d(cin, cout, k, s, 1)
+    xcl = x.float().permute(0, 2, 1).contiguous().view(B, 1, L, cin).to(dev())
+    dycl = dy.float().permute(0, 2, 1).contiguous().view(B, 1, -1, cout).to(dev())
+    dw = ops.conv_weight_grad(xcl, dycl, geom)
+    assert rel(dw.view(cout, cin, k), w.grad) < TF32_TOL

@@ -343,7 +343,7 @@ def main():
     ap.add_argument("--impl", default="own")
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU (BASELINE configs[1]: 32)")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--math", default="tf32", choices=["fp32", "tf32", "tf32-tma"],
+    ap.add_argument("--math", default="tf32-tma", choices=["fp32", "tf32", "tf32-tma"],
                     help="convolution math: fp32 FFMA kernels or tcgen05 TF32 tensor-core kernels (fp32 accumulate)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -4,7 +4,7 @@
 
 * own arm: one process per GPU (torchrun for N>1), per-GPU batch 32 x 64-frame clips (weak scaling), synthetic data,
   one flat NCCL all-reduce per step; prints ONE JSON line with `value` (inputs resident in HBM), `e2e` (host batch ->
-  H2D -> step -> D2H of the loss scalars, through Voice2PoseTrainer.train_step), `roofline` of the dominant kernel
+  H2D -> step -> D2H of the loss scalars every step, through Voice2PoseTrainer.run_epoch), `roofline` of the dominant kernel
   family measured live with CUDA events, `cpu_baseline` (the CPU oracle port on the host cores, bounded sample),
   `clocks` sampled with nvidia-smi during the timed regions.
 * --impl reference: the reference's CPU implementation of the same step = the oracle port (the reference is Python
@@ -253,11 +253,13 @@ def run_own(args):
     barrier()
     t0 = time.perf_counter()
     e0.record()
-    last = None
-    for k in range(K):
-        out = tr.train_step(host_batches[k % len(host_batches)])
-        last = tr.losses_to_host(out)
+    per_step = []
+    # Voice2PoseTrainer.run_epoch = the reference's `for batch in dataloader: train_step; log` loop: every step's batch
+    # is copied host->device (copy stream, one batch ahead) and every step's scalars are read back (one step behind)
+    tr.run_epoch((host_batches[k % len(host_batches)] for k in range(K)), on_losses=lambda i, d: per_step.append(d))
     e1.record()
+    assert len(per_step) == K
+    last = per_step[-1]
     barrier()
     ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), 0.0))
     wall_e2e = time.perf_counter() - t0
@@ -265,7 +267,7 @@ def run_own(args):
     hb = host_batches[0]
     h2d = sum(t.numel() * t.element_size() for t in (hb["audio"], hb["poses"], hb["clip_index"])) + \
         sum(t.numel() * t.element_size() for t in hb["speaker_stat"].values())
-    d2h = 8 * 6
+    d2h = 8 * 8
 
     # ---- roofline of the dominant kernel family: one eager step bracketed with CUDA events per launch
     prof = EventProfiler()

@@ -161,6 +161,24 @@ int sdt_rownorm_act_bwd(const float* g_y, const float* x, const float* mean, con
 int sdt_scale_shift_act(const float* x, const float* scale, const float* shift, int B, int P, int C, int bstride,
                         float slope, float* y, void* stream);
 
+/* ---- first block of the audio encoder, special-cased ------------------------------------------------
+ * Conv2d(1 -> 64, 3x3, s1, p1, no bias) + InstanceNorm2d + LeakyReLU (generator.py:17 via building_blocks.py
+ * ConvNormRelu): the largest map of the network and pure HBM traffic.  x (B,H,W) is the one-channel input (the mel
+ * image), w (64,1,3,3) the reference weight.  With one input channel the InstanceNorm statistics follow in closed form
+ * from the 9 tap means + 45 tap second moments of each image (`moments`, (B,54) f64), so the forward writes the
+ * activated map act (B,H,W,64) in ONE pass and never stores the raw convolution; scale/shift (B,64) receive rstd and
+ * -mean*rstd.  mom_partial: (B, sdt_first_layer_units(H,W), 54) f64 scratch. */
+int sdt_first_layer_units(int H, int W);
+int sdt_first_layer_fwd(const float* x, const float* w, int B, int H, int W, int C, float eps, float slope,
+                        double* mom_partial, double* moments, float* scale, float* shift, float* act, void* stream);
+/* Weight gradient of that block from g_act = dLoss/d act in ONE pass over (g_act, act): the InstanceNorm + LeakyReLU
+ * backward is folded into per-(image, channel) sums and combined in closed form (f64) with the forward's moments; the
+ * block's input needs no gradient (it is the mel spectrogram).  Requires slope > 0 (the pre-activation is recovered
+ * from act).  partial: (B, units, 11, 64) f32 scratch; dw (64,1,3,3) is overwritten. */
+int sdt_first_layer_bwd(const float* g_act, const float* act, const float* x, const float* w, const double* moments,
+                        const float* scale, const float* shift, int B, int H, int W, int C, float slope, float* partial,
+                        float* dw, void* stream);
+
 /* ---- resampling / concatenation ----------------------------------------------------------------
  * F.interpolate(x, (1, F), mode='bilinear') + squeeze (generator.py:41-42) fused with the code broadcast +
  * concat (generator.py:109-111): reads the last encoder block's raw output (B,H,W,C) through its

@@ -53,6 +53,9 @@ SIGNATURES = {
     "sdt_rownorm_act_fwd": [c_ptr, i32, i32, f32, f32, c_ptr, c_ptr, c_ptr, c_ptr],
     "sdt_rownorm_act_bwd": [c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, f32, c_ptr, c_ptr],
     "sdt_scale_shift_act": [c_ptr, c_ptr, c_ptr, i32, i32, i32, i32, f32, c_ptr, c_ptr],
+    "sdt_first_layer_units": [i32, i32],
+    "sdt_first_layer_fwd": [c_ptr, c_ptr, i32, i32, i32, i32, f32, f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
+    "sdt_first_layer_bwd": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, i32, i32, f32, c_ptr, c_ptr, c_ptr],
     "sdt_enc_to_seq_fwd": [c_ptr, c_ptr, c_ptr, i32, f32, i32, i32, i32, i32, c_ptr, i32, i32, c_ptr, c_ptr],
     "sdt_enc_to_seq_bwd": [c_ptr, i32, i32, i32, i32, i32, i32, c_ptr, c_ptr, c_ptr],
     "sdt_upsample_add_fwd": [c_ptr, c_ptr, i32, i32, i32, i32, c_ptr, c_ptr],
@@ -77,12 +80,14 @@ SIGNATURES = {
 }
 _RESTYPES = {"sdt_last_error": C.c_char_p, "sdt_tc_launches": C.c_int64}
 # entry points whose int return value is a result, not a status
-_NOT_STATUS = {"sdt_last_error", "sdt_version", "sdt_get_conv_math", "sdt_conv_row_tiles", "sdt_tc_launches"}
+_NOT_STATUS = {"sdt_last_error", "sdt_version", "sdt_get_conv_math", "sdt_conv_row_tiles", "sdt_tc_launches",
+               "sdt_first_layer_units"}
 
 _lib = None
 launch_count = 0     # number of CUDA kernels launched through this binding (bench.py's gpu_launches)
 # entry points that launch more than one kernel
-_KERNELS_PER_CALL = {"sdt_l1_loss": 2, "sdt_pose_metrics": 2, "sdt_enc_to_seq_bwd": 2}
+_KERNELS_PER_CALL = {"sdt_l1_loss": 2, "sdt_pose_metrics": 2, "sdt_enc_to_seq_bwd": 2, "sdt_first_layer_fwd": 3,
+                     "sdt_first_layer_bwd": 2}
 # optional (pre, post) callables invoked around every kernel-launching call: bench.py brackets calls with CUDA events
 hooks = None
 

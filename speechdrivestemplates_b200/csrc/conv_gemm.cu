@@ -470,6 +470,37 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ wpart, int splits,
     grad[e] = accumulate ? grad[e] + s : s;
 }
 
+// C % 32 == 0: CTA = (output channel n, 32 input channels); warp w sums taps w, w+8, .. over the splits with 128-byte
+// coalesced reads of the (T, C) partials, the (c, t) transpose into the reference layout goes through shared memory.
+__global__ void __launch_bounds__(256) wgrad_reduce_tiled_kernel(const float* __restrict__ wpart, int splits, int N, int C, int T,
+                                                                 float* __restrict__ grad, int accumulate) {
+    extern __shared__ float s_t[];          // [T][33]
+    const int cchunks = C >> 5;
+    const int n = blockIdx.x / cchunks, c0 = (blockIdx.x - n * cchunks) << 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t stride = (size_t)N * T * C;
+    for (int t = warp; t < T; t += 8) {
+        const float* p = wpart + ((size_t)n * T + t) * C + c0 + lane;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int z = 0;
+        for (; z + 4 <= splits; z += 4) {
+            s0 += __ldg(p + (size_t)z * stride);
+            s1 += __ldg(p + (size_t)(z + 1) * stride);
+            s2 += __ldg(p + (size_t)(z + 2) * stride);
+            s3 += __ldg(p + (size_t)(z + 3) * stride);
+        }
+        for (; z < splits; ++z) s0 += __ldg(p + (size_t)z * stride);
+        s_t[t * 33 + lane] = (s0 + s1) + (s2 + s3);
+    }
+    __syncthreads();
+    float* out = grad + ((size_t)n * C + c0) * T;
+    for (int i = threadIdx.x; i < 32 * T; i += 256) {
+        const int c = i / T, t = i - c * T;
+        const float v = s_t[t * 33 + c];
+        out[i] = accumulate ? out[i] + v : v;
+    }
+}
+
 __global__ void weight_prep_kernel(const float* __restrict__ w, int Cout, int Cin, int KH, int KW, int mode, int ky0,
                                    int kx0, int kstep, int TH, int TW, float* __restrict__ out) {
     const long long total = (long long)TH * TW * Cin * Cout;
@@ -701,7 +732,11 @@ extern "C" int sdt_conv_wgrad_reduce(const float* wpart, int splits, int N, int 
                                      void* stream) {
     SDT_REQUIRE(wpart && grad && splits >= 1 && N > 0 && C > 0 && T > 0, "sdt_conv_wgrad_reduce: bad arguments");
     const long long total = (long long)N * C * T;
-    wgrad_reduce_kernel<<<sdt::ceil_div(total, 256), 256, 0, sdt::as_stream(stream)>>>(wpart, splits, N, C, T, grad, accumulate);
+    if (C % 32 == 0 && T <= 256)
+        wgrad_reduce_tiled_kernel<<<N * (C / 32), 256, (size_t)T * 33 * sizeof(float), sdt::as_stream(stream)>>>(
+            wpart, splits, N, C, T, grad, accumulate);
+    else
+        wgrad_reduce_kernel<<<sdt::ceil_div(total, 256), 256, 0, sdt::as_stream(stream)>>>(wpart, splits, N, C, T, grad, accumulate);
     SDT_LAUNCH_OK("wgrad_reduce_kernel");
     return SDT_OK;
 }

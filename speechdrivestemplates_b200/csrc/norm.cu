@@ -1,27 +1,49 @@
 // Normalisation kernels: InstanceNorm2d / BatchNorm{1,2}d statistics finalisation and backward, and the
 // channel-LayerNorm that the reference's "InstanceNorm1d on the permuted tensor" amounts to
 // (core/networks/building_blocks.py:23-27,38-43,50-54).  All reductions are fixed-order (deterministic).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
 
 // ---- statistics finalisation ---------------------------------------------------------------------
+// sum of the (tiles, 2, C) partials of one (group, channel): the 8 warps of the CTA split the tiles, lane = channel
+// (128-byte coalesced reads), doubles combined through shared memory.  CTA = (group, 32 channels).
+__device__ __forceinline__ void sum_partials_32ch(const float* __restrict__ p, int tiles, int C, int c, bool valid,
+                                                  double (*s_red)[2][32], double& s, double& q) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double a = 0.0, b = 0.0;
+    if (valid)
+        for (int t = warp; t < tiles; t += 8) {
+            a += (double)__ldg(p + ((size_t)t * 2 + 0) * C + c);
+            b += (double)__ldg(p + ((size_t)t * 2 + 1) * C + c);
+        }
+    s_red[warp][0][lane] = a;
+    s_red[warp][1][lane] = b;
+    __syncthreads();
+    s = 0.0; q = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        s += s_red[w][0][lane];
+        q += s_red[w][1][lane];
+    }
+}
+
 __global__ void norm_finalize_kernel(const float* __restrict__ partial, int groups, int tiles_per_group, int C,
                                      double count, const float* __restrict__ gamma, const float* __restrict__ beta,
                                      float eps, float* __restrict__ scale, float* __restrict__ shift,
                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                      float* __restrict__ running_mean, float* __restrict__ running_var,
                                      int64_t* __restrict__ nbt, float momentum) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e == 0 && nbt != nullptr) *nbt += 1;
-    if (e >= groups * C) return;
-    const int g = e / C, c = e % C;
-    double s = 0.0, q = 0.0;
-    const float* p = partial + (size_t)g * tiles_per_group * 2 * C;
-    for (int t = 0; t < tiles_per_group; ++t) {
-        s += (double)p[((size_t)t * 2 + 0) * C + c];
-        q += (double)p[((size_t)t * 2 + 1) * C + c];
-    }
+    __shared__ double s_red[8][2][32];
+    const int cchunks = (C + 31) / 32;
+    const int g = blockIdx.x / cchunks, c = (blockIdx.x % cchunks) * 32 + (threadIdx.x & 31);
+    const int e = g * C + c;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && nbt != nullptr) *nbt += 1;
+    double s, q;
+    sum_partials_32ch(partial + (size_t)g * tiles_per_group * 2 * C, tiles_per_group, C, c, c < C, s_red, s, q);
+    if (threadIdx.x >= 32 || c >= C) return;
     const double mean = s / count;
     double var = q / count - mean * mean;   // biased
     if (var < 0.0) var = 0.0;
@@ -113,15 +135,13 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float* __res
 __global__ void norm_bwd_finalize_kernel(const float* __restrict__ partial, int groups, int tiles_per_group, int C,
                                          double count, float* __restrict__ m1, float* __restrict__ m2,
                                          float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= groups * C) return;
-    const int gidx = e / C, c = e % C;
-    double s1 = 0.0, s2 = 0.0;
-    const float* p = partial + (size_t)gidx * tiles_per_group * 2 * C;
-    for (int t = 0; t < tiles_per_group; ++t) {
-        s1 += (double)p[((size_t)t * 2 + 0) * C + c];
-        s2 += (double)p[((size_t)t * 2 + 1) * C + c];
-    }
+    __shared__ double s_red[8][2][32];
+    const int cchunks = (C + 31) / 32;
+    const int gidx = blockIdx.x / cchunks, c = (blockIdx.x % cchunks) * 32 + (threadIdx.x & 31);
+    const int e = gidx * C + c;
+    double s1, s2;
+    sum_partials_32ch(partial + (size_t)gidx * tiles_per_group * 2 * C, tiles_per_group, C, c, c < C, s_red, s1, s2);
+    if (threadIdx.x >= 32 || c >= C) return;
     m1[e] = (float)(s1 / count);
     m2[e] = (float)(s2 / count);
     if (dgamma != nullptr && gidx == 0) {   // BatchNorm affine gradients: dgamma = sum g'*xhat, dbeta = sum g'
@@ -155,6 +175,98 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(float* __restrict__
         gg[q] = rs * ga * (gp - m1[so + q] - xh * m2[so + q]);
     }
     *reinterpret_cast<float4*>(g + e) = make_float4(gg[0], gg[1], gg[2], gg[3]);
+}
+
+// C in {64, 128, 256}: every thread owns one float4 channel group for the whole tile (all 256 threads busy for the
+// 64-channel maps, which are the largest), statistics hoisted into registers, rows unrolled for loads in flight.
+__global__ void __launch_bounds__(256) norm_bwd_reduce_pow2_kernel(const float* __restrict__ g, const float* __restrict__ x,
+                                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                   int P, int C, int groups_is_batch, float slope,
+                                                                   float* __restrict__ partial, int tiles_per_image) {
+    __shared__ float red[2][1024];
+    const int b = blockIdx.x / tiles_per_image, tile = blockIdx.x % tiles_per_image;
+    const int c4n = C >> 2, nrl = 256 / c4n;
+    const int cq = threadIdx.x % c4n, rl = threadIdx.x / c4n;
+    const int c = cq * 4;
+    const int p0 = tile * kBwdRows, p1 = min(P, p0 + kBwdRows);
+    const int so = (groups_is_batch ? b * C : 0) + c;
+    const float4 mu = *reinterpret_cast<const float4*>(mean + so), rs = *reinterpret_cast<const float4*>(rstd + so);
+    const float4 ga = gamma ? *reinterpret_cast<const float4*>(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 be = beta ? *reinterpret_cast<const float4*>(beta + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float mu_[4] = {mu.x, mu.y, mu.z, mu.w}, rs_[4] = {rs.x, rs.y, rs.z, rs.w};
+    const float ga_[4] = {ga.x, ga.y, ga.z, ga.w}, be_[4] = {be.x, be.y, be.z, be.w};
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    const float4* gp4 = reinterpret_cast<const float4*>(g + (size_t)b * P * C) + cq;
+    const float4* xp4 = reinterpret_cast<const float4*>(x + (size_t)b * P * C) + cq;
+#pragma unroll 4
+    for (int p = p0 + rl; p < p1; p += nrl) {
+        const float4 gv = __ldg(gp4 + (size_t)p * c4n);
+        const float4 xv = __ldg(xp4 + (size_t)p * c4n);
+        const float gg[4] = {gv.x, gv.y, gv.z, gv.w}, xx[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float xh = (xx[q] - mu_[q]) * rs_[q];
+            const float y = fmaf(xh, ga_[q], be_[q]);
+            const float gp = gg[q] * sdt::leaky_grad(y, slope);
+            s1[q] += gp;
+            s2[q] = fmaf(gp, xh, s2[q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        red[0][rl * C + c + q] = s1[q];
+        red[1][rl * C + c + q] = s2[q];
+    }
+    __syncthreads();
+    if (threadIdx.x < C) {
+        float a = 0.f, bsum = 0.f;
+        for (int r = 0; r < nrl; ++r) {
+            a += red[0][r * C + threadIdx.x];
+            bsum += red[1][r * C + threadIdx.x];
+        }
+        partial[((size_t)blockIdx.x * 2 + 0) * C + threadIdx.x] = a;
+        partial[((size_t)blockIdx.x * 2 + 1) * C + threadIdx.x] = bsum;
+    }
+}
+
+// grid (x, B): image from the block, a thread keeps ONE channel group across its grid-stride loop (stride is a
+// multiple of C/4), so the six statistic vectors are loaded once.
+__global__ void __launch_bounds__(256) norm_bwd_apply_pow2_kernel(float* __restrict__ g, const float* __restrict__ x,
+                                                                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  const float* __restrict__ m1, const float* __restrict__ m2,
+                                                                  long long per_image4, int C, int groups_is_batch, float slope) {
+    const int b = blockIdx.y;
+    const int c4n = C >> 2;
+    const long long e0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (int)(e0 % c4n) * 4;
+    const int so = (groups_is_batch ? b * C : 0) + c;
+    const float4 mu = *reinterpret_cast<const float4*>(mean + so), rs = *reinterpret_cast<const float4*>(rstd + so);
+    const float4 a1 = *reinterpret_cast<const float4*>(m1 + so), a2 = *reinterpret_cast<const float4*>(m2 + so);
+    const float4 ga = gamma ? *reinterpret_cast<const float4*>(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 be = beta ? *reinterpret_cast<const float4*>(beta + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float mu_[4] = {mu.x, mu.y, mu.z, mu.w}, rs_[4] = {rs.x, rs.y, rs.z, rs.w};
+    const float a1_[4] = {a1.x, a1.y, a1.z, a1.w}, a2_[4] = {a2.x, a2.y, a2.z, a2.w};
+    const float ga_[4] = {ga.x, ga.y, ga.z, ga.w}, be_[4] = {be.x, be.y, be.z, be.w};
+    float4* gi = reinterpret_cast<float4*>(g) + (size_t)b * per_image4;
+    const float4* xi = reinterpret_cast<const float4*>(x) + (size_t)b * per_image4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+#pragma unroll 4
+    for (long long e = e0; e < per_image4; e += stride) {
+        const float4 gv = gi[e];
+        const float4 xv = __ldg(xi + e);
+        float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+        const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float xh = (xx[q] - mu_[q]) * rs_[q];
+            const float y = fmaf(xh, ga_[q], be_[q]);
+            const float gp = gg[q] * sdt::leaky_grad(y, slope);
+            gg[q] = rs_[q] * ga_[q] * (gp - a1_[q] - xh * a2_[q]);
+        }
+        gi[e] = make_float4(gg[0], gg[1], gg[2], gg[3]);
+    }
 }
 
 // ---- channel LayerNorm (+ activation) over rows of (R, C): one warp per row ---------------------------
@@ -270,7 +382,7 @@ extern "C" int sdt_norm_finalize(const float* partial, int groups, int tiles_per
     SDT_REQUIRE(groups > 0 && tiles_per_group > 0 && C > 0 && count > 0, "sdt_norm_finalize: bad extents");
     SDT_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "sdt_norm_finalize: running stats come together");
     SDT_REQUIRE(running_mean == nullptr || groups == 1, "sdt_norm_finalize: running statistics need groups == 1 (BatchNorm)");
-    norm_finalize_kernel<<<sdt::ceil_div((long long)groups * C, 128), 128, 0, sdt::as_stream(stream)>>>(
+    norm_finalize_kernel<<<groups * sdt::ceil_div(C, 32), 256, 0, sdt::as_stream(stream)>>>(
         partial, groups, tiles_per_group, C, count, gamma, beta, eps, scale, shift, mean, rstd, running_mean, running_var,
         num_batches_tracked, momentum);
     SDT_LAUNCH_OK("norm_finalize_kernel");
@@ -293,9 +405,13 @@ extern "C" int sdt_norm_bwd_reduce(const float* g, const float* x, const float* 
     SDT_REQUIRE(B > 0 && P > 0 && C > 0 && C % 4 == 0, "sdt_norm_bwd_reduce: need C %% 4 == 0 (C=%d)", C);
     SDT_REQUIRE(groups == B || groups == 1, "sdt_norm_bwd_reduce: groups must be B or 1");
     SDT_REQUIRE(tiles_per_image == sdt::ceil_div(P, kBwdRows), "sdt_norm_bwd_reduce: tiles_per_image must be ceil(P/%d)", kBwdRows);
-    norm_bwd_reduce_kernel<<<B * tiles_per_image, 256, 0, sdt::as_stream(stream)>>>(g, x, mean, rstd, gamma, beta, P, C,
-                                                                                    groups == B ? 1 : 0,
-                                                                                    slope, partial, tiles_per_image);
+    if (C == 64 || C == 128 || C == 256)
+        norm_bwd_reduce_pow2_kernel<<<B * tiles_per_image, 256, 0, sdt::as_stream(stream)>>>(
+            g, x, mean, rstd, gamma, beta, P, C, groups == B ? 1 : 0, slope, partial, tiles_per_image);
+    else
+        norm_bwd_reduce_kernel<<<B * tiles_per_image, 256, 0, sdt::as_stream(stream)>>>(g, x, mean, rstd, gamma, beta, P, C,
+                                                                                        groups == B ? 1 : 0,
+                                                                                        slope, partial, tiles_per_image);
     SDT_LAUNCH_OK("norm_bwd_reduce_kernel");
     return SDT_OK;
 }
@@ -305,7 +421,7 @@ extern "C" int sdt_norm_bwd_finalize(const float* partial, int groups, int tiles
     SDT_REQUIRE(partial && m1 && m2, "sdt_norm_bwd_finalize: null pointer");
     SDT_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "sdt_norm_bwd_finalize: dgamma/dbeta come together");
     SDT_REQUIRE(dgamma == nullptr || groups == 1, "sdt_norm_bwd_finalize: affine gradients need groups == 1");
-    norm_bwd_finalize_kernel<<<sdt::ceil_div((long long)groups * C, 128), 128, 0, sdt::as_stream(stream)>>>(
+    norm_bwd_finalize_kernel<<<groups * sdt::ceil_div(C, 32), 256, 0, sdt::as_stream(stream)>>>(
         partial, groups, tiles_per_group, C, count, m1, m2, dgamma, dbeta, accumulate);
     SDT_LAUNCH_OK("norm_bwd_finalize_kernel");
     return SDT_OK;
@@ -318,8 +434,14 @@ extern "C" int sdt_norm_bwd_apply(float* g, const float* x, const float* mean, c
     SDT_REQUIRE(C % 4 == 0, "sdt_norm_bwd_apply: need C %% 4 == 0 (C=%d)", C);
     SDT_REQUIRE(groups == B || groups == 1, "sdt_norm_bwd_apply: groups must be B or 1");
     const long long total4 = (long long)B * P * C / 4;
-    norm_bwd_apply_kernel<<<sdt::ceil_div(total4, 256), 256, 0, sdt::as_stream(stream)>>>(g, x, mean, rstd, gamma, beta, m1, m2,
-                                                                                         total4, P, C, groups == B ? 1 : 0, slope);
+    if ((C == 64 || C == 128 || C == 256) && B <= 65535) {
+        const long long per_image4 = (long long)P * C / 4;
+        const int gx = (int)std::min<long long>(sdt::ceil_div(per_image4, 256 * 4), 4096);
+        norm_bwd_apply_pow2_kernel<<<dim3(gx, B), 256, 0, sdt::as_stream(stream)>>>(g, x, mean, rstd, gamma, beta, m1, m2,
+                                                                                  per_image4, C, groups == B ? 1 : 0, slope);
+    } else
+        norm_bwd_apply_kernel<<<sdt::ceil_div(total4, 256), 256, 0, sdt::as_stream(stream)>>>(g, x, mean, rstd, gamma, beta, m1, m2,
+                                                                                             total4, P, C, groups == B ? 1 : 0, slope);
     SDT_LAUNCH_OK("norm_bwd_apply_kernel");
     return SDT_OK;
 }

@@ -35,9 +35,11 @@ struct TileGeom {
     int tiles_x, tiles_y;  // patches per image
 };
 
-template <int BN>
+// DEEP: grids of at most one CTA per SM (the 1-D stacks) are latency-bound on the k loop, not on occupancy: give the
+// single resident CTA the whole shared memory as a 6-8 stage ring instead of leaving room for a second CTA.
+template <int BN, bool DEEP>
 struct TmaCfg {
-    static constexpr int STAGES = BN == 64 ? 4 : 3;
+    static constexpr int STAGES = DEEP ? (BN == 64 ? 8 : 6) : (BN == 64 ? 4 : 3);
     static constexpr int A_BYTES = BM * 128;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int BAR_BYTES = 256;
@@ -61,11 +63,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
-template <int BN>
-__global__ void __launch_bounds__(THREADS, 2) tc_conv_tma_kernel(const __grid_constant__ CUtensorMap tmA,
+template <int BN, bool DEEP>
+__global__ void __launch_bounds__(THREADS, DEEP ? 1 : 2) tc_conv_tma_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmB,
                                                                  const sdt_conv_desc d, const TileGeom tg) {
-    using Cfg = TmaCfg<BN>;
+    using Cfg = TmaCfg<BN, DEEP>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -238,13 +240,14 @@ TileGeom pick_geom(const sdt_conv_desc* d) {
     return best;
 }
 
-template <int BN>
+template <int BN, bool DEEP>
 int launch_tma(const sdt_conv_desc* d, const TileGeom& tg, cudaStream_t st) {
     EncodeTiledFn enc = get_encode();
     SDT_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
     static bool attr_set = false;
     if (!attr_set) {
-        SDT_CUDA_OK(cudaFuncSetAttribute(tc_conv_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TmaCfg<BN>::SMEM));
+        SDT_CUDA_OK(cudaFuncSetAttribute(tc_conv_tma_kernel<BN, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TmaCfg<BN, DEEP>::SMEM));
         attr_set = true;
     }
     alignas(64) CUtensorMap tmA, tmB;
@@ -270,7 +273,7 @@ int launch_tma(const sdt_conv_desc* d, const TileGeom& tg, cudaStream_t st) {
         SDT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed with %d", (int)r);
     }
     dim3 grid(d->B * tg.tiles_x * tg.tiles_y, d->N / BN);
-    tc_conv_tma_kernel<BN><<<grid, THREADS, TmaCfg<BN>::SMEM, st>>>(tmA, tmB, *d, tg);
+    tc_conv_tma_kernel<BN, DEEP><<<grid, THREADS, TmaCfg<BN, DEEP>::SMEM, st>>>(tmA, tmB, *d, tg);
     SDT_LAUNCH_OK("tc_conv_tma_kernel");
     sdt_note_tc_launch();
     return SDT_OK;
@@ -296,6 +299,7 @@ int sdt_tc_conv_tma_launch(const sdt_conv_desc* d, cudaStream_t st) {
     const long long tiles = (long long)d->B * tg.tiles_x * tg.tiles_y;
     int bn = d->N % 128 == 0 ? 128 : 64;
     if (bn == 128 && tiles * (d->N / 128) < 2 * 148) bn = 64;               // small problems: more CTAs
-    if (bn == 128) return launch_tma<128>(d, tg, st);
-    return launch_tma<64>(d, tg, st);
+    const bool deep = tiles * (d->N / bn) <= 148;
+    if (bn == 128) return deep ? launch_tma<128, true>(d, tg, st) : launch_tma<128, false>(d, tg, st);
+    return deep ? launch_tma<64, true>(d, tg, st) : launch_tma<64, false>(d, tg, st);
 }

@@ -250,6 +250,9 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
     self._mel = mel
     self._params = params
     self.materialize = ops.get_conv_math() == 2
+    # math mode 2 with InstanceNorm and an invertible activation: the 1 -> 64 first block runs as the single-pass special
+    # case (csrc/first_layer.cu): no raw map, no separate normalisation pass, closed-form weight gradient
+    self.fused_first = self.materialize and self.norm == "IN" and slope > 0.0
     self.wprep.ensure(self._all_layers(), params, with_dgrad=training)
     self.wprep.run()
     # ---- 2-D encoder: raw conv output + statistics; normalise/activate in the consumer's loader
@@ -259,12 +262,19 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
         name = ENC_PREFIX + lname
         H, W = self.enc_hw[l]
         oh, ow = self.enc_hw[l + 1]
+        sc = A.get("scale:" + name, (groups, co))
+        sh = A.get("shift:" + name, (groups, co))
+        if l == 0 and self.fused_first:
+            act = A.get("act2d:" + name, (B, oh, ow, co))
+            ops.first_layer_fwd(mel, params[name + ".conv.weight"], slope,
+                                out=(act, sc, sh, A.get("mom:" + name, (B, 54), torch.float64)),
+                                scratch=A.get("mom_partial:" + name, (B, ops.first_layer_units(H, W), 54), torch.float64))
+            src, xf = act, None
+            continue
         wt, wt_nk = self._prep_weight(name, params[name + ".conv.weight"], g)
         raw = A.get("raw:" + name, (B, oh, ow, co))
         use_batch_stats = self.norm == "IN" or training
         d = ops.fwd_desc(g, src, wt, raw, B, H, W, xf, slope, per_image=True, wt_nk=wt_nk)
-        sc = A.get("scale:" + name, (groups, co))
-        sh = A.get("shift:" + name, (groups, co))
         if use_batch_stats:
             partial = A.get("partial:" + name, (ops.row_tiles(d), 2, co))
             d.stat_partial = partial.data_ptr()
@@ -450,6 +460,12 @@ def _gen_backward(self, g_pred, grads, g_code=None):
         name = ENC_PREFIX + lname
         H, W = self.enc_hw[l]
         oh, ow = self.enc_hw[l + 1]
+        if l == 0 and self.fused_first:
+            ops.first_layer_bwd(g_enc, A.get("act2d:" + name, (B, oh, ow, co)), self._mel, params[name + ".conv.weight"],
+                                A.get("mom:" + name, (B, 54), torch.float64), A.get("scale:" + name, (groups, co)),
+                                A.get("shift:" + name, (groups, co)), slope, grads[name + ".conv.weight"],
+                                scratch=A.get("fl_partial:" + name, (B, ops.first_layer_units(H, W), 11, co)))
+            break
         raw = A.get("raw:" + name, (B, oh, ow, co))
         tpi = -(-(oh * ow) // ops.BWD_ROWS)
         scratch = (A.get("nb_partial:" + name, (B * tpi, 2, co)), A.get("nb_m1:" + name, (groups, co)), A.get("nb_m2:" + name, (groups, co)))

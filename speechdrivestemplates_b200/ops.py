@@ -389,6 +389,36 @@ def scale_shift_act(x, scale, shift, bstride, slope, out=None):
     return y
 
 
+def first_layer_units(H, W):
+    return call("sdt_first_layer_units", H, W)
+
+
+def first_layer_fwd(x, w, slope, eps=None, out=None, scratch=None):
+    """x (B,H,W) one-channel image, w (64,1,3,3) -> (act (B,H,W,64), scale (B,64), shift (B,64), moments (B,54) f64):
+    Conv2d(1,64,3,1,1) + InstanceNorm2d + LeakyReLU in one pass over the output (generator.py:17)."""
+    B, H, W = x.shape
+    Cc = w.shape[0]
+    units = first_layer_units(H, W)
+    if out is None:
+        out = (torch.empty(B, H, W, Cc, device=x.device), torch.empty(B, Cc, device=x.device),
+               torch.empty(B, Cc, device=x.device), torch.empty(B, 54, device=x.device, dtype=torch.float64))
+    act, sc, sh, mom = out
+    part = scratch if scratch is not None else torch.empty(B, units, 54, device=x.device, dtype=torch.float64)
+    call("sdt_first_layer_fwd", _p(x), _p(w), B, H, W, Cc, EPS_NORM if eps is None else eps, slope, _p(part), _p(mom), _p(sc), _p(sh), _p(act), _stream())
+    return act, sc, sh, mom
+
+
+def first_layer_bwd(g_act, act, x, w, mom, sc, sh, slope, dw, scratch=None):
+    """Weight gradient of the first block from dLoss/d act (IN + LeakyReLU backward folded in); dw (64,1,3,3) overwritten."""
+    B, H, W = x.shape
+    Cc = w.shape[0]
+    units = first_layer_units(H, W)
+    part = scratch if scratch is not None else torch.empty(B, units, 11, Cc, device=x.device)
+    call("sdt_first_layer_bwd", _p(g_act), _p(act), _p(x), _p(w), _p(mom), _p(sc), _p(sh), B, H, W, Cc, slope, _p(part), _p(dw),
+         _stream())
+    return dw
+
+
 # ------------------------------------------------------------------------------------------------
 # resampling / losses / heads / optimizer
 # ------------------------------------------------------------------------------------------------

@@ -451,6 +451,10 @@ class Voice2PoseTrainer:
         m.netG.engine().wg_stream = self._wg_stream
         self._overlap = True
         self._aux = None
+        self._inbox, self._prefetched = None, None
+        self._scal = torch.zeros(8, device=self.device, dtype=torch.float64)
+        self._scal_host = torch.zeros(2, 8, dtype=torch.float64).pin_memory()
+        self._scal_ev = [torch.cuda.Event(), torch.cuda.Event()]
         self._staging = None
         self._graphs = None
         self._warm = 0
@@ -485,6 +489,14 @@ class Voice2PoseTrainer:
                 scale=torch.empty(tuple(st["scale_factor"].shape), device=dev, dtype=torch.float64))
             self._graphs = None
         s = self._staging
+        if batch is self._prefetched:                   # uploaded ahead of time by prefetch(): device -> device hand-over
+            main = torch.cuda.current_stream()
+            main.wait_event(self._inbox_ready)
+            for k in ("audio", "poses", "idx", "mean", "std", "scale"):
+                s[k].copy_(self._inbox[k], non_blocking=True)
+            self._inbox_free.record(main)
+            self._prefetched = None
+            return s
         s["audio"].copy_(audio, non_blocking=True)
         s["poses"].copy_(poses, non_blocking=True)
         s["idx"].copy_(idx, non_blocking=True)
@@ -492,6 +504,27 @@ class Voice2PoseTrainer:
         s["std"].copy_(torch.as_tensor(st["std"]), non_blocking=True)
         s["scale"].copy_(torch.as_tensor(st["scale_factor"]), non_blocking=True)
         return s
+
+    def prefetch(self, batch):
+        """Start the host->device copy of a FUTURE batch on a copy stream, overlapping the step in flight.  The next
+        ``train_step(batch)`` with this very object picks the device copy up (one inbox: prefetch one batch ahead)."""
+        dev = self.device
+        st = batch["speaker_stat"]
+        src = dict(audio=batch["audio"], poses=batch["poses"], idx=batch["clip_index"], mean=torch.as_tensor(st["mean"]),
+                   std=torch.as_tensor(st["std"]), scale=torch.as_tensor(st["scale_factor"]))
+        if self._inbox is None or any(self._inbox[k].shape != v.shape for k, v in src.items()):
+            dt = dict(audio=torch.float32, poses=torch.float32, idx=torch.long, mean=torch.float64, std=torch.float64, scale=torch.float64)
+            self._inbox = {k: torch.empty(tuple(v.shape), device=dev, dtype=dt[k]) for k, v in src.items()}
+            self._copy_stream = torch.cuda.Stream()
+            self._inbox_ready, self._inbox_free = torch.cuda.Event(), torch.cuda.Event()
+            self._inbox_free.record(torch.cuda.current_stream())
+        cs = self._copy_stream
+        cs.wait_event(self._inbox_free)                 # the previous occupant has been handed over to the step's staging
+        with torch.cuda.stream(cs):
+            for k, v in src.items():
+                self._inbox[k].copy_(v, non_blocking=True)
+            self._inbox_ready.record(cs)
+        self._prefetched = batch
 
     # ---- the device program, in two halves around the all-reduce
     def _fwd_bwd(self):
@@ -501,6 +534,7 @@ class Voice2PoseTrainer:
         if not self._overlap:
             self.out = self.engine.forward(s["audio"], s["poses"], s["idx"], (s["mean"], s["std"], s["scale"]))
             self.engine.backward(self.grads, self.g_table)
+            self._pack_scalars()
             return
         self.out = self.engine.forward(s["audio"], s["poses"], s["idx"], (s["mean"], s["std"], s["scale"]), defer_side=True)
         # fork: FGD features + f64 results/metrics on a second stream while the backward pass runs on this one
@@ -515,6 +549,7 @@ class Voice2PoseTrainer:
             join.record(self._aux)
         self.engine.backward(self.grads, self.g_table)
         main.wait_event(join)
+        self._pack_scalars()
 
     def _optim(self):
         gs = 1.0 / self.world
@@ -568,14 +603,56 @@ class Voice2PoseTrainer:
         self._stage(batch)
         return self.run_staged()
 
-    def losses_to_host(self, out):
-        """One small D2H read of the step's scalars (the reference logs these every LOG_INTERVAL steps)."""
-        keys = ["G_reg_loss", "G_loss", "L2_dist", "lip_sync_error_n"] + (["G_clipcode_kl_loss", "kl_applied"] if "kl_applied" in out else [])
-        vals = torch.cat([out[k].double().view(1) for k in keys]).cpu().tolist()
-        d = dict(zip(keys, vals))
-        if "kl_applied" in d and d.pop("kl_applied") == 0.0:
+    _SCALARS = ("G_reg_loss", "G_loss", "L2_dist", "lip_sync_error_n", "G_clipcode_kl_loss", "kl_applied")
+
+    def _pack_scalars(self):
+        """Last node of the step: the loss / metric scalars as one f64 vector (a single 64-byte D2H read per step)."""
+        for i, k in enumerate(self._SCALARS):
+            if k in self.out:
+                self._scal[i:i + 1].copy_(self.out[k])
+
+    def _scalars_dict(self, vals):
+        d = {k: v for k, v in zip(self._SCALARS, vals) if k in self.out}
+        if "kl_applied" in d and d.pop("kl_applied") == 0.0:          # the reference's guard (voice2pose.py:154)
             d.pop("G_clipcode_kl_loss")
         return d
+
+    def losses_to_host(self, out=None):
+        """One small D2H read of the last step's scalars (the reference logs these every LOG_INTERVAL steps). Blocking."""
+        return self._scalars_dict(self._scal.cpu().tolist())
+
+    def post_losses(self, slot):
+        """Asynchronous variant: enqueue the D2H of the last step's scalars into pinned slot 0/1; collect_losses(slot)
+        waits for exactly that copy, so the host can run one step ahead of the device."""
+        self._scal_host[slot].copy_(self._scal, non_blocking=True)
+        self._scal_ev[slot].record(torch.cuda.current_stream())
+
+    def collect_losses(self, slot):
+        self._scal_ev[slot].synchronize()
+        return self._scalars_dict(self._scal_host[slot].tolist())
+
+    def run_epoch(self, batches, on_losses=None):
+        """The reference's inner loop (trainer.py: ``for batch in dataloader: train_step; log``) as a software pipeline:
+        batch k+1 is uploaded on a copy stream while step k runs, and the scalars of step k are read while step k+1 is
+        already enqueued.  ``on_losses(step_index, dict)`` is called for EVERY step, in order.  Returns the step count."""
+        it = iter(batches)
+        nxt = next(it, None)
+        if nxt is not None:
+            self.prefetch(nxt)
+        k, pending = 0, None
+        while nxt is not None:
+            self.train_step(nxt)
+            nxt = next(it, None)
+            if nxt is not None:
+                self.prefetch(nxt)
+            self.post_losses(k & 1)
+            if pending is not None and on_losses is not None:
+                on_losses(pending, self.collect_losses(pending & 1))
+            pending = k
+            k += 1
+        if pending is not None and on_losses is not None:
+            on_losses(pending, self.collect_losses(pending & 1))
+        return k
 
 
 # ------------------------------------------------------------------------------------------------

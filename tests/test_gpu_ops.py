@@ -172,8 +172,9 @@ def test_conv1d_dgrad_wgrad(ops, cfg):
 
 # ---------------------------------------------------------------- normalisation
 @pytest.mark.parametrize("mode", ["IN", "BN"])
-def test_norm_finalize_and_backward(ops, mode):
-    B, Cc, H, W = 4, 64, 9, 31
+@pytest.mark.parametrize("Cc", [64, 128, 256, 40])
+def test_norm_finalize_and_backward(ops, mode, Cc):
+    B, H, W = 4, 9, 31         # 279 pixels: one full 256-row tile + a ragged one; Cc=40 takes the generic kernels
     g = torch.Generator().manual_seed(5)
     x = (torch.randn(B, Cc, H, W, generator=g, dtype=torch.float64) * 2 + 0.3).requires_grad_(True)
     gamma = (torch.rand(Cc, generator=g, dtype=torch.float64) + 0.5).requires_grad_(True)
@@ -375,3 +376,41 @@ def test_pose_kernels_bit_exact(ops, parted):
     om = O.evaluate_step(ref, other)
     assert abs(met[0] - om["L2_dist"]) < 1e-12 * om["L2_dist"]
     assert abs(met[1] - om["lip_sync_error_n"]) < 1e-12 * max(1.0, om["lip_sync_error_n"])
+
+
+# ---------------------------------------------------------------- first block of the audio encoder (special case)
+@pytest.mark.parametrize("shape", [(3, 80, 427), (2, 7, 1100), (1, 80, 33)])
+@pytest.mark.parametrize("slope", [0.2, 1.0])
+def test_first_layer_fwd_bwd_vs_fp64_torch(ops, shape, slope):
+    """Conv2d(1,64,3,1,1, bias=False) + InstanceNorm2d + LeakyReLU (generator.py:17): single-pass forward from the
+    closed-form statistics and closed-form weight gradient, against torch in fp64 (autograd for the gradient).  The
+    input is a power mel-like image (positive, heavy-tailed), where E[x^2]-E[x]^2 would cancel in fp32."""
+    B, H, W = shape
+    gen = torch.Generator().manual_seed(5)
+    x = (torch.randn(B, H, W, generator=gen).abs() ** 3 * 4.0 + 50.0 * torch.rand(B, 1, W, generator=gen)).float()
+    w = (torch.randn(64, 1, 3, 3, generator=gen) / 3.0).float()
+    g = torch.randn(B, H, W, 64, generator=gen).float() * 1e-3
+    wd = w.double().requires_grad_(True)
+    raw = F.conv2d(x.double().unsqueeze(1), wd, padding=1)
+    ref = F.leaky_relu(F.instance_norm(raw, eps=1e-5), slope)
+    ref.backward(from_cl(g.double()))
+    act, sc, sh, mom = ops.first_layer_fwd(x.to(dev()), w.to(dev()), slope)
+    torch.cuda.synchronize()
+    mean = raw.mean((2, 3)).detach()
+    rstd = 1.0 / torch.sqrt(raw.var((2, 3), unbiased=False) + 1e-5).detach()
+    assert rel(sc, rstd) < 1e-5 and rel(sh, -mean * rstd) < 1e-5
+    assert rel(act, to_cl(ref)) < 2e-5
+    dw = torch.empty(64, 1, 3, 3, device=dev())
+    # the kernel recovers the pre-activation from act: feed it its own forward output, as the engine does
+    ops.first_layer_bwd(g.to(dev()), act, x.to(dev()), w.to(dev()), mom, sc, sh, slope, dw)
+    torch.cuda.synchronize()
+    assert rel(dw, wd.grad) < (2e-4 if slope == 1.0 else 3e-3), rel(dw, wd.grad)     # slope<1: a few sign flips near 0
+
+
+def test_first_layer_rejects_non_invertible_activation(ops):
+    from speechdrivestemplates_b200._lib import SdtError
+    x = torch.rand(1, 8, 16, device=dev())
+    w = torch.rand(64, 1, 3, 3, device=dev())
+    act, sc, sh, mom = ops.first_layer_fwd(x, w, 0.0)
+    with pytest.raises(SdtError):
+        ops.first_layer_bwd(torch.zeros_like(act), act, x, w, mom, sc, sh, 0.0, torch.empty_like(w))

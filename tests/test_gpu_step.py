@@ -250,6 +250,39 @@ def test_full_size_properties():
     assert float(g_table[touched.to(dev())].abs().min()) >= 0.0 and float(g_table.abs().max()) > 0.0
 
 
+def test_run_epoch_pipeline_equals_step_by_step():
+    """Voice2PoseTrainer.run_epoch (H2D prefetch one batch ahead on a copy stream, scalars read one step behind, CUDA
+    graphs) gives bit-identical losses and parameters to calling train_step + losses_to_host batch by batch."""
+    from speechdrivestemplates_b200 import pipeline
+    from oracle import sdt_oracle as O
+    n_train, bs, steps = 64, 4, 7
+    batches = []
+    for i in range(steps):
+        hb = _to_host_batch(O.synthetic_batch(bs, n_train, oliver_stat(True), seed=300 + i))
+        batches.append({k: (v.pin_memory() if torch.is_tensor(v) and k != "num_frames" else v) for k, v in hb.items()})
+    runs = []
+    for mode in ("serial", "pipelined"):
+        tr = pipeline.Voice2PoseTrainer(_cfg("voice2pose_sdt_bp"), n_train, dev(), use_cuda_graph=True, seed=0)
+        tr.model.clips_code.data.copy_(0.1 * torch.randn(n_train, 32, generator=torch.Generator().manual_seed(11)))
+        got = []
+        if mode == "serial":
+            for b in batches:
+                got.append(tr.losses_to_host(tr.train_step(b)))
+        else:
+            order = []
+            n = tr.run_epoch(iter(batches), on_losses=lambda i, d: (order.append(i), got.append(d)))
+            assert n == steps and order == list(range(steps))
+        torch.cuda.synchronize()
+        assert tr._graphs is not None
+        runs.append((got, tr.flat_p.clone(), tr.exp_avg_sq.clone()))
+    for a, b in zip(runs[0][0], runs[1][0]):
+        assert a.keys() == b.keys()
+        for k in a:
+            assert a[k] == b[k], (k, a[k], b[k])
+    assert torch.equal(runs[0][1], runs[1][1]) and torch.equal(runs[0][2], runs[1][2])
+
+
+@pytest.mark.gpu
 def test_sdt_vae_step_external_frozen_code(tmp_path):
     """BASELINE configs[2] (voice2pose_sdt_vae): the clip code is a frozen lookup into clip_code_mu of a pose2pose
     checkpoint (voice2pose.py:40-55); the KL term is computed but constant; FGD encoder weights come from the same file."""

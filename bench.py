@@ -204,7 +204,7 @@ def run_own(args):
         pg = dist.group.WORLD
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
 
-    conv_math = {"fp32": 0, "tf32": 1, "tf32-tma": 2}[args.math]
+    conv_math = {"fp32": 0, "tf32": 1, "tf32-tma": 2, "tf32-reuse": 3}[args.math]
     tr = pipeline.Voice2PoseTrainer(config.get_cfg("voice2pose_sdt_bp"), N_TRAIN, dev, use_cuda_graph=not args.no_graph,
                                     process_group=pg, seed=0, conv_math=conv_math)
     tr.model.clips_code.data.copy_(0.1 * torch.randn(N_TRAIN, 32, generator=torch.Generator().manual_seed(11)))
@@ -325,7 +325,9 @@ def run_own(args):
                    "n_train_clips": N_TRAIN, "cuda_graph": tr._graphs is not None,
                    "l2": "no explicit flush: each step streams ~%.1f GB of activations/gradients (>> 126 MB L2) and rotates over 4 distinct input batches" % (tr.model.netG.engine().arena.nbytes() / 1e9),
                    "conv_math": ["fp32 FFMA", "tcgen05 TF32 operands, fp32 accumulate (FFMA for ineligible layers)",
-                                 "tcgen05 TF32, TMA-fed operands for forward/dgrad, fp32 accumulate (FFMA for ineligible layers)"][conv_math]},
+                                 "tcgen05 TF32, TMA-fed operands for forward/dgrad, fp32 accumulate (FFMA for ineligible layers)",
+                                 "tcgen05 TF32, TMA-fed operands reused across vertical taps and accumulators in shared memory, fp32 "
+                                 "accumulate (FFMA for ineligible layers)"][conv_math]},
         "e2e": {"value": clips / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / K, "wall_s": wall_e2e},
         "gpu_launches": launches_per_step * K * 2,
@@ -345,7 +347,7 @@ def main():
     ap.add_argument("--impl", default="own")
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU (BASELINE configs[1]: 32)")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--math", default="tf32-tma", choices=["fp32", "tf32", "tf32-tma"],
+    ap.add_argument("--math", default="tf32-reuse", choices=["fp32", "tf32", "tf32-tma", "tf32-reuse"],
                     help="convolution math: fp32 FFMA kernels or tcgen05 TF32 tensor-core kernels (fp32 accumulate)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

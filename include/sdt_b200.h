@@ -37,7 +37,11 @@ int sdt_version(void);
  *   1 = tcgen05 tensor cores, TF32 operands, fp32 accumulation in TMEM, operand tiles built by producer warps
  *       (supports the loader transform) -- for shapes with C % 32 == 0 and N in {64,128,256}, FFMA otherwise;
  *   2 = as 1, plus TMA (cp.async.bulk.tensor) operand delivery for forward / data-gradient launches whose source is a
- *       plain tensor (no loader transform): the caller materialises activations for those layers. */
+ *       plain tensor (no loader transform): the caller materialises activations for those layers;
+ *   3 = as 2, plus operand reuse in shared memory for 2-D maps (csrc/tc_conv_ytap.cu): one TMA box serves all the
+ *       vertical taps of a kernel column and one weight box serves several accumulators -- the L2 -> shared-memory
+ *       traffic, which bounds mode 2, drops 2-3x.  Same arithmetic as mode 2 (same products, fp32 accumulation in a
+ *       different order). */
 int sdt_set_conv_math(int mode);
 int sdt_get_conv_math(void);
 /* number of tcgen05 kernel launches made by this process so far (lets callers/tests verify which path ran) */
@@ -98,6 +102,10 @@ typedef struct sdt_conv_desc {
 /* number of row tiles sdt_conv_gemm will use for this descriptor (size of stat_partial's first dim) */
 int sdt_conv_row_tiles(const sdt_conv_desc* d);
 int sdt_conv_gemm(const sdt_conv_desc* d, void* stream);
+/* which kernel sdt_conv_gemm would launch for this descriptor under the current math mode (host-only, no launch):
+ * out10[0] = 0 fp32 FFMA, 1 tcgen05 (producer warps), 2 tcgen05 + TMA, 3 tcgen05 + TMA + shared-memory reuse; for 3 also
+ * out10[1..9] = N tile, accumulators per CTA, patch rows, patch cols, box rows, A stages, B stages, shared memory, CTAs */
+int sdt_conv_plan(const sdt_conv_desc* d, int32_t* out10);
 /* wgrad: contractions with K = TH*TW*C <= 16 and N <= 64 (first encoder layer) use a streaming kernel whose CTA count
  * equals `splits`; otherwise split-K GEMM tiles (FFMA, or tcgen05 in math mode 1 when C % 32 == 0, N in {64,128,256}). */
 int sdt_conv_wgrad(const sdt_conv_desc* d, void* stream);

@@ -25,7 +25,7 @@ void set_error(const char* fmt, ...) {
 extern "C" const char* sdt_last_error(void) { return g_err; }
 extern "C" int sdt_version(void) { return 100; }
 extern "C" int sdt_set_conv_math(int mode) {
-    SDT_REQUIRE(mode >= 0 && mode <= 2, "sdt_set_conv_math: mode must be 0 (fp32 FFMA), 1 (tcgen05 TF32) or 2 (tcgen05 TF32 + TMA operands)");
+    SDT_REQUIRE(mode >= 0 && mode <= 3, "sdt_set_conv_math: mode must be 0 (fp32 FFMA), 1 (tcgen05 TF32), 2 (tcgen05 TF32 + TMA operands) or 3 (2 + shared-memory operand reuse)");
     g_conv_math.store(mode);
     return SDT_OK;
 }

@@ -658,13 +658,30 @@ inline int pick_bm(const sdt_conv_desc* d) {
 
 }  // namespace
 
-inline bool use_tma(const sdt_conv_desc* d) { return sdt_get_conv_math() == 2 && sdt_tc_conv_tma_eligible(d); }
+inline bool use_ytap(const sdt_conv_desc* d) { return sdt_get_conv_math() == 3 && sdt_tc_conv_ytap_eligible(d); }
+inline bool use_tma(const sdt_conv_desc* d) { return sdt_get_conv_math() >= 2 && sdt_tc_conv_tma_eligible(d); }
 inline bool use_tc(const sdt_conv_desc* d) { return sdt_get_conv_math() >= 1 && sdt_tc_conv_eligible(d); }
 
 extern "C" int sdt_conv_row_tiles(const sdt_conv_desc* d) {
     if (check_desc(d, "sdt_conv_row_tiles") != SDT_OK) return -1;
+    if (use_ytap(d)) return sdt_tc_conv_ytap_row_tiles(d);
     if (use_tma(d)) return sdt_tc_conv_tma_row_tiles(d);
     return row_tiles_for(d, use_tc(d) ? 128 : pick_bm(d));
+}
+
+extern "C" int sdt_conv_plan(const sdt_conv_desc* d, int32_t* out10) {
+    if (int rc = check_desc(d, "sdt_conv_plan")) return rc;
+    SDT_REQUIRE(out10 != nullptr, "sdt_conv_plan: null output");
+    for (int i = 0; i < 10; ++i) out10[i] = 0;
+    if (sdt_get_conv_math() == 3 && sdt_tc_conv_ytap_shape_ok(d)) {
+        out10[0] = 3;
+        sdt_tc_conv_ytap_describe(d, out10);
+    } else if (use_tma(d)) {
+        out10[0] = 2;
+    } else if (use_tc(d)) {
+        out10[0] = 1;
+    }
+    return SDT_OK;
 }
 
 extern "C" int sdt_conv_gemm(const sdt_conv_desc* d, void* stream) {
@@ -673,6 +690,7 @@ extern "C" int sdt_conv_gemm(const sdt_conv_desc* d, void* stream) {
     SDT_REQUIRE(!(d->stat_partial && d->bias), "sdt_conv_gemm: statistics epilogue excludes bias");
     SDT_REQUIRE(!(d->stat_partial && d->accumulate), "sdt_conv_gemm: statistics epilogue excludes accumulate");
     cudaStream_t st = sdt::as_stream(stream);
+    if (use_ytap(d)) return sdt_tc_conv_ytap_launch(d, st);                     // math mode 3: + operand reuse in shared memory
     if (use_tma(d)) return sdt_tc_conv_tma_launch(d, st);                       // math mode 2: tcgen05 TF32, TMA operands
     if (use_tc(d)) return sdt_tc_conv_launch(d, row_tiles_for(d, 128), st);   // math mode 1/2: tcgen05 TF32
     SDT_REQUIRE(d->wt != nullptr, "sdt_conv_gemm: the FFMA path needs the (K,N) operand `wt` (tcgen05 path not eligible here)");
@@ -703,7 +721,7 @@ extern "C" int sdt_conv_wgrad(const sdt_conv_desc* d, void* stream) {
     const int Kc = d->TH * d->TW * d->C;
     const bool veca = (d->N % 4) == 0, vecb = (d->C % 4) == 0;
     cudaStream_t st = sdt::as_stream(stream);
-    if (sdt_get_conv_math() == 2 && sdt_tc_wgrad_tma_eligible(d)) return sdt_tc_wgrad_tma_launch(d, st);   // tcgen05 + TMA
+    if (sdt_get_conv_math() >= 2 && sdt_tc_wgrad_tma_eligible(d)) return sdt_tc_wgrad_tma_launch(d, st);   // tcgen05 + TMA
     if (sdt_get_conv_math() >= 1 && sdt_tc_wgrad_eligible(d)) return sdt_tc_wgrad_launch(d, st);   // tcgen05 TF32
     if (Kc <= 16 && d->N <= 64) {       // tiny contraction: streaming kernel, one partial per CTA (gridDim.x == splits)
         conv_wgrad_smallk_kernel<<<d->splits, 256, 0, st>>>(*d);

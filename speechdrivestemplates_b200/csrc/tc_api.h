@@ -11,6 +11,11 @@ int sdt_tc_wgrad_launch(const sdt_conv_desc* d, cudaStream_t st);
 bool sdt_tc_conv_tma_eligible(const sdt_conv_desc* d);
 int sdt_tc_conv_tma_row_tiles(const sdt_conv_desc* d);
 int sdt_tc_conv_tma_launch(const sdt_conv_desc* d, cudaStream_t st);
+bool sdt_tc_conv_ytap_eligible(const sdt_conv_desc* d);
+bool sdt_tc_conv_ytap_shape_ok(const sdt_conv_desc* d);
+int sdt_tc_conv_ytap_row_tiles(const sdt_conv_desc* d);
+int sdt_tc_conv_ytap_describe(const sdt_conv_desc* d, int32_t* out10);
+int sdt_tc_conv_ytap_launch(const sdt_conv_desc* d, cudaStream_t st);
 bool sdt_tc_wgrad_tma_eligible(const sdt_conv_desc* d);
 int sdt_tc_wgrad_tma_launch(const sdt_conv_desc* d, cudaStream_t st);
 void sdt_note_tc_launch();

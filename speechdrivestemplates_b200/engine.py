@@ -249,7 +249,7 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
     self.fwd_id += 1
     self._mel = mel
     self._params = params
-    self.materialize = ops.get_conv_math() == 2
+    self.materialize = ops.get_conv_math() >= 2
     # math mode 2 with InstanceNorm and an invertible activation: the 1 -> 64 first block runs as the single-pass special
     # case (csrc/first_layer.cu): no raw map, no separate normalisation pass, closed-form weight gradient
     self.fused_first = self.materialize and self.norm == "IN" and slope > 0.0

@@ -127,7 +127,8 @@ class ConvGeom:
 
 
 def set_conv_math(mode):
-    """0 = fp32 FFMA kernels, 1 = tcgen05 TF32 tensor-core kernels where a layer is eligible (process-wide)."""
+    """0 = fp32 FFMA kernels, 1 = tcgen05 TF32 tensor-core kernels where a layer is eligible, 2 = 1 with TMA-delivered
+    operands, 3 = 2 with shared-memory operand reuse across vertical taps / accumulators (process-wide)."""
     call("sdt_set_conv_math", int(mode))
 
 

@@ -193,13 +193,76 @@ def test_sdt_bp_train_step_tf32_mode_vs_reference_fixture(mode):
         o.set_conv_math(0)
 
 
-# ---------------------------------------------------------------- math mode 2: TMA-fed tcgen05 kernel
-@pytest.fixture()
-def ops_tma():
+# ---------------------------------------------------------------- math modes 2 / 3: TMA-fed tcgen05 kernels
+# (3 = operand reuse across vertical taps and accumulators in shared memory, csrc/tc_conv_ytap.cu)
+@pytest.fixture(params=[2, 3], ids=["tma", "reuse"])
+def ops_tma(request):
     from speechdrivestemplates_b200 import ops as o
-    o.set_conv_math(2)
+    o.set_conv_math(request.param)
     yield o
     o.set_conv_math(0)
+
+
+# geometries that stress the sub-tile bookkeeping of mode 3: odd sub-tile counts (last CTA partially filled), maps much
+# smaller than a patch, tall kernels, batch 1
+REUSE_GEOMS = [
+    # cin, cout, kh, kw, s, p, H, W, B
+    (64, 64, 3, 3, 1, 1, 7, 9, 1),
+    (64, 64, 3, 3, 1, 1, 40, 213, 1),
+    (64, 128, 3, 3, 1, 1, 33, 50, 3),
+    (128, 64, 4, 4, 2, 1, 30, 62, 5),
+    (64, 256, 6, 3, 1, 0, 10, 53, 3),
+    (128, 256, 3, 3, 1, 1, 17, 23, 2),
+    (64, 64, 5, 5, 1, 2, 19, 21, 2),
+]
+
+
+@pytest.mark.parametrize("cfg", REUSE_GEOMS)
+def test_reuse_forward_and_dgrad_odd_geometries(cfg):
+    from speechdrivestemplates_b200 import ops
+    cin, cout, kh, kw, s, p, H, W, B = cfg
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(B, cin, H, W, generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(cout, cin, kh, kw, generator=g, dtype=torch.float64) / math.sqrt(cin * kh * kw)
+    y = F.conv2d(x, w, None, s, p)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(dy)
+    geom = ops.ConvGeom.conv2d(cin, cout, kh, kw, s, p)
+    ops.set_conv_math(3)
+    try:
+        n0 = tc_launches()
+        yk, partial = ops.conv_forward(to_cl(x.detach().float()).to(dev()), w.float().to(dev()).contiguous(), geom, want_stats=True,
+                                       per_image=True)
+        dx = ops.conv_dgrad(to_cl(dy.float()).to(dev()), w.float().to(dev()).contiguous(), geom, H, W)
+        torch.cuda.synchronize()
+        assert tc_launches() > n0
+    finally:
+        ops.set_conv_math(0)
+    assert rel(from_cl(yk), y) < TF32_TOL
+    assert rel(from_cl(dx), x.grad) < TF32_TOL
+    tiles = partial.shape[0] // B
+    ps = partial.view(B, tiles, 2, cout).double().sum(1).cpu()
+    got = from_cl(yk).double().cpu()
+    assert rel(ps[:, 0], got.sum((2, 3))) < 1e-4
+    assert rel(ps[:, 1], (got * got).sum((2, 3))) < 1e-4
+
+
+def test_reuse_matches_tma_mode_bitwise_products():
+    """Modes 2 and 3 multiply the same TF32-rounded operands; only the fp32 accumulation order differs."""
+    from speechdrivestemplates_b200 import ops
+    cin, cout, kh, kw, s, p, H, W, B = GEOMS[1]
+    g = torch.Generator().manual_seed(42)
+    x = to_cl(torch.randn(B, cin, H, W, generator=g)).to(dev())
+    w = (torch.randn(cout, cin, kh, kw, generator=g) / math.sqrt(cin * kh * kw)).to(dev())
+    geom = ops.ConvGeom.conv2d(cin, cout, kh, kw, s, p)
+    outs = []
+    for mode in (2, 3):
+        ops.set_conv_math(mode)
+        try:
+            outs.append(ops.conv_forward(x, w, geom).clone())
+        finally:
+            ops.set_conv_math(0)
+    assert rel(outs[1], outs[0]) < 2e-6
 
 
 @pytest.mark.parametrize("cfg", GEOMS)

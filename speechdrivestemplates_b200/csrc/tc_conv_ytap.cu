@@ -1,23 +1,33 @@
-// Convolution forward / data-gradient on tcgen05 (TF32), TMA operands, with operand REUSE in shared memory (math mode 3).
+// Convolution forward / data-gradient on tcgen05 (TF32), TMA operands, operand reuse in shared memory, persistent CTAs
+// with double-buffered accumulators (math mode 3).
 //
-// Why: tc_conv_tma.cu fetches one 128-pixel x 32-channel A box (16 KB) and one weight box per (tap, channel chunk), i.e.
-// 24-32 KB of L2 -> shared-memory traffic per 128x{64,128}x32 MMA block.  Every encoder layer measured at the same
-// ~12 TB/s of L2 -> SM traffic (profiles/r2_l2_bound_analysis.md): the kernel sits on the chip's L2 bandwidth cap
-// (~6300 B/clk), not on the tensor pipe (22-33 %).  This kernel moves fewer bytes per FLOP:
+// What the measurements on tc_conv_tma.cu (mode 2) said (tests/diag_conv_timeline.py, profiles/r1_conv_mode3_*.txt):
+//   * its issue loops run inside `if (lane == 0)`: ptxas then treats every operand as lane-varying and wraps each
+//     UTCHMMA / UTMALDG in an ELECT + 5 x R2UR + BRA.U.ANY waterfall -- ~200 clk of issue per 64-clk MMA;
+//   * one tile per CTA: the co-resident CTAs of an SM, and in fact the whole chip, run in lockstep -- a main-loop phase with
+//     idle HBM, then an epilogue phase (every CTA storing) with an idle tensor pipe, each about half of the time;
+//   * the epilogue stored from the tcgen05.ld layout: 16 bytes to each of 32 different lines per instruction, and the
+//     address arithmetic (runtime division by the patch width) dominated its instruction count.
+// This kernel:
+//   * whole-warp issue loops, `elect.sync` only around the instructions that must come from one thread; all operands are
+//     warp-uniform (uniform registers, no waterfall); descriptors are built from a constant high word + a 32-bit low word;
+//   * the issuing warps have the HIGHEST warp ids (the SM sub-partition arbiter prefers high warp ids): the instruction-heavy
+//     epilogue warps never delay an MMA / TMA issue;
+//   * persistent: one CTA per SM walks tiles round-robin; the accumulators of tile i (MT*BN TMEM columns) are drained by the
+//     epilogue warps while the MMA warp fills the other set with tile i+1; the TMA rings run ahead across tiles;
+//   * y-tap reuse: GEMM rows of a sub-tile are a (bh x bw) patch of output pixels ordered (py, px) with bw % 8 == 0, so the
+//     A operands of the vertical taps of one kernel column are the SAME box shifted by whole patch rows = multiples of the
+//     1024-byte swizzle atom: ONE box of (bh + taps - 1) patch rows per (channel chunk, tx, y-phase), each tap a different
+//     start address in the matrix descriptor (3x3: 3 boxes of 18 rows instead of 9 of 16);
+//   * weight reuse: MT sub-tiles (MT accumulators) per CTA share every weight box;
+//   * epilogue: TMEM -> registers -> padded shared-memory chunk -> full 128-byte row segments, 4 rows per store instruction,
+//     row pointers computed once per sub-tile; masked column statistics from the staged chunk.
 //
-//   * y-tap reuse.  GEMM rows of a sub-tile are a (bh x bw) patch of output pixels ordered (py, px) with bw % 8 == 0.
-//     For a fixed horizontal tap tx, the A operands of the vertical taps ty are the SAME pixels shifted by whole patch
-//     rows, i.e. by bw rows of 128 B = a multiple of the 1024-byte swizzle atom.  So ONE box of (bh + max_shift) patch
-//     rows is loaded per (channel chunk, tx, y-phase) and each ty is just a different start address in the shared-memory
-//     matrix descriptor (3x3: 3 boxes of 18 rows instead of 9 boxes of 16; 4x4 stride 2: two y-phases x 4 tx boxes of
-//     17 rows instead of 16 boxes of 16).
-//   * weight reuse.  A CTA owns MT sub-tiles (MT accumulators in TMEM, MT*BN columns); every weight box is used by
-//     MT * 4 MMAs instead of 4.
+//   * two MMA-issuing warps, one per accumulator (sub-tile): the tensor pipe accepts about one MMA ahead of the one it is
+//     executing (measured: per tap, time = issue-loop overhead + 8 x 64 clk, not the maximum of the two), so a single
+//     issuing thread's loop overhead (~50 clk per MMA) is exposed; two threads hide each other's.
 //
-//   warp 0  : TMA producer (one thread), two rings: A stages (MT boxes each) and B stages (one weight box per tap).
-//   warp 1  : MMA issuer (one thread), owns the TMEM allocation.
-//   warps 2-5: epilogue per sub-tile: tcgen05.ld, bias / accumulate, 128-byte row stores, masked column statistics.
-// Two CTAs per SM (<= ~110 KB shared memory, <= 256 TMEM columns each): one CTA's epilogue overlaps the other's main loop.
+//   warps 0-3: epilogue (TMEM lane quadrant = warp id)   warp 4: TMA producer   warps 5,6: MMA issuers (5 owns the TMEM allocation)
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -29,27 +39,45 @@ namespace {
 using namespace sdt_tc;
 
 constexpr int BKF = 32;
-constexpr int THREADS = 192;
+constexpr int THREADS = 224;          // 4 epilogue warps, TMA producer, two MMA issuers
+constexpr int EPI_THREADS = 128;
 constexpr int MAX_TH = 8;
+constexpr int MAX_GROUPS = 4;
 constexpr int B_RING_MAX = 6, A_RING_MAX = 4;
-constexpr int SMEM_TWO_PER_SM = 113 * 1024;   // 2 x (113 + 1 reserved) KB == 228 KB
-constexpr int SMEM_ONE_PER_SM = 200 * 1024;
-constexpr int TAIL_BYTES = (2 * A_RING_MAX + 2 * B_RING_MAX + 1) * 8 + 16;   // barriers, TMEM slot
+constexpr int SMEM_MAX = 227 * 1024;          // one persistent CTA per SM
+constexpr int N_BARS = 2 * A_RING_MAX + 2 * B_RING_MAX + 4;
+constexpr int TAIL_BYTES = N_BARS * 8 + 16;   // barriers, TMEM slot
+constexpr int STG_PITCH = 36;                 // floats per staged row: 32 columns + 4 (conflict-free 128-bit rows)
+// epilogue scratch: 4 warps x 32 rows x STG_PITCH staging + statistics partials [MT][2][4][BN]
+#define EPI_BYTES(BN_, MT_) (4 * 32 * STG_PITCH * 4 + (MT_) * 2 * 4 * (BN_) * 4)
 
 struct YGeom {
     int bw, bh;              // sub-tile patch (bw * bh == 128, bw % 8 == 0)
+    int lbw;                 // log2(bw)
     int tiles_x, tiles_y;    // patches per image
     int subtiles;            // B * tiles_x * tiles_y
-    int box_rows;            // bh + max vertical shift
+    int box_rows;            // bh + (taps per group - 1)
     int a_box_bytes;         // box_rows * bw * 128
-    int n_phase;             // distinct y phases (boxes per (chunk, tx))
     int a_stages, b_stages;
-    int y_org;               // added to y0*y_mul + y_off + phase for the box origin
-    int bar_off;             // byte offset of the barrier block = max(ring bytes, epilogue staging bytes)
-    int phase[MAX_TH];       // per ty
-    int shift[MAX_TH];       // per ty, in patch rows
+    int n_groups;            // tap groups = boxes per (channel chunk, tx)
+    // per group, 16 bits: [3:0] y_add + 8 (box origin = y0*y_mul + y_off + y_add), [7:4] taps, [11:8] first ty, [15:12] ty step + 8;
+    // tap j of a group reads the box shifted by j patch rows
+    unsigned long long groups;
 };
+__host__ __device__ __forceinline__ int grp_y_add(unsigned long long p, int gi) { return (int)((p >> (16 * gi)) & 15u) - 8; }
+__host__ __device__ __forceinline__ int grp_taps(unsigned long long p, int gi) { return (int)((p >> (16 * gi + 4)) & 15u); }
+__host__ __device__ __forceinline__ int grp_ty0(unsigned long long p, int gi) { return (int)((p >> (16 * gi + 8)) & 15u); }
+__host__ __device__ __forceinline__ int grp_step(unsigned long long p, int gi) { return (int)((p >> (16 * gi + 12)) & 15u) - 8; }
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -65,264 +93,338 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+// K-major SWIZZLE_128B descriptor = constant high word (SBO 1024 B, version 1, layout SWIZZLE_128B) + low word
+// (address >> 4 | LBO 16 B << 16): only a 32-bit add per MMA
+constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (kSwizzle128B << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return (smem_addr >> 4) | (1u << 16); }
+__device__ __forceinline__ void mma_tf32_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// unbounded wait for the issue loops (the bounded, diagnosing mbar_wait costs ~20 instructions on their critical path)
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
 
-// optional per-CTA timeline (profiling aid, tests/diag_conv_timeline.py): 8 x int64 per CTA
-__device__ long long* g_timeline = nullptr;
+// profiling aids (tests/diag_conv_timeline.py); only the DBG instantiations read them
+__device__ long long* g_timeline = nullptr;      // 8 x int64 per CTA
 __device__ int g_timeline_ctas = 0;
+__device__ int g_dbg_flags = 0;                  // 1 no TMA traffic, 2 epilogue drains TMEM only, 4 no MMAs (results are wrong)
 __device__ __forceinline__ long long gtimer() {
     long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-#define TL(slot, val)                                                                                         \
-    do {                                                                                                      \
-        if (tl != nullptr) tl[slot] = (val);                                                                  \
-    } while (0)
 
-template <int BN, int MT>
-__global__ void __launch_bounds__(THREADS, 2) tc_conv_ytap_kernel(const __grid_constant__ CUtensorMap tmA,
+template <int BN, int MT, bool DBG>
+__global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const sdt_conv_desc d, const YGeom g) {
     constexpr int B_BYTES = BN * 128;
+    constexpr int ACC_COLS = MT * BN;                 // one accumulator set; two sets (double buffer) are allocated
+    constexpr int N_ISS = MT >= 2 ? 2 : 1;            // MMA-issuing warps; issuer i owns sub-tiles i, i + N_ISS, ...
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const uint32_t raw_addr = smem_u32(smem_raw);
-    const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;   // 0: the dynamic window is 1024-byte aligned (checked below)
-    uint8_t* sm = smem_raw + pad;
+    const uint32_t smA = smem_u32(smem_raw);
     const int a_stage_bytes = MT * g.a_box_bytes;
+    const int ring_bytes = g.a_stages * a_stage_bytes + g.b_stages * B_BYTES;
     {
         uint32_t dyn;
         asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
-        if (pad + g.bar_off + TAIL_BYTES > dyn || g.a_stages * a_stage_bytes + g.b_stages * B_BYTES > g.bar_off) {
-            if (threadIdx.x == 0) printf("tc_conv_ytap_kernel: shared-memory window misaligned (pad %u)\n", pad);
+        if ((smA & 1023u) != 0 || ring_bytes + EPI_BYTES(BN, MT) + TAIL_BYTES > (int)dyn) {
+            if (threadIdx.x == 0) printf("tc_conv_ytap_kernel: shared-memory window misaligned or too small\n");
             __trap();
         }
     }
-    const uint32_t smA = raw_addr + pad;
     const uint32_t smB = smA + g.a_stages * a_stage_bytes;
-    const uint32_t bars = smA + g.bar_off;              // fullA[A_RING_MAX], emptyA[..], fullB[B_RING_MAX], emptyB[..], tmem_full
-    uint8_t* after = sm + g.bar_off;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(after + (2 * A_RING_MAX + 2 * B_RING_MAX + 1) * 8);
-    constexpr int STG_PITCH = BN + 4;                  // floats; the epilogue's staging tile and s_red alias the rings
+    float* stg_all = reinterpret_cast<float*>(smem_raw + ring_bytes);              // 4 warps x 32 rows x STG_PITCH floats
+    float* s_red = stg_all + 4 * 32 * STG_PITCH;                                   // [MT][2][4][BN]
+    const uint32_t bars = smA + ring_bytes + EPI_BYTES(BN, MT);
+    // barriers: fullA[A_RING_MAX], emptyA[..], fullB[B_RING_MAX], emptyB[..], tmem_full[2], tmem_empty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + ring_bytes + EPI_BYTES(BN, MT) + N_BARS * 8);
     auto fullA = [&](int s) { return bars + 8u * s; };
     auto emptyA = [&](int s) { return bars + 8u * (A_RING_MAX + s); };
     auto fullB = [&](int s) { return bars + 8u * (2 * A_RING_MAX + s); };
     auto emptyB = [&](int s) { return bars + 8u * (2 * A_RING_MAX + B_RING_MAX + s); };
-    const uint32_t tmem_full_bar = bars + 8u * (2 * A_RING_MAX + 2 * B_RING_MAX);
+    auto tmem_full = [&](int a) { return bars + 8u * (2 * A_RING_MAX + 2 * B_RING_MAX + a); };
+    auto tmem_empty = [&](int a) { return bars + 8u * (2 * A_RING_MAX + 2 * B_RING_MAX + 2 + a); };
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = d.N;
-    const int n0 = blockIdx.y * BN;
-    const int t0 = blockIdx.x * MT;
-    const int cta_lin = blockIdx.y * gridDim.x + blockIdx.x;
-    long long* tl = (g_timeline != nullptr && cta_lin < g_timeline_ctas) ? g_timeline + 8 * cta_lin : nullptr;
-    if (tid == 0 && tl != nullptr) {
-        uint32_t smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        tl[0] = smid;
-        tl[1] = gtimer();
-    }
-    const int nvalid = min(MT, g.subtiles - t0);
+    const int n_ntiles = N / BN;
+    const int n_tiles = ((g.subtiles + MT - 1) / MT) * n_ntiles;
     const int tpi = g.tiles_x * g.tiles_y;
     const int chunks = d.C / BKF;
+    const int dbg = DBG ? g_dbg_flags : 0;
+    long long* tl = nullptr;
+    if (DBG) {
+        tl = (g_timeline != nullptr && (int)blockIdx.x < g_timeline_ctas) ? g_timeline + 8 * blockIdx.x : nullptr;
+        if (tid == 0 && tl != nullptr) {
+            uint32_t smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            tl[0] = -clock64();
+            tl[1] = gtimer();
+        }
+    }
 
     if (tid == 0) {
         for (int s = 0; s < A_RING_MAX; ++s) {
             mbar_init(fullA(s), 1);
-            mbar_init(emptyA(s), 1);
+            mbar_init(emptyA(s), N_ISS);
         }
         for (int s = 0; s < B_RING_MAX; ++s) {
             mbar_init(fullB(s), 1);
-            mbar_init(emptyB(s), 1);
+            mbar_init(emptyB(s), N_ISS);
         }
-        mbar_init(tmem_full_bar, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full(a), N_ISS);
+            mbar_init(tmem_empty(a), 4);            // one arrival per epilogue warp
+        }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), MT * BN);
+    if (warp == 5) tmem_alloc(smem_u32(tmem_slot), 2 * ACC_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (DBG && tl && tid == 0) tl[2] = gtimer();
 
-    if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
+    if (warp == 4) {
+        // ================= TMA producer (whole warp walks the loop, one elected lane issues) =================
+        int sa = 0, pa = 1, sbi = 0, pb = 1;      // ring slot + parity to wait on the empty barriers (first lap passes)
+        long long wait_empty = 0;
+        for (int tile = blockIdx.x; tile < n_tiles && !(dbg & 1); tile += gridDim.x) {
+            const int grp_idx = tile / n_ntiles;
+            const int n0 = (tile - grp_idx * n_ntiles) * BN;
+            const int t0 = grp_idx * MT;
+            const int nvalid = min(MT, g.subtiles - t0);
             int sb[MT], sy[MT], sx[MT];
 #pragma unroll
             for (int m = 0; m < MT; ++m) {
                 const int t = min(t0 + m, g.subtiles - 1);
                 sb[m] = t / tpi;
                 const int rem = t - sb[m] * tpi;
-                sy[m] = (rem / g.tiles_x) * g.bh * d.y_mul + d.y_off + g.y_org;
+                sy[m] = (rem / g.tiles_x) * g.bh * d.y_mul + d.y_off;
                 sx[m] = (rem % g.tiles_x) * g.bw * d.x_mul + d.x_off;
             }
-            int sa = 0, pa = 1, sbi = 0, pb = 1;      // ring slot + parity to wait on the empty barriers (first lap passes)
-            long long wait_empty = 0;
             for (int ch = 0; ch < chunks; ++ch) {
                 const int c0 = ch * BKF;
                 for (int tx = 0; tx < d.TW; ++tx) {
-                    for (int ph = 0; ph < g.n_phase; ++ph) {
-                        long long tw = tl ? clock64() : 0;
-                        mbar_wait(emptyA(sa), (uint32_t)pa);
-                        if (tl) wait_empty += clock64() - tw;
-                        mbar_expect_tx(fullA(sa), (uint32_t)(nvalid * g.a_box_bytes));
+                    for (int gi = 0; gi < g.n_groups; ++gi) {
+                        const int y_add = grp_y_add(g.groups, gi), taps = grp_taps(g.groups, gi);
+                        const int step = grp_step(g.groups, gi);
+                        int ty = grp_ty0(g.groups, gi);
+                        long long tw = 0;
+                        if (DBG && tl) tw = clock64();
+                        mbar_wait_spin(emptyA(sa), (uint32_t)pa);
+                        if (DBG && tl) wait_empty += clock64() - tw;
+                        if (elect_one()) {
+                            mbar_expect_tx(fullA(sa), (uint32_t)(nvalid * g.a_box_bytes));
 #pragma unroll
-                        for (int m = 0; m < MT; ++m)
-                            if (m < nvalid)
-                                tma_load_4d(smA + sa * a_stage_bytes + m * g.a_box_bytes, &tmA, c0, sx[m] + tx * d.tx_mul, sy[m] + ph,
-                                            sb[m], fullA(sa));
+                            for (int m = 0; m < MT; ++m)
+                                if (m < nvalid)
+                                    tma_load_4d(smA + sa * a_stage_bytes + m * g.a_box_bytes, &tmA, c0, sx[m] + tx * d.tx_mul, sy[m] + y_add,
+                                                sb[m], fullA(sa));
+                        }
+                        __syncwarp();
                         if (++sa == g.a_stages) { sa = 0; pa ^= 1; }
-                        for (int ty = 0; ty < d.TH; ++ty) {
-                            if (g.phase[ty] != ph) continue;
-                            tw = tl ? clock64() : 0;
-                            mbar_wait(emptyB(sbi), (uint32_t)pb);
-                            if (tl) wait_empty += clock64() - tw;
-                            mbar_expect_tx(fullB(sbi), B_BYTES);
-                            tma_load_2d(smB + sbi * B_BYTES, &tmB, (ty * d.TW + tx) * d.C + c0, n0, fullB(sbi));
+                        for (int j = 0; j < taps; ++j, ty += step) {
+                            if (DBG && tl) tw = clock64();
+                            mbar_wait_spin(emptyB(sbi), (uint32_t)pb);
+                            if (DBG && tl) wait_empty += clock64() - tw;
+                            if (elect_one()) {
+                                mbar_expect_tx(fullB(sbi), B_BYTES);
+                                tma_load_2d(smB + sbi * B_BYTES, &tmB, (ty * d.TW + tx) * d.C + c0, n0, fullB(sbi));
+                            }
+                            __syncwarp();
                             if (++sbi == g.b_stages) { sbi = 0; pb ^= 1; }
                         }
                     }
                 }
             }
-            TL(6, wait_empty);
         }
-        __syncwarp();
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(BN, 0, 0);
-            int sa = 0, pa = 0, sbi = 0, pb = 0;
+        if (DBG && tl && lane == 0) tl[6] = wait_empty;
+    } else if (warp >= 5) {
+        // ================= MMA issuers (whole warp walks the loop, one elected lane issues) =================
+        const int iss = warp - 5;
+        if (iss < N_ISS) {
+        const uint32_t idesc = make_idesc_tf32(BN, 0, 0);
+        const uint32_t shift_lo = (uint32_t)(g.bw * 128) >> 4;           // one patch row, in descriptor address units
+        const uint32_t box_lo = (uint32_t)g.a_box_bytes >> 4;
+        int sa = 0, pa = 0, sbi = 0, pb = 0;
+        long long wait_full = 0, wait_acc = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int grp_idx = tile / n_ntiles;
+            const int nvalid = min(MT, g.subtiles - grp_idx * MT);
+            const int acc = it & 1;
+            const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * ACC_COLS);
+            long long tw = 0;
+            if (DBG && tl) tw = clock64();
+            mbar_wait_spin(tmem_empty(acc), (uint32_t)(((it >> 1) & 1) ^ 1));     // the epilogue has drained this accumulator set
+            if (DBG && tl) wait_acc += clock64() - tw;
+            tc_fence_after();
             uint32_t started = 0;
-            long long wait_full = 0;
-            TL(2, gtimer());
             for (int ch = 0; ch < chunks; ++ch) {
                 for (int tx = 0; tx < d.TW; ++tx) {
-                    for (int ph = 0; ph < g.n_phase; ++ph) {
-                        long long tw = tl ? clock64() : 0;
-                        mbar_wait(fullA(sa), (uint32_t)pa);
-                        if (tl) wait_full += clock64() - tw;
-                        for (int ty = 0; ty < d.TH; ++ty) {
-                            if (g.phase[ty] != ph) continue;
-                            tw = tl ? clock64() : 0;
-                            mbar_wait(fullB(sbi), (uint32_t)pb);
-                            if (tl) wait_full += clock64() - tw;
-                            if (tl && !started) tl[3] = gtimer();
-                            tc_fence_after();
-                            const uint64_t db = make_smem_desc(smB + sbi * B_BYTES, 16, 1024);
-                            const uint32_t a_off = (uint32_t)(g.shift[ty] * g.bw * 128);
+                    for (int gi = 0; gi < g.n_groups; ++gi) {
+                        const int taps = grp_taps(g.groups, gi);
+                        if (DBG && tl) tw = clock64();
+                        if (!(dbg & 1)) mbar_wait_spin(fullA(sa), (uint32_t)pa);
+                        if (DBG && tl) wait_full += clock64() - tw;
+                        uint32_t a_lo = desc_lo(smA + sa * a_stage_bytes);
+                        for (int j = 0; j < taps; ++j, a_lo += shift_lo) {
+                            if (DBG && tl) tw = clock64();
+                            if (!(dbg & 1)) mbar_wait_spin(fullB(sbi), (uint32_t)pb);
+                            if (DBG && tl) wait_full += clock64() - tw;
+                            if (!(dbg & 16)) tc_fence_after();
+                            const uint32_t b_lo = desc_lo(smB + sbi * B_BYTES);
+                            if (!(dbg & 64) && elect_one()) {
 #pragma unroll
-                            for (int m = 0; m < MT; ++m) {
-                                if (m < nvalid) {
-                                    const uint64_t da = make_smem_desc(smA + sa * a_stage_bytes + m * g.a_box_bytes + a_off, 16, 1024);
+                                for (int mm = 0; mm < MT / N_ISS; ++mm) {
+                                    const int m = iss + mm * N_ISS;
+                                    if (m < nvalid && !(dbg & 4)) {
 #pragma unroll
-                                    for (int k4 = 0; k4 < 4; ++k4)
-                                        mma_tf32(tmem_base + (uint32_t)(m * BN), da + 2u * k4, db + 2u * k4, idesc, started | (uint32_t)k4);
+                                        for (int k4 = 0; k4 < 4; ++k4)
+                                            mma_tf32_lo(tmem_acc + (uint32_t)(m * BN), a_lo + m * box_lo + 2u * k4, b_lo + 2u * k4, idesc,
+                                                        started | (uint32_t)k4);
+                                    }
                                 }
+                                if (!(dbg & 8)) mma_commit(emptyB(sbi));
                             }
+                            if (!(dbg & 64)) __syncwarp();
                             started = 1;
-                            mma_commit(emptyB(sbi));
                             if (++sbi == g.b_stages) { sbi = 0; pb ^= 1; }
                         }
-                        mma_commit(emptyA(sa));
+                        if (!(dbg & 32) && elect_one()) mma_commit(emptyA(sa));
+                        __syncwarp();
                         if (++sa == g.a_stages) { sa = 0; pa ^= 1; }
                     }
                 }
             }
-            mma_commit(tmem_full_bar);
-            TL(7, wait_full);
-        }
-        __syncwarp();
-    } else {
-        // ================= epilogue (warps 2..5; TMEM lane quadrant = warp % 4) =================
-        // TMEM -> registers (thread = row) -> padded shared-memory tile -> full-row coalesced global stores.  A direct
-        // store from the tcgen05.ld layout writes 16 bytes to each of 32 different lines per instruction and cost as much
-        // as the whole main loop (tests/diag_conv_timeline.py).  Each warp stages and writes back only its own 32 rows.
-        const int q = warp & 3;
-        const int r = q * 32 + lane;
-        const int py = r / g.bw, px = r - py * g.bw;
-        float* stg = reinterpret_cast<float*>(sm) + (size_t)(q * 32) * STG_PITCH;      // this warp's 32 rows
-        float* s_red = reinterpret_cast<float*>(sm) + (size_t)128 * STG_PITCH;           // [MT][2][4][BN]
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
-        if (tid == 64) TL(4, gtimer());
-        for (int m = 0; m < nvalid; ++m) {
-            const int t = t0 + m;
-            const int b = t / tpi;
-            const int rem = t - b * tpi;
-            const int ty0 = (rem / g.tiles_x) * g.bh, tx0 = (rem % g.tiles_x) * g.bw;
-            const bool ok = (ty0 + py) < d.GH && (tx0 + px) < d.GW;
-            const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
-#pragma unroll
-            for (int c = 0; c < BN / 32; ++c) {
-                float v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * BN + c * 32), v);
-                float4* row = reinterpret_cast<float4*>(stg + (size_t)lane * STG_PITCH + c * 32);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) row[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
+            if (elect_one()) mma_commit(tmem_full(acc));
             __syncwarp();
-            if (d.stat_partial != nullptr) {
-                // column sums over this warp's valid rows (rows of the patch outside the output grid are masked out)
+            if (DBG && tl && lane == 0 && iss == 0 && it == 0) tl[3] = gtimer();
+        }
+        if (DBG && tl && lane == 0 && iss == 0) {
+            tl[7] = wait_full;
+            tl[4] = gtimer();
+        }
+        }
+    } else {
+        // ================= epilogue (warps 0..3 = TMEM lane quadrants), one tile behind the MMA issuer =================
+        const int q = warp;
+        const int r = q * 32 + lane;
+        const int py = r >> g.lbw, px = r & (g.bw - 1);
+        float* stg = stg_all + (size_t)(q * 32) * STG_PITCH;
+        const int sub = lane >> 3, col4 = lane & 7;          // write-back: 8 lanes per 128-byte row segment
+        long long wait_tmem = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int grp_idx = tile / n_ntiles;
+            const int n0 = (tile - grp_idx * n_ntiles) * BN;
+            const int t0 = grp_idx * MT;
+            const int nvalid = min(MT, g.subtiles - t0);
+            const int acc = it & 1;
+            long long tw = 0;
+            if (DBG && tl) tw = clock64();
+            mbar_wait(tmem_full(acc), (uint32_t)((it >> 1) & 1));
+            if (DBG && tl) wait_tmem += clock64() - tw;
+            tc_fence_after();
+            for (int m = 0; m < nvalid; ++m) {
+                const int t = t0 + m;
+                const int b = t / tpi;
+                const int rem = t - b * tpi;
+                const int ty0 = (rem / g.tiles_x) * g.bh, tx0 = (rem % g.tiles_x) * g.bw;
+                const bool ok = (ty0 + py) < d.GH && (tx0 + px) < d.GW;
+                const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
+                // destination of the 8 rows this lane writes back (rows sub, sub+4, ... of the warp's 32), column n0
+                float* rowp[8];
 #pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int rr = q * 32 + 4 * k + sub;
+                    const int gy = ty0 + (rr >> g.lbw), gx = tx0 + (rr & (g.bw - 1));
+                    rowp[k] = d.dst + (((long long)b * d.DH + (gy * d.dy_mul + d.dy_off)) * d.DW + (gx * d.dx_mul + d.dx_off)) * N + n0 + col4 * 4;
+                }
                 for (int c = 0; c < BN / 32; ++c) {
-                    float s1 = 0.f, s2 = 0.f;
+                    float v[32];
+                    if (!(DBG && (dbg & 128)))
+                        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + m * BN + c * 32), v);
+                    if (m == nvalid - 1 && c == BN / 32 - 1) {       // last read of this accumulator set: hand it back to the MMA issuer
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tmem_empty(acc));
+                    }
+                    if (DBG && (dbg & 2)) continue;
+                    float4* row = reinterpret_cast<float4*>(stg + (size_t)lane * STG_PITCH);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) row[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    __syncwarp();
+                    if (d.stat_partial != nullptr) {
+                        float s1 = 0.f, s2 = 0.f;
 #pragma unroll 8
-                    for (int i = 0; i < 32; ++i) {
-                        const float x = stg[(size_t)i * STG_PITCH + c * 32 + lane];
+                        for (int i = 0; i < 32; ++i) {
+                            const float x = stg[(size_t)i * STG_PITCH + lane];
+                            if ((okmask >> i) & 1u) {
+                                s1 += x;
+                                s2 += x * x;
+                            }
+                        }
+                        s_red[((m * 2 + 0) * 4 + q) * BN + c * 32 + lane] = s1;
+                        s_red[((m * 2 + 1) * 4 + q) * BN + c * 32 + lane] = s2;
+                    }
+                    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (d.bias != nullptr) bb = __ldg(reinterpret_cast<const float4*>(d.bias + n0 + c * 32) + col4);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int i = 4 * k + sub;
                         if ((okmask >> i) & 1u) {
-                            s1 += x;
-                            s2 += x * x;
+                            float4* p = reinterpret_cast<float4*>(rowp[k] + c * 32);
+                            float4 o = *reinterpret_cast<const float4*>(stg + (size_t)i * STG_PITCH + col4 * 4);
+                            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                            if (d.accumulate) {
+                                const float4 old = *p;
+                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                            }
+                            *p = o;
                         }
                     }
-                    s_red[((m * 2 + 0) * 4 + q) * BN + c * 32 + lane] = s1;
-                    s_red[((m * 2 + 1) * 4 + q) * BN + c * 32 + lane] = s2;
+                    __syncwarp();
                 }
             }
-            // write back: ROWS_PER_STORE rows per instruction, each row BN*4 contiguous bytes
-            constexpr int LANES_PER_ROW = BN / 4, ROWS_PER_STORE = 32 / LANES_PER_ROW;
-            const int sub = lane / LANES_PER_ROW, col4 = lane % LANES_PER_ROW;
-            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (d.bias != nullptr) bb = __ldg(reinterpret_cast<const float4*>(d.bias + n0) + col4);
-#pragma unroll 4
-            for (int i0 = 0; i0 < 32; i0 += ROWS_PER_STORE) {
-                const int i = i0 + sub;
-                if ((okmask >> i) & 1u) {
-                    const int rr = q * 32 + i;
-                    const int gy = ty0 + rr / g.bw, gx = tx0 + rr % g.bw;
-                    float4* p = reinterpret_cast<float4*>(
-                                    d.dst + (((long long)b * d.DH + (gy * d.dy_mul + d.dy_off)) * d.DW + (gx * d.dx_mul + d.dx_off)) * N + n0) + col4;
-                    float4 o = *reinterpret_cast<const float4*>(stg + (size_t)i * STG_PITCH + col4 * 4);
-                    o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-                    if (d.accumulate) {
-                        const float4 old = *p;
-                        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            if (d.stat_partial != nullptr) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps
+                for (int i = tid; i < nvalid * BN; i += EPI_THREADS) {
+                    const int m = i / BN, c = i - m * BN;
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        s1 += s_red[((m * 2 + 0) * 4 + qq) * BN + c];
+                        s2 += s_red[((m * 2 + 1) * 4 + qq) * BN + c];
                     }
-                    *p = o;
+                    d.stat_partial[((size_t)(t0 + m) * 2 + 0) * N + n0 + c] = s1;
+                    d.stat_partial[((size_t)(t0 + m) * 2 + 1) * N + n0 + c] = s2;
                 }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
             }
-            __syncwarp();
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (d.stat_partial != nullptr) {
-        const float* s_red = reinterpret_cast<const float*>(sm) + (size_t)128 * STG_PITCH;
-        for (int i = tid; i < nvalid * BN; i += THREADS) {
-            const int m = i / BN, c = i - m * BN;
-            float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                s1 += s_red[((m * 2 + 0) * 4 + q) * BN + c];
-                s2 += s_red[((m * 2 + 1) * 4 + q) * BN + c];
-            }
-            d.stat_partial[((size_t)(t0 + m) * 2 + 0) * N + n0 + c] = s1;
-            d.stat_partial[((size_t)(t0 + m) * 2 + 1) * N + n0 + c] = s2;
-        }
-    }
-    if (warp == 1) {
+    if (warp == 5) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, MT * BN);
+        tmem_dealloc(tmem_base, 2 * ACC_COLS);
     }
-    if (tid == 0) TL(5, gtimer());
+    if (DBG && tl && tid == 0) {
+        tl[5] = gtimer();
+        tl[0] += clock64();
+    }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -342,38 +444,34 @@ EncodeTiledFn get_encode() {
 
 struct Plan {
     bool ok;
-    int bn, mt;
+    int bn, mt, tiles;
     YGeom g;
     int smem;
     double cost;
 };
 
-
-// Vertical tap structure: which box (phase) and which patch-row shift each ty reads.
-bool tap_structure(const sdt_conv_desc* d, YGeom* g, int* max_shift) {
-    if (d->TH > MAX_TH) return false;
-    if (d->ty_mul == 1) {                       // y = gy*y_mul + y_off + ty  ->  phase ty % y_mul, shift ty / y_mul
-        g->n_phase = d->TH < d->y_mul ? d->TH : d->y_mul;
-        g->y_org = 0;
-        *max_shift = 0;
-        for (int ty = 0; ty < d->TH; ++ty) {
-            g->phase[ty] = ty % d->y_mul;
-            g->shift[ty] = ty / d->y_mul;
-            if (g->shift[ty] > *max_shift) *max_shift = g->shift[ty];
+// Vertical tap structure: the groups of taps that share one box.  Returns the taps per group (max), 0 if unsupported.
+int tap_structure(const sdt_conv_desc* d, YGeom* g) {
+    if (d->TH > MAX_TH) return 0;
+    g->groups = 0;
+    if (d->ty_mul == 1) {                       // y = gy*y_mul + y_off + ty: taps ty = p, p + y_mul, ... share the box of phase p
+        const int n = d->TH < d->y_mul ? d->TH : d->y_mul;
+        if (n > MAX_GROUPS || d->y_mul > 7) return 0;
+        g->n_groups = n;
+        int max_taps = 0;
+        for (int p = 0; p < n; ++p) {
+            const int taps = (d->TH - p + d->y_mul - 1) / d->y_mul;
+            if (taps > max_taps) max_taps = taps;
+            g->groups |= (unsigned long long)((p + 8) | (taps << 4) | (p << 8) | ((d->y_mul + 8) << 12)) << (16 * p);
         }
-        return true;
+        return max_taps;
     }
-    if (d->ty_mul == -1 && d->y_mul == 1) {     // data gradient: y = gy + y_off - ty
-        g->n_phase = 1;
-        g->y_org = -(d->TH - 1);
-        *max_shift = d->TH - 1;
-        for (int ty = 0; ty < d->TH; ++ty) {
-            g->phase[ty] = 0;
-            g->shift[ty] = d->TH - 1 - ty;
-        }
-        return true;
+    if (d->ty_mul == -1 && d->y_mul == 1) {     // data gradient: y = gy + y_off - ty: one box from ty = TH-1 (shift 0) down to 0
+        g->n_groups = 1;
+        g->groups = (unsigned long long)((-(d->TH - 1) + 8) | (d->TH << 4) | ((d->TH - 1) << 8) | ((-1 + 8) << 12));
+        return d->TH;
     }
-    return false;
+    return 0;
 }
 
 Plan make_plan(const sdt_conv_desc* d) {
@@ -381,50 +479,55 @@ Plan make_plan(const sdt_conv_desc* d) {
     best.ok = false;
     if (d->N % 64 != 0 || d->C % 32 != 0) return best;
     const int K = d->TH * d->TW * d->C;
+    static const int force_bn = getenv("SDT_YTAP_BN") ? atoi(getenv("SDT_YTAP_BN")) : 0;      // tuning overrides
+    static const int force_mt = getenv("SDT_YTAP_MT") ? atoi(getenv("SDT_YTAP_MT")) : 0;
+    static const int force_bw = getenv("SDT_YTAP_BW") ? atoi(getenv("SDT_YTAP_BW")) : 0;
     for (int bn = 128; bn >= 64; bn /= 2) {
-        if (d->N % bn != 0) continue;
+        if (d->N % bn != 0 || (force_bn && bn != force_bn && d->N % force_bn == 0)) continue;
         for (int mt = 4; mt >= 1; mt /= 2) {
-            if (mt * bn > 256) continue;
+            if (mt * bn > 256 || (force_mt && mt != force_mt && force_mt * bn <= 256)) continue;
             for (int bw = 8; bw <= 128; bw *= 2) {
+                if (force_bw && bw != force_bw) continue;
                 YGeom g{};
-                int max_shift = 0;
-                if (!tap_structure(d, &g, &max_shift)) return best;
+                const int max_taps = tap_structure(d, &g);
+                if (max_taps == 0) return best;
                 g.bw = bw;
+                for (g.lbw = 0; (1 << g.lbw) < bw; ++g.lbw) {}
                 g.bh = 128 / bw;
-                g.box_rows = g.bh + max_shift;
+                g.box_rows = g.bh + max_taps - 1;
                 if (bw * d->x_mul > 256 || g.box_rows * d->y_mul > 256) continue;
                 g.a_box_bytes = g.box_rows * bw * 128;
                 g.tiles_x = (d->GW + bw - 1) / bw;
                 g.tiles_y = (d->GH + g.bh - 1) / g.bh;
                 g.subtiles = d->B * g.tiles_x * g.tiles_y;
-                const long long ctas = (long long)((g.subtiles + mt - 1) / mt) * (d->N / bn);
-                const int budget = ctas > 148 ? SMEM_TWO_PER_SM : SMEM_ONE_PER_SM;
+                const long long tiles = (long long)((g.subtiles + mt - 1) / mt) * (d->N / bn);
+                const int budget = SMEM_MAX - EPI_BYTES(bn, mt) - TAIL_BYTES;
                 const int a_stage = mt * g.a_box_bytes, b_stage = bn * 128;
                 int as = 2, bs = 2;
-                if (as * a_stage + bs * b_stage + TAIL_BYTES > budget) continue;
+                if (as * a_stage + bs * b_stage > budget) continue;
                 for (bool grew = true; grew;) {      // spend what is left: weight boxes first (finer grained), then A stages
                     grew = false;
-                    if (bs < B_RING_MAX && bs < 2 * as + 1 && as * a_stage + (bs + 1) * b_stage + TAIL_BYTES <= budget) { ++bs; grew = true; }
-                    else if (as < A_RING_MAX && (as + 1) * a_stage + bs * b_stage + TAIL_BYTES <= budget) { ++as; grew = true; }
+                    if (bs < B_RING_MAX && bs < 2 * as + 1 && as * a_stage + (bs + 1) * b_stage <= budget) { ++bs; grew = true; }
+                    else if (as < A_RING_MAX && (as + 1) * a_stage + bs * b_stage <= budget) { ++as; grew = true; }
                 }
                 g.a_stages = as;
                 g.b_stages = bs;
-                // cost model (clocks per SM): L2 -> shared-memory bytes at ~42 B/clk/SM against tensor-pipe clocks
-                const double a_bytes = (double)(d->C / BKF) * d->TW * g.n_phase * g.a_box_bytes * g.subtiles * (d->N / bn);
-                const double b_bytes = (double)ctas * K * bn * 4.0;
-                const double mma_clk = (double)g.subtiles * (d->N / bn) * (K / 8) * (bn / 2.0);
-                const double waves = (double)((ctas + 295) / 296) * 296.0 / (double)ctas;   // quantisation on 148 x 2 slots
-                const double mem_clk = (a_bytes + b_bytes) / 42.0;
-                const double cost = ((mem_clk > mma_clk ? mem_clk : mma_clk) + 0.15 * (mem_clk + mma_clk)) * (ctas > 296 ? waves : 1.0);
+                // cost model (clocks per tile): shared-memory traffic (TMA fill + tensor-core operand reads, 128 B/clk) against
+                // tensor-pipe clocks; the persistent CTAs (one per SM) run ceil(tiles / 148) tiles each
+                const double fill = (double)(d->C / BKF) * d->TW * g.n_groups * g.a_box_bytes * mt + (double)K * bn * 4.0;
+                const double reads = (double)mt * (K / 8) * (128 + bn) * 32.0;
+                const double mma_clk = (double)mt * (K / 8) * (bn / 2.0);
+                const double smem_clk = (fill + reads) / 128.0;
+                const double rounds = (double)((tiles + 147) / 148);
+                // a single issuing warp (MT == 1) exposes its loop overhead: measured ~1.5x slower per MMA than two issuers
+                const double cost = (smem_clk > mma_clk ? smem_clk : mma_clk) * rounds * (mt == 1 ? 1.5 : 1.0);
                 if (!best.ok || cost < best.cost) {
                     best.ok = true;
                     best.bn = bn;
                     best.mt = mt;
                     best.g = g;
-                    const int ring = as * a_stage + bs * b_stage;
-                    const int staging = 128 * (bn + 4) * 4 + mt * 8 * bn * 4;        // epilogue tile + statistics scratch
-                    best.g.bar_off = ring > staging ? ring : staging;
-                    best.smem = best.g.bar_off + TAIL_BYTES;
+                    best.tiles = (int)tiles;
+                    best.smem = as * a_stage + bs * b_stage + EPI_BYTES(bn, mt) + TAIL_BYTES;
                     best.cost = cost;
                 }
             }
@@ -433,15 +536,32 @@ Plan make_plan(const sdt_conv_desc* d) {
     return best;
 }
 
+bool g_host_debug = false;       // set by sdt_debug_conv_timeline / sdt_debug_conv_flags: launch the DBG instantiation
+
+template <int BN, int MT, bool DBG>
+int launch_ytap2(const sdt_conv_desc* d, const Plan& pl, const CUtensorMap& tmA, const CUtensorMap& tmB, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        SDT_CUDA_OK(cudaFuncSetAttribute(tc_conv_ytap_kernel<BN, MT, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+        attr_set = true;
+    }
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        SDT_CUDA_OK(cudaGetDevice(&dev));
+        SDT_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int grid = pl.tiles < sm_count ? pl.tiles : sm_count;      // persistent: one CTA per SM, static round-robin tiles
+    tc_conv_ytap_kernel<BN, MT, DBG><<<grid, THREADS, pl.smem, st>>>(tmA, tmB, *d, pl.g);
+    SDT_LAUNCH_OK("tc_conv_ytap_kernel");
+    sdt_note_tc_launch();
+    return SDT_OK;
+}
+
 template <int BN, int MT>
 int launch_ytap(const sdt_conv_desc* d, const Plan& pl, cudaStream_t st) {
     EncodeTiledFn enc = get_encode();
     SDT_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
-    static int attr_smem = 0;
-    if (pl.smem > attr_smem) {
-        SDT_CUDA_OK(cudaFuncSetAttribute(tc_conv_ytap_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ONE_PER_SM));
-        attr_smem = SMEM_ONE_PER_SM;
-    }
     const YGeom& g = pl.g;
     alignas(64) CUtensorMap tmA, tmB;
     {
@@ -465,11 +585,8 @@ int launch_ytap(const sdt_conv_desc* d, const Plan& pl, cudaStream_t st) {
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SDT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B, y-tap) failed with %d", (int)r);
     }
-    dim3 grid((g.subtiles + MT - 1) / MT, d->N / BN);
-    tc_conv_ytap_kernel<BN, MT><<<grid, THREADS, pl.smem, st>>>(tmA, tmB, *d, g);
-    SDT_LAUNCH_OK("tc_conv_ytap_kernel");
-    sdt_note_tc_launch();
-    return SDT_OK;
+    if (g_host_debug) return launch_ytap2<BN, MT, true>(d, pl, tmA, tmB, st);
+    return launch_ytap2<BN, MT, false>(d, pl, tmA, tmB, st);
 }
 
 }  // namespace
@@ -487,12 +604,18 @@ bool sdt_tc_conv_ytap_shape_ok(const sdt_conv_desc* d) {
 
 int sdt_tc_conv_ytap_row_tiles(const sdt_conv_desc* d) { return make_plan(d).g.subtiles; }
 
-
-// profiling aid (not part of the public header): per-CTA timeline buffer of 8 x int64 records, or NULL to switch off
+// profiling aids (not part of the public header)
+extern "C" int sdt_debug_conv_flags(int flags) {
+    SDT_CUDA_OK(cudaMemcpyToSymbol(g_dbg_flags, &flags, sizeof(flags)));
+    g_host_debug = flags != 0;
+    return SDT_OK;
+}
+// per-CTA timeline buffer of 8 x int64 records, or NULL to switch off
 extern "C" int sdt_debug_conv_timeline(void* buf, int ctas) {
     long long* p = static_cast<long long*>(buf);
     SDT_CUDA_OK(cudaMemcpyToSymbol(g_timeline, &p, sizeof(p)));
     SDT_CUDA_OK(cudaMemcpyToSymbol(g_timeline_ctas, &ctas, sizeof(ctas)));
+    g_host_debug = p != nullptr;
     return SDT_OK;
 }
 
@@ -501,18 +624,13 @@ int sdt_tc_conv_ytap_describe(const sdt_conv_desc* d, int32_t* out10) {
     if (!pl.ok) return 0;
     out10[1] = pl.bn; out10[2] = pl.mt; out10[3] = pl.g.bh; out10[4] = pl.g.bw; out10[5] = pl.g.box_rows;
     out10[6] = pl.g.a_stages; out10[7] = pl.g.b_stages; out10[8] = pl.smem;
-    out10[9] = ((pl.g.subtiles + pl.mt - 1) / pl.mt) * (d->N / pl.bn);
+    out10[9] = pl.tiles;
     return 1;
 }
 
 int sdt_tc_conv_ytap_launch(const sdt_conv_desc* d, cudaStream_t st) {
     const Plan pl = make_plan(d);
     SDT_REQUIRE(pl.ok, "sdt_tc_conv_ytap_launch: no plan for this descriptor");
-    static const bool debug = getenv("SDT_YTAP_DEBUG") != nullptr;
-    if (debug)
-        fprintf(stderr, "ytap: B%d C%d N%d G%dx%d T%dx%d ymul%d tymul%d -> BN%d MT%d patch %dx%d box_rows %d A%d B%d smem %d ctas %d\n", d->B, d->C,
-                d->N, d->GH, d->GW, d->TH, d->TW, d->y_mul, d->ty_mul, pl.bn, pl.mt, pl.g.bh, pl.g.bw, pl.g.box_rows, pl.g.a_stages,
-                pl.g.b_stages, pl.smem, ((pl.g.subtiles + pl.mt - 1) / pl.mt) * (d->N / pl.bn));
     if (pl.bn == 128) {
         if (pl.mt == 2) return launch_ytap<128, 2>(d, pl, st);
         return launch_ytap<128, 1>(d, pl, st);

@@ -1,8 +1,7 @@
 """Diagnostic (not a test): per-CTA timeline of the mode-3 convolution kernel on the encoder layer shapes.
     python tests/diag_conv_timeline.py [batch]
-Columns (ns, mean over CTAs): life = CTA start -> end, setup = start -> MMA thread ready, first = ready -> first operands landed,
-main = first operands -> accumulators complete, epi = accumulators complete -> CTA end; wait_full / wait_empty = clocks the MMA
-thread / the TMA thread spent blocked on the ring barriers."""
+Per persistent CTA: life = CTA start -> end; clocks the MMA thread spent blocked on operands (wait_full) and on the epilogue
+handing an accumulator set back (wait_acc), the TMA thread on ring slots (wait_empty), an epilogue warp on accumulators (wait_tmem)."""
 import ctypes as C
 import math
 import os
@@ -22,6 +21,7 @@ LAYERS = [(64, 64, 4, 4, 2, 1, 80, 427), (64, 128, 3, 3, 1, 1, 40, 213), (128, 1
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
     modes = [int(m) for m in sys.argv[2].split(",")] if len(sys.argv) > 2 else [2, 3]
+    flags_list = [int(f) for f in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0]
     dev = torch.device("cuda:0")
     lib = _lib.load()
     lib.sdt_debug_conv_timeline.argtypes = [C.c_void_p, C.c_int]
@@ -57,25 +57,31 @@ def main():
             ms = e0.elapsed_time(e1) / 10
             line = "L %3d->%3d %dx%d s%d %3dx%3d mode %d: %.1f us  %.0f TFLOP/s  plan %s" % (
                 cin, cout, kh, kw, s, H, W, mode, ms * 1e3, flops / ms / 1e9, list(plan))
-            if mode == 3 and plan[0] == 3:
+            for fl in (flags_list if (mode == 3 and plan[0] == 3) else []):
+                lib.sdt_debug_conv_flags(fl)
+                for _ in range(2):
+                    ops.conv_gemm(d)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(10):
+                    ops.conv_gemm(d)
+                e1.record()
+                torch.cuda.synchronize()
+                line += "\n      flags %d: %.1f us" % (fl, e0.elapsed_time(e1) * 100)
                 tlbuf.zero_()
                 lib.sdt_debug_conv_timeline(C.c_void_p(tlbuf.data_ptr()), ncta)
                 ops.conv_gemm(d)
                 torch.cuda.synchronize()
                 lib.sdt_debug_conv_timeline(None, 0)
-                n = min(plan[9], ncta)
+                n = min(plan[9], 148)
                 t = tlbuf[:n].cpu().double()
-                life, setup, first = t[:, 5] - t[:, 1], t[:, 2] - t[:, 1], t[:, 3] - t[:, 2]
-                mainl, epi = t[:, 4] - t[:, 3], t[:, 5] - t[:, 4]
+                life = t[:, 5] - t[:, 1]
                 span = float(t[:, 5].max() - t[:, 1].min())
-                line += "\n      ctas %d span %.1f us | ns: life %.0f setup %.0f first %.0f main %.0f epi %.0f | clk: wait_full %.0f wait_empty %.0f" % (
-                    n, span / 1e3, life.mean(), setup.mean(), first.mean(), mainl.mean(), epi.mean(), t[:, 7].mean(), t[:, 6].mean())
-                # concurrency on SM of CTA 0
-                sm0 = t[0, 0]
-                on = t[t[:, 0] == sm0]
-                line += "\n      SM %d ran %d CTAs; their (start,end) us: %s" % (
-                    int(sm0), on.shape[0], " ".join("(%.1f,%.1f)" % ((a - t[:, 1].min()) / 1e3, (b - t[:, 1].min()) / 1e3)
-                                                      for a, b in sorted(zip(on[:, 1].tolist(), on[:, 5].tolist()))[:10]))
+                t0 = t[:, 1:2]
+                rel = (t[:, 1:6] - t0) / 1e3
+                line += "\n      ctas %d span %.1f us | mean us since CTA start: prologue done %.2f, first tile issued %.2f, all tiles issued %.2f, end %.2f (max %.2f) | clk: mma wait_full %.0f | tma wait_empty %.0f | SM clock %.0f MHz" % (
+                    n, span / 1e3, rel[:, 1].mean(), rel[:, 2].mean(), rel[:, 3].mean(), rel[:, 4].mean(), rel[:, 4].max(), t[:, 7].mean(), t[:, 6].mean(), float((t[:, 0] / (t[:, 5] - t[:, 1])).mean() * 1e3))
+            lib.sdt_debug_conv_flags(0)
             print(line, flush=True)
     ops.set_conv_math(0)
 

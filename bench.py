@@ -49,17 +49,60 @@ def peaks():
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed regions (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons during the timed regions (B200_PROFILING.md recipe), sampled in-process through NVML
+    every 20 ms.  (A polling `nvidia-smi -lms` child was measured to stall the host-synchronised e2e loop by ~2 ms per
+    step -- each query takes driver locks -- so it is only the fallback when NVML cannot be loaded.)"""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.thread = None
+        self.how = None
+
+    def _nvml_loop(self, nv, h):
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = int(get_reasons(h))
+                for n, b in bits.items():
+                    if r & b:
+                        self.reasons.add(n)
+            except Exception:            # noqa: BLE001 - a failed sample is just skipped
+                pass
+            self._stop.wait(0.02)
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may remap indices: resolve through the PCI bus id of the torch device
+            bus = torch.cuda.get_device_properties(self.index).pci_bus_id if hasattr(torch.cuda.get_device_properties(self.index), "pci_bus_id") else None
+            h = None
+            if bus is not None:
+                for i in range(nv.nvmlDeviceGetCount()):
+                    hi = nv.nvmlDeviceGetHandleByIndex(i)
+                    if int(nv.nvmlDeviceGetPciInfo(hi).bus) == int(bus):
+                        h = hi
+                        break
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.how = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:                # noqa: BLE001 - fall back to the nvidia-smi child
+            self.how = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.how = "nvidia-smi"
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:
@@ -70,6 +113,15 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.how == "nvml":
+            self._stop.set()
+            self.thread.join(timeout=2)
+            sm = self.samples
+            if not sm:
+                return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"], "how": "nvml"}
+            busy = sorted(sm)[len(sm) // 2:]          # upper half = samples under load
+            return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(sm),
+                    "how": "nvml, 20 ms period"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -78,7 +130,6 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 6:
@@ -88,13 +139,14 @@ class ClockSampler:
                 mx.append(float(f[1]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[2:6]):
+            for n, v in zip(self.NAMES, f[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         busy = sorted(sm)[len(sm) // 2:]          # upper half = samples under load
-        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "how": "nvidia-smi -lms 100"}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -13,9 +13,9 @@
 //             strided convolutions and the stride-parity classes of the data gradient are plain boxes, the zero padding
 //             is TMA's out-of-bounds fill (negative / too large coordinates).  Row r of the box = (r / bw, r % bw).
 //   B tile  : 2-D box {32, BN} of the K-major (N, K) weight copy at (k, n0).
-//   warp 0  : TMA producer (one thread): wait empty[s] -> arrive.expect_tx(full[s]) -> two bulk tensor copies.
-//   warp 1  : MMA issuer (one thread): 4 x tcgen05.mma per stage, tcgen05.commit -> empty[s]; owns the TMEM allocation.
-//   warps 2-5: epilogue: tcgen05.ld, bias / accumulate, 128-byte row stores, masked column statistics.
+//   warps 0-3: epilogue: tcgen05.ld, bias / accumulate, 128-byte row stores, masked column statistics.
+//   warp 4  : TMA producer: wait empty[s] -> arrive.expect_tx(full[s]) -> two bulk tensor copies.
+//   warp 5  : MMA issuer: 4 x tcgen05.mma per stage, tcgen05.commit -> empty[s]; owns the TMEM allocation.
 // 3 stages of 32 KB (BN = 128) -> two CTAs per SM.
 #include <cuda.h>
 
@@ -46,22 +46,6 @@ struct TmaCfg {
     static constexpr int RED_BYTES = 2 * 4 * BN * 4;
     static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + RED_BYTES + 1024;
 };
-
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
-        : "memory");
-}
 
 template <int BN, bool DEEP>
 __global__ void __launch_bounds__(THREADS, DEEP ? 1 : 2) tc_conv_tma_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -101,52 +85,60 @@ __global__ void __launch_bounds__(THREADS, DEEP ? 1 : 2) tc_conv_tma_kernel(cons
         mbar_init(tmem_full_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), BN);
+    if (warp == 5) tmem_alloc(smem_u32(tmem_slot), BN);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    // warps 0-3: epilogue (TMEM lane quadrant = warp id); warp 4: TMA producer; warp 5: MMA issuer.  The issuing warps walk
+    // their loops as whole warps and elect one lane per instruction (tc_common.cuh: elect_one), and have the highest warp ids.
+    if (warp == 4) {
         // ================= TMA producer =================
         const int taps = d.TH * d.TW;
-        for (int kb = 0; kb < KB; ++kb) {
-            if (lane == 0) {
-                const int s = kb % STAGES, round = kb / STAGES;
-                mbar_wait(empty_bar(s), (uint32_t)((round & 1) ^ 1));
-                // k-block order: channel chunk major, tap minor (consecutive taps hit the same L2 lines)
-                const int cchunk = kb / taps, tap = kb - cchunk * taps;
-                const int c0 = cchunk * BKF;
-                const int tyy = tap / d.TW, txx = tap - tyy * d.TW;
-                const int wx = x0 * d.x_mul + d.x_off + txx * d.tx_mul;
+        int s = 0, par = 1;
+        // k-block order: channel chunk major, tap minor (consecutive taps hit the same L2 lines)
+        for (int c0 = 0; c0 < d.C; c0 += BKF) {
+            for (int tyy = 0; tyy < d.TH; ++tyy) {
                 const int wy = y0 * d.y_mul + d.y_off + tyy * d.ty_mul;
-                mbar_expect_tx(full_bar(s), Cfg::A_BYTES + Cfg::B_BYTES);
-                tma_load_4d(smA + s * Cfg::A_BYTES, &tmA, c0, wx, wy, b, full_bar(s));
-                tma_load_2d(smB + s * Cfg::B_BYTES, &tmB, tap * d.C + c0, n0, full_bar(s));
+                for (int txx = 0; txx < d.TW; ++txx) {
+                    const int wx = x0 * d.x_mul + d.x_off + txx * d.tx_mul;
+                    mbar_wait_spin(empty_bar(s), (uint32_t)par);
+                    if (elect_one()) {
+                        mbar_expect_tx(full_bar(s), Cfg::A_BYTES + Cfg::B_BYTES);
+                        tma_load_4d(smA + s * Cfg::A_BYTES, &tmA, c0, wx, wy, b, full_bar(s));
+                        tma_load_2d(smB + s * Cfg::B_BYTES, &tmB, (tyy * d.TW + txx) * d.C + c0, n0, full_bar(s));
+                    }
+                    __syncwarp();
+                    if (++s == STAGES) { s = 0; par ^= 1; }
+                }
             }
-            __syncwarp();
         }
-    } else if (warp == 1) {
+        (void)taps;
+    } else if (warp == 5) {
         // ================= MMA issuer =================
         const uint32_t idesc = make_idesc_tf32(BN, 0, 0);
+        constexpr uint32_t HI = desc_hi(1024, kSwizzle128B);
+        int s = 0, par = 0;
+        uint32_t started = 0;
         for (int kb = 0; kb < KB; ++kb) {
-            if (lane == 0) {
-                const int s = kb % STAGES, round = kb / STAGES;
-                mbar_wait(full_bar(s), (uint32_t)(round & 1));
-                tc_fence_after();
-                const uint64_t da = make_smem_desc(smA + s * Cfg::A_BYTES, 16, 1024);
-                const uint64_t db = make_smem_desc(smB + s * Cfg::B_BYTES, 16, 1024);
+            mbar_wait_spin(full_bar(s), (uint32_t)par);
+            tc_fence_after();
+            const uint32_t a_lo = desc_lo(smA + s * Cfg::A_BYTES, 16), b_lo = desc_lo(smB + s * Cfg::B_BYTES, 16);
+            if (elect_one()) {
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) mma_tf32(tmem_base, da + 2u * k4, db + 2u * k4, idesc, (uint32_t)((kb | k4) != 0));
+                for (int k4 = 0; k4 < 4; ++k4) mma_tf32_lohi(tmem_base, a_lo + 2u * k4, b_lo + 2u * k4, HI, idesc, started | (uint32_t)k4);
                 mma_commit(empty_bar(s));
             }
             __syncwarp();
+            started = 1;
+            if (++s == STAGES) { s = 0; par ^= 1; }
         }
-        if (lane == 0) mma_commit(tmem_full_bar);
+        if (elect_one()) mma_commit(tmem_full_bar);
         __syncwarp();
     } else {
         // ================= epilogue (warps 2..5; TMEM lane quadrant = warp % 4) =================
-        const int q = warp & 3;
+        const int q = warp;
         const int r = q * 32 + lane;
         const int py = r / tg.bw, px = r - py * tg.bw;
         const int gy = y0 + py, gx = x0 + px;
@@ -203,7 +195,7 @@ __global__ void __launch_bounds__(THREADS, DEEP ? 1 : 2) tc_conv_tma_kernel(cons
             d.stat_partial[((size_t)blockIdx.x * 2 + 1) * N + n0 + c] = s2;
         }
     }
-    if (warp == 1) {
+    if (warp == 5) {
         tc_fence_after();
         tmem_dealloc(tmem_base, BN);
     }

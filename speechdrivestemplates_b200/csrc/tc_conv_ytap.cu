@@ -69,48 +69,10 @@ __host__ __device__ __forceinline__ int grp_taps(unsigned long long p, int gi) {
 __host__ __device__ __forceinline__ int grp_ty0(unsigned long long p, int gi) { return (int)((p >> (16 * gi + 8)) & 15u); }
 __host__ __device__ __forceinline__ int grp_step(unsigned long long p, int gi) { return (int)((p >> (16 * gi + 12)) & 15u) - 8; }
 
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
-        : "memory");
-}
-// K-major SWIZZLE_128B descriptor = constant high word (SBO 1024 B, version 1, layout SWIZZLE_128B) + low word
-// (address >> 4 | LBO 16 B << 16): only a 32-bit add per MMA
-constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (kSwizzle128B << 29);
-__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return (smem_addr >> 4) | (1u << 16); }
+constexpr uint32_t DESC_HI = desc_hi(1024, kSwizzle128B);        // K-major SWIZZLE_128B: 8-row groups 1024 B apart
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return sdt_tc::desc_lo(smem_addr, 16); }
 __device__ __forceinline__ void mma_tf32_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-        "setp.ne.b32 p, %5, 0;\n\t"
-        "mov.b64 da, {%1, %3};\n\t"
-        "mov.b64 db, {%2, %3};\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
-        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(DESC_HI), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// unbounded wait for the issue loops (the bounded, diagnosing mbar_wait costs ~20 instructions on their critical path)
-__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {
-    }
+    mma_tf32_lohi(tmem_d, a_lo, b_lo, DESC_HI, idesc, accumulate);
 }
 
 // profiling aids (tests/diag_conv_timeline.py); only the DBG instantiations read them

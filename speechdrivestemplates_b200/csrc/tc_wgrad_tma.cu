@@ -36,16 +36,6 @@ struct WgTmaCfg {
     static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + 1024;
 };
 
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
-        : "memory");
-}
-
 template <int BN>
 __global__ void __launch_bounds__(THREADS, 2) tc_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmB,
@@ -94,13 +84,15 @@ __global__ void __launch_bounds__(THREADS, 2) tc_wgrad_tma_kernel(const __grid_c
         mbar_init(tmem_full_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), BN);
+    if (warp == 5) tmem_alloc(smem_u32(tmem_slot), BN);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    // warps 0-3: epilogue (TMEM lane quadrant = warp id); warp 4: TMA producer; warp 5: MMA issuer.  The issuing warps walk
+    // their loops as whole warps and elect one lane per instruction (tc_common.cuh: elect_one), and have the highest warp ids.
+    if (warp == 4) {
         // ================= TMA producer =================
         // the four 32-channel chunks of this CTA's 128 k-indices: tap and channel offset are loop invariant
         int c0[4], dyo[4], dxo[4];
@@ -119,15 +111,16 @@ __global__ void __launch_bounds__(THREADS, 2) tc_wgrad_tma_kernel(const __grid_c
             }
         }
         const uint32_t tx_bytes = (uint32_t)(n_chunks * 4096 + Cfg::B_BYTES);
+        const int per_image = bg.ny * bg.nx;
+        int s = 0, par = 1;
         for (int kb = 0; kb < KB; ++kb) {
-            if (lane == 0) {
-                const int s = kb % STAGES, round = kb / STAGES;
-                mbar_wait(empty_bar(s), (uint32_t)((round & 1) ^ 1));
-                const int pi = p_begin + kb;
-                const int bb = pi / (bg.ny * bg.nx);
-                const int rem = pi - bb * bg.ny * bg.nx;
-                const int yy = rem / bg.nx, xx = rem - yy * bg.nx;
-                const int b0 = bb * bg.pb, y0 = yy * bg.ph, x0 = xx * bg.pw;
+            mbar_wait_spin(empty_bar(s), (uint32_t)par);
+            const int pi = p_begin + kb;
+            const int bb = pi / per_image;
+            const int rem = pi - bb * per_image;
+            const int yy = rem / bg.nx, xx = rem - yy * bg.nx;
+            const int b0 = bb * bg.pb, y0 = yy * bg.ph, x0 = xx * bg.pw;
+            if (elect_one()) {
                 mbar_expect_tx(full_bar(s), tx_bytes);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
@@ -138,31 +131,34 @@ __global__ void __launch_bounds__(THREADS, 2) tc_wgrad_tma_kernel(const __grid_c
                     tma_load_4d(smB + s * Cfg::B_BYTES + j * 4096, &tmB, n0 + j * 32, x0, y0, b0, full_bar(s));
             }
             __syncwarp();
+            if (++s == STAGES) { s = 0; par ^= 1; }
         }
-    } else if (warp == 1) {
+    } else if (warp == 5) {
         // ================= MMA issuer =================
         const uint32_t idesc = make_idesc_tf32(BN, 1, 1);
+        // MN-major SWIZZLE_128B_BASE32B: 8 pixels = two K-atoms 512 B apart (SBO); 32-channel chunks (MN atoms) 4 KB apart (LBO)
+        constexpr uint32_t HI = desc_hi(512, kSwizzle128B_Base32B);
+        int s = 0, par = 0;
+        uint32_t started = 0;
         for (int kb = 0; kb < KB; ++kb) {
-            if (lane == 0) {
-                const int s = kb % STAGES, round = kb / STAGES;
-                mbar_wait(full_bar(s), (uint32_t)(round & 1));
-                tc_fence_after();
+            mbar_wait_spin(full_bar(s), (uint32_t)par);
+            tc_fence_after();
+            const uint32_t a_lo = desc_lo(smA + s * Cfg::A_BYTES, 4096), b_lo = desc_lo(smB + s * Cfg::B_BYTES, 4096);
+            if (elect_one()) {
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                    // 8 pixels = two K-atoms (512 B apart); 32-channel chunks (MN atoms) 4 KB apart
-                    const uint64_t da = make_smem_desc(smA + s * Cfg::A_BYTES + k4 * 1024, 4096, 512, kSwizzle128B_Base32B);
-                    const uint64_t db = make_smem_desc(smB + s * Cfg::B_BYTES + k4 * 1024, 4096, 512, kSwizzle128B_Base32B);
-                    mma_tf32(tmem_base, da, db, idesc, (uint32_t)((kb | k4) != 0));
-                }
+                for (int k4 = 0; k4 < 4; ++k4)
+                    mma_tf32_lohi(tmem_base, a_lo + (uint32_t)(k4 * 64), b_lo + (uint32_t)(k4 * 64), HI, idesc, started | (uint32_t)k4);
                 mma_commit(empty_bar(s));
             }
             __syncwarp();
+            started = 1;
+            if (++s == STAGES) { s = 0; par ^= 1; }
         }
-        if (lane == 0) mma_commit(tmem_full_bar);
+        if (elect_one()) mma_commit(tmem_full_bar);
         __syncwarp();
     } else {
         // ================= epilogue: D[m][n] -> wpart[z][n0 + n][kidx0 + m] =================
-        const int q = warp & 3;
+        const int q = warp;
         const int m = q * 32 + lane;
         const bool m_ok = kidx0 + m < Kc;
         mbar_wait(tmem_full_bar, 0);
@@ -178,7 +174,7 @@ __global__ void __launch_bounds__(THREADS, 2) tc_wgrad_tma_kernel(const __grid_c
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 5) {
         tc_fence_after();
         tmem_dealloc(tmem_base, BN);
     }

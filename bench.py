@@ -302,15 +302,21 @@ def run_own(args):
     ms_dev = max_over_ranks(e0.elapsed_time(e1))
 
     # ---- e2e: pinned host batch -> H2D -> step -> D2H of the loss scalars, every step
+    # Voice2PoseTrainer.run_epoch = the reference's `for batch in dataloader: train_step; log` loop: every step's batch
+    # is copied host->device (copy stream, one batch ahead) and every step's scalars are read back (one step behind)
+    tr.run_epoch((host_batches[k % len(host_batches)] for k in range(W)), on_losses=lambda i, d: None)   # warm-up of this path
     barrier()
     t0 = time.perf_counter()
     e0.record()
-    per_step = []
-    # Voice2PoseTrainer.run_epoch = the reference's `for batch in dataloader: train_step; log` loop: every step's batch
-    # is copied host->device (copy stream, one batch ahead) and every step's scalars are read back (one step behind)
-    tr.run_epoch((host_batches[k % len(host_batches)] for k in range(K)), on_losses=lambda i, d: per_step.append(d))
+    per_step, stamps = [], [t0]
+
+    def on_losses(i, d):
+        per_step.append(d)
+        stamps.append(time.perf_counter())
+    tr.run_epoch((host_batches[k % len(host_batches)] for k in range(K)), on_losses=on_losses)
     e1.record()
     assert len(per_step) == K
+    gaps = sorted((b - a) * 1e3 for a, b in zip(stamps[:-1], stamps[1:]))
     last = per_step[-1]
     barrier()
     ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), 0.0))
@@ -381,7 +387,7 @@ def run_own(args):
                                  "tcgen05 TF32, TMA-fed operands reused across vertical taps and accumulators in shared memory, fp32 "
                                  "accumulate (FFMA for ineligible layers)"][conv_math]},
         "e2e": {"value": clips / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / K, "wall_s": wall_e2e},
+                "ms_per_step": ms_e2e / K, "wall_s": wall_e2e, "host_gap_ms": {"median": gaps[len(gaps) // 2], "max": gaps[-1]}},
         "gpu_launches": launches_per_step * K * 2,
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "last_losses": last,

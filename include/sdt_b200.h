@@ -127,7 +127,10 @@ int sdt_weight_prep(const float* w, int Cout, int Cin, int KH, int KW, int mode,
 typedef struct sdt_prep_item {
     const float* w;            /* (Cout, Cin, KH, KW) parameter */
     float* out;                /* operand buffer */
-    int32_t Cout, Cin, KH, KW, mode, ky0, kx0, kstep, TH, TW, pad0, pad1;
+    int32_t Cout, Cin, KH, KW, mode, ky0, kx0, kstep, TH, TW;
+    int32_t pad0;              /* mode 2 only: input channels of the operand, zero-padded (> Cin), e.g. 242 -> 256 so that a
+                                * layer becomes tensor-core eligible; 0 = Cin */
+    int32_t pad1;
 } sdt_prep_item;
 int sdt_weight_prep_batch(const sdt_prep_item* items_device, int n_items, long long max_elems, void* stream);
 

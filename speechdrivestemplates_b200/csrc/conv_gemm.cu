@@ -617,11 +617,15 @@ struct PrepItem {     // mirrors sdt_prep_item
 
 __global__ void weight_prep_batch_kernel(const PrepItem* __restrict__ items) {
     const PrepItem it = items[blockIdx.y];
-    const long long total = (long long)it.TH * it.TW * it.Cin * it.Cout;
+    const int cin_p = (it.mode == 2 && it.pad0 > it.Cin) ? it.pad0 : it.Cin;      // mode 2: input channels zero-padded to pad0
+    const long long total = (long long)it.TH * it.TW * cin_p * it.Cout;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         int co, ci, tap;
         const int T = it.TH * it.TW;
-        if (it.mode == 2) { ci = (int)(e % it.Cin); tap = (int)((e / it.Cin) % T); co = (int)(e / ((long long)it.Cin * T)); }
+        if (it.mode == 2) {
+            ci = (int)(e % cin_p); tap = (int)((e / cin_p) % T); co = (int)(e / ((long long)cin_p * T));
+            if (ci >= it.Cin) { it.out[e] = 0.f; continue; }
+        }
         else if (it.mode == 3) { co = (int)(e % it.Cout); tap = (int)((e / it.Cout) % T); ci = (int)(e / ((long long)it.Cout * T)); }
         else if (it.mode == 0) { co = (int)(e % it.Cout); ci = (int)((e / it.Cout) % it.Cin); tap = (int)(e / ((long long)it.Cout * it.Cin)); }
         else { ci = (int)(e % it.Cin); co = (int)((e / it.Cin) % it.Cout); tap = (int)(e / ((long long)it.Cout * it.Cin)); }

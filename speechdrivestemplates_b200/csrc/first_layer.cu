@@ -217,7 +217,22 @@ __global__ void __launch_bounds__(256) fl_bwd_kernel(const float* __restrict__ g
     }
 }
 
-// one block per output channel: sums over image rows in double, then the closed-form combination over the batch
+// one block per image, one thread per (q, c): the sum over the image's units in double (coalesced: consecutive threads read
+// consecutive floats), stored IN PLACE as a float-float pair in the image's unit rows 0 (high part) and 1 (low part).
+// (The finalize kernel used to walk the units itself, one 4-byte read per 2.8 KB stride and thread: 85 us.)
+__global__ void __launch_bounds__(kBwdQ * kC) fl_bwd_colsum_kernel(float* __restrict__ partial, int units) {
+    const int b = blockIdx.x, t = threadIdx.x;
+    float* base = partial + (size_t)b * units * kBwdQ * kC;
+    double s = 0.0;
+#pragma unroll 8
+    for (int i = 0; i < units; ++i) s += (double)base[(size_t)i * kBwdQ * kC + t];
+    __syncthreads();                            // rows 0 and 1 have been read by everybody
+    const float hi = (float)s;
+    base[t] = hi;
+    base[kBwdQ * kC + t] = (float)(s - (double)hi);
+}
+
+// one block per output channel: the closed-form combination over the batch
 __global__ void __launch_bounds__(128) fl_bwd_finalize_kernel(const float* __restrict__ partial, const double* __restrict__ moments,
                                                               const float* __restrict__ w, const float* __restrict__ scale,
                                                               const float* __restrict__ shift, int B, int units,
@@ -226,8 +241,13 @@ __global__ void __launch_bounds__(128) fl_bwd_finalize_kernel(const float* __res
     const int c = blockIdx.x;
     for (int i = threadIdx.x; i < B * kBwdQ; i += blockDim.x) {
         const int b = i / kBwdQ, q = i - b * kBwdQ;
-        double s = 0.0;
-        for (int i2 = 0; i2 < units; ++i2) s += (double)partial[(((size_t)b * units + i2) * kBwdQ + q) * kC + c];
+        const float* row = partial + ((size_t)b * units * kBwdQ + q) * kC + c;
+        double s;
+        if (units >= 2) {                       // reduced by fl_bwd_colsum_kernel
+            s = (double)row[0] + (double)row[(size_t)kBwdQ * kC];
+        } else {
+            s = (double)row[0];
+        }
         s_sum[i] = s;
     }
     __syncthreads();
@@ -283,6 +303,10 @@ extern "C" int sdt_first_layer_bwd(const float* g_act, const float* act, const f
     cudaStream_t st = sdt::as_stream(stream);
     fl_bwd_kernel<<<dim3(units, B), 256, 0, st>>>(g_act, act, x, H, W, slope, partial);
     SDT_LAUNCH_OK("fl_bwd_kernel");
+    if (units >= 2) {
+        fl_bwd_colsum_kernel<<<B, kBwdQ * kC, 0, st>>>(partial, units);
+        SDT_LAUNCH_OK("fl_bwd_colsum_kernel");
+    }
     fl_bwd_finalize_kernel<<<kC, 128, fsmem, st>>>(partial, moments, w, scale, shift, B, units, dw);
     SDT_LAUNCH_OK("fl_bwd_finalize_kernel");
     return SDT_OK;

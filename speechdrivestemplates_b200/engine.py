@@ -64,7 +64,7 @@ class WeightPrep:
         scale/shift per CTA, so layers whose loader transform spans a batch-wide statistic stay on the FFMA kernel)."""
         import numpy as np
         tc = ops.get_conv_math() >= 1
-        key = (tc, with_dgrad) + tuple(params[l[1]].data_ptr() for l in layers)
+        key = (tc, with_dgrad, tuple(l[6] if len(l) > 6 else 0 for l in layers)) + tuple(params[l[1]].data_ptr() for l in layers)
         if key == self.key:
             return
         self.key = key
@@ -73,17 +73,23 @@ class WeightPrep:
         items, max_elems = [], 1
         self.fwd, self.dgrad = {}, {}
 
-        def add(w, out, g, mode, ky0, kx0, th, tw):
+        def add(w, out, g, mode, ky0, kx0, th, tw, cin_pad=0):
             nonlocal max_elems
             kstep = g.sw if mode in (1, 3) else 1          # forward operands take every tap; dgrad classes every s-th
-            items.append((w.data_ptr(), out.data_ptr(), (g.cout, g.cin, g.kh, g.kw, mode, ky0, kx0, kstep, th, tw, 0, 0)))
-            max_elems = max(max_elems, th * tw * g.cin * g.cout)
+            items.append((w.data_ptr(), out.data_ptr(), (g.cout, g.cin, g.kh, g.kw, mode, ky0, kx0, kstep, th, tw, cin_pad, 0)))
+            max_elems = max(max_elems, th * tw * max(g.cin, cin_pad) * g.cout)
 
         for layer in layers:
             name, wkey, g, (H, W), needs_dgrad = layer[:5]
             tc_ok = layer[5] if len(layer) > 5 else True
+            cin_pad = layer[6] if len(layer) > 6 else 0    # forward-only layers: input channels zero-padded (242 -> 256)
             w = params[wkey]
-            if tc and tc_ok and ops.tc_eligible(g.cin, g.cout):
+            if tc and tc_ok and cin_pad and ops.tc_eligible(cin_pad, g.cout):
+                assert not needs_dgrad
+                nk = A.get("wt_fnk:" + name, (g.cout, g.kh * g.kw * cin_pad))
+                add(w, nk, g, 2, 0, 0, g.kh, g.kw, cin_pad)
+                self.fwd[name] = (None, nk)
+            elif tc and tc_ok and ops.tc_eligible(g.cin, g.cout):
                 nk = A.get("wt_fnk:" + name, (g.cout, g.k))
                 add(w, nk, g, 2, 0, 0, g.kh, g.kw)
                 self.fwd[name] = (None, nk)
@@ -524,14 +530,24 @@ class PoseEncoderEngine:
         A = self.arena
         B, L = poses.shape[0], poses.shape[1]
         src, xf = poses.view(B, 1, L, self.kp2), None
+        # TMA-fed tensor-core path (math modes 2, 3): the 242 input channels are zero-padded to 256 (K-block = 32 channels)
+        # and every block's activation is materialised (2 MB), because TMA delivers plain tensors only
+        tma = ops.get_conv_math() >= 2
+        cpad = -(-self.kp2 // 32) * 32 if tma else 0
         if tag in ("", "/pred"):        # the two FGD passes of a step share one weight refresh
-            self.wprep.ensure([("blocks.%d" % i, "blocks.%d.conv.weight" % i, g, (1, 1), False)
+            self.wprep.ensure([("blocks.%d" % i, "blocks.%d.conv.weight" % i, g, (1, 1), False, True, cpad if i == 0 else 0)
                                for i, g in enumerate(self.geoms)], params, False)
             self.wprep.run()
+        if tma and cpad != self.kp2:
+            padded = A.get("poses_padded" + tag, (B, 1, L, cpad), zero=True)      # the pad columns stay zero
+            padded[..., :self.kp2].copy_(src)
+            src = padded
         for i, g in enumerate(self.geoms):
             name = "blocks.%d" % i
             lo = g.out_hw(1, L)[1]
             wt, wt_nk = self.wprep.fwd[name]
+            if i == 0 and src.shape[-1] != g.cin:
+                g = ConvGeom.conv1d(src.shape[-1], g.cout, g.kw, g.sw, g.pw)
             raw = A.get("raw%s:%s" % (tag, name), (B, 1, lo, g.cout))
             # BN statistics span the batch (row tiles may straddle clips); scale/shift are per channel (bstride 0)
             d = ops.fwd_desc(g, src, wt, raw, B, 1, L, xf, self.slope, wt_nk=wt_nk)
@@ -549,7 +565,12 @@ class PoseEncoderEngine:
                 ops.conv_gemm(d)
                 ops.bn_eval_scale_shift(buffers[name + ".norm.running_mean"], buffers[name + ".norm.running_var"],
                                         params[name + ".norm.weight"], params[name + ".norm.bias"], out=(sc, sh))
-            src, xf, L = raw, (sc, sh, 0), lo
+            if tma and i + 1 < len(self.geoms):
+                act = A.get("act%s:%s" % (tag, name), (B, 1, lo, g.cout))
+                ops.scale_shift_act(raw.view(B, lo, g.cout), sc, sh, 0, self.slope, out=act.view(B, lo, g.cout))
+                src, xf, L = act, None, lo
+            else:
+                src, xf, L = raw, (sc, sh, 0), lo
         mu = A.get("mu" + tag, (B, self.code2 // 2))
         logvar = A.get("logvar" + tag, (B, self.code2 // 2))
         ops.pose_head_fwd(src.view(B, L, self.code2), xf[0], xf[1], self.slope, mu, logvar)

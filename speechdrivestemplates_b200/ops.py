@@ -202,12 +202,14 @@ def wgrad_desc(g, x, dy, wpart, B, H, W, splits, xf=None, slope=1.0):
 
 
 def wgrad_splits(g, B, oh, ow, target_ctas=444):
-    """Number of K (pixel) splits so that the weight-gradient GEMM fills the 148 SMs ~3 times over."""
+    """Number of K (pixel) splits so that the weight-gradient GEMM fills the 148 SMs ~3 times over -- but never fewer than
+    256 pixels (8 k-blocks of the tensor-core kernel) per split: every split writes, and the reduction re-reads, a full
+    copy of the layer's gradient, which for the 1-D stacks (2048 pixels, 0.8 MB of weights) used to be 32 copies per layer."""
     if g.k <= 16 and g.cout <= 64:          # streaming small-K kernel: one partial per CTA, 4 CTAs per SM
         return min(148 * 4, max(1, -(-(B * oh * ow) // 64)))
     tiles = -(-g.k // 128) * -(-g.cout // (64 if g.cout <= 64 else 128))
     pixels = B * oh * ow
-    return max(1, min(-(-target_ctas // tiles), -(-pixels // 64)))
+    return max(1, min(-(-target_ctas // tiles), -(-pixels // 256)))
 
 
 def row_tiles(desc):

@@ -13,7 +13,7 @@ from speechdrivestemplates_b200 import config, pipeline  # noqa: E402
 
 def main():
     dev = torch.device("cuda:0")
-    tr = pipeline.Voice2PoseTrainer(config.get_cfg("voice2pose_sdt_bp"), bench.N_TRAIN, dev, conv_math=2)
+    tr = pipeline.Voice2PoseTrainer(config.get_cfg("voice2pose_sdt_bp"), bench.N_TRAIN, dev, conv_math=3)
     hbs = bench.make_batches(32, 0)
     dbs = [{"audio": h["audio"].to(dev), "poses": h["poses"].to(dev), "clip_index": h["clip_index"].to(dev),
             "speaker_stat": {k: v.to(dev) for k, v in h["speaker_stat"].items()}} for h in hbs]
@@ -89,6 +89,15 @@ def main():
         k += 1
     torch.cuda.synchronize()
     print({k2: round(v / K * 1e3, 3) for k2, v in ph.items()})
+
+    # with the bench's clock sampler running
+    for rep in range(3):
+        smp = bench.ClockSampler(0)
+        smp.start()
+        time.sleep(0.2)
+        timed("run_epoch + NVML sampler (rep %d)" % rep, prefetch_losses)
+        print("   ", smp.stop())
+        timed("run_epoch, sampler off (rep %d)" % rep, prefetch_losses)
 
     # H2D alone
     def h2d_only():

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(kBwdQ * kC) fl_bwd_colsum_kernel(float* __rest
 }
 
 // one block per output channel: the closed-form combination over the batch
-__global__ void __launch_bounds__(128) fl_bwd_finalize_kernel(const float* __restrict__ partial, const double* __restrict__ moments,
+__global__ void __launch_bounds__(256) fl_bwd_finalize_kernel(const float* __restrict__ partial, const double* __restrict__ moments,
                                                               const float* __restrict__ w, const float* __restrict__ scale,
                                                               const float* __restrict__ shift, int B, int units,
                                                               float* __restrict__ dw) {
@@ -251,21 +251,26 @@ __global__ void __launch_bounds__(128) fl_bwd_finalize_kernel(const float* __res
         s_sum[i] = s;
     }
     __syncthreads();
-    const int t = threadIdx.x;
-    if (t >= kTaps) return;
+    // thread (b, t): the closed form of image b for tap t; then a fixed-order sum over the batch (deterministic)
     double wc[kTaps];
 #pragma unroll
     for (int k = 0; k < kTaps; ++k) wc[k] = (double)w[c * kTaps + k];
-    double out = 0.0;
-    for (int b = 0; b < B; ++b) {
+    double* s_out = s_sum + (size_t)B * kBwdQ;          // [B][kTaps]
+    for (int i = threadIdx.x; i < B * kTaps; i += blockDim.x) {
+        const int b = i / kTaps, t = i - b * kTaps;
         const double* m = moments + (size_t)b * kMom;
         const double sc = (double)scale[(size_t)b * kC + c], sh = (double)shift[(size_t)b * kC + c];
         const double S1 = s_sum[b * kBwdQ + 0], S2 = s_sum[b * kBwdQ + 1], G = s_sum[b * kBwdQ + 2 + t];
         double mw = 0.0;
 #pragma unroll
         for (int k = 0; k < kTaps; ++k) mw += m[kTaps + (t <= k ? tri(t, k) : tri(k, t))] * wc[k];
-        out += sc * (G - S1 * m[t] - S2 * (sc * mw + sh * m[t]));
+        s_out[i] = sc * (G - S1 * m[t] - S2 * (sc * mw + sh * m[t]));
     }
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t >= kTaps) return;
+    double out = 0.0;
+    for (int b = 0; b < B; ++b) out += s_out[b * kTaps + t];
     dw[c * kTaps + t] = (float)out;
 }
 
@@ -298,7 +303,7 @@ extern "C" int sdt_first_layer_bwd(const float* g_act, const float* act, const f
     SDT_REQUIRE(slope > 0.f, "sdt_first_layer_bwd: needs an invertible activation (slope > 0), got %g", (double)slope);
     SDT_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535, "sdt_first_layer_bwd: bad extents");
     const int units = sdt_first_layer_units(H, W);
-    const size_t fsmem = (size_t)B * kBwdQ * sizeof(double);
+    const size_t fsmem = (size_t)B * (kBwdQ + kTaps) * sizeof(double);
     SDT_REQUIRE(fsmem <= 40 * 1024, "sdt_first_layer_bwd: batch %d too large for the finalize kernel", B);
     cudaStream_t st = sdt::as_stream(stream);
     fl_bwd_kernel<<<dim3(units, B), 256, 0, st>>>(g_act, act, x, H, W, slope, partial);
@@ -307,7 +312,7 @@ extern "C" int sdt_first_layer_bwd(const float* g_act, const float* act, const f
         fl_bwd_colsum_kernel<<<B, kBwdQ * kC, 0, st>>>(partial, units);
         SDT_LAUNCH_OK("fl_bwd_colsum_kernel");
     }
-    fl_bwd_finalize_kernel<<<kC, 128, fsmem, st>>>(partial, moments, w, scale, shift, B, units, dw);
+    fl_bwd_finalize_kernel<<<kC, 256, fsmem, st>>>(partial, moments, w, scale, shift, B, units, dw);
     SDT_LAUNCH_OK("fl_bwd_finalize_kernel");
     return SDT_OK;
 }

@@ -359,9 +359,14 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
     return pred
 
 
+_DIAG_SKIP_WGRAD = bool(__import__("os").environ.get("SDT_DIAG_SKIP_WGRAD"))
+
+
 def _wgrad(self, g, x, dy, B, H, W, grad_out, xf=None, slope=1.0):
     """Weight gradient of one layer.  Nothing downstream in the backward pass depends on it, so when the engine has a
     `wg_stream` it is enqueued there (after an event marking dy ready) and overlaps the dgrad chain on the main stream."""
+    if _DIAG_SKIP_WGRAD:              # diagnostic only (wrong gradients): how much of the step do the weight gradients cost?
+        return
     wg = getattr(self, "wg_stream", None)
     if wg is not None:
         ev = torch.cuda.Event()

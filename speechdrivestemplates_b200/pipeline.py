@@ -9,6 +9,8 @@ of core/pipelines/voice2pose.py:281-312 as ONE fused device program: host batch 
 import math
 from collections import OrderedDict
 
+import os
+
 import torch
 from torch import nn
 
@@ -545,7 +547,8 @@ class Voice2PoseTrainer:
         fork.record(main)
         with torch.cuda.stream(self._aux):
             self._aux.wait_event(fork)
-            self.engine.run_side()
+            if not os.environ.get("SDT_DIAG_SKIP_SIDE"):       # diagnostic only: cost of the FGD / metrics side stream
+                self.engine.run_side()
             join.record(self._aux)
         self.engine.backward(self.grads, self.g_table)
         main.wait_event(join)

@@ -75,7 +75,6 @@ __global__ void bn_eval_kernel(const float* __restrict__ rm, const float* __rest
 
 // ---- backward of normalise -> affine -> activation over (B, P, C) ----------------------------------
 // CTA = 256 threads = 8 row-lanes x 32 channel-quads (C handled in chunks of 128), tile of ROWS_PER_TILE pixels.
-constexpr int kBwdRows = 256;
 
 __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float* __restrict__ g, const float* __restrict__ x,
                                                               const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -85,8 +84,9 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float* __res
     __shared__ float red[2][8][128];
     const int b = blockIdx.x / tiles_per_image, tile = blockIdx.x % tiles_per_image;
     const int cq = threadIdx.x % 32, rl = threadIdx.x / 32;
-    const int p0 = tile * kBwdRows;
-    const int p1 = min(P, p0 + kBwdRows);
+    const int rows = (P + tiles_per_image - 1) / tiles_per_image;
+    const int p0 = tile * rows;
+    const int p1 = min(P, p0 + rows);
     for (int cb = 0; cb < C; cb += 128) {
         const int c = cb + cq * 4;
         float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -189,7 +189,8 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_pow2_kernel(const float* 
     const int c4n = C >> 2, nrl = 256 / c4n;
     const int cq = threadIdx.x % c4n, rl = threadIdx.x / c4n;
     const int c = cq * 4;
-    const int p0 = tile * kBwdRows, p1 = min(P, p0 + kBwdRows);
+    const int rows = (P + tiles_per_image - 1) / tiles_per_image;       // tiles_per_image is the caller's choice of parallelism
+    const int p0 = tile * rows, p1 = min(P, p0 + rows);
     const int so = (groups_is_batch ? b * C : 0) + c;
     const float4 mu = *reinterpret_cast<const float4*>(mean + so), rs = *reinterpret_cast<const float4*>(rstd + so);
     const float4 ga = gamma ? *reinterpret_cast<const float4*>(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
@@ -404,7 +405,7 @@ extern "C" int sdt_norm_bwd_reduce(const float* g, const float* x, const float* 
     SDT_REQUIRE(g && x && mean && rstd && partial, "sdt_norm_bwd_reduce: null pointer");
     SDT_REQUIRE(B > 0 && P > 0 && C > 0 && C % 4 == 0, "sdt_norm_bwd_reduce: need C %% 4 == 0 (C=%d)", C);
     SDT_REQUIRE(groups == B || groups == 1, "sdt_norm_bwd_reduce: groups must be B or 1");
-    SDT_REQUIRE(tiles_per_image == sdt::ceil_div(P, kBwdRows), "sdt_norm_bwd_reduce: tiles_per_image must be ceil(P/%d)", kBwdRows);
+    SDT_REQUIRE(tiles_per_image >= 1 && tiles_per_image <= P, "sdt_norm_bwd_reduce: tiles_per_image=%d outside [1, P=%d]", tiles_per_image, P);
     if (C == 64 || C == 128 || C == 256)
         norm_bwd_reduce_pow2_kernel<<<B * tiles_per_image, 256, 0, sdt::as_stream(stream)>>>(
             g, x, mean, rstd, gamma, beta, P, C, groups == B ? 1 : 0, slope, partial, tiles_per_image);

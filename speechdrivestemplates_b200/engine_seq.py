@@ -59,7 +59,7 @@ class SeqBlock:
         xin, L_in, L_out = self.saved[tag]
         if self.norm == "BN":
             raw = A.get("raw%s:%s" % (tag, name), (B, L_out, g.cout))
-            tpi = -(-L_out // ops.BWD_ROWS)
+            tpi = ops.bwd_tiles(L_out, B)
             scratch = (A.get("nb_partial:" + name, (B * tpi, 2, g.cout)), A.get("nb_m1:" + name, (1, g.cout)), A.get("nb_m2:" + name, (1, g.cout)))
             ops.norm_backward(g_act, raw, A.get("mean%s:%s" % (tag, name), (1, g.cout)), A.get("rstd%s:%s" % (tag, name), (1, g.cout)), 1,
                               self.slope, params[name + ".norm.weight"], params[name + ".norm.bias"],

@@ -1,5 +1,6 @@
 // Library-level entry points of libsdt_b200: error string, version, math-mode switch.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -14,6 +15,13 @@ std::atomic<long long> g_tc_launches{0};
 void sdt_note_tc_launch() { g_tc_launches.fetch_add(1); }
 
 namespace sdt {
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("SDT_PDL");
+        return !(e != nullptr && e[0] == '0');
+    }();
+    return on;
+}
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);

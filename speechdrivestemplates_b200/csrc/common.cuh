@@ -39,6 +39,34 @@ void set_error(const char* fmt, ...);
     } while (0)
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- programmatic dependent launch -----------------------------------------------------------------------------
+// A train step is ~250 mostly small, mostly dependent launches.  Every kernel of this library starts with pdl_wait()
+// (griddepcontrol.wait: returns once the preceding kernel of the stream has completed and its writes are visible; a no-op
+// for a kernel launched without the attribute) followed by pdl_launch_dependents(), and every launch goes through
+// sdt::launch(), which sets cudaLaunchAttributeProgrammaticStreamSerialization: the NEXT kernel's CTAs are scheduled, its
+// parameters loaded and (tcgen05 kernels) its barriers / TMEM allocation done while this kernel's tail is still running.
+// SDT_PDL=0 in the environment switches the attribute off (plain stream order).
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);      // errors surface through SDT_LAUNCH_OK (cudaPeekAtLastError)
+}
+#endif
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 __device__ __forceinline__ float leaky(float v, float slope) { return v > 0.f ? v : v * slope; }

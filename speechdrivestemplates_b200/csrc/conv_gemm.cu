@@ -29,6 +29,8 @@ __device__ __forceinline__ float xf_apply(float v, float sc, float sh, float slo
 // ------------------------------------------------------------------------------------------------
 template <int BM, int BN, int TM, int TN, bool VEC>
 __global__ void __launch_bounds__(NTHREADS, 2) conv_gemm_kernel(const sdt_conv_desc d) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     static_assert((BM / TM) * (BN / TN) == NTHREADS, "thread tile");
     constexpr int LDA = BM + 4, LDB = BN + 4;
     constexpr int GM = TM / 4, GN = TN / 4;
@@ -267,6 +269,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_gemm_kernel(const sdt_conv_d
 // ------------------------------------------------------------------------------------------------
 template <int BM, int TM, bool VECA, bool VECB>
 __global__ void __launch_bounds__(NTHREADS, 2) conv_wgrad_kernel(const sdt_conv_desc d) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     constexpr int BN = 128, TN = 8;
     static_assert((BM / TM) * (BN / TN) == NTHREADS, "thread tile");
     constexpr int LDA = BM + 4, LDB = BN + 4;
@@ -456,6 +460,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) conv_wgrad_kernel(const sdt_conv_
 
 __global__ void wgrad_reduce_kernel(const float* __restrict__ wpart, int splits, int N, int C, int T,
                                     float* __restrict__ grad, int accumulate) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     // one thread per element of the reference-layout gradient (n, c, t); reads are strided but the tensor is small
     const long long total = (long long)N * C * T;
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -474,6 +480,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ wpart, int splits,
 // coalesced reads of the (T, C) partials, the (c, t) transpose into the reference layout goes through shared memory.
 __global__ void __launch_bounds__(256) wgrad_reduce_tiled_kernel(const float* __restrict__ wpart, int splits, int N, int C, int T,
                                                                  float* __restrict__ grad, int accumulate) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     extern __shared__ float s_t[];          // [T][33]
     const int cchunks = C >> 5;
     const int n = blockIdx.x / cchunks, c0 = (blockIdx.x - n * cchunks) << 5;
@@ -503,6 +511,8 @@ __global__ void __launch_bounds__(256) wgrad_reduce_tiled_kernel(const float* __
 
 __global__ void weight_prep_kernel(const float* __restrict__ w, int Cout, int Cin, int KH, int KW, int mode, int ky0,
                                    int kx0, int kstep, int TH, int TW, float* __restrict__ out) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     const long long total = (long long)TH * TW * Cin * Cout;
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
@@ -540,6 +550,8 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, int Cout, int Ci
 // ------------------------------------------------------------------------------------------------
 constexpr int SK_PIX = 64;
 __global__ void __launch_bounds__(256) conv_wgrad_smallk_kernel(const sdt_conv_desc d) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     __shared__ __align__(16) float dy_s[SK_PIX][64 + 1];
     __shared__ __align__(16) float a_s[SK_PIX][16];
     __shared__ float red[4][64][16 + 1];
@@ -616,6 +628,8 @@ struct PrepItem {     // mirrors sdt_prep_item
 };
 
 __global__ void weight_prep_batch_kernel(const PrepItem* __restrict__ items) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     const PrepItem it = items[blockIdx.y];
     const int cin_p = (it.mode == 2 && it.pad0 > it.Cin) ? it.pad0 : it.Cin;      // mode 2: input channels zero-padded to pad0
     const long long total = (long long)it.TH * it.TW * cin_p * it.Cout;
@@ -703,16 +717,16 @@ extern "C" int sdt_conv_gemm(const sdt_conv_desc* d, void* stream) {
     const sdt_conv_desc dd = *d;
     if (bm == 64) {
         dim3 grid(row_tiles_for(d, 64), sdt::ceil_div(d->N, 64));
-        if (vec) conv_gemm_kernel<64, 64, 4, 4, true><<<grid, NTHREADS, 0, st>>>(dd);
-        else conv_gemm_kernel<64, 64, 4, 4, false><<<grid, NTHREADS, 0, st>>>(dd);
+        if (vec) sdt::launch(conv_gemm_kernel<64, 64, 4, 4, true>, dim3(grid), dim3(NTHREADS), 0, st, dd);
+        else sdt::launch(conv_gemm_kernel<64, 64, 4, 4, false>, dim3(grid), dim3(NTHREADS), 0, st, dd);
     } else if (d->N <= 64) {
         dim3 grid(row_tiles_for(d, 128), sdt::ceil_div(d->N, 64));
-        if (vec) conv_gemm_kernel<128, 64, 8, 4, true><<<grid, NTHREADS, 0, st>>>(dd);
-        else conv_gemm_kernel<128, 64, 8, 4, false><<<grid, NTHREADS, 0, st>>>(dd);
+        if (vec) sdt::launch(conv_gemm_kernel<128, 64, 8, 4, true>, dim3(grid), dim3(NTHREADS), 0, st, dd);
+        else sdt::launch(conv_gemm_kernel<128, 64, 8, 4, false>, dim3(grid), dim3(NTHREADS), 0, st, dd);
     } else {
         dim3 grid(row_tiles_for(d, 128), sdt::ceil_div(d->N, 128));
-        if (vec) conv_gemm_kernel<128, 128, 8, 8, true><<<grid, NTHREADS, 0, st>>>(dd);
-        else conv_gemm_kernel<128, 128, 8, 8, false><<<grid, NTHREADS, 0, st>>>(dd);
+        if (vec) sdt::launch(conv_gemm_kernel<128, 128, 8, 8, true>, dim3(grid), dim3(NTHREADS), 0, st, dd);
+        else sdt::launch(conv_gemm_kernel<128, 128, 8, 8, false>, dim3(grid), dim3(NTHREADS), 0, st, dd);
     }
     SDT_LAUNCH_OK("conv_gemm_kernel");
     return SDT_OK;
@@ -728,23 +742,23 @@ extern "C" int sdt_conv_wgrad(const sdt_conv_desc* d, void* stream) {
     if (sdt_get_conv_math() >= 2 && sdt_tc_wgrad_tma_eligible(d)) return sdt_tc_wgrad_tma_launch(d, st);   // tcgen05 + TMA
     if (sdt_get_conv_math() >= 1 && sdt_tc_wgrad_eligible(d)) return sdt_tc_wgrad_launch(d, st);   // tcgen05 TF32
     if (Kc <= 16 && d->N <= 64) {       // tiny contraction: streaming kernel, one partial per CTA (gridDim.x == splits)
-        conv_wgrad_smallk_kernel<<<d->splits, 256, 0, st>>>(*d);
+        sdt::launch(conv_wgrad_smallk_kernel, dim3(d->splits), dim3(256), 0, st, *d);
         SDT_LAUNCH_OK("conv_wgrad_smallk_kernel");
         return SDT_OK;
     }
     const sdt_conv_desc dd = *d;
     if (d->N <= 64) {
         dim3 grid(sdt::ceil_div(Kc, 128), sdt::ceil_div(d->N, 64), d->splits);
-        if (veca && vecb) conv_wgrad_kernel<64, 4, true, true><<<grid, NTHREADS, 0, st>>>(dd);
-        else if (veca) conv_wgrad_kernel<64, 4, true, false><<<grid, NTHREADS, 0, st>>>(dd);
-        else if (vecb) conv_wgrad_kernel<64, 4, false, true><<<grid, NTHREADS, 0, st>>>(dd);
-        else conv_wgrad_kernel<64, 4, false, false><<<grid, NTHREADS, 0, st>>>(dd);
+        if (veca && vecb) sdt::launch(conv_wgrad_kernel<64, 4, true, true>, dim3(grid), dim3(NTHREADS), 0, st, dd);
+        else if (veca) sdt::launch(conv_wgrad_kernel<64, 4, true, false>, dim3(grid), dim3(NTHREADS), 0, st, dd);
+        else if (vecb) sdt::launch(conv_wgrad_kernel<64, 4, false, true>, dim3(grid), dim3(NTHREADS), 0, st, dd);
+        else sdt::launch(conv_wgrad_kernel<64, 4, false, false>, dim3(grid), dim3(NTHREADS), 0, st, dd);
     } else {
         dim3 grid(sdt::ceil_div(Kc, 128), sdt::ceil_div(d->N, 128), d->splits);
-        if (veca && vecb) conv_wgrad_kernel<128, 8, true, true><<<grid, NTHREADS, 0, st>>>(dd);
-        else if (veca) conv_wgrad_kernel<128, 8, true, false><<<grid, NTHREADS, 0, st>>>(dd);
-        else if (vecb) conv_wgrad_kernel<128, 8, false, true><<<grid, NTHREADS, 0, st>>>(dd);
-        else conv_wgrad_kernel<128, 8, false, false><<<grid, NTHREADS, 0, st>>>(dd);
+        if (veca && vecb) sdt::launch(conv_wgrad_kernel<128, 8, true, true>, dim3(grid), dim3(NTHREADS), 0, st, dd);
+        else if (veca) sdt::launch(conv_wgrad_kernel<128, 8, true, false>, dim3(grid), dim3(NTHREADS), 0, st, dd);
+        else if (vecb) sdt::launch(conv_wgrad_kernel<128, 8, false, true>, dim3(grid), dim3(NTHREADS), 0, st, dd);
+        else sdt::launch(conv_wgrad_kernel<128, 8, false, false>, dim3(grid), dim3(NTHREADS), 0, st, dd);
     }
     SDT_LAUNCH_OK("conv_wgrad_kernel");
     return SDT_OK;
@@ -755,10 +769,9 @@ extern "C" int sdt_conv_wgrad_reduce(const float* wpart, int splits, int N, int 
     SDT_REQUIRE(wpart && grad && splits >= 1 && N > 0 && C > 0 && T > 0, "sdt_conv_wgrad_reduce: bad arguments");
     const long long total = (long long)N * C * T;
     if (C % 32 == 0 && T <= 256)
-        wgrad_reduce_tiled_kernel<<<N * (C / 32), 256, (size_t)T * 33 * sizeof(float), sdt::as_stream(stream)>>>(
-            wpart, splits, N, C, T, grad, accumulate);
+        sdt::launch(wgrad_reduce_tiled_kernel, dim3(N * (C / 32)), dim3(256), (size_t)T * 33 * sizeof(float), sdt::as_stream(stream), wpart, splits, N, C, T, grad, accumulate);
     else
-        wgrad_reduce_kernel<<<sdt::ceil_div(total, 256), 256, 0, sdt::as_stream(stream)>>>(wpart, splits, N, C, T, grad, accumulate);
+        sdt::launch(wgrad_reduce_kernel, dim3(sdt::ceil_div(total, 256)), dim3(256), 0, sdt::as_stream(stream), wpart, splits, N, C, T, grad, accumulate);
     SDT_LAUNCH_OK("wgrad_reduce_kernel");
     return SDT_OK;
 }
@@ -771,7 +784,7 @@ extern "C" int sdt_weight_prep(const float* w, int Cout, int Cin, int KH, int KW
     SDT_REQUIRE(ky0 >= 0 && kx0 >= 0 && ky0 + kstep * (TH - 1) < KH && kx0 + kstep * (TW - 1) < KW,
                 "sdt_weight_prep: tap selection outside the %dx%d kernel", KH, KW);
     const long long total = (long long)TH * TW * Cin * Cout;
-    weight_prep_kernel<<<sdt::ceil_div(total, 256), 256, 0, sdt::as_stream(stream)>>>(w, Cout, Cin, KH, KW, mode, ky0, kx0,
+    sdt::launch(weight_prep_kernel, dim3(sdt::ceil_div(total, 256)), dim3(256), 0, sdt::as_stream(stream), w, Cout, Cin, KH, KW, mode, ky0, kx0,
                                                                                        kstep, TH, TW, out);
     SDT_LAUNCH_OK("weight_prep_kernel");
     return SDT_OK;
@@ -782,7 +795,7 @@ extern "C" int sdt_weight_prep_batch(const sdt_prep_item* items_device, int n_it
     static_assert(sizeof(PrepItem) == sizeof(sdt_prep_item), "sdt_prep_item layout");
     int gx = sdt::ceil_div(max_elems, 256 * 4);
     if (gx > 1024) gx = 1024;
-    weight_prep_batch_kernel<<<dim3(gx, n_items), 256, 0, sdt::as_stream(stream)>>>(reinterpret_cast<const PrepItem*>(items_device));
+    sdt::launch(weight_prep_batch_kernel, dim3(gx, n_items), dim3(256), 0, sdt::as_stream(stream), reinterpret_cast<const PrepItem*>(items_device));
     SDT_LAUNCH_OK("weight_prep_batch_kernel");
     return SDT_OK;
 }

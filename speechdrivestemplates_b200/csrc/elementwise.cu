@@ -20,6 +20,8 @@ __device__ __forceinline__ void lerp_coeff(int j, int in_size, int out_size, int
 __global__ void enc_to_seq_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                       const float* __restrict__ shift, int bstride, float slope, int B, int H, int W, int C,
                                       const float* __restrict__ code, int D, int F, float* __restrict__ out) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     const long long total = (long long)B * F * (C + D);
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
@@ -43,6 +45,8 @@ __global__ void enc_to_seq_fwd_kernel(const float* __restrict__ x, const float* 
 // adjoint in gather form (deterministic): every (b, y, x, c) sums the output frames that sampled it
 __global__ void enc_to_seq_bwd_kernel(const float* __restrict__ g_out, int B, int H, int W, int C, int D, int F,
                                       float* __restrict__ g_act) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     const long long total = (long long)B * H * W * C;
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
@@ -73,6 +77,8 @@ __global__ void enc_to_seq_bwd_kernel(const float* __restrict__ g_out, int B, in
 
 __global__ void code_grad_from_seq_kernel(const float* __restrict__ g_out, int B, int C, int D, int F,
                                           float* __restrict__ g_code) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= B * D) return;
     const int b = e / D, dd = e % D;
@@ -84,6 +90,8 @@ __global__ void code_grad_from_seq_kernel(const float* __restrict__ g_out, int B
 // ---- F.interpolate(x, Lout, 'linear') (+ skip): generator.py:79-83, autoencoder.py:62-66 ----------------------------
 __global__ void upsample_add_fwd_kernel(const float* __restrict__ x, const float* __restrict__ skip, int B, int Lin,
                                         int Lout, int C, float* __restrict__ out) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     const long long total = (long long)B * Lout * C;
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
@@ -100,6 +108,8 @@ __global__ void upsample_add_fwd_kernel(const float* __restrict__ x, const float
 
 __global__ void upsample_bwd_kernel(const float* __restrict__ g_out, int B, int Lin, int Lout, int C,
                                     float* __restrict__ g_x, int accumulate) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     const long long total = (long long)B * Lin * C;
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
@@ -130,6 +140,8 @@ constexpr int kLossBlocks = 256;
 __global__ void __launch_bounds__(256) l1_partial_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
                                                          long long n, float lambda, float* __restrict__ g_pred,
                                                          float* __restrict__ partial) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     __shared__ float red[8];
     float acc = 0.f;
     const float gscale = lambda / (float)n;
@@ -149,6 +161,8 @@ __global__ void __launch_bounds__(256) l1_partial_kernel(const float* __restrict
 }
 
 __global__ void sum_partials_kernel(const float* __restrict__ partial, int count, double denom, float* __restrict__ out) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         double s = 0.0;
         for (int i = 0; i < count; ++i) s += (double)partial[i];
@@ -160,6 +174,8 @@ __global__ void sum_partials_kernel(const float* __restrict__ partial, int count
 __global__ void code_gather_kl_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx, int B, int D,
                                       float lambda, float* __restrict__ code, float* __restrict__ out,
                                       float* __restrict__ g_code) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     // one CTA; thread dd < D owns one code dimension
     __shared__ int all_nonzero;
     __shared__ float terms[1024];
@@ -205,6 +221,8 @@ __global__ void code_gather_kl_kernel(const float* __restrict__ table, const int
 
 __global__ void code_scatter_grad_kernel(const float* __restrict__ ga, const float* __restrict__ gb,
                                          const int64_t* __restrict__ idx, int B, int D, float* __restrict__ g_table) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= B * D) return;
     const int b = e / D, dd = e % D;
@@ -219,6 +237,8 @@ __global__ void code_scatter_grad_kernel(const float* __restrict__ ga, const flo
 
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ g, int R, int C, float* __restrict__ out,
                                                      int accumulate) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     // one CTA per 32 columns; 8 row-lanes; fixed order
     __shared__ float red[8][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
@@ -236,6 +256,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ g
 
 __global__ void __launch_bounds__(1024) mse_const_kernel(const float* __restrict__ s, long long n, float target, float lambda,
                                                          float* __restrict__ out, float* __restrict__ g_s) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     __shared__ float red[32];
     float acc = 0.f;
     const float gscale = lambda * 2.f / (float)n;
@@ -255,6 +277,8 @@ __global__ void __launch_bounds__(1024) mse_const_kernel(const float* __restrict
 }
 
 __global__ void motion_diff_fwd_kernel(const float* __restrict__ x, int B, int T, int C, float* __restrict__ out) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     const long long total = (long long)B * (T - 1) * C;
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
@@ -267,6 +291,8 @@ __global__ void motion_diff_fwd_kernel(const float* __restrict__ x, int B, int T
 
 __global__ void motion_diff_bwd_kernel(const float* __restrict__ g_out, int B, int T, int C, float* __restrict__ g_x,
                                        int accumulate) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     const long long total = (long long)B * T * C;
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
@@ -283,6 +309,8 @@ __global__ void motion_diff_bwd_kernel(const float* __restrict__ g_out, int B, i
 __global__ void pose_head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                      const float* __restrict__ shift, float slope, int B, int L, int D2,
                                      float* __restrict__ mu, float* __restrict__ logvar) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= B * D2) return;
     const int b = e / D2, ch = e % D2;
@@ -294,6 +322,8 @@ __global__ void pose_head_fwd_kernel(const float* __restrict__ x, const float* _
 __global__ void __launch_bounds__(1024) vae_reparam_kl_kernel(const float* __restrict__ mu, const float* __restrict__ logvar,
                                                               const float* __restrict__ eps, int n, float lambda,
                                                               float* __restrict__ code, float* __restrict__ out) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     __shared__ float red[32];
     float acc = 0.f;
     for (int e = threadIdx.x; e < n; e += blockDim.x) {
@@ -316,6 +346,8 @@ __global__ void __launch_bounds__(1024) vae_reparam_kl_kernel(const float* __res
 __global__ void vae_reparam_kl_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ logvar,
                                           const float* __restrict__ eps, const float* __restrict__ g_code, int n, float lambda,
                                           float* __restrict__ g_mu, float* __restrict__ g_logvar) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     const float m = mu[e], lv = logvar[e], gc = g_code[e];
@@ -327,6 +359,8 @@ __global__ void vae_reparam_kl_bwd_kernel(const float* __restrict__ mu, const fl
 // g_mu and odd channels g_logvar
 __global__ void pose_head_bwd_kernel(const float* __restrict__ g_mu, const float* __restrict__ g_logvar, int B, int L, int D2,
                                      float* __restrict__ g_act) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= B * L * D2) return;
     const int ch = e % D2, t = (e / D2) % L, b = e / (D2 * L);
@@ -339,6 +373,8 @@ __global__ void pose_head_bwd_kernel(const float* __restrict__ g_mu, const float
 // scalars: [0] step_size = lr / (1 - beta1^t), [1] 1/sqrt(1 - beta2^t), [2] t (as float, informational),
 //          [3] learning rate used when the lr argument is negative; 8 bytes at scalars+4 hold t as int64.
 __global__ void adam_advance_kernel(float* scalars, float lr, double beta1, double beta2) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     long long* tptr = reinterpret_cast<long long*>(scalars + 4);
     const long long t = *tptr + 1;
     *tptr = t;
@@ -354,6 +390,8 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
                                                         float* __restrict__ m, float* __restrict__ v, long long n,
                                                         const float* __restrict__ scalars, float beta1, float beta2,
                                                         float omb1, float omb2, float eps, float grad_scale) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     // omb1/omb2 = (float)(1 - beta) evaluated in double on the host, as torch does for add_(alpha=1-beta1)
     const float step_size = scalars[0], inv_sqrt_bc2 = scalars[1];
     const long long n4 = n / 4;
@@ -396,7 +434,7 @@ extern "C" int sdt_enc_to_seq_fwd(const float* x, const float* scale, const floa
     SDT_REQUIRE(x && scale && shift && out, "sdt_enc_to_seq_fwd: null pointer");
     SDT_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && F > 0 && D >= 0, "sdt_enc_to_seq_fwd: bad extents");
     SDT_REQUIRE(D == 0 || code != nullptr, "sdt_enc_to_seq_fwd: D > 0 needs code");
-    enc_to_seq_fwd_kernel<<<GRID1D((long long)B * F * (C + D))>>>(x, scale, shift, xf_bstride, slope, B, H, W, C, code, D, F, out);
+    sdt::launch(enc_to_seq_fwd_kernel, dim3(sdt::ceil_div((long long)((long long)B * F * (C + D)), 256)), dim3(256), 0, sdt::as_stream(stream), x, scale, shift, xf_bstride, slope, B, H, W, C, code, D, F, out);
     SDT_LAUNCH_OK("enc_to_seq_fwd_kernel");
     return SDT_OK;
 }
@@ -405,10 +443,10 @@ extern "C" int sdt_enc_to_seq_bwd(const float* g_out, int B, int H, int W, int C
                                   void* stream) {
     SDT_REQUIRE(g_out && g_act, "sdt_enc_to_seq_bwd: null pointer");
     SDT_REQUIRE(D == 0 || g_code != nullptr, "sdt_enc_to_seq_bwd: D > 0 needs g_code");
-    enc_to_seq_bwd_kernel<<<GRID1D((long long)B * H * W * C)>>>(g_out, B, H, W, C, D, F, g_act);
+    sdt::launch(enc_to_seq_bwd_kernel, dim3(sdt::ceil_div((long long)((long long)B * H * W * C), 256)), dim3(256), 0, sdt::as_stream(stream), g_out, B, H, W, C, D, F, g_act);
     SDT_LAUNCH_OK("enc_to_seq_bwd_kernel");
     if (D > 0) {
-        code_grad_from_seq_kernel<<<GRID1D(B * D)>>>(g_out, B, C, D, F, g_code);
+        sdt::launch(code_grad_from_seq_kernel, dim3(sdt::ceil_div((long long)(B * D), 256)), dim3(256), 0, sdt::as_stream(stream), g_out, B, C, D, F, g_code);
         SDT_LAUNCH_OK("code_grad_from_seq_kernel");
     }
     return SDT_OK;
@@ -417,14 +455,14 @@ extern "C" int sdt_enc_to_seq_bwd(const float* g_out, int B, int H, int W, int C
 extern "C" int sdt_upsample_add_fwd(const float* x, const float* skip, int B, int Lin, int Lout, int C, float* out,
                                     void* stream) {
     SDT_REQUIRE(x && out && B > 0 && Lin > 0 && Lout > 0 && C > 0, "sdt_upsample_add_fwd: bad arguments");
-    upsample_add_fwd_kernel<<<GRID1D((long long)B * Lout * C)>>>(x, skip, B, Lin, Lout, C, out);
+    sdt::launch(upsample_add_fwd_kernel, dim3(sdt::ceil_div((long long)((long long)B * Lout * C), 256)), dim3(256), 0, sdt::as_stream(stream), x, skip, B, Lin, Lout, C, out);
     SDT_LAUNCH_OK("upsample_add_fwd_kernel");
     return SDT_OK;
 }
 
 extern "C" int sdt_upsample_bwd(const float* g_out, int B, int Lin, int Lout, int C, float* g_x, int accumulate, void* stream) {
     SDT_REQUIRE(g_out && g_x && B > 0 && Lin > 0 && Lout > 0 && C > 0, "sdt_upsample_bwd: bad arguments");
-    upsample_bwd_kernel<<<GRID1D((long long)B * Lin * C)>>>(g_out, B, Lin, Lout, C, g_x, accumulate);
+    sdt::launch(upsample_bwd_kernel, dim3(sdt::ceil_div((long long)((long long)B * Lin * C), 256)), dim3(256), 0, sdt::as_stream(stream), g_out, B, Lin, Lout, C, g_x, accumulate);
     SDT_LAUNCH_OK("upsample_bwd_kernel");
     return SDT_OK;
 }
@@ -432,9 +470,9 @@ extern "C" int sdt_upsample_bwd(const float* g_out, int B, int Lin, int Lout, in
 extern "C" int sdt_l1_loss(const float* pred, const float* gt, int64_t n, float lambda, float* loss_out, float* g_pred,
                            float* partial, void* stream) {
     SDT_REQUIRE(pred && gt && loss_out && partial && n > 0, "sdt_l1_loss: bad arguments");
-    l1_partial_kernel<<<kLossBlocks, 256, 0, sdt::as_stream(stream)>>>(pred, gt, n, lambda, g_pred, partial);
+    sdt::launch(l1_partial_kernel, dim3(kLossBlocks), dim3(256), 0, sdt::as_stream(stream), pred, gt, n, lambda, g_pred, partial);
     SDT_LAUNCH_OK("l1_partial_kernel");
-    sum_partials_kernel<<<1, 32, 0, sdt::as_stream(stream)>>>(partial, kLossBlocks, (double)n, loss_out);
+    sdt::launch(sum_partials_kernel, dim3(1), dim3(32), 0, sdt::as_stream(stream), partial, kLossBlocks, (double)n, loss_out);
     SDT_LAUNCH_OK("sum_partials_kernel");
     return SDT_OK;
 }
@@ -443,7 +481,7 @@ extern "C" int sdt_code_gather_kl(const float* table, const int64_t* idx, int B,
                                   float* g_code, void* stream) {
     SDT_REQUIRE(table && idx && code && out && g_code, "sdt_code_gather_kl: null pointer");
     SDT_REQUIRE(B > 0 && D > 0 && D <= 1024, "sdt_code_gather_kl: need 0 < D <= 1024");
-    code_gather_kl_kernel<<<1, ((D + 31) / 32) * 32, 0, sdt::as_stream(stream)>>>(table, idx, B, D, lambda, code, out, g_code);
+    sdt::launch(code_gather_kl_kernel, dim3(1), dim3(((D + 31) / 32) * 32), 0, sdt::as_stream(stream), table, idx, B, D, lambda, code, out, g_code);
     SDT_LAUNCH_OK("code_gather_kl_kernel");
     return SDT_OK;
 }
@@ -451,35 +489,35 @@ extern "C" int sdt_code_gather_kl(const float* table, const int64_t* idx, int B,
 extern "C" int sdt_code_scatter_grad(const float* g_code_a, const float* g_code_b, const int64_t* idx, int B, int D,
                                      float* g_table, void* stream) {
     SDT_REQUIRE(idx && g_table && (g_code_a || g_code_b), "sdt_code_scatter_grad: null pointer");
-    code_scatter_grad_kernel<<<GRID1D(B * D)>>>(g_code_a, g_code_b, idx, B, D, g_table);
+    sdt::launch(code_scatter_grad_kernel, dim3(sdt::ceil_div((long long)(B * D), 256)), dim3(256), 0, sdt::as_stream(stream), g_code_a, g_code_b, idx, B, D, g_table);
     SDT_LAUNCH_OK("code_scatter_grad_kernel");
     return SDT_OK;
 }
 
 extern "C" int sdt_colsum(const float* g, int R, int C, float* out, int accumulate, void* stream) {
     SDT_REQUIRE(g && out && R > 0 && C > 0, "sdt_colsum: bad arguments");
-    colsum_kernel<<<sdt::ceil_div(C, 32), 256, 0, sdt::as_stream(stream)>>>(g, R, C, out, accumulate);
+    sdt::launch(colsum_kernel, dim3(sdt::ceil_div(C, 32)), dim3(256), 0, sdt::as_stream(stream), g, R, C, out, accumulate);
     SDT_LAUNCH_OK("colsum_kernel");
     return SDT_OK;
 }
 
 extern "C" int sdt_mse_const_loss(const float* s, int64_t n, float target, float lambda, float* out, float* g_s, void* stream) {
     SDT_REQUIRE(s && out && n > 0, "sdt_mse_const_loss: bad arguments");
-    mse_const_kernel<<<1, 1024, 0, sdt::as_stream(stream)>>>(s, n, target, lambda, out, g_s);
+    sdt::launch(mse_const_kernel, dim3(1), dim3(1024), 0, sdt::as_stream(stream), s, n, target, lambda, out, g_s);
     SDT_LAUNCH_OK("mse_const_kernel");
     return SDT_OK;
 }
 
 extern "C" int sdt_motion_diff_fwd(const float* x, int B, int T, int C, float* out, void* stream) {
     SDT_REQUIRE(x && out && B > 0 && T > 1 && C > 0, "sdt_motion_diff_fwd: bad arguments");
-    motion_diff_fwd_kernel<<<GRID1D((long long)B * (T - 1) * C)>>>(x, B, T, C, out);
+    sdt::launch(motion_diff_fwd_kernel, dim3(sdt::ceil_div((long long)((long long)B * (T - 1) * C), 256)), dim3(256), 0, sdt::as_stream(stream), x, B, T, C, out);
     SDT_LAUNCH_OK("motion_diff_fwd_kernel");
     return SDT_OK;
 }
 
 extern "C" int sdt_motion_diff_bwd(const float* g_out, int B, int T, int C, float* g_x, int accumulate, void* stream) {
     SDT_REQUIRE(g_out && g_x && B > 0 && T > 1 && C > 0, "sdt_motion_diff_bwd: bad arguments");
-    motion_diff_bwd_kernel<<<GRID1D((long long)B * T * C)>>>(g_out, B, T, C, g_x, accumulate);
+    sdt::launch(motion_diff_bwd_kernel, dim3(sdt::ceil_div((long long)((long long)B * T * C), 256)), dim3(256), 0, sdt::as_stream(stream), g_out, B, T, C, g_x, accumulate);
     SDT_LAUNCH_OK("motion_diff_bwd_kernel");
     return SDT_OK;
 }
@@ -488,7 +526,7 @@ extern "C" int sdt_pose_head_fwd(const float* x, const float* scale, const float
                                  float* mu, float* logvar, void* stream) {
     SDT_REQUIRE(x && scale && shift && mu && logvar, "sdt_pose_head_fwd: null pointer");
     SDT_REQUIRE(B > 0 && L > 0 && D2 > 0 && D2 % 2 == 0, "sdt_pose_head_fwd: bad extents");
-    pose_head_fwd_kernel<<<GRID1D(B * D2)>>>(x, scale, shift, slope, B, L, D2, mu, logvar);
+    sdt::launch(pose_head_fwd_kernel, dim3(sdt::ceil_div((long long)(B * D2), 256)), dim3(256), 0, sdt::as_stream(stream), x, scale, shift, slope, B, L, D2, mu, logvar);
     SDT_LAUNCH_OK("pose_head_fwd_kernel");
     return SDT_OK;
 }
@@ -496,14 +534,14 @@ extern "C" int sdt_pose_head_fwd(const float* x, const float* scale, const float
 extern "C" int sdt_vae_reparam_kl(const float* mu, const float* logvar, const float* eps, int n, float lambda, float* code,
                                   float* out, void* stream) {
     SDT_REQUIRE(mu && logvar && eps && code && out && n > 0, "sdt_vae_reparam_kl: bad arguments");
-    vae_reparam_kl_kernel<<<1, 1024, 0, sdt::as_stream(stream)>>>(mu, logvar, eps, n, lambda, code, out);
+    sdt::launch(vae_reparam_kl_kernel, dim3(1), dim3(1024), 0, sdt::as_stream(stream), mu, logvar, eps, n, lambda, code, out);
     SDT_LAUNCH_OK("vae_reparam_kl_kernel");
     return SDT_OK;
 }
 
 extern "C" int sdt_adam_advance(float* scalars, float lr, double beta1, double beta2, void* stream) {
     SDT_REQUIRE(scalars, "sdt_adam_advance: null pointer");
-    adam_advance_kernel<<<1, 1, 0, sdt::as_stream(stream)>>>(scalars, lr, beta1, beta2);
+    sdt::launch(adam_advance_kernel, dim3(1), dim3(1), 0, sdt::as_stream(stream), scalars, lr, beta1, beta2);
     SDT_LAUNCH_OK("adam_advance_kernel");
     return SDT_OK;
 }
@@ -515,7 +553,7 @@ extern "C" int sdt_adam_flat(float* param, const float* grad, float* exp_avg, fl
                 "sdt_adam_flat: buffers must be 16-byte aligned");
     int blocks = sdt::ceil_div(n / 4 + 1, 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    adam_flat_kernel<<<blocks, 256, 0, sdt::as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, scalars, (float)beta1,
+    sdt::launch(adam_flat_kernel, dim3(blocks), dim3(256), 0, sdt::as_stream(stream), param, grad, exp_avg, exp_avg_sq, n, scalars, (float)beta1,
                                                                  (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2),
                                                                  (float)eps, grad_scale);
     SDT_LAUNCH_OK("adam_flat_kernel");
@@ -525,14 +563,14 @@ extern "C" int sdt_adam_flat(float* param, const float* grad, float* exp_avg, fl
 extern "C" int sdt_vae_reparam_kl_bwd(const float* mu, const float* logvar, const float* eps, const float* g_code, int n,
                                       float lambda, float* g_mu, float* g_logvar, void* stream) {
     SDT_REQUIRE(mu && logvar && eps && g_code && g_mu && g_logvar && n > 0, "sdt_vae_reparam_kl_bwd: bad arguments");
-    vae_reparam_kl_bwd_kernel<<<GRID1D(n)>>>(mu, logvar, eps, g_code, n, lambda, g_mu, g_logvar);
+    sdt::launch(vae_reparam_kl_bwd_kernel, dim3(sdt::ceil_div((long long)(n), 256)), dim3(256), 0, sdt::as_stream(stream), mu, logvar, eps, g_code, n, lambda, g_mu, g_logvar);
     SDT_LAUNCH_OK("vae_reparam_kl_bwd_kernel");
     return SDT_OK;
 }
 
 extern "C" int sdt_pose_head_bwd(const float* g_mu, const float* g_logvar, int B, int L, int D2, float* g_act, void* stream) {
     SDT_REQUIRE(g_mu && g_logvar && g_act && B > 0 && L > 0 && D2 > 0 && D2 % 2 == 0, "sdt_pose_head_bwd: bad arguments");
-    pose_head_bwd_kernel<<<GRID1D(B * L * D2)>>>(g_mu, g_logvar, B, L, D2, g_act);
+    sdt::launch(pose_head_bwd_kernel, dim3(sdt::ceil_div((long long)(B * L * D2), 256)), dim3(256), 0, sdt::as_stream(stream), g_mu, g_logvar, B, L, D2, g_act);
     SDT_LAUNCH_OK("pose_head_bwd_kernel");
     return SDT_OK;
 }

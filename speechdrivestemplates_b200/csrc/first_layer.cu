@@ -53,6 +53,8 @@ __device__ __forceinline__ void stage_rows(const float* __restrict__ x, int b, c
 }
 
 __global__ void __launch_bounds__(128) fl_moments_kernel(const float* __restrict__ x, int H, int W, double* __restrict__ partial) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     __shared__ float s_rows[3 * kPitch];
     __shared__ double s_red[4][kMom];
     const int b = blockIdx.y;
@@ -91,6 +93,8 @@ __global__ void __launch_bounds__(128) fl_moments_kernel(const float* __restrict
 __global__ void __launch_bounds__(128) fl_stats_kernel(const double* __restrict__ partial, const float* __restrict__ w, int units,
                                                        double count, float eps, double* __restrict__ moments,
                                                        float* __restrict__ scale, float* __restrict__ shift) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     __shared__ double s_m[kMom];
     const int b = blockIdx.x;
     if (threadIdx.x < kMom) {
@@ -127,6 +131,8 @@ __global__ void __launch_bounds__(128) fl_stats_kernel(const double* __restrict_
 __global__ void __launch_bounds__(256) fl_act_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                      const float* __restrict__ scale, const float* __restrict__ shift, int H,
                                                      int W, float slope, float* __restrict__ act) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     __shared__ float s_rows[3 * kPitch];
     const int b = blockIdx.y;
     const Unit u = unit_of_block(W);
@@ -166,6 +172,8 @@ __global__ void __launch_bounds__(256) fl_act_kernel(const float* __restrict__ x
 __global__ void __launch_bounds__(256) fl_bwd_kernel(const float* __restrict__ g, const float* __restrict__ act,
                                                      const float* __restrict__ x, int H, int W, float slope,
                                                      float* __restrict__ partial) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     __shared__ float s_rows[3 * kPitch];
     __shared__ float s_red[kBwdQ][8][kC];
     const int b = blockIdx.y;
@@ -221,6 +229,8 @@ __global__ void __launch_bounds__(256) fl_bwd_kernel(const float* __restrict__ g
 // consecutive floats), stored IN PLACE as a float-float pair in the image's unit rows 0 (high part) and 1 (low part).
 // (The finalize kernel used to walk the units itself, one 4-byte read per 2.8 KB stride and thread: 85 us.)
 __global__ void __launch_bounds__(kBwdQ * kC) fl_bwd_colsum_kernel(float* __restrict__ partial, int units) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     const int b = blockIdx.x, t = threadIdx.x;
     float* base = partial + (size_t)b * units * kBwdQ * kC;
     double s = 0.0;
@@ -237,6 +247,8 @@ __global__ void __launch_bounds__(256) fl_bwd_finalize_kernel(const float* __res
                                                               const float* __restrict__ w, const float* __restrict__ scale,
                                                               const float* __restrict__ shift, int B, int units,
                                                               float* __restrict__ dw) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     extern __shared__ double s_sum[];          // [B][kBwdQ]
     const int c = blockIdx.x;
     for (int i = threadIdx.x; i < B * kBwdQ; i += blockDim.x) {
@@ -286,11 +298,11 @@ extern "C" int sdt_first_layer_fwd(const float* x, const float* w, int B, int H,
     SDT_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535, "sdt_first_layer_fwd: bad extents");
     const int units = sdt_first_layer_units(H, W);
     cudaStream_t st = sdt::as_stream(stream);
-    fl_moments_kernel<<<dim3(units, B), 128, 0, st>>>(x, H, W, mom_partial);
+    sdt::launch(fl_moments_kernel, dim3(units, B), dim3(128), 0, st, x, H, W, mom_partial);
     SDT_LAUNCH_OK("fl_moments_kernel");
-    fl_stats_kernel<<<B, 128, 0, st>>>(mom_partial, w, units, (double)H * W, eps, moments, scale, shift);
+    sdt::launch(fl_stats_kernel, dim3(B), dim3(128), 0, st, mom_partial, w, units, (double)H * W, eps, moments, scale, shift);
     SDT_LAUNCH_OK("fl_stats_kernel");
-    fl_act_kernel<<<dim3(units, B), 256, 0, st>>>(x, w, scale, shift, H, W, slope, act);
+    sdt::launch(fl_act_kernel, dim3(units, B), dim3(256), 0, st, x, w, scale, shift, H, W, slope, act);
     SDT_LAUNCH_OK("fl_act_kernel");
     return SDT_OK;
 }
@@ -306,13 +318,13 @@ extern "C" int sdt_first_layer_bwd(const float* g_act, const float* act, const f
     const size_t fsmem = (size_t)B * (kBwdQ + kTaps) * sizeof(double);
     SDT_REQUIRE(fsmem <= 40 * 1024, "sdt_first_layer_bwd: batch %d too large for the finalize kernel", B);
     cudaStream_t st = sdt::as_stream(stream);
-    fl_bwd_kernel<<<dim3(units, B), 256, 0, st>>>(g_act, act, x, H, W, slope, partial);
+    sdt::launch(fl_bwd_kernel, dim3(units, B), dim3(256), 0, st, g_act, act, x, H, W, slope, partial);
     SDT_LAUNCH_OK("fl_bwd_kernel");
     if (units >= 2) {
-        fl_bwd_colsum_kernel<<<B, kBwdQ * kC, 0, st>>>(partial, units);
+        sdt::launch(fl_bwd_colsum_kernel, dim3(B), dim3(kBwdQ * kC), 0, st, partial, units);
         SDT_LAUNCH_OK("fl_bwd_colsum_kernel");
     }
-    fl_bwd_finalize_kernel<<<kC, 256, fsmem, st>>>(partial, moments, w, scale, shift, B, units, dw);
+    sdt::launch(fl_bwd_finalize_kernel, dim3(kC), dim3(256), fsmem, st, partial, moments, w, scale, shift, B, units, dw);
     SDT_LAUNCH_OK("fl_bwd_finalize_kernel");
     return SDT_OK;
 }

@@ -41,6 +41,8 @@ __global__ void __launch_bounds__(kWarps * 32) mel_kernel(const float* __restric
                                                           const int32_t* __restrict__ fb_count,
                                                           const float* __restrict__ fb_weight, int fb_stride,
                                                           float* __restrict__ mel) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MelSmem& s = *reinterpret_cast<MelSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -133,7 +135,7 @@ extern "C" int sdt_mel_fwd(const float* audio, int B, int L, const float* window
         attr_set = true;
     }
     dim3 grid(sdt::ceil_div(T, kFramesPerCta), B);
-    mel_kernel<<<grid, kWarps * 32, sizeof(MelSmem), sdt::as_stream(stream)>>>(audio, L, T, window, fb_start, fb_count,
+    sdt::launch(mel_kernel, dim3(grid), dim3(kWarps * 32), sizeof(MelSmem), sdt::as_stream(stream), audio, L, T, window, fb_start, fb_count,
                                                                                  fb_weight, fb_stride, mel);
     SDT_LAUNCH_OK("mel_kernel");
     return SDT_OK;

@@ -36,6 +36,8 @@ __global__ void norm_finalize_kernel(const float* __restrict__ partial, int grou
                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                      float* __restrict__ running_mean, float* __restrict__ running_var,
                                      int64_t* __restrict__ nbt, float momentum) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     __shared__ double s_red[8][2][32];
     const int cchunks = (C + 31) / 32;
     const int g = blockIdx.x / cchunks, c = (blockIdx.x % cchunks) * 32 + (threadIdx.x & 31);
@@ -65,6 +67,8 @@ __global__ void norm_finalize_kernel(const float* __restrict__ partial, int grou
 __global__ void bn_eval_kernel(const float* __restrict__ rm, const float* __restrict__ rv, const float* __restrict__ gamma,
                                const float* __restrict__ beta, float eps, int C, float* __restrict__ scale,
                                float* __restrict__ shift) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float rstd = 1.0f / sqrtf(rv[c] + eps);
@@ -81,6 +85,8 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float* __res
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               int P, int C, int groups_is_batch, float slope,
                                                               float* __restrict__ partial, int tiles_per_image) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     __shared__ float red[2][8][128];
     const int b = blockIdx.x / tiles_per_image, tile = blockIdx.x % tiles_per_image;
     const int cq = threadIdx.x % 32, rl = threadIdx.x / 32;
@@ -135,6 +141,8 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(const float* __res
 __global__ void norm_bwd_finalize_kernel(const float* __restrict__ partial, int groups, int tiles_per_group, int C,
                                          double count, float* __restrict__ m1, float* __restrict__ m2,
                                          float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     __shared__ double s_red[8][2][32];
     const int cchunks = (C + 31) / 32;
     const int gidx = blockIdx.x / cchunks, c = (blockIdx.x % cchunks) * 32 + (threadIdx.x & 31);
@@ -155,6 +163,8 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(float* __restrict__
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              const float* __restrict__ m1, const float* __restrict__ m2,
                                                              long long total4, int P, int C, int groups_is_batch, float slope) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     const long long e4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e4 >= total4) return;
     const long long e = e4 * 4;
@@ -184,6 +194,8 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_pow2_kernel(const float* 
                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                    int P, int C, int groups_is_batch, float slope,
                                                                    float* __restrict__ partial, int tiles_per_image) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     __shared__ float red[2][1024];
     const int b = blockIdx.x / tiles_per_image, tile = blockIdx.x % tiles_per_image;
     const int c4n = C >> 2, nrl = 256 / c4n;
@@ -238,6 +250,8 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_pow2_kernel(float* __restr
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                   const float* __restrict__ m1, const float* __restrict__ m2,
                                                                   long long per_image4, int C, int groups_is_batch, float slope) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     const int b = blockIdx.y;
     const int c4n = C >> 2;
     const long long e0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -275,6 +289,8 @@ template <int MAXV>
 __global__ void __launch_bounds__(256) rownorm_fwd_kernel(const float* __restrict__ x, int R, int C, float eps, float slope,
                                                           float* __restrict__ y, float* __restrict__ mean,
                                                           float* __restrict__ rstd) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     const int row = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
     if (row >= R) return;
     const float* xr = x + (size_t)row * C;
@@ -312,6 +328,8 @@ template <int MAXV>
 __global__ void __launch_bounds__(256) rownorm_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x,
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
                                                           int R, int C, float slope, float* __restrict__ gx) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     const int row = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
     if (row >= R) return;
     const float mu = mean[row], rs = rstd[row];
@@ -342,6 +360,8 @@ __global__ void __launch_bounds__(256) rownorm_bwd_kernel(const float* __restric
 __global__ void scale_shift_act_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                        const float* __restrict__ shift, long long total, int P, int C, int bstride,
                                        float slope, float* __restrict__ y) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
     const int c = (int)(e % C);
@@ -354,6 +374,8 @@ __global__ void scale_shift_act_kernel(const float* __restrict__ x, const float*
 __global__ void __launch_bounds__(256) scale_shift_act_v4_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                                                  const float* __restrict__ shift, long long per_image4, int C,
                                                                  int bstride, float slope, float* __restrict__ y) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     const int b = blockIdx.y;
     const float4* xi = reinterpret_cast<const float4*>(x) + (size_t)b * per_image4;
     float4* yi = reinterpret_cast<float4*>(y) + (size_t)b * per_image4;
@@ -383,8 +405,7 @@ extern "C" int sdt_norm_finalize(const float* partial, int groups, int tiles_per
     SDT_REQUIRE(groups > 0 && tiles_per_group > 0 && C > 0 && count > 0, "sdt_norm_finalize: bad extents");
     SDT_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "sdt_norm_finalize: running stats come together");
     SDT_REQUIRE(running_mean == nullptr || groups == 1, "sdt_norm_finalize: running statistics need groups == 1 (BatchNorm)");
-    norm_finalize_kernel<<<groups * sdt::ceil_div(C, 32), 256, 0, sdt::as_stream(stream)>>>(
-        partial, groups, tiles_per_group, C, count, gamma, beta, eps, scale, shift, mean, rstd, running_mean, running_var,
+    sdt::launch(norm_finalize_kernel, dim3(groups * sdt::ceil_div(C, 32)), dim3(256), 0, sdt::as_stream(stream), partial, groups, tiles_per_group, C, count, gamma, beta, eps, scale, shift, mean, rstd, running_mean, running_var,
         num_batches_tracked, momentum);
     SDT_LAUNCH_OK("norm_finalize_kernel");
     return SDT_OK;
@@ -393,7 +414,7 @@ extern "C" int sdt_norm_finalize(const float* partial, int groups, int tiles_per
 extern "C" int sdt_bn_eval_scale_shift(const float* running_mean, const float* running_var, const float* gamma,
                                        const float* beta, float eps, int C, float* scale, float* shift, void* stream) {
     SDT_REQUIRE(running_mean && running_var && scale && shift && C > 0, "sdt_bn_eval_scale_shift: bad arguments");
-    bn_eval_kernel<<<sdt::ceil_div(C, 128), 128, 0, sdt::as_stream(stream)>>>(running_mean, running_var, gamma, beta, eps, C,
+    sdt::launch(bn_eval_kernel, dim3(sdt::ceil_div(C, 128)), dim3(128), 0, sdt::as_stream(stream), running_mean, running_var, gamma, beta, eps, C,
                                                                              scale, shift);
     SDT_LAUNCH_OK("bn_eval_kernel");
     return SDT_OK;
@@ -407,10 +428,9 @@ extern "C" int sdt_norm_bwd_reduce(const float* g, const float* x, const float* 
     SDT_REQUIRE(groups == B || groups == 1, "sdt_norm_bwd_reduce: groups must be B or 1");
     SDT_REQUIRE(tiles_per_image >= 1 && tiles_per_image <= P, "sdt_norm_bwd_reduce: tiles_per_image=%d outside [1, P=%d]", tiles_per_image, P);
     if (C == 64 || C == 128 || C == 256)
-        norm_bwd_reduce_pow2_kernel<<<B * tiles_per_image, 256, 0, sdt::as_stream(stream)>>>(
-            g, x, mean, rstd, gamma, beta, P, C, groups == B ? 1 : 0, slope, partial, tiles_per_image);
+        sdt::launch(norm_bwd_reduce_pow2_kernel, dim3(B * tiles_per_image), dim3(256), 0, sdt::as_stream(stream), g, x, mean, rstd, gamma, beta, P, C, groups == B ? 1 : 0, slope, partial, tiles_per_image);
     else
-        norm_bwd_reduce_kernel<<<B * tiles_per_image, 256, 0, sdt::as_stream(stream)>>>(g, x, mean, rstd, gamma, beta, P, C,
+        sdt::launch(norm_bwd_reduce_kernel, dim3(B * tiles_per_image), dim3(256), 0, sdt::as_stream(stream), g, x, mean, rstd, gamma, beta, P, C,
                                                                                         groups == B ? 1 : 0,
                                                                                         slope, partial, tiles_per_image);
     SDT_LAUNCH_OK("norm_bwd_reduce_kernel");
@@ -422,8 +442,7 @@ extern "C" int sdt_norm_bwd_finalize(const float* partial, int groups, int tiles
     SDT_REQUIRE(partial && m1 && m2, "sdt_norm_bwd_finalize: null pointer");
     SDT_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "sdt_norm_bwd_finalize: dgamma/dbeta come together");
     SDT_REQUIRE(dgamma == nullptr || groups == 1, "sdt_norm_bwd_finalize: affine gradients need groups == 1");
-    norm_bwd_finalize_kernel<<<groups * sdt::ceil_div(C, 32), 256, 0, sdt::as_stream(stream)>>>(
-        partial, groups, tiles_per_group, C, count, m1, m2, dgamma, dbeta, accumulate);
+    sdt::launch(norm_bwd_finalize_kernel, dim3(groups * sdt::ceil_div(C, 32)), dim3(256), 0, sdt::as_stream(stream), partial, groups, tiles_per_group, C, count, m1, m2, dgamma, dbeta, accumulate);
     SDT_LAUNCH_OK("norm_bwd_finalize_kernel");
     return SDT_OK;
 }
@@ -438,10 +457,10 @@ extern "C" int sdt_norm_bwd_apply(float* g, const float* x, const float* mean, c
     if ((C == 64 || C == 128 || C == 256) && B <= 65535) {
         const long long per_image4 = (long long)P * C / 4;
         const int gx = (int)std::min<long long>(sdt::ceil_div(per_image4, 256 * 4), 4096);
-        norm_bwd_apply_pow2_kernel<<<dim3(gx, B), 256, 0, sdt::as_stream(stream)>>>(g, x, mean, rstd, gamma, beta, m1, m2,
+        sdt::launch(norm_bwd_apply_pow2_kernel, dim3(gx, B), dim3(256), 0, sdt::as_stream(stream), g, x, mean, rstd, gamma, beta, m1, m2,
                                                                                   per_image4, C, groups == B ? 1 : 0, slope);
     } else
-        norm_bwd_apply_kernel<<<sdt::ceil_div(total4, 256), 256, 0, sdt::as_stream(stream)>>>(g, x, mean, rstd, gamma, beta, m1, m2,
+        sdt::launch(norm_bwd_apply_kernel, dim3(sdt::ceil_div(total4, 256)), dim3(256), 0, sdt::as_stream(stream), g, x, mean, rstd, gamma, beta, m1, m2,
                                                                                              total4, P, C, groups == B ? 1 : 0, slope);
     SDT_LAUNCH_OK("norm_bwd_apply_kernel");
     return SDT_OK;
@@ -453,8 +472,8 @@ extern "C" int sdt_rownorm_act_fwd(const float* x, int R, int C, float eps, floa
     SDT_REQUIRE(C <= 1024, "sdt_rownorm_act_fwd: C=%d > 1024 unsupported", C);
     cudaStream_t st = sdt::as_stream(stream);
     const int grid = sdt::ceil_div(R, 8);
-    if (C <= 256) rownorm_fwd_kernel<8><<<grid, 256, 0, st>>>(x, R, C, eps, slope, y, mean, rstd);
-    else rownorm_fwd_kernel<32><<<grid, 256, 0, st>>>(x, R, C, eps, slope, y, mean, rstd);
+    if (C <= 256) sdt::launch(rownorm_fwd_kernel<8>, dim3(grid), dim3(256), 0, st, x, R, C, eps, slope, y, mean, rstd);
+    else sdt::launch(rownorm_fwd_kernel<32>, dim3(grid), dim3(256), 0, st, x, R, C, eps, slope, y, mean, rstd);
     SDT_LAUNCH_OK("rownorm_fwd_kernel");
     return SDT_OK;
 }
@@ -465,8 +484,8 @@ extern "C" int sdt_rownorm_act_bwd(const float* g_y, const float* x, const float
     SDT_REQUIRE(C <= 1024, "sdt_rownorm_act_bwd: C=%d > 1024 unsupported", C);
     cudaStream_t st = sdt::as_stream(stream);
     const int grid = sdt::ceil_div(R, 8);
-    if (C <= 256) rownorm_bwd_kernel<8><<<grid, 256, 0, st>>>(g_y, x, mean, rstd, R, C, slope, g_x);
-    else rownorm_bwd_kernel<32><<<grid, 256, 0, st>>>(g_y, x, mean, rstd, R, C, slope, g_x);
+    if (C <= 256) sdt::launch(rownorm_bwd_kernel<8>, dim3(grid), dim3(256), 0, st, g_y, x, mean, rstd, R, C, slope, g_x);
+    else sdt::launch(rownorm_bwd_kernel<32>, dim3(grid), dim3(256), 0, st, g_y, x, mean, rstd, R, C, slope, g_x);
     SDT_LAUNCH_OK("rownorm_bwd_kernel");
     return SDT_OK;
 }
@@ -479,11 +498,11 @@ extern "C" int sdt_scale_shift_act(const float* x, const float* scale, const flo
         const long long per_image4 = (long long)P * C / 4;
         int gx = sdt::ceil_div(per_image4, 256 * 2);
         if (gx > 2048) gx = 2048;
-        scale_shift_act_v4_kernel<<<dim3(gx, B), 256, 0, sdt::as_stream(stream)>>>(x, scale, shift, per_image4, C, bstride, slope, y);
+        sdt::launch(scale_shift_act_v4_kernel, dim3(gx, B), dim3(256), 0, sdt::as_stream(stream), x, scale, shift, per_image4, C, bstride, slope, y);
         SDT_LAUNCH_OK("scale_shift_act_v4_kernel");
         return SDT_OK;
     }
-    scale_shift_act_kernel<<<sdt::ceil_div(total, 256), 256, 0, sdt::as_stream(stream)>>>(x, scale, shift, total, P, C, bstride,
+    sdt::launch(scale_shift_act_kernel, dim3(sdt::ceil_div(total, 256)), dim3(256), 0, sdt::as_stream(stream), x, scale, shift, total, P, C, bstride,
                                                                                          slope, y);
     SDT_LAUNCH_OK("scale_shift_act_kernel");
     return SDT_OK;

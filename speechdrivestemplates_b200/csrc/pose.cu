@@ -28,6 +28,8 @@ __device__ __forceinline__ int part_root(int k) {
 // raw (T,3,137) -> normalised (T,2,121); gesture_dataset.py:95-105,131-191
 __global__ void pose_preprocess_kernel(const float* __restrict__ raw, int T, const float* __restrict__ mean,
                                        const float* __restrict__ stdv, int hierarchical, float* __restrict__ out) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= T * 2 * K121) return;
     const int k = e % K121, xy = (e / K121) % 2, t = e / (2 * K121);
@@ -46,6 +48,8 @@ __global__ void pose_preprocess_kernel(const float* __restrict__ raw, int T, con
 __global__ void pose_final_kernel(const float* __restrict__ poses, int B, int T, const double* __restrict__ mean,
                                   const double* __restrict__ stdv, const double* __restrict__ scale, int hierarchical,
                                   double* __restrict__ out) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     const long long total = (long long)B * T * 2 * K121;
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
@@ -73,6 +77,8 @@ __global__ void pose_final_kernel(const float* __restrict__ poses, int B, int T,
 __global__ void pose_parted2global_kernel(const float* __restrict__ poses, long long total, const float* __restrict__ mean_p,
                                           const float* __restrict__ std_p, const float* __restrict__ mean_g,
                                           const float* __restrict__ std_g, float* __restrict__ out) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
     const int k = (int)(e % K121);
@@ -90,6 +96,8 @@ __global__ void pose_parted2global_kernel(const float* __restrict__ poses, long 
 // evaluate_step (voice2pose.py:412-430): per-clip partial sums, then a fixed-order finish.
 __global__ void __launch_bounds__(256) pose_metrics_partial_kernel(const double* __restrict__ pred, const double* __restrict__ gt,
                                                                    int T, double* __restrict__ partial) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     __shared__ double red[8];
     __shared__ double lipg[1024], lipp[1024];
     __shared__ double maxg;
@@ -128,6 +136,8 @@ __global__ void __launch_bounds__(256) pose_metrics_partial_kernel(const double*
 }
 
 __global__ void pose_metrics_finish_kernel(const double* __restrict__ partial, int B, int T, double* __restrict__ out) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double l2 = 0.0, lip = 0.0;
     for (int b = 0; b < B; ++b) {
@@ -143,7 +153,7 @@ __global__ void pose_metrics_finish_kernel(const double* __restrict__ partial, i
 extern "C" int sdt_pose_preprocess(const float* raw, int T, const float* mean, const float* std, int hierarchical, float* out,
                                    void* stream) {
     SDT_REQUIRE(raw && mean && std && out && T > 0, "sdt_pose_preprocess: bad arguments");
-    pose_preprocess_kernel<<<sdt::ceil_div(T * 2 * K121, 256), 256, 0, sdt::as_stream(stream)>>>(raw, T, mean, std, hierarchical, out);
+    sdt::launch(pose_preprocess_kernel, dim3(sdt::ceil_div(T * 2 * K121, 256)), dim3(256), 0, sdt::as_stream(stream), raw, T, mean, std, hierarchical, out);
     SDT_LAUNCH_OK("pose_preprocess_kernel");
     return SDT_OK;
 }
@@ -152,7 +162,7 @@ extern "C" int sdt_pose_final_results(const float* poses, int B, int T, const do
                                       const double* scale, int hierarchical, double* out, void* stream) {
     SDT_REQUIRE(poses && mean && std && scale && out && B > 0 && T > 0, "sdt_pose_final_results: bad arguments");
     const long long total = (long long)B * T * 2 * K121;
-    pose_final_kernel<<<sdt::ceil_div(total, 256), 256, 0, sdt::as_stream(stream)>>>(poses, B, T, mean, std, scale, hierarchical, out);
+    sdt::launch(pose_final_kernel, dim3(sdt::ceil_div(total, 256)), dim3(256), 0, sdt::as_stream(stream), poses, B, T, mean, std, scale, hierarchical, out);
     SDT_LAUNCH_OK("pose_final_kernel");
     return SDT_OK;
 }
@@ -160,9 +170,9 @@ extern "C" int sdt_pose_final_results(const float* poses, int B, int T, const do
 extern "C" int sdt_pose_metrics(const double* pred, const double* gt, int B, int T, double* partial, double* out, void* stream) {
     SDT_REQUIRE(pred && gt && partial && out && B > 0 && T > 0, "sdt_pose_metrics: bad arguments");
     SDT_REQUIRE(T <= 1024, "sdt_pose_metrics: T=%d > 1024 unsupported", T);
-    pose_metrics_partial_kernel<<<B, 256, 0, sdt::as_stream(stream)>>>(pred, gt, T, partial);
+    sdt::launch(pose_metrics_partial_kernel, dim3(B), dim3(256), 0, sdt::as_stream(stream), pred, gt, T, partial);
     SDT_LAUNCH_OK("pose_metrics_partial_kernel");
-    pose_metrics_finish_kernel<<<1, 32, 0, sdt::as_stream(stream)>>>(partial, B, T, out);
+    sdt::launch(pose_metrics_finish_kernel, dim3(1), dim3(32), 0, sdt::as_stream(stream), partial, B, T, out);
     SDT_LAUNCH_OK("pose_metrics_finish_kernel");
     return SDT_OK;
 }
@@ -171,7 +181,7 @@ extern "C" int sdt_pose_parted2global(const float* poses, int64_t n_rows, const 
                                       const float* mean_global, const float* std_global, float* out, void* stream) {
     SDT_REQUIRE(poses && mean_parted && std_parted && mean_global && std_global && out && n_rows > 0, "sdt_pose_parted2global: bad arguments");
     const long long total = (long long)n_rows * 2 * K121;
-    pose_parted2global_kernel<<<sdt::ceil_div(total, 256), 256, 0, sdt::as_stream(stream)>>>(poses, total, mean_parted, std_parted,
+    sdt::launch(pose_parted2global_kernel, dim3(sdt::ceil_div(total, 256)), dim3(256), 0, sdt::as_stream(stream), poses, total, mean_parted, std_parted,
                                                                                             mean_global, std_global, out);
     SDT_LAUNCH_OK("pose_parted2global_kernel");
     return SDT_OK;

@@ -50,6 +50,8 @@ struct TcCfg {
 
 template <int BN>
 __global__ void __launch_bounds__(THREADS, 1) tc_conv_kernel(const sdt_conv_desc d) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     using Cfg = TcCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -276,7 +278,7 @@ int launch_tc(const sdt_conv_desc* d, int row_tiles, cudaStream_t st) {
         attr_set = true;
     }
     dim3 grid(row_tiles, d->N / BN);
-    tc_conv_kernel<BN><<<grid, THREADS, TcCfg<BN>::SMEM, st>>>(*d);
+    sdt::launch(tc_conv_kernel<BN>, dim3(grid), dim3(THREADS), TcCfg<BN>::SMEM, st, *d);
     SDT_LAUNCH_OK("tc_conv_kernel");
     sdt_note_tc_launch();
     return SDT_OK;

@@ -90,6 +90,9 @@ __global__ void __launch_bounds__(THREADS, DEEP ? 1 : 2) tc_conv_tma_kernel(cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above (barrier init, TMEM allocation) overlapped the tail of the preceding kernel; global memory from here on
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
 
     // warps 0-3: epilogue (TMEM lane quadrant = warp id); warp 4: TMA producer; warp 5: MMA issuer.  The issuing warps walk
     // their loops as whole warps and elect one lane per instruction (tc_common.cuh: elect_one), and have the highest warp ids.
@@ -265,7 +268,7 @@ int launch_tma(const sdt_conv_desc* d, const TileGeom& tg, cudaStream_t st) {
         SDT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed with %d", (int)r);
     }
     dim3 grid(d->B * tg.tiles_x * tg.tiles_y, d->N / BN);
-    tc_conv_tma_kernel<BN, DEEP><<<grid, THREADS, TmaCfg<BN, DEEP>::SMEM, st>>>(tmA, tmB, *d, tg);
+    sdt::launch(tc_conv_tma_kernel<BN, DEEP>, dim3(grid), dim3(THREADS), TmaCfg<BN, DEEP>::SMEM, st, tmA, tmB, *d, tg);
     SDT_LAUNCH_OK("tc_conv_tma_kernel");
     sdt_note_tc_launch();
     return SDT_OK;

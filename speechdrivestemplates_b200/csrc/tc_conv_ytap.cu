@@ -155,6 +155,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above (barrier init, TMEM allocation) overlapped the tail of the preceding kernel; global memory from here on
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     if (DBG && tl && tid == 0) tl[2] = gtimer();
 
     if (warp == 4) {
@@ -514,7 +517,7 @@ int launch_ytap2(const sdt_conv_desc* d, const Plan& pl, const CUtensorMap& tmA,
         SDT_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
     const int grid = pl.tiles < sm_count ? pl.tiles : sm_count;      // persistent: one CTA per SM, static round-robin tiles
-    tc_conv_ytap_kernel<BN, MT, DBG><<<grid, THREADS, pl.smem, st>>>(tmA, tmB, *d, pl.g);
+    sdt::launch(tc_conv_ytap_kernel<BN, MT, DBG>, dim3(grid), dim3(THREADS), pl.smem, st, tmA, tmB, *d, pl.g);
     SDT_LAUNCH_OK("tc_conv_ytap_kernel");
     sdt_note_tc_launch();
     return SDT_OK;

@@ -33,6 +33,8 @@ struct WgCfg {
 
 template <int BN>
 __global__ void __launch_bounds__(THREADS, 1) tc_wgrad_kernel(const sdt_conv_desc d) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
     using Cfg = WgCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int NCH = BN / 32;                         // 32-channel chunks of dy per pixel
@@ -219,7 +221,7 @@ int launch_wg(const sdt_conv_desc* d, cudaStream_t st) {
     }
     const int Kc = d->TH * d->TW * d->C;
     dim3 grid((Kc + BM - 1) / BM, 1, d->splits);
-    tc_wgrad_kernel<BN><<<grid, THREADS, WgCfg<BN>::SMEM, st>>>(*d);
+    sdt::launch(tc_wgrad_kernel<BN>, dim3(grid), dim3(THREADS), WgCfg<BN>::SMEM, st, *d);
     SDT_LAUNCH_OK("tc_wgrad_kernel");
     sdt_note_tc_launch();
     return SDT_OK;

@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(THREADS, 2) tc_wgrad_tma_kernel(const __grid_c
     float* out = d.wpart + (size_t)blockIdx.z * Ntot * Kc;
 
     if (KB == 0) {
+        sdt::pdl_wait();
         for (int e = tid; e < BN * BM; e += THREADS) {
             const int n = e / BM, m = e % BM;
             if (kidx0 + m < Kc) out[(size_t)(n0 + n) * Kc + kidx0 + m] = 0.f;
@@ -89,6 +90,9 @@ __global__ void __launch_bounds__(THREADS, 2) tc_wgrad_tma_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above (barrier init, TMEM allocation) overlapped the tail of the preceding kernel; global memory from here on
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
 
     // warps 0-3: epilogue (TMEM lane quadrant = warp id); warp 4: TMA producer; warp 5: MMA issuer.  The issuing warps walk
     // their loops as whole warps and elect one lane per instruction (tc_common.cuh: elect_one), and have the highest warp ids.
@@ -245,7 +249,7 @@ int launch_wg_tma(const sdt_conv_desc* d, const BoxGeom& bg, cudaStream_t st) {
     }
     const int Kc = d->TH * d->TW * d->C;
     dim3 grid((Kc + BM - 1) / BM, d->N / BN, d->splits);
-    tc_wgrad_tma_kernel<BN><<<grid, THREADS, WgTmaCfg<BN>::SMEM, st>>>(tmA, tmB, *d, bg);
+    sdt::launch(tc_wgrad_tma_kernel<BN>, dim3(grid), dim3(THREADS), WgTmaCfg<BN>::SMEM, st, tmA, tmB, *d, bg);
     SDT_LAUNCH_OK("tc_wgrad_tma_kernel");
     sdt_note_tc_launch();
     return SDT_OK;

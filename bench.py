@@ -223,6 +223,14 @@ class EventProfiler:
         if name in ("sdt_conv_gemm", "sdt_conv_wgrad"):
             d = args[0]._obj
             flops = 2.0 * d.B * d.GH * d.GW * d.N * d.TH * d.TW * d.C
+            if name == "sdt_conv_gemm":
+                # which kernel does the library launch for this descriptor?  3 = tc_conv_ytap_kernel (2-D convolutions)
+                import ctypes as C
+                from speechdrivestemplates_b200 import _lib
+                plan = (C.c_int32 * 10)()
+                _lib.load().sdt_conv_plan(args[0], plan)
+                if plan[0] == 3:
+                    name = "sdt_conv_gemm[tc_conv_ytap_kernel]"
         return (name, e0, flops)
 
     def post(self, tok):
@@ -342,22 +350,47 @@ def run_own(args):
     tr.set_overlap(True)
     tr._graphs, tr.use_graph = graphs, not args.no_graph
     total_ms = sum(a[0] for a in agg.values())
-    conv_ms = agg.get("sdt_conv_gemm", [0, 0, 0])[0] + agg.get("sdt_conv_wgrad", [0, 0, 0])[0]
-    conv_fl = agg.get("sdt_conv_gemm", [0, 0, 0])[2] + agg.get("sdt_conv_wgrad", [0, 0, 0])[2]
-    conv_n = agg.get("sdt_conv_gemm", [0, 0, 0])[1] + agg.get("sdt_conv_wgrad", [0, 0, 0])[1]
+    fam_keys = ("sdt_conv_gemm", "sdt_conv_gemm[tc_conv_ytap_kernel]", "sdt_conv_wgrad")
+    conv_ms = sum(agg.get(k, [0, 0, 0])[0] for k in fam_keys)
+    conv_fl = sum(agg.get(k, [0, 0, 0])[2] for k in fam_keys)
+    conv_n = sum(agg.get(k, [0, 0, 0])[1] for k in fam_keys)
     pk = peaks()
-    achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-    roofline = {
-        "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-        "frac": achieved / pk["tf_sustained"], "traffic": None,
-        "kernel": "implicit-GEMM convolutions: " + ("conv_gemm_kernel + conv_wgrad_kernel (fp32 FFMA)" if conv_math == 0
-                                                      else "tc_conv_kernel + tc_wgrad_kernel (tcgen05 TF32) + FFMA kernels for ineligible layers"),
-        "share_of_step": conv_ms / total_ms if total_ms else None,
-        "launches_per_step": conv_n // reps, "avg_launch_ms": conv_ms / max(conv_n, 1),
-        "peak_source": pk["src"] + " bf16 dense, sustained (kernel timed inside a long step)",
-        "by_kernel_ms_per_step": {k: round(v[0] / reps, 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:8]},
-        "hbm_peak_gbs": pk["hbm"],
-    }
+    family = {"kernels": "all implicit-GEMM convolution launches (2-D + 1-D forward / data-gradient, weight gradients, FFMA leftovers)",
+              "achieved_tflops": conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0,
+              "share_of_step": conv_ms / total_ms if total_ms else None, "launches_per_step": conv_n // reps}
+    dom = agg.get("sdt_conv_gemm[tc_conv_ytap_kernel]")
+    if dom is not None and dom[0] > 0:
+        # dominant kernel: the persistent tcgen05 kernel of the 2-D encoder convolutions (forward + data gradient)
+        achieved = dom[2] / (dom[0] * 1e-3) / 1e12
+        roofline = {
+            "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+            "frac": achieved / pk["tf_sustained"],
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the 8 launches of one `ncu --set full` capture of
+            # this command (profiles/r1_ncu_tc_conv_mode3.txt)
+            "traffic": 102.3e6,
+            "kernel": "tc_conv_ytap_kernel (tcgen05 kind::tf32, TMA operands, persistent, double-buffered TMEM): 2-D encoder "
+                      "convolutions forward + data gradient",
+            "algorithmic_flops_per_launch": dom[2] / max(dom[1], 1),
+            "share_of_step": dom[0] / total_ms if total_ms else None,
+            "launches_per_step": dom[1] // reps, "avg_launch_ms": dom[0] / max(dom[1], 1),
+            "peak_source": pk["src"] + " bf16 dense, sustained (kernel timed inside a long step); the kernel computes in TF32, whose "
+                                       "nominal dense rate is half of bf16 (1.1 vs 2.25 PFLOP/s)",
+            "ncu_tensor_pipe_active_pct": "57-85 (Cout >= 128), 41 (64->64 stride 2): profiles/r1_ncu_tc_conv_mode3.txt",
+        }
+    else:
+        achieved = family["achieved_tflops"]
+        roofline = {
+            "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+            "frac": achieved / pk["tf_sustained"], "traffic": None,
+            "kernel": "implicit-GEMM convolutions: " + ("conv_gemm_kernel + conv_wgrad_kernel (fp32 FFMA)" if conv_math == 0
+                                                          else "tc_conv_kernel + tc_wgrad_kernel (tcgen05 TF32) + FFMA kernels for ineligible layers"),
+            "share_of_step": family["share_of_step"], "launches_per_step": family["launches_per_step"],
+            "avg_launch_ms": conv_ms / max(conv_n, 1),
+            "peak_source": pk["src"] + " bf16 dense, sustained (kernel timed inside a long step)",
+        }
+    roofline["conv_family"] = family
+    roofline["by_kernel_ms_per_step"] = {k: round(v[0] / reps, 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:8]}
+    roofline["hbm_peak_gbs"] = pk["hbm"]
 
     if world > 1:
         dist.barrier()

@@ -154,6 +154,7 @@ int sdt_bn_eval_scale_shift(const float* running_mean, const float* running_var,
  * pass 1 reduces  s1 = sum g', s2 = sum g'*xhat  (g' = g_act * act'(y)) into partial (B*tiles, 2, C);
  * finalize gives the means (groups, C) and, for BatchNorm, dgamma/dbeta; pass 2 writes
  * g_x = rstd*gamma*(g' - m1 - xhat*m2) in place over g. groups = B (IN) or 1 (BN). */
+/* tiles_per_image in [1, P] is the caller's choice of parallelism for pass 1 (rows per tile = ceil(P / tiles)). */
 int sdt_norm_bwd_reduce(const float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
                         const float* beta, int B, int P, int C, int groups, float slope, float* partial,
                         int tiles_per_image, void* stream);

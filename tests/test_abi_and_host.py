@@ -140,3 +140,86 @@ def test_plugin_registers_into_reference_registries():
     assert sorted(m.state_dict().keys()) == ref_keys
     m2 = ref_p2p.Pose2PoseModel(refshim.get_cfg("pose2pose"), num_train_samples=4)
     assert "clip_code_mu" in m2.state_dict() and "ae.decoder.blocks.4.bias" in m2.state_dict()
+
+
+# ---------------------------------------------------------------- tile planner of the mode-3 convolution (host only)
+ENC_LAYERS = [(64, 64, 4, 4, 2, 1, 80, 427), (64, 128, 3, 3, 1, 1, 40, 213), (128, 128, 4, 4, 2, 1, 40, 213),
+              (128, 256, 3, 3, 1, 1, 20, 106), (256, 256, 4, 4, 2, 1, 20, 106), (256, 256, 3, 3, 1, 1, 10, 53),
+              (256, 256, 6, 3, 1, 0, 10, 53)]
+
+
+def _fake_fwd_desc(ops, cin, cout, kh, kw, s, p, H, W, B):
+    g = ops.ConvGeom.conv2d(cin, cout, kh, kw, s, p)
+    oh, ow = g.out_hw(H, W)
+    d = ops.ConvDesc()
+    d.src = d.wt = d.wt_nk = d.dst = 0x1000                 # never dereferenced: sdt_conv_plan is host-only
+    d.B, d.SH, d.SW, d.C = B, H, W, cin
+    d.GH, d.GW, d.TH, d.TW = oh, ow, kh, kw
+    d.y_mul, d.ty_mul, d.y_off = s, 1, -p
+    d.x_mul, d.tx_mul, d.x_off = s, 1, -p
+    d.N, d.DH, d.DW, d.dy_mul, d.dy_off, d.dx_mul, d.dx_off = cout, oh, ow, 1, 0, 1, 0
+    d.per_image_tiles = 1
+    return d, oh, ow
+
+
+@pytest.mark.parametrize("B", [1, 2, 32, 128])
+def test_conv_plan_for_the_encoder_layers(B):
+    """Math mode 3 plans every 2-D encoder layer on the persistent tcgen05 kernel, within the hardware limits: TMEM columns
+    (2 accumulator sets), shared memory of one CTA per SM, TMA box extents, and enough sub-tiles to cover the output grid."""
+    _built()
+    from speechdrivestemplates_b200 import _lib, ops
+    lib = _lib.load()
+    assert lib.sdt_set_conv_math(3) == 0
+    try:
+        for cfg in ENC_LAYERS:
+            d, oh, ow = _fake_fwd_desc(ops, *cfg, B)
+            out = (ctypes.c_int32 * 10)()
+            assert lib.sdt_conv_plan(ctypes.byref(d), out) == 0
+            kind, bn, mt, bh, bw, box_rows, a_st, b_st, smem, tiles = list(out)
+            assert kind == 3, (cfg, list(out))
+            assert bn in (64, 128) and mt in (1, 2, 4) and 2 * mt * bn <= 512
+            assert bh * bw == 128 and bw % 8 == 0
+            assert smem <= 227 * 1024 and a_st >= 2 and b_st >= 2
+            assert bw * cfg[4] <= 256 and box_rows * cfg[4] <= 256
+            sub = B * (-(-oh // bh)) * (-(-ow // bw))
+            assert tiles == -(-sub // mt) * (cfg[1] // bn)
+            if torch.cuda.is_available():                        # needs the driver's cuTensorMapEncodeTiled to be eligible
+                assert lib.sdt_conv_row_tiles(ctypes.byref(d)) == sub      # one statistics row per sub-tile
+    finally:
+        lib.sdt_set_conv_math(0)
+
+
+def test_conv_plan_falls_back_outside_mode_3_and_for_1d():
+    _built()
+    from speechdrivestemplates_b200 import _lib, ops
+    lib = _lib.load()
+    out = (ctypes.c_int32 * 10)()
+    d, _, _ = _fake_fwd_desc(ops, *ENC_LAYERS[1], 4)
+    for mode in (0, 1, 2):
+        lib.sdt_set_conv_math(mode)
+        assert lib.sdt_conv_plan(ctypes.byref(d), out) == 0 and out[0] != 3
+    lib.sdt_set_conv_math(3)
+    try:
+        d1 = ops.ConvDesc()                                  # a 1-D layer (GH == 1) has no vertical taps to reuse
+        d1.src = d1.wt = d1.wt_nk = d1.dst = 0x1000
+        d1.B, d1.SH, d1.SW, d1.C = 4, 1, 64, 256
+        d1.GH, d1.GW, d1.TH, d1.TW = 1, 64, 1, 3
+        d1.y_mul, d1.ty_mul, d1.y_off, d1.x_mul, d1.tx_mul, d1.x_off = 1, 1, 0, 1, 1, -1
+        d1.N, d1.DH, d1.DW, d1.dy_mul, d1.dx_mul = 256, 1, 64, 1, 1
+        assert lib.sdt_conv_plan(ctypes.byref(d1), out) == 0 and out[0] != 3
+        with pytest.raises(_lib.SdtError):
+            _lib.call("sdt_conv_plan", ctypes.byref(d1), None)
+    finally:
+        lib.sdt_set_conv_math(0)
+
+
+def test_wgrad_splits_keep_at_least_256_pixels_per_split():
+    from speechdrivestemplates_b200 import ops
+    g1d = ops.ConvGeom.conv1d(256, 256, 3, 1, 1)
+    assert ops.wgrad_splits(g1d, 32, 1, 64) == 8             # 2048 pixels
+    assert ops.wgrad_splits(g1d, 1, 1, 2) == 1
+    g2d = ops.ConvGeom.conv2d(64, 128, 3, 3, 1, 1)
+    s = ops.wgrad_splits(g2d, 32, 40, 213)
+    assert 1 <= s <= 32 * 40 * 213 // 256 and s * 5 >= 400   # ~3 CTAs per SM
+    assert ops.bwd_tiles(255, 32) >= 8 and ops.bwd_tiles(255, 32) * 32 >= 255 // 8
+    assert ops.bwd_tiles(40 * 213, 32) == -(-40 * 213 // 256)

@@ -488,3 +488,38 @@ def test_s2g_dropin_train_step_with_discriminator_vs_reference_fixture():
         err = np.abs(samples_of(v).astype(np.float64) - ref).max()
         assert err <= 1e-3 * np.abs(ref).max() + 2.5e-4, (k, err)
     assert int(model.netD_pose.seq[0].norm.num_batches_tracked) == 3        # real, fake, fake.detach()
+
+
+def test_programmatic_dependent_launch_does_not_change_results():
+    """SDT_PDL=0 (plain stream order) and the default (every kernel launched with the programmatic-serialization attribute,
+    griddepcontrol.wait at its top) must give bitwise identical steps: same kernels, same order, only the launch overlap
+    differs.  Run in subprocesses because the switch is read once per process."""
+    import json
+    import os
+    import subprocess
+    import sys
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import json, sys, torch\n"
+        "sys.path.insert(0, %r)\n"
+        "import bench\n"
+        "from speechdrivestemplates_b200 import config, pipeline\n"
+        "tr = pipeline.Voice2PoseTrainer(config.get_cfg('voice2pose_sdt_bp'), 64, torch.device('cuda:0'), seed=0, conv_math=3)\n"
+        "tr.model.clips_code.data.copy_(0.1 * torch.randn(64, 32, generator=torch.Generator().manual_seed(11)))\n"
+        "from oracle import sdt_oracle as O\n"
+        "st = bench.oliver_stat()\n"
+        "outs = []\n"
+        "for i in range(5):\n"
+        "    b = O.synthetic_batch(4, 64, st, seed=300 + i)\n"
+        "    b['speaker_stat'] = {k: torch.from_numpy(__import__('numpy').asarray(v)) for k, v in b['speaker_stat'].items()}\n"
+        "    tr.train_step(b)\n"
+        "    outs.append(tr.losses_to_host())\n"
+        "w = sum(float(p.double().abs().sum()) for p in tr.model.netG.parameters())\n"
+        "print(json.dumps({'losses': outs, 'wsum': w}))\n" % ROOT)
+    res = {}
+    for flag in ("1", "0"):
+        env = dict(os.environ, SDT_PDL=flag)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        res[flag] = json.loads(out.stdout.strip().splitlines()[-1])
+    assert res["1"] == res["0"]

@@ -524,11 +524,12 @@ def pose_head_bwd(g_mu, g_logvar, L, g_act):
     call("sdt_pose_head_bwd", _p(g_mu), _p(g_logvar), B, L, 2 * D, _p(g_act), _stream())
 
 
-def pose_preprocess(raw, mean, std, hierarchical=True):
-    """raw (T,3,137) f32 -> normalised (T,2,121) f32; bit-exact with gesture_dataset.py:95-105."""
+def pose_preprocess(raw, mean, std, hierarchical=True, out=None):
+    """raw (T,3,137) f32 -> normalised (T,2,121) f32; bit-exact with gesture_dataset.py:95-105.  T may be B*frames."""
     _chk(raw, name="raw")
     T = raw.shape[0]
-    out = torch.empty(T, 2, 121, device=raw.device)
+    if out is None:
+        out = torch.empty(T, 2, 121, device=raw.device)
     call("sdt_pose_preprocess", _p(raw), T, _p(_chk(mean, name="mean")), _p(_chk(std, name="std")), int(hierarchical), _p(out),
          _stream())
     return out

@@ -401,9 +401,10 @@ class Voice2PoseTrainer:
         self.device = torch.device(device)
         if conv_math is not None:          # 0 = fp32 FFMA, 1 = tcgen05 TF32 (the reference's own GPU default: cudnn.allow_tf32)
             ops.set_conv_math(conv_math)
-        if cfg.VOICE2POSE.POSE_DISCRIMINATOR.NAME is not None:
-            raise NotImplementedError("the fused trainer covers the SDT configs; voice2pose_s2g (discriminator) trains through the "
-                                      "drop-in Voice2PoseModel + the reference's optimizer choreography (see tests/test_gpu_step.py)")
+        self.has_d = cfg.VOICE2POSE.POSE_DISCRIMINATOR.NAME is not None
+        if self.has_d and cfg.VOICE2POSE.POSE_DISCRIMINATOR.WHITE_LIST is not None:
+            raise NotImplementedError("the fused trainer feeds the discriminator all keypoints (POSE_DISCRIMINATOR.WHITE_LIST=None); "
+                                      "a white list trains through the drop-in Voice2PoseModel (tests/test_gpu_step.py)")
         torch.manual_seed(seed)                                       # main.py:37
         self.model = Voice2PoseModel(cfg, num_train_samples=num_train_samples).to(self.device)
         ae_ckpt = cfg.VOICE2POSE.POSE_ENCODER.AE_CHECKPOINT
@@ -421,11 +422,16 @@ class Voice2PoseTrainer:
         self.g_names = [n for n, _ in m.netG.named_parameters()]
         g_params = [p for _, p in m.netG.named_parameters()]
         self.train_code = isinstance(m.clips_code, nn.Parameter) and m.clips_code.requires_grad
-        # flat layout: [netG parameters | pad to a multiple of 4 | clips_code (N*D) | pad]
+        # flat layout: [netG parameters | pad to a multiple of 4 | clips_code (N*D) | pad | netD_pose parameters | pad]
         self.n_g = sum(p.numel() for p in g_params)
         self.n_g_pad = self.n_g + ((-self.n_g) % 4)
         self.n_code = m.clips_code.numel() if self.train_code else 0
-        self.flat_p = torch.zeros(self.n_g_pad + self.n_code + ((-self.n_code) % 4), device=self.device)
+        self.n_code_pad = self.n_code + ((-self.n_code) % 4)
+        self.d_names = [n for n, _ in m.netD_pose.named_parameters()] if self.has_d else []
+        d_params = [p for _, p in m.netD_pose.named_parameters()] if self.has_d else []
+        self.n_d = sum(p.numel() for p in d_params)
+        self.off_d = self.n_g_pad + self.n_code_pad
+        self.flat_p = torch.zeros(self.off_d + self.n_d + ((-self.n_d) % 4), device=self.device)
         off = 0
         for p in g_params:
             v = self.flat_p[off:off + p.numel()].view(p.shape)
@@ -445,8 +451,22 @@ class Voice2PoseTrainer:
             self.grads[n] = self.flat_g[off:off + p.numel()].view(p.shape)
             off += p.numel()
         self.g_table = self.flat_g[self.n_g_pad:self.n_g_pad + self.n_code].view(-1, m.clips_code.shape[1]) if self.train_code else None
+        self.d_grads, self.d_scratch = {}, {}
+        if self.has_d:
+            off = self.off_d
+            scratch = torch.zeros(self.n_d, device=self.device)       # parameter gradients of the fake pass of G_loss: discarded
+            so = 0                                                    # (the reference zeroes them before D_loss.backward, voice2pose.py:306)
+            for n, p in zip(self.d_names, d_params):
+                v = self.flat_p[off:off + p.numel()].view(p.shape)
+                v.copy_(p.data)
+                p.data = v
+                self.d_grads[n] = self.flat_g[off:off + p.numel()].view(p.shape)
+                self.d_scratch[n] = scratch[so:so + p.numel()].view(p.shape)
+                off += p.numel()
+                so += p.numel()
         self.adam_g = torch.zeros(8, device=self.device)
         self.adam_c = torch.zeros(8, device=self.device)
+        self.adam_d = torch.zeros(8, device=self.device)
         self.set_lr(self.lr)
         self.engine = m.step_engine()
         self._wg_stream = torch.cuda.Stream()                # weight gradients overlap the dgrad chain (engine._wgrad)
@@ -454,8 +474,8 @@ class Voice2PoseTrainer:
         self._overlap = True
         self._aux = None
         self._inbox, self._prefetched = None, None
-        self._scal = torch.zeros(8, device=self.device, dtype=torch.float64)
-        self._scal_host = torch.zeros(2, 8, dtype=torch.float64).pin_memory()
+        self._scal = torch.zeros(12, device=self.device, dtype=torch.float64)
+        self._scal_host = torch.zeros(2, 12, dtype=torch.float64).pin_memory()
         self._scal_ev = [torch.cuda.Event(), torch.cuda.Event()]
         self._staging = None
         self._graphs = None
@@ -476,6 +496,7 @@ class Voice2PoseTrainer:
         self.code_lr = self.lr * float(self.cfg.VOICE2POSE.GENERATOR.CLIP_CODE.LR_SCALING)
         self.adam_g[3] = self.lr
         self.adam_c[3] = self.code_lr
+        self.adam_d[3] = self.lr                                       # optimizerD_pose, same schedule (voice2pose.py:262-268)
 
     # ---- host -> device staging
     def _stage(self, batch):
@@ -528,17 +549,78 @@ class Voice2PoseTrainer:
             self._inbox_ready.record(cs)
         self._prefetched = batch
 
+    def set_p2g_stats(self, stat_parted, stat_global):
+        """HIERARCHICAL_POSE=False (voice2pose_s2g): the speaker's parted and global statistics for the FGD extractor's input
+        transform (dataset.transform_normalized_parted2global, voice2pose.py:168-169).  {'mean': (242), 'std': (242)} each."""
+        def f32(v):
+            return torch.as_tensor(__import__("numpy").asarray(v, "float64").astype("float32").reshape(-1)).to(self.device)
+        self._p2g = (f32(stat_parted["mean"]), f32(stat_parted["std"]), f32(stat_global["mean"]), f32(stat_global["std"]))
+
+    def _gan(self):
+        """Discriminator passes + LSGAN terms of the step (voice2pose.py:179-208) and their backward passes.
+
+        score_real = D(real), score_fake = D(fake), score_fake_detach = D(fake.detach()): three forward passes with their own
+        BatchNorm batch statistics and running-stat updates, in the reference's order.  G_loss gets MSE(score_fake, 1) * lambda:
+        its gradient goes through D to the prediction (the D parameter gradients of that pass are the ones the reference
+        zeroes again before D_loss.backward).  D_loss = (MSE(score_real, 1) + MSE(score_fake_detach, 0)) * lambda gives the
+        discriminator gradients.  Optimizer order (G step before D_loss.backward, :298-309) does not matter for the values: the
+        D passes all ran on the pre-step generator output.  Returns the total gradient w.r.t. the prediction (B,F,2K)."""
+        cfg, m, s = self.cfg, self.model, self._staging
+        dcfg = cfg.VOICE2POSE.POSE_DISCRIMINATOR
+        lam = float(dcfg.LAMBDA_GAN)
+        A = self.engine._arena(self.device)
+        out = self.out
+        B, F = s["poses"].shape[0], s["poses"].shape[1]
+        K2 = s["poses"].shape[2] * s["poses"].shape[3]
+        pred, gt = out["poses_pred_batch"].view(B, F, K2), s["poses"].view(B, F, K2)
+        if dcfg.MOTION:                                                 # frame differences (voice2pose.py:187-189)
+            real = ops.motion_diff_fwd(gt, out=A.get("gan_real", (B, F - 1, K2)))
+            fake = ops.motion_diff_fwd(pred, out=A.get("gan_fake", (B, F - 1, K2)))
+        else:
+            real, fake = gt, pred
+        D = m.netD_pose.engine()
+        dp = {n: p.detach() for n, p in m.netD_pose.named_parameters()}
+        dbuf = m.netD_pose._buffers_dict()
+        T = real.shape[1]
+        D.prepare(dp, T)
+        s_real = D.forward(real, dp, dbuf, True, "/real")
+        s_fake = D.forward(fake, dp, dbuf, True, "/fake")
+        s_fd = D.forward(fake, dp, dbuf, True, "/fake_detach")
+        g_fake, g_real, g_fd = (A.get("gan_g_" + k, tuple(s_fake.shape)) for k in ("fake", "real", "fd"))
+        gan, d_real, d_fake = A.get("gan_loss", (1,)), A.get("gan_d_real", (1,)), A.get("gan_d_fake", (1,))
+        ops.mse_const_loss(s_fake, 1.0, lam, gan, g_fake)               # G_pose_gan_loss
+        ops.mse_const_loss(s_real, 1.0, lam, d_real, g_real)
+        ops.mse_const_loss(s_fd, 0.0, lam, d_fake, g_fd)
+        out["G_pose_gan_loss"] = gan
+        out["D_pose_gan_loss"] = torch.add(d_real, d_fake, out=A.get("gan_d_loss", (1,)))
+        out["pose_score_fake"] = torch.mean(s_fake, dim=(0, 1), keepdim=False, out=A.get("gan_sf", ()))
+        out["pose_score_real"] = torch.mean(s_real, dim=(0, 1), keepdim=False, out=A.get("gan_sr", ()))
+        torch.add(out["G_loss"], gan, out=out["G_loss"])                # G_loss = reg (+ kl) + gan
+        # generator path: d G_pose_gan_loss / d prediction
+        dx = D.backward(g_fake, dp, self.d_scratch, "/fake", True, False)
+        g_total = A.get("gan_g_pred", (B, F, K2))
+        g_total.copy_(self.engine._g_pred)
+        if dcfg.MOTION:
+            ops.motion_diff_bwd(dx.view(B, T, K2), out=g_total, accumulate=True)
+        else:
+            g_total.add_(dx.view(B, F, K2))
+        # discriminator path: real, then fake.detach() accumulated on top
+        D.backward(g_real, dp, self.d_grads, "/real", False, False)
+        D.backward(g_fd, dp, self.d_grads, "/fake_detach", False, True)
+        return g_total
+
     # ---- the device program, in two halves around the all-reduce
     def _fwd_bwd(self):
         s = self._staging
         if self.train_code:
             self.g_table.zero_()                                       # optimizerClipCode.zero_grad(); dense grad (K12)
+        p2g = getattr(self, "_p2g", None)
         if not self._overlap:
-            self.out = self.engine.forward(s["audio"], s["poses"], s["idx"], (s["mean"], s["std"], s["scale"]))
-            self.engine.backward(self.grads, self.g_table)
+            self.out = self.engine.forward(s["audio"], s["poses"], s["idx"], (s["mean"], s["std"], s["scale"]), p2g_stats=p2g)
+            self.engine.backward(self.grads, self.g_table, g_pred=self._gan() if self.has_d else None)
             self._pack_scalars()
             return
-        self.out = self.engine.forward(s["audio"], s["poses"], s["idx"], (s["mean"], s["std"], s["scale"]), defer_side=True)
+        self.out = self.engine.forward(s["audio"], s["poses"], s["idx"], (s["mean"], s["std"], s["scale"]), p2g_stats=p2g, defer_side=True)
         # fork: FGD features + f64 results/metrics on a second stream while the backward pass runs on this one
         main = torch.cuda.current_stream()
         if self._aux is None:
@@ -550,7 +632,7 @@ class Voice2PoseTrainer:
             if not os.environ.get("SDT_DIAG_SKIP_SIDE"):       # diagnostic only: cost of the FGD / metrics side stream
                 self.engine.run_side()
             join.record(self._aux)
-        self.engine.backward(self.grads, self.g_table)
+        self.engine.backward(self.grads, self.g_table, g_pred=self._gan() if self.has_d else None)
         main.wait_event(join)
         self._pack_scalars()
 
@@ -561,8 +643,12 @@ class Voice2PoseTrainer:
                       self.exp_avg_sq[:self.n_g_pad], self.adam_g, grad_scale=gs)
         if self.train_code:
             ops.adam_advance(self.adam_c, -1.0)
-            sl = slice(self.n_g_pad, self.flat_p.numel())
+            sl = slice(self.n_g_pad, self.n_g_pad + self.n_code_pad)
             ops.adam_flat(self.flat_p[sl], self.flat_g[sl], self.exp_avg[sl], self.exp_avg_sq[sl], self.adam_c, grad_scale=gs)
+        if self.has_d:                                                 # optimizerD_pose (voice2pose.py:305-309)
+            ops.adam_advance(self.adam_d, -1.0)
+            sl = slice(self.off_d, self.flat_p.numel())
+            ops.adam_flat(self.flat_p[sl], self.flat_g[sl], self.exp_avg[sl], self.exp_avg_sq[sl], self.adam_d, grad_scale=gs)
 
     def _allreduce(self):
         if self.world > 1:
@@ -606,7 +692,8 @@ class Voice2PoseTrainer:
         self._stage(batch)
         return self.run_staged()
 
-    _SCALARS = ("G_reg_loss", "G_loss", "L2_dist", "lip_sync_error_n", "G_clipcode_kl_loss", "kl_applied")
+    _SCALARS = ("G_reg_loss", "G_loss", "L2_dist", "lip_sync_error_n", "G_clipcode_kl_loss", "kl_applied",
+                "G_pose_gan_loss", "D_pose_gan_loss", "pose_score_fake", "pose_score_real")
 
     def _pack_scalars(self):
         """Last node of the step: the loss / metric scalars as one f64 vector (a single 64-byte D2H read per step)."""
@@ -617,7 +704,7 @@ class Voice2PoseTrainer:
     def _scalars_dict(self, vals):
         d = {k: v for k, v in zip(self._SCALARS, vals) if k in self.out}
         if "kl_applied" in d and d.pop("kl_applied") == 0.0:          # the reference's guard (voice2pose.py:154)
-            d.pop("G_clipcode_kl_loss")
+            d.pop("G_clipcode_kl_loss", None)
         return d
 
     def losses_to_host(self, out=None):

@@ -523,3 +523,57 @@ def test_programmatic_dependent_launch_does_not_change_results():
         assert out.returncode == 0, out.stderr[-2000:]
         res[flag] = json.loads(out.stdout.strip().splitlines()[-1])
     assert res["1"] == res["0"]
+
+
+def test_s2g_fused_trainer_vs_reference_fixture():
+    """voice2pose_s2g through the FUSED trainer (flat parameter / gradient / Adam buffers for netG and netD_pose, the three
+    discriminator passes, LSGAN terms and both optimizers inside one device program) against the reference's recorded steps."""
+    from speechdrivestemplates_b200 import pipeline
+    from oracle import sdt_oracle as O
+    g = golden("s2g_step_golden")
+    n_train, bs = int(g["n_train"]), int(g["batch_size"])
+    cfg = _cfg("voice2pose_s2g")
+    tr = pipeline.Voice2PoseTrainer(cfg, n_train, dev(), use_cuda_graph=False, seed=0)
+    tr.set_p2g_stats(oliver_stat(True), oliver_stat(False))
+    for k, v in tr.model.state_dict().items():
+        assert np.array_equal(samples_of(v), g["init/%s/samples" % k]), k
+    steps = int(g["steps"]) if "steps" in g.files else 1
+    for s in range(steps):
+        batch = O.synthetic_batch(bs, n_train, oliver_stat(False), seed=100 + s, stat_parted=oliver_stat(True), stat_global=oliver_stat(False))
+        out = tr.train_step(_to_host_batch(batch))
+        host = tr.losses_to_host(out)
+        p = "step%d" % s
+        ftol = 2e-4 if s == 0 else 2e-2       # BN at batch 2 + Adam's sign-like first step amplify fp32 noise from step 1 on
+        for k in ("G_reg_loss", "G_pose_gan_loss", "G_loss", "D_pose_gan_loss", "pose_score_fake", "pose_score_real"):
+            ref = float(g["%s/loss/%s" % (p, k)])
+            assert abs(host[k] - ref) <= ftol * max(1.0, abs(ref)), (s, k, host[k], ref)
+        if s == 0:
+            assert rel_err(out["poses_pred_batch"].cpu().numpy(), g[p + "/pred"]) < 1e-4
+            assert rel_err(out["mu_gt"].cpu().numpy(), g[p + "/mu_gt"]) < 1e-3
+            _check_against_fixture(g, p + "/grad", {"netG." + n: t for n, t in tr.grads.items()}, 5e-2, "G grad", outlier_frac=0.05)
+            _check_against_fixture(g, p + "/grad", {"netD_pose." + n: t for n, t in tr.d_grads.items()}, 1e-2, "D grad", outlier_frac=0.02)
+            for k, v in tr.model.state_dict().items():
+                ref = g["%s/state/%s/samples" % (p, k)].astype(np.float64)
+                err = np.abs(samples_of(v).astype(np.float64) - ref).max()
+                assert err <= 1e-3 * np.abs(ref).max() + 2.5e-4, (k, err)
+            assert int(tr.model.netD_pose.seq[0].norm.num_batches_tracked) == 3        # real, fake, fake.detach()
+
+
+def test_s2g_fused_trainer_graph_replay_equals_eager():
+    """The captured two-graph program of the s2g step replays to the same parameters as eager execution."""
+    from speechdrivestemplates_b200 import pipeline
+    from oracle import sdt_oracle as O
+    cfg = _cfg("voice2pose_s2g")
+    sums = []
+    for graph in (False, True):
+        tr = pipeline.Voice2PoseTrainer(cfg, 16, dev(), use_cuda_graph=graph, seed=0)
+        tr.set_p2g_stats(oliver_stat(True), oliver_stat(False))
+        for s in range(5):
+            batch = O.synthetic_batch(4, 16, oliver_stat(False), seed=500 + s, stat_parted=oliver_stat(True), stat_global=oliver_stat(False))
+            tr.train_step(_to_host_batch(batch))
+        host = tr.losses_to_host()
+        sums.append((host, float(tr.flat_p.double().abs().sum())))
+    assert sums[0][0].keys() == sums[1][0].keys()
+    for k in sums[0][0]:
+        assert abs(sums[0][0][k] - sums[1][0][k]) <= 1e-5 * max(1.0, abs(sums[0][0][k])), k
+    assert abs(sums[0][1] - sums[1][1]) <= 1e-6 * sums[0][1]

@@ -229,7 +229,7 @@ class EventProfiler:
                 from speechdrivestemplates_b200 import _lib
                 plan = (C.c_int32 * 10)()
                 _lib.load().sdt_conv_plan(args[0], plan)
-                if plan[0] == 3:
+                if plan[0] in (3, 4):
                     name = "sdt_conv_gemm[tc_conv_ytap_kernel]"
         return (name, e0, flops)
 
@@ -264,7 +264,7 @@ def run_own(args):
         pg = dist.group.WORLD
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
 
-    conv_math = {"fp32": 0, "tf32": 1, "tf32-tma": 2, "tf32-reuse": 3}[args.math]
+    conv_math = {"fp32": 0, "tf32": 1, "tf32-tma": 2, "tf32-reuse": 3, "tf32-pair": 4}[args.math]
     tr = pipeline.Voice2PoseTrainer(config.get_cfg("voice2pose_sdt_bp"), N_TRAIN, dev, use_cuda_graph=not args.no_graph,
                                     process_group=pg, seed=0, conv_math=conv_math)
     tr.model.clips_code.data.copy_(0.1 * torch.randn(N_TRAIN, 32, generator=torch.Generator().manual_seed(11)))
@@ -376,6 +376,8 @@ def run_own(args):
             "peak_source": pk["src"] + " bf16 dense, sustained (kernel timed inside a long step); the kernel computes in TF32, whose "
                                        "nominal dense rate is half of bf16 (1.1 vs 2.25 PFLOP/s)",
             "ncu_tensor_pipe_active_pct": "57-85 (Cout >= 128), 41 (64->64 stride 2): profiles/r1_ncu_tc_conv_mode3.txt",
+            # the same measured peak scaled to the arithmetic type the kernel uses (TF32 = half the bf16 rate)
+            "frac_of_tf32_equivalent_peak": achieved / (0.5 * pk["tf_sustained"]),
         }
     else:
         achieved = family["achieved_tflops"]
@@ -418,7 +420,8 @@ def run_own(args):
                    "conv_math": ["fp32 FFMA", "tcgen05 TF32 operands, fp32 accumulate (FFMA for ineligible layers)",
                                  "tcgen05 TF32, TMA-fed operands for forward/dgrad, fp32 accumulate (FFMA for ineligible layers)",
                                  "tcgen05 TF32, TMA-fed operands reused across vertical taps and accumulators in shared memory, fp32 "
-                                 "accumulate (FFMA for ineligible layers)"][conv_math]},
+                                 "accumulate (FFMA for ineligible layers)",
+                                 "as tf32-reuse plus CTA pairs (cta_group::2) where N % 128 == 0 (experimental)"][conv_math]},
         "e2e": {"value": clips / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / K, "wall_s": wall_e2e, "host_gap_ms": {"median": gaps[len(gaps) // 2], "max": gaps[-1]}},
         "gpu_launches": launches_per_step * K * 2,
@@ -438,7 +441,7 @@ def main():
     ap.add_argument("--impl", default="own")
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU (BASELINE configs[1]: 32)")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--math", default="tf32-reuse", choices=["fp32", "tf32", "tf32-tma", "tf32-reuse"],
+    ap.add_argument("--math", default="tf32-reuse", choices=["fp32", "tf32", "tf32-tma", "tf32-reuse", "tf32-pair"],
                     help="convolution math: fp32 FFMA kernels or tcgen05 TF32 tensor-core kernels (fp32 accumulate)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

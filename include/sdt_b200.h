@@ -41,7 +41,9 @@ int sdt_version(void);
  *   3 = as 2, plus operand reuse in shared memory for 2-D maps (csrc/tc_conv_ytap.cu): one TMA box serves all the
  *       vertical taps of a kernel column and one weight box serves several accumulators -- the L2 -> shared-memory
  *       traffic, which bounds mode 2, drops 2-3x.  Same arithmetic as mode 2 (same products, fp32 accumulation in a
- *       different order). */
+ *       different order);
+ *   4 = as 3, plus CTA pairs (tcgen05 cta_group::2, 256-row MMAs, each CTA supplying half of the weight tile) for 2-D
+ *       convolutions with N % 128 == 0 (csrc/tc_conv_pair.cu) -- experimental. */
 int sdt_set_conv_math(int mode);
 int sdt_get_conv_math(void);
 /* number of tcgen05 kernel launches made by this process so far (lets callers/tests verify which path ran) */
@@ -103,7 +105,7 @@ typedef struct sdt_conv_desc {
 int sdt_conv_row_tiles(const sdt_conv_desc* d);
 int sdt_conv_gemm(const sdt_conv_desc* d, void* stream);
 /* which kernel sdt_conv_gemm would launch for this descriptor under the current math mode (host-only, no launch):
- * out10[0] = 0 fp32 FFMA, 1 tcgen05 (producer warps), 2 tcgen05 + TMA, 3 tcgen05 + TMA + shared-memory reuse; for 3 also
+ * out10[0] = 0 fp32 FFMA, 1 tcgen05 (producer warps), 2 tcgen05 + TMA, 3 tcgen05 + TMA + shared-memory reuse, 4 CTA pairs; for 3/4 also
  * out10[1..9] = N tile, accumulators per CTA, patch rows, patch cols, box rows, A stages, B stages, shared memory, CTAs */
 int sdt_conv_plan(const sdt_conv_desc* d, int32_t* out10);
 /* wgrad: contractions with K = TH*TW*C <= 16 and N <= 64 (first encoder layer) use a streaming kernel whose CTA count

@@ -33,7 +33,7 @@ void set_error(const char* fmt, ...) {
 extern "C" const char* sdt_last_error(void) { return g_err; }
 extern "C" int sdt_version(void) { return 100; }
 extern "C" int sdt_set_conv_math(int mode) {
-    SDT_REQUIRE(mode >= 0 && mode <= 3, "sdt_set_conv_math: mode must be 0 (fp32 FFMA), 1 (tcgen05 TF32), 2 (tcgen05 TF32 + TMA operands) or 3 (2 + shared-memory operand reuse)");
+    SDT_REQUIRE(mode >= 0 && mode <= 4, "sdt_set_conv_math: mode must be 0 (fp32 FFMA), 1 (tcgen05 TF32), 2 (+ TMA operands), 3 (+ persistent kernel with operand reuse) or 4 (+ CTA pairs, experimental)");
     g_conv_math.store(mode);
     return SDT_OK;
 }

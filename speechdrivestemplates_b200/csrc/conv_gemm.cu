@@ -676,12 +676,14 @@ inline int pick_bm(const sdt_conv_desc* d) {
 
 }  // namespace
 
-inline bool use_ytap(const sdt_conv_desc* d) { return sdt_get_conv_math() == 3 && sdt_tc_conv_ytap_eligible(d); }
+inline bool use_pair(const sdt_conv_desc* d) { return sdt_get_conv_math() == 4 && sdt_tc_conv_pair_eligible(d); }
+inline bool use_ytap(const sdt_conv_desc* d) { return sdt_get_conv_math() >= 3 && sdt_tc_conv_ytap_eligible(d); }
 inline bool use_tma(const sdt_conv_desc* d) { return sdt_get_conv_math() >= 2 && sdt_tc_conv_tma_eligible(d); }
 inline bool use_tc(const sdt_conv_desc* d) { return sdt_get_conv_math() >= 1 && sdt_tc_conv_eligible(d); }
 
 extern "C" int sdt_conv_row_tiles(const sdt_conv_desc* d) {
     if (check_desc(d, "sdt_conv_row_tiles") != SDT_OK) return -1;
+    if (use_pair(d)) return sdt_tc_conv_pair_row_tiles(d);
     if (use_ytap(d)) return sdt_tc_conv_ytap_row_tiles(d);
     if (use_tma(d)) return sdt_tc_conv_tma_row_tiles(d);
     return row_tiles_for(d, use_tc(d) ? 128 : pick_bm(d));
@@ -691,7 +693,10 @@ extern "C" int sdt_conv_plan(const sdt_conv_desc* d, int32_t* out10) {
     if (int rc = check_desc(d, "sdt_conv_plan")) return rc;
     SDT_REQUIRE(out10 != nullptr, "sdt_conv_plan: null output");
     for (int i = 0; i < 10; ++i) out10[i] = 0;
-    if (sdt_get_conv_math() == 3 && sdt_tc_conv_ytap_shape_ok(d)) {
+    if (sdt_get_conv_math() == 4 && sdt_tc_conv_pair_shape_ok(d)) {
+        out10[0] = 4;
+        sdt_tc_conv_pair_describe(d, out10);
+    } else if (sdt_get_conv_math() >= 3 && sdt_tc_conv_ytap_shape_ok(d)) {
         out10[0] = 3;
         sdt_tc_conv_ytap_describe(d, out10);
     } else if (use_tma(d)) {
@@ -708,6 +713,7 @@ extern "C" int sdt_conv_gemm(const sdt_conv_desc* d, void* stream) {
     SDT_REQUIRE(!(d->stat_partial && d->bias), "sdt_conv_gemm: statistics epilogue excludes bias");
     SDT_REQUIRE(!(d->stat_partial && d->accumulate), "sdt_conv_gemm: statistics epilogue excludes accumulate");
     cudaStream_t st = sdt::as_stream(stream);
+    if (use_pair(d)) return sdt_tc_conv_pair_launch(d, st);                     // math mode 4: CTA pairs (cta_group::2), experimental
     if (use_ytap(d)) return sdt_tc_conv_ytap_launch(d, st);                     // math mode 3: + operand reuse in shared memory
     if (use_tma(d)) return sdt_tc_conv_tma_launch(d, st);                       // math mode 2: tcgen05 TF32, TMA operands
     if (use_tc(d)) return sdt_tc_conv_launch(d, row_tiles_for(d, 128), st);   // math mode 1/2: tcgen05 TF32

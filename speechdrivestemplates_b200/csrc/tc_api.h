@@ -16,6 +16,11 @@ bool sdt_tc_conv_ytap_shape_ok(const sdt_conv_desc* d);
 int sdt_tc_conv_ytap_row_tiles(const sdt_conv_desc* d);
 int sdt_tc_conv_ytap_describe(const sdt_conv_desc* d, int32_t* out10);
 int sdt_tc_conv_ytap_launch(const sdt_conv_desc* d, cudaStream_t st);
+bool sdt_tc_conv_pair_eligible(const sdt_conv_desc* d);
+bool sdt_tc_conv_pair_shape_ok(const sdt_conv_desc* d);
+int sdt_tc_conv_pair_row_tiles(const sdt_conv_desc* d);
+int sdt_tc_conv_pair_describe(const sdt_conv_desc* d, int32_t* out10);
+int sdt_tc_conv_pair_launch(const sdt_conv_desc* d, cudaStream_t st);
 bool sdt_tc_wgrad_tma_eligible(const sdt_conv_desc* d);
 int sdt_tc_wgrad_tma_launch(const sdt_conv_desc* d, cudaStream_t st);
 void sdt_note_tc_launch();

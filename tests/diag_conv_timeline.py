@@ -57,7 +57,7 @@ def main():
             ms = e0.elapsed_time(e1) / 10
             line = "L %3d->%3d %dx%d s%d %3dx%3d mode %d: %.1f us  %.0f TFLOP/s  plan %s" % (
                 cin, cout, kh, kw, s, H, W, mode, ms * 1e3, flops / ms / 1e9, list(plan))
-            for fl in (flags_list if (mode == 3 and plan[0] == 3) else []):
+            for fl in (flags_list if (mode == 3 and plan[0] == 3 and len(sys.argv) > 3) else []):
                 lib.sdt_debug_conv_flags(fl)
                 for _ in range(2):
                     ops.conv_gemm(d)

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.sdt_version() >= 100
-    assert lib.sdt_get_conv_math() in (0, 1, 2, 3)
+    assert lib.sdt_get_conv_math() in (0, 1, 2, 3, 4)
 
 
 def test_conv_desc_mirror_matches_header():

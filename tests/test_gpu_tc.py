@@ -195,7 +195,7 @@ def test_sdt_bp_train_step_tf32_mode_vs_reference_fixture(mode):
 
 # ---------------------------------------------------------------- math modes 2 / 3: TMA-fed tcgen05 kernels
 # (3 = operand reuse across vertical taps and accumulators in shared memory, csrc/tc_conv_ytap.cu)
-@pytest.fixture(params=[2, 3], ids=["tma", "reuse"])
+@pytest.fixture(params=[2, 3, 4], ids=["tma", "reuse", "pair"])
 def ops_tma(request):
     from speechdrivestemplates_b200 import ops as o
     o.set_conv_math(request.param)

@@ -8,6 +8,8 @@
 //
 // Tiling: BMxBNx16 CTA tiles, 256 threads, 8x8 / 8x4 / 4x4 register tiles, register-prefetch double buffering.
 #include "common.cuh"
+#include <stdlib.h>
+
 #include "tc_api.h"
 
 namespace {
@@ -676,6 +678,27 @@ inline int pick_bm(const sdt_conv_desc* d) {
 
 }  // namespace
 
+// 1-D layers arrive as B images of one row (B,1,L,C).  The persistent kernel tiles (rows x columns) patches inside ONE image, so
+// for it the batch becomes the image height: (B,1,L,C) and (1,B,L,C) are the same memory, a patch of bh clips x bw positions
+// fills all 128 GEMM rows (a per-clip patch of a 64-frame sequence fills half), and zero padding along the sequence is still
+// TMA's out-of-bounds fill in x.  There are no vertical taps (TH == 1), so rows never mix clips.
+// Measured (B = 32): the 36 small 1-D launches of a step are 0.1 ms SLOWER this way than on tc_conv_tma.cu (a persistent CTA with
+// the whole shared memory and 512 TMEM columns per SM is a heavy vehicle for 16-64 tiles), so it is off unless SDT_REMAP_1D=1.
+inline bool remap_1d(const sdt_conv_desc* d, sdt_conv_desc* out) {
+    static const bool on = getenv("SDT_REMAP_1D") != nullptr && getenv("SDT_REMAP_1D")[0] == '1';
+    if (!on || sdt_get_conv_math() < 3) return false;
+    if (!(d->SH == 1 && d->GH == 1 && d->DH == 1 && d->TH == 1 && d->B > 1 && d->per_image_tiles == 0)) return false;
+    *out = *d;
+    out->SH = out->GH = out->DH = d->B;
+    out->B = 1;
+    out->y_mul = 1;
+    out->ty_mul = 1;
+    out->y_off = 0;
+    out->dy_mul = 1;
+    out->dy_off = 0;
+    return true;
+}
+
 inline bool use_pair(const sdt_conv_desc* d) { return sdt_get_conv_math() == 4 && sdt_tc_conv_pair_eligible(d); }
 inline bool use_ytap(const sdt_conv_desc* d) { return sdt_get_conv_math() >= 3 && sdt_tc_conv_ytap_eligible(d); }
 inline bool use_tma(const sdt_conv_desc* d) { return sdt_get_conv_math() >= 2 && sdt_tc_conv_tma_eligible(d); }
@@ -683,6 +706,8 @@ inline bool use_tc(const sdt_conv_desc* d) { return sdt_get_conv_math() >= 1 && 
 
 extern "C" int sdt_conv_row_tiles(const sdt_conv_desc* d) {
     if (check_desc(d, "sdt_conv_row_tiles") != SDT_OK) return -1;
+    sdt_conv_desc r;
+    if (remap_1d(d, &r) && use_ytap(&r)) return sdt_tc_conv_ytap_row_tiles(&r);
     if (use_pair(d)) return sdt_tc_conv_pair_row_tiles(d);
     if (use_ytap(d)) return sdt_tc_conv_ytap_row_tiles(d);
     if (use_tma(d)) return sdt_tc_conv_tma_row_tiles(d);
@@ -693,7 +718,11 @@ extern "C" int sdt_conv_plan(const sdt_conv_desc* d, int32_t* out10) {
     if (int rc = check_desc(d, "sdt_conv_plan")) return rc;
     SDT_REQUIRE(out10 != nullptr, "sdt_conv_plan: null output");
     for (int i = 0; i < 10; ++i) out10[i] = 0;
-    if (sdt_get_conv_math() == 4 && sdt_tc_conv_pair_shape_ok(d)) {
+    sdt_conv_desc r1;
+    if (remap_1d(d, &r1) && sdt_tc_conv_ytap_shape_ok(&r1)) {
+        out10[0] = 3;
+        sdt_tc_conv_ytap_describe(&r1, out10);
+    } else if (sdt_get_conv_math() == 4 && sdt_tc_conv_pair_shape_ok(d)) {
         out10[0] = 4;
         sdt_tc_conv_pair_describe(d, out10);
     } else if (sdt_get_conv_math() >= 3 && sdt_tc_conv_ytap_shape_ok(d)) {
@@ -713,6 +742,8 @@ extern "C" int sdt_conv_gemm(const sdt_conv_desc* d, void* stream) {
     SDT_REQUIRE(!(d->stat_partial && d->bias), "sdt_conv_gemm: statistics epilogue excludes bias");
     SDT_REQUIRE(!(d->stat_partial && d->accumulate), "sdt_conv_gemm: statistics epilogue excludes accumulate");
     cudaStream_t st = sdt::as_stream(stream);
+    sdt_conv_desc r1;
+    if (remap_1d(d, &r1) && use_ytap(&r1)) return sdt_tc_conv_ytap_launch(&r1, st);   // 1-D layers on the persistent kernel
     if (use_pair(d)) return sdt_tc_conv_pair_launch(d, st);                     // math mode 4: CTA pairs (cta_group::2), experimental
     if (use_ytap(d)) return sdt_tc_conv_ytap_launch(d, st);                     // math mode 3: + operand reuse in shared memory
     if (use_tma(d)) return sdt_tc_conv_tma_launch(d, st);                       // math mode 2: tcgen05 TF32, TMA operands

@@ -561,7 +561,7 @@ bool sdt_tc_conv_ytap_eligible(const sdt_conv_desc* d) { return sdt_tc_conv_ytap
 bool sdt_tc_conv_ytap_shape_ok(const sdt_conv_desc* d) {
     if (d->wt_nk == nullptr || d->xf_scale != nullptr) return false;        // plain (already activated) source only
     if (d->C % 32 != 0 || d->N % 64 != 0) return false;
-    if (d->GH < 2 || d->TH < 2) return false;                                // nothing to reuse vertically: tc_conv_tma.cu
+    if (d->GH < 2) return false;                                             // single-row maps: tc_conv_tma.cu (1-D layers are remapped by the dispatcher)
     if (d->x_mul < 1 || d->x_mul > 8 || d->y_mul < 1 || d->y_mul > 8) return false;
     if ((((uintptr_t)d->src | (uintptr_t)d->wt_nk | (uintptr_t)d->dst | (uintptr_t)d->bias) & 15) != 0) return false;
     return make_plan(d).ok;

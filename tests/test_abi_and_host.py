@@ -189,7 +189,7 @@ def test_conv_plan_for_the_encoder_layers(B):
         lib.sdt_set_conv_math(0)
 
 
-def test_conv_plan_falls_back_outside_mode_3_and_for_1d():
+def test_conv_plan_falls_back_outside_mode_3_and_remaps_1d():
     _built()
     from speechdrivestemplates_b200 import _lib, ops
     lib = _lib.load()
@@ -200,12 +200,17 @@ def test_conv_plan_falls_back_outside_mode_3_and_for_1d():
         assert lib.sdt_conv_plan(ctypes.byref(d), out) == 0 and out[0] != 3
     lib.sdt_set_conv_math(3)
     try:
-        d1 = ops.ConvDesc()                                  # a 1-D layer (GH == 1) has no vertical taps to reuse
+        d1 = ops.ConvDesc()                                  # a 1-D layer: the batch becomes the image height for the planner
         d1.src = d1.wt = d1.wt_nk = d1.dst = 0x1000
         d1.B, d1.SH, d1.SW, d1.C = 4, 1, 64, 256
         d1.GH, d1.GW, d1.TH, d1.TW = 1, 64, 1, 3
         d1.y_mul, d1.ty_mul, d1.y_off, d1.x_mul, d1.tx_mul, d1.x_off = 1, 1, 0, 1, 1, -1
         d1.N, d1.DH, d1.DW, d1.dy_mul, d1.dx_mul = 256, 1, 64, 1, 1
+        if os.environ.get("SDT_REMAP_1D") == "1":           # experimental switch (slower at B = 32, see conv_gemm.cu)
+            assert lib.sdt_conv_plan(ctypes.byref(d1), out) == 0 and out[0] == 3 and out[3] * out[4] == 128 and out[5] == out[3]
+        else:
+            assert lib.sdt_conv_plan(ctypes.byref(d1), out) == 0 and out[0] != 3
+        d1.B = 1                                             # a single clip has nothing to stack: TMA kernel of mode 2
         assert lib.sdt_conv_plan(ctypes.byref(d1), out) == 0 and out[0] != 3
         with pytest.raises(_lib.SdtError):
             _lib.call("sdt_conv_plan", ctypes.byref(d1), None)

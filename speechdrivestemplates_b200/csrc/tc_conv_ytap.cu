@@ -1,7 +1,7 @@
 // Convolution forward / data-gradient on tcgen05 (TF32), TMA operands, operand reuse in shared memory, persistent CTAs
 // with double-buffered accumulators (math mode 3).
 //
-// What the measurements on tc_conv_tma.cu (mode 2) said (tests/diag_conv_timeline.py, profiles/r1_conv_mode3_*.txt):
+// What the measurements on tc_conv_tma.cu (mode 2) said (tests/diag_conv_timeline.py, profiles/r1_conv_timeline_*.txt):
 //   * its issue loops run inside `if (lane == 0)`: ptxas then treats every operand as lane-varying and wraps each
 //     UTCHMMA / UTMALDG in an ELECT + 5 x R2UR + BRA.U.ANY waterfall -- ~200 clk of issue per 64-clk MMA;
 //   * one tile per CTA: the co-resident CTAs of an SM, and in fact the whole chip, run in lockstep -- a main-loop phase with
@@ -128,8 +128,6 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
     if (DBG) {
         tl = (g_timeline != nullptr && (int)blockIdx.x < g_timeline_ctas) ? g_timeline + 8 * blockIdx.x : nullptr;
         if (tid == 0 && tl != nullptr) {
-            uint32_t smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
             tl[0] = -clock64();
             tl[1] = gtimer();
         }

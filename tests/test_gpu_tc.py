@@ -155,7 +155,7 @@ def test_tc_wgrad_conv1d(ops):
     assert rel(dw.view(cout, cin, 4), w.grad) < TF32_TOL
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
 def test_sdt_bp_train_step_tf32_mode_vs_reference_fixture(mode):
     """Whole fused train step with the tcgen05 TF32 convolutions against the reference's recorded fp32 step.
     Stated TF32 tolerance: losses 1e-3, prediction 5e-3 of its range, final f64 results 5e-3; gradients agree in

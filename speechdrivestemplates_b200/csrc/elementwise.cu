@@ -62,7 +62,11 @@ __global__ void enc_to_seq_bwd_kernel(const float* __restrict__ g_out, int B, in
     if (yy == y1) wy += wy1;
     float acc = 0.f;
     if (wy != 0.f) {
-        for (int j = 0; j < F; ++j) {
+        // only frames whose source position (j + 0.5) * W / F - 0.5 lies within one pixel of xx can have sampled it: a window
+        // of ~2 F / W + 4 frames instead of all F (same terms in the same ascending order, the others had weight 0)
+        const int jlo = max(0, (int)(((long long)(xx - 1) * F) / W) - 2);
+        const int jhi = min(F - 1, (int)(((long long)(xx + 2) * F + W - 1) / W) + 2);
+        for (int j = jlo; j <= jhi; ++j) {
             int x0, x1;
             float wx0, wx1;
             lerp_coeff(j, W, F, x0, x1, wx0, wx1);

@@ -776,6 +776,7 @@ extern "C" int sdt_conv_wgrad(const sdt_conv_desc* d, void* stream) {
     const int Kc = d->TH * d->TW * d->C;
     const bool veca = (d->N % 4) == 0, vecb = (d->C % 4) == 0;
     cudaStream_t st = sdt::as_stream(stream);
+    if (sdt_get_conv_math() >= 3 && sdt_tc_wgrad_ytap_eligible(d)) return sdt_tc_wgrad_ytap_launch(d, st);   // + vertical-tap reuse
     if (sdt_get_conv_math() >= 2 && sdt_tc_wgrad_tma_eligible(d)) return sdt_tc_wgrad_tma_launch(d, st);   // tcgen05 + TMA
     if (sdt_get_conv_math() >= 1 && sdt_tc_wgrad_eligible(d)) return sdt_tc_wgrad_launch(d, st);   // tcgen05 TF32
     if (Kc <= 16 && d->N <= 64) {       // tiny contraction: streaming kernel, one partial per CTA (gridDim.x == splits)

@@ -23,4 +23,6 @@ int sdt_tc_conv_pair_describe(const sdt_conv_desc* d, int32_t* out10);
 int sdt_tc_conv_pair_launch(const sdt_conv_desc* d, cudaStream_t st);
 bool sdt_tc_wgrad_tma_eligible(const sdt_conv_desc* d);
 int sdt_tc_wgrad_tma_launch(const sdt_conv_desc* d, cudaStream_t st);
+bool sdt_tc_wgrad_ytap_eligible(const sdt_conv_desc* d);
+int sdt_tc_wgrad_ytap_launch(const sdt_conv_desc* d, cudaStream_t st);
 void sdt_note_tc_launch();

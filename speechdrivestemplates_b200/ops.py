@@ -207,6 +207,11 @@ def wgrad_splits(g, B, oh, ow, target_ctas=444):
     copy of the layer's gradient, which for the 1-D stacks (2048 pixels, 0.8 MB of weights) used to be 32 copies per layer."""
     if g.k <= 16 and g.cout <= 64:          # streaming small-K kernel: one partial per CTA, 4 CTAs per SM
         return min(148 * 4, max(1, -(-(B * oh * ow) // 64)))
+    if get_conv_math() >= 3 and g.cin % 128 == 0 and g.cout % 128 == 0 and g.kh >= 2 and oh >= 2:
+        # csrc/tc_wgrad_ytap.cu: one CTA per SM and per (128-channel block, kernel column, group of <= 3 vertical taps, N tile)
+        groups = sum(-(-(-(-(g.kh - p) // g.sh)) // 3) for p in range(min(g.sh, g.kh)))
+        tiles = (g.cin // 128) * g.kw * groups * (g.cout // 128)
+        return max(1, min(148 // tiles, -(-(B * oh * ow) // 256)))
     tiles = -(-g.k // 128) * -(-g.cout // (64 if g.cout <= 64 else 128))
     pixels = B * oh * ow
     return max(1, min(-(-target_ctas // tiles), -(-pixels // 256)))

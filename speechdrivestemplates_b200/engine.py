@@ -233,7 +233,32 @@ class GeneratorEngine:
             else:                                   # up(prev)+skip: resampled to the skip's (== this layer's) length
                 lin = self.seq_len[name]
             out.append((name, name + ".conv.weight", g, (1, lin), True))
-        out.append(("decoder.4", "decoder.4.weight", ConvGeom.conv1d(256, self.kp2, 1, 1, 0), (1, self.F), True))
+        if self._head_pad():
+            out.append(("decoder.4", "decoder.4.weight_pad", ConvGeom.conv1d(256, self._head_pad(), 1, 1, 0), (1, self.F), True))
+        else:
+            out.append(("decoder.4", "decoder.4.weight", ConvGeom.conv1d(256, self.kp2, 1, 1, 0), (1, self.F), True))
+        return out
+
+    def _head_pad(self):
+        """The pose head is a 1x1 convolution to 2*K = 242 channels, which no tensor-core tile divides.  In the TMA math modes it runs
+        as a 256 -> 256 layer on zero-padded copies (weight rows / bias entries / gradient channels 242..255 are zero, 0.3 MB) so that
+        its forward, data gradient and weight gradient use the tcgen05 kernels instead of three ~50 us FFMA launches.  0 = no padding."""
+        if ops.get_conv_math() >= 2 and self.kp2 % 64 != 0:
+            return -(-self.kp2 // 64) * 64
+        return 0
+
+    def _padded_head_params(self, params):
+        """params + zero-padded copies of decoder.4.weight / .bias (refreshed from the parameters every step)."""
+        npad = self._head_pad()
+        if not npad:
+            return params
+        A = self.arena
+        wp = A.get("head_w_pad", (npad, 256, 1), zero=True)
+        bp = A.get("head_b_pad", (npad,), zero=True)
+        wp[:self.kp2].copy_(params["decoder.4.weight"])
+        bp[:self.kp2].copy_(params["decoder.4.bias"])
+        out = dict(params)
+        out["decoder.4.weight_pad"], out["decoder.4.bias_pad"] = wp, bp
         return out
 
     # ---- forward ----------------------------------------------------------------------------------
@@ -259,6 +284,8 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
     # math mode 2 with InstanceNorm and an invertible activation: the 1 -> 64 first block runs as the single-pass special
     # case (csrc/first_layer.cu): no raw map, no separate normalisation pass, closed-form weight gradient
     self.fused_first = self.materialize and self.norm == "IN" and slope > 0.0
+    params = self._padded_head_params(params)
+    self._params = params
     self.wprep.ensure(self._all_layers(), params, with_dgrad=training)
     # the batched weight-operand refresh (0.12 ms) is not needed by the single-pass first block: run it beside that block on
     # the side stream and join before the first convolution that reads a prepared operand
@@ -368,9 +395,17 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
         acts[name] = act
     self._acts = acts
     # ---- final 1x1 conv + bias (generator.py:103); channels-last output IS (B,F,2,K) (generator.py:116)
+    pred = A.get("pred", (B, num_frames, self.kp2))
+    npad = self._head_pad()
+    if npad:
+        gl = ConvGeom.conv1d(256, npad, 1, 1, 0)
+        wt, wt_nk = self._prep_weight("decoder.4", params["decoder.4.weight_pad"], gl)
+        pred_pad = A.get("pred_pad", (B, num_frames, npad))
+        ops.conv_gemm(ops.fwd_desc(gl, acts["decoder.3"], wt, pred_pad, B, 1, num_frames, bias=params["decoder.4.bias_pad"], wt_nk=wt_nk))
+        pred.copy_(pred_pad[..., :self.kp2])
+        return pred
     gl = ConvGeom.conv1d(256, self.kp2, 1, 1, 0)
     wt, wt_nk = self._prep_weight("decoder.4", params["decoder.4.weight"], gl)
-    pred = A.get("pred", (B, num_frames, self.kp2))
     ops.conv_gemm(ops.fwd_desc(gl, acts["decoder.3"], wt, pred, B, 1, num_frames, bias=params["decoder.4.bias"], wt_nk=wt_nk))
     return pred
 
@@ -378,7 +413,7 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
 _DIAG_SKIP_WGRAD = bool(__import__("os").environ.get("SDT_DIAG_SKIP_WGRAD"))
 
 
-def _wgrad(self, g, x, dy, B, H, W, grad_out, xf=None, slope=1.0):
+def _wgrad(self, g, x, dy, B, H, W, grad_out, xf=None, slope=1.0, post=None):
     """Weight gradient of one layer.  Nothing downstream in the backward pass depends on it, so when the engine has a
     `wg_stream` it is enqueued there (after an event marking dy ready) and overlaps the dgrad chain on the main stream."""
     if _DIAG_SKIP_WGRAD:              # diagnostic only (wrong gradients): how much of the step do the weight gradients cost?
@@ -390,9 +425,13 @@ def _wgrad(self, g, x, dy, B, H, W, grad_out, xf=None, slope=1.0):
         with torch.cuda.stream(wg):
             wg.wait_event(ev)
             _wgrad_now(self, g, x, dy, B, H, W, grad_out, xf, slope)
+            if post is not None:
+                post()
         self._wg_pending = True
         return
     _wgrad_now(self, g, x, dy, B, H, W, grad_out, xf, slope)
+    if post is not None:
+        post()
 
 
 def _wgrad_join(self):
@@ -431,12 +470,22 @@ def _gen_backward(self, g_pred, grads, g_code=None):
     bn = self.norm == "BN"
     params, acts = self._params, self._acts
     # ---- final conv
-    gl = ConvGeom.conv1d(256, self.kp2, 1, 1, 0)
-    _wgrad(self, gl, acts["decoder.3"], g_pred, B, 1, F, grads["decoder.4.weight"])
     ops.colsum(g_pred, grads["decoder.4.bias"])
     g_act = {}
     g_act["decoder.3"] = A.get("g_act:decoder.3", (B, F, 256))
-    _dgrad(self, "decoder.4", gl, g_pred, params["decoder.4.weight"], g_act["decoder.3"], B, 1, F)
+    npad = self._head_pad()
+    if npad:
+        gl = ConvGeom.conv1d(256, npad, 1, 1, 0)
+        g_pad = A.get("g_pred_pad", (B, F, npad), zero=True)             # channels 242..255 stay zero
+        g_pad[..., :self.kp2].copy_(g_pred.view(B, F, self.kp2))
+        gw_pad = A.get("head_gw_pad", (npad, 256, 1))
+        dst = grads["decoder.4.weight"]
+        _wgrad(self, gl, acts["decoder.3"], g_pad, B, 1, F, gw_pad, post=lambda: dst.copy_(gw_pad[:self.kp2]))
+        _dgrad(self, "decoder.4", gl, g_pad, params["decoder.4.weight_pad"], g_act["decoder.3"], B, 1, F)
+    else:
+        gl = ConvGeom.conv1d(256, self.kp2, 1, 1, 0)
+        _wgrad(self, gl, acts["decoder.3"], g_pred, B, 1, F, grads["decoder.4.weight"])
+        _dgrad(self, "decoder.4", gl, g_pred, params["decoder.4.weight"], g_act["decoder.3"], B, 1, F)
     # ---- 1-D stack in reverse
     layers = self.seq_layers()
     g_x0 = None

@@ -106,7 +106,8 @@ int sdt_conv_row_tiles(const sdt_conv_desc* d);
 int sdt_conv_gemm(const sdt_conv_desc* d, void* stream);
 /* which kernel sdt_conv_gemm would launch for this descriptor under the current math mode (host-only, no launch):
  * out10[0] = 0 fp32 FFMA, 1 tcgen05 (producer warps), 2 tcgen05 + TMA, 3 tcgen05 + TMA + shared-memory reuse, 4 CTA pairs; for 3/4 also
- * out10[1..9] = N tile, accumulators per CTA, patch rows, patch cols, box rows, A stages, B stages, shared memory, CTAs */
+ * out10[1..9] = N tile, accumulators per CTA, patch rows | images per patch << 8, patch cols, box rows, A stages, B stages,
+ * shared memory, tiles */
 int sdt_conv_plan(const sdt_conv_desc* d, int32_t* out10);
 /* wgrad: contractions with K = TH*TW*C <= 16 and N <= 64 (first encoder layer) use a streaming kernel whose CTA count
  * equals `splits`; otherwise split-K GEMM tiles (FFMA, or tcgen05 in math mode 1 when C % 32 == 0, N in {64,128,256}). */

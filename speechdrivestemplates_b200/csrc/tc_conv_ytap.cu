@@ -20,6 +20,10 @@
 //     1024-byte swizzle atom: ONE box of (bh + taps - 1) patch rows per (channel chunk, tx, y-phase), each tap a different
 //     start address in the matrix descriptor (3x3: 3 boxes of 18 rows instead of 9 of 16);
 //   * weight reuse: MT sub-tiles (MT accumulators) per CTA share every weight box;
+//   * image-spanning patches: on the small maps of the deep layers (10 x 53, 20 x 106) a 128-pixel patch of ONE image wastes up
+//     to a third of the GEMM rows on padding.  A sub-tile may therefore take its (bh x bw) patch from nb consecutive images
+//     (bw * bh * nb == 128).  The box is loaded through a tensor map whose dimensions are ordered (C, W, B, H), so shared
+//     memory holds rows ordered (py, image, px): a vertical tap is still ONE start-address shift (of nb * bw rows);
 //   * epilogue: TMEM -> registers -> padded shared-memory chunk -> full 128-byte row segments, 4 rows per store instruction,
 //     row pointers computed once per sub-tile; masked column statistics from the staged chunk.
 //
@@ -48,16 +52,22 @@ constexpr int SMEM_MAX = 227 * 1024;          // one persistent CTA per SM
 constexpr int N_BARS = 2 * A_RING_MAX + 2 * B_RING_MAX + 4;
 constexpr int TAIL_BYTES = N_BARS * 8 + 16;   // barriers, TMEM slot
 constexpr int STG_PITCH = 36;                 // floats per staged row: 32 columns + 4 (conflict-free 128-bit rows)
-// epilogue scratch: 4 warps x 32 rows x STG_PITCH staging + statistics partials [MT][2][4][BN]
-#define EPI_BYTES(BN_, MT_) (4 * 32 * STG_PITCH * 4 + (MT_) * 2 * 4 * (BN_) * 4)
+// epilogue scratch: 4 warps x 32 rows x STG_PITCH staging + statistics partials [2][slots][BN] per sub-tile; a slot is a run of
+// GEMM rows of one image: 32 rows (4 slots, one per epilogue warp) for single-image patches, min(bw, 32) rows for image-spanning
+// ones (up to 16).  With 4 slots all MT sub-tiles keep their own partials and the epilogue warps meet once per tile; with more
+// slots one set is reused (two barriers per sub-tile; those are the deep, main-loop-bound layers).
+__host__ __device__ constexpr int epi_bytes(int bn, int mt, int slots) {
+    return 4 * 32 * STG_PITCH * 4 + (slots > 4 ? 1 : mt) * 2 * slots * bn * 4;
+}
 
 struct YGeom {
-    int bw, bh;              // sub-tile patch (bw * bh == 128, bw % 8 == 0)
-    int lbw;                 // log2(bw)
+    int bw, bh, nb;          // sub-tile patch: bw x bh pixels of nb consecutive images (bw * bh * nb == 128, bw % 8 == 0)
+    int lbw, lnb;            // log2(bw), log2(nb)
+    int lrun;                // log2 of the statistics run length (rows of one image that are adjacent in the GEMM tile)
     int tiles_x, tiles_y;    // patches per image
-    int subtiles;            // B * tiles_x * tiles_y
+    int subtiles;            // ceil(B / nb) * tiles_x * tiles_y
     int box_rows;            // bh + (taps per group - 1)
-    int a_box_bytes;         // box_rows * bw * 128
+    int a_box_bytes;         // box_rows * nb * bw * 128
     int a_stages, b_stages;
     int n_groups;            // tap groups = boxes per (channel chunk, tx)
     // per group, 16 bits: [3:0] y_add + 8 (box origin = y0*y_mul + y_off + y_add), [7:4] taps, [11:8] first ty, [15:12] ty step + 8;
@@ -96,20 +106,22 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
     const uint32_t smA = smem_u32(smem_raw);
     const int a_stage_bytes = MT * g.a_box_bytes;
     const int ring_bytes = g.a_stages * a_stage_bytes + g.b_stages * B_BYTES;
+    const int slots = 128 >> g.lrun;
+    const int epi = epi_bytes(BN, MT, slots);
     {
         uint32_t dyn;
         asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
-        if ((smA & 1023u) != 0 || ring_bytes + EPI_BYTES(BN, MT) + TAIL_BYTES > (int)dyn) {
+        if ((smA & 1023u) != 0 || ring_bytes + epi + TAIL_BYTES > (int)dyn) {
             if (threadIdx.x == 0) printf("tc_conv_ytap_kernel: shared-memory window misaligned or too small\n");
             __trap();
         }
     }
     const uint32_t smB = smA + g.a_stages * a_stage_bytes;
     float* stg_all = reinterpret_cast<float*>(smem_raw + ring_bytes);              // 4 warps x 32 rows x STG_PITCH floats
-    float* s_red = stg_all + 4 * 32 * STG_PITCH;                                   // [MT][2][4][BN]
-    const uint32_t bars = smA + ring_bytes + EPI_BYTES(BN, MT);
+    float* s_red = stg_all + 4 * 32 * STG_PITCH;                                   // [MT or 1][2][slots][BN]
+    const uint32_t bars = smA + ring_bytes + epi;
     // barriers: fullA[A_RING_MAX], emptyA[..], fullB[B_RING_MAX], emptyB[..], tmem_full[2], tmem_empty[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + ring_bytes + EPI_BYTES(BN, MT) + N_BARS * 8);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + ring_bytes + epi + N_BARS * 8);
     auto fullA = [&](int s) { return bars + 8u * s; };
     auto emptyA = [&](int s) { return bars + 8u * (A_RING_MAX + s); };
     auto fullB = [&](int s) { return bars + 8u * (2 * A_RING_MAX + s); };
@@ -173,6 +185,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
                 const int t = min(t0 + m, g.subtiles - 1);
                 sb[m] = t / tpi;
                 const int rem = t - sb[m] * tpi;
+                sb[m] <<= g.lnb;                               // first image of the patch
                 sy[m] = (rem / g.tiles_x) * g.bh * d.y_mul + d.y_off;
                 sx[m] = (rem % g.tiles_x) * g.bw * d.x_mul + d.x_off;
             }
@@ -191,9 +204,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
                             mbar_expect_tx(fullA(sa), (uint32_t)(nvalid * g.a_box_bytes));
 #pragma unroll
                             for (int m = 0; m < MT; ++m)
-                                if (m < nvalid)
-                                    tma_load_4d(smA + sa * a_stage_bytes + m * g.a_box_bytes, &tmA, c0, sx[m] + tx * d.tx_mul, sy[m] + y_add,
-                                                sb[m], fullA(sa));
+                                if (m < nvalid) {
+                                    // tensor-map dimensions: (C, W, H, B), or (C, W, B, H) for image-spanning patches
+                                    const int yy = sy[m] + y_add;
+                                    tma_load_4d(smA + sa * a_stage_bytes + m * g.a_box_bytes, &tmA, c0, sx[m] + tx * d.tx_mul,
+                                                g.nb > 1 ? sb[m] : yy, g.nb > 1 ? yy : sb[m], fullA(sa));
+                                }
                         }
                         __syncwarp();
                         if (++sa == g.a_stages) { sa = 0; pa ^= 1; }
@@ -218,7 +234,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
         const int iss = warp - 5;
         if (iss < N_ISS) {
         const uint32_t idesc = make_idesc_tf32(BN, 0, 0);
-        const uint32_t shift_lo = (uint32_t)(g.bw * 128) >> 4;           // one patch row, in descriptor address units
+        const uint32_t shift_lo = (uint32_t)(g.bw * g.nb * 128) >> 4;    // one patch row (of all nb images), in descriptor address units
         const uint32_t box_lo = (uint32_t)g.a_box_bytes >> 4;
         int sa = 0, pa = 0, sbi = 0, pb = 0;
         long long wait_full = 0, wait_acc = 0;
@@ -284,7 +300,25 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
         // ================= epilogue (warps 0..3 = TMEM lane quadrants), one tile behind the MMA issuer =================
         const int q = warp;
         const int r = q * 32 + lane;
-        const int py = r >> g.lbw, px = r & (g.bw - 1);
+        // GEMM row -> (py, image, px)
+        const int py = r >> (g.lbw + g.lnb), pn = (r >> g.lbw) & (g.nb - 1), px = r & (g.bw - 1);
+        const bool per_m = slots > 4;                        // one set of statistics partials, reduced after every sub-tile
+        // column sums of one sub-tile: the runs of each image, in row order -> partial rows [B][tiles_x * tiles_y][2][N]
+        auto reduce_stats = [&](const float* red, int b0, int rem, int n0) {
+            for (int i = tid; i < BN << g.lnb; i += EPI_THREADS) {
+                const int c = i % BN, n = i / BN;
+                if (b0 + n >= d.B) continue;
+                float s1 = 0.f, s2 = 0.f;
+                for (int sl = 0; sl < slots; ++sl) {
+                    if ((((sl << g.lrun) >> g.lbw) & (g.nb - 1)) != n) continue;
+                    s1 += red[(0 * slots + sl) * BN + c];
+                    s2 += red[(1 * slots + sl) * BN + c];
+                }
+                const size_t prow = (size_t)(b0 + n) * tpi + rem;
+                d.stat_partial[(prow * 2 + 0) * N + n0 + c] = s1;
+                d.stat_partial[(prow * 2 + 1) * N + n0 + c] = s2;
+            }
+        };
         float* stg = stg_all + (size_t)(q * 32) * STG_PITCH;
         const int sub = lane >> 3, col4 = lane & 7;          // write-back: 8 lanes per 128-byte row segment
         long long wait_tmem = 0;
@@ -302,17 +336,20 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
             tc_fence_after();
             for (int m = 0; m < nvalid; ++m) {
                 const int t = t0 + m;
-                const int b = t / tpi;
-                const int rem = t - b * tpi;
+                const int ib = t / tpi;
+                const int rem = t - ib * tpi;
+                const int b0 = ib << g.lnb;
                 const int ty0 = (rem / g.tiles_x) * g.bh, tx0 = (rem % g.tiles_x) * g.bw;
-                const bool ok = (ty0 + py) < d.GH && (tx0 + px) < d.GW;
+                const bool ok = (ty0 + py) < d.GH && (tx0 + px) < d.GW && (b0 + pn) < d.B;
+                float* red_m = s_red + (per_m ? 0 : m * 2 * slots * BN);
                 const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
                 // destination of the 8 rows this lane writes back (rows sub, sub+4, ... of the warp's 32), column n0
                 float* rowp[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int rr = q * 32 + 4 * k + sub;
-                    const int gy = ty0 + (rr >> g.lbw), gx = tx0 + (rr & (g.bw - 1));
+                    const int gy = ty0 + (rr >> (g.lbw + g.lnb)), gx = tx0 + (rr & (g.bw - 1));
+                    const int b = b0 + ((rr >> g.lbw) & (g.nb - 1));
                     rowp[k] = d.dst + (((long long)b * d.DH + (gy * d.dy_mul + d.dy_off)) * d.DW + (gx * d.dx_mul + d.dx_off)) * N + n0 + col4 * 4;
                 }
                 for (int c = 0; c < BN / 32; ++c) {
@@ -330,17 +367,41 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
                     for (int j = 0; j < 8; ++j) row[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     __syncwarp();
                     if (d.stat_partial != nullptr) {
-                        float s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
-                        for (int i = 0; i < 32; ++i) {
-                            const float x = stg[(size_t)i * STG_PITCH + lane];
-                            if ((okmask >> i) & 1u) {
-                                s1 += x;
-                                s2 += x * x;
+                        // masked column sums of the staged chunk in four blocks of 8 rows (all loads before any store: the
+                        // partials live in the same shared memory), combined into runs of 8, 16 or 32 rows of one image
+                        float b1[4], b2[4];
+#pragma unroll
+                        for (int blk = 0; blk < 4; ++blk) {
+                            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int i = blk * 8 + j;
+                                const float x = stg[(size_t)i * STG_PITCH + lane];
+                                if ((okmask >> i) & 1u) {
+                                    s1 += x;
+                                    s2 += x * x;
+                                }
                             }
+                            b1[blk] = s1;
+                            b2[blk] = s2;
                         }
-                        s_red[((m * 2 + 0) * 4 + q) * BN + c * 32 + lane] = s1;
-                        s_red[((m * 2 + 1) * 4 + q) * BN + c * 32 + lane] = s2;
+                        float* r1 = red_m + c * 32 + lane;
+                        float* r2 = r1 + slots * BN;
+                        if (g.lrun == 3) {
+#pragma unroll
+                            for (int blk = 0; blk < 4; ++blk) {
+                                r1[(q * 4 + blk) * BN] = b1[blk];
+                                r2[(q * 4 + blk) * BN] = b2[blk];
+                            }
+                        } else if (g.lrun == 4) {
+                            r1[(q * 2 + 0) * BN] = b1[0] + b1[1];
+                            r2[(q * 2 + 0) * BN] = b2[0] + b2[1];
+                            r1[(q * 2 + 1) * BN] = b1[2] + b1[3];
+                            r2[(q * 2 + 1) * BN] = b2[2] + b2[3];
+                        } else {
+                            r1[q * BN] = (b1[0] + b1[1]) + (b1[2] + b1[3]);
+                            r2[q * BN] = (b2[0] + b2[1]) + (b2[2] + b2[3]);
+                        }
                     }
                     float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (d.bias != nullptr) bb = __ldg(reinterpret_cast<const float4*>(d.bias + n0 + c * 32) + col4);
@@ -360,19 +421,17 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
                     }
                     __syncwarp();
                 }
+                if (d.stat_partial != nullptr && per_m) {
+                    asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps
+                    reduce_stats(s_red, b0, rem, n0);
+                    asm volatile("bar.sync 1, 128;" ::: "memory");          // s_red is reused by the next sub-tile
+                }
             }
-            if (d.stat_partial != nullptr) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps
-                for (int i = tid; i < nvalid * BN; i += EPI_THREADS) {
-                    const int m = i / BN, c = i - m * BN;
-                    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-                    for (int qq = 0; qq < 4; ++qq) {
-                        s1 += s_red[((m * 2 + 0) * 4 + qq) * BN + c];
-                        s2 += s_red[((m * 2 + 1) * 4 + qq) * BN + c];
-                    }
-                    d.stat_partial[((size_t)(t0 + m) * 2 + 0) * N + n0 + c] = s1;
-                    d.stat_partial[((size_t)(t0 + m) * 2 + 1) * N + n0 + c] = s2;
+            if (d.stat_partial != nullptr && !per_m) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int m = 0; m < nvalid; ++m) {
+                    const int ib = (t0 + m) / tpi;
+                    reduce_stats(s_red + m * 2 * slots * BN, ib << g.lnb, t0 + m - ib * tpi, n0);
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
@@ -437,34 +496,67 @@ int tap_structure(const sdt_conv_desc* d, YGeom* g) {
     return 0;
 }
 
+// Image-spanning patches need a tensor map whose dimension order is (C, W, B, H): strides not ascending.  Probe the driver
+// once (encoding dereferences nothing); without it the planner keeps to single-image patches.
+bool spanning_maps_ok() {
+    static int ok = -1;
+    if (ok < 0) {
+        ok = 0;
+        EncodeTiledFn enc = get_encode();
+        if (enc != nullptr) {
+            alignas(64) CUtensorMap tm;
+            const cuuint64_t dims[4] = {64, 53, 32, 10};
+            const cuuint64_t strides[3] = {64 * 4, 10 * 53 * 64 * 4, 53 * 64 * 4};
+            const cuuint32_t box[4] = {32, 8, 8, 4};
+            const cuuint32_t estr[4] = {1, 1, 1, 1};
+            ok = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, reinterpret_cast<void*>(0x10000), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        } else {
+            ok = 1;          // no driver (host-only planning, e.g. sdt_conv_plan in the CPU tests): plan as the GPU box would
+        }
+    }
+    return ok == 1;
+}
+
+// tuning / test overrides of the planner: N tile, accumulators per CTA, patch width, images per patch (0 = planner's choice);
+// initialised from SDT_YTAP_BN / _MT / _BW / _NB, changed by sdt_debug_conv_force (tests force the image-spanning geometries)
+int env_int(const char* name) { return getenv(name) ? atoi(getenv(name)) : 0; }
+int g_force[4] = {env_int("SDT_YTAP_BN"), env_int("SDT_YTAP_MT"), env_int("SDT_YTAP_BW"), env_int("SDT_YTAP_NB")};
+
 Plan make_plan(const sdt_conv_desc* d) {
     Plan best{};
     best.ok = false;
     if (d->N % 64 != 0 || d->C % 32 != 0) return best;
     const int K = d->TH * d->TW * d->C;
-    static const int force_bn = getenv("SDT_YTAP_BN") ? atoi(getenv("SDT_YTAP_BN")) : 0;      // tuning overrides
-    static const int force_mt = getenv("SDT_YTAP_MT") ? atoi(getenv("SDT_YTAP_MT")) : 0;
-    static const int force_bw = getenv("SDT_YTAP_BW") ? atoi(getenv("SDT_YTAP_BW")) : 0;
+    const int force_bn = g_force[0], force_mt = g_force[1], force_bw = g_force[2], force_nb = g_force[3];
+    const int nb_max = spanning_maps_ok() ? 16 : 1;
     for (int bn = 128; bn >= 64; bn /= 2) {
         if (d->N % bn != 0 || (force_bn && bn != force_bn && d->N % force_bn == 0)) continue;
         for (int mt = 4; mt >= 1; mt /= 2) {
             if (mt * bn > 256 || (force_mt && mt != force_mt && force_mt * bn <= 256)) continue;
-            for (int bw = 8; bw <= 128; bw *= 2) {
-                if (force_bw && bw != force_bw) continue;
+            for (int bw = 8; bw <= 128; bw *= 2)
+            for (int nb = 1; nb * bw <= 128 && nb <= nb_max; nb *= 2) {
+                if ((force_bw && bw != force_bw) || (force_nb && nb != force_nb && force_nb * bw <= 128)) continue;
+                if (nb > 1 && nb / 2 >= d->B) continue;               // never more than one half-empty patch of images
                 YGeom g{};
                 const int max_taps = tap_structure(d, &g);
                 if (max_taps == 0) return best;
                 g.bw = bw;
+                g.nb = nb;
                 for (g.lbw = 0; (1 << g.lbw) < bw; ++g.lbw) {}
-                g.bh = 128 / bw;
+                for (g.lnb = 0; (1 << g.lnb) < nb; ++g.lnb) {}
+                g.lrun = (nb == 1 || bw >= 32) ? 5 : g.lbw;
+                const int slots = 128 >> g.lrun;
+                g.bh = 128 / (bw * nb);
                 g.box_rows = g.bh + max_taps - 1;
                 if (bw * d->x_mul > 256 || g.box_rows * d->y_mul > 256) continue;
-                g.a_box_bytes = g.box_rows * bw * 128;
+                g.a_box_bytes = g.box_rows * nb * bw * 128;
                 g.tiles_x = (d->GW + bw - 1) / bw;
                 g.tiles_y = (d->GH + g.bh - 1) / g.bh;
-                g.subtiles = d->B * g.tiles_x * g.tiles_y;
+                g.subtiles = ((d->B + nb - 1) / nb) * g.tiles_x * g.tiles_y;
                 const long long tiles = (long long)((g.subtiles + mt - 1) / mt) * (d->N / bn);
-                const int budget = SMEM_MAX - EPI_BYTES(bn, mt) - TAIL_BYTES;
+                const int budget = SMEM_MAX - epi_bytes(bn, mt, slots) - TAIL_BYTES;
                 const int a_stage = mt * g.a_box_bytes, b_stage = bn * 128;
                 int as = 2, bs = 2;
                 if (as * a_stage + bs * b_stage > budget) continue;
@@ -483,14 +575,15 @@ Plan make_plan(const sdt_conv_desc* d) {
                 const double smem_clk = (fill + reads) / 128.0;
                 const double rounds = (double)((tiles + 147) / 148);
                 // a single issuing warp (MT == 1) exposes its loop overhead: measured ~1.5x slower per MMA than two issuers
-                const double cost = (smem_clk > mma_clk ? smem_clk : mma_clk) * rounds * (mt == 1 ? 1.5 : 1.0);
+                // (image-spanning patches only where they save tiles: at equal cost the single-image geometry wins)
+                const double cost = (smem_clk > mma_clk ? smem_clk : mma_clk) * rounds * (mt == 1 ? 1.5 : 1.0) * (nb > 1 ? 1.03 : 1.0);
                 if (!best.ok || cost < best.cost) {
                     best.ok = true;
                     best.bn = bn;
                     best.mt = mt;
                     best.g = g;
                     best.tiles = (int)tiles;
-                    best.smem = as * a_stage + bs * b_stage + EPI_BYTES(bn, mt) + TAIL_BYTES;
+                    best.smem = as * a_stage + bs * b_stage + epi_bytes(bn, mt, slots) + TAIL_BYTES;
                     best.cost = cost;
                 }
             }
@@ -528,10 +621,14 @@ int launch_ytap(const sdt_conv_desc* d, const Plan& pl, cudaStream_t st) {
     const YGeom& g = pl.g;
     alignas(64) CUtensorMap tmA, tmB;
     {
-        const cuuint64_t dims[4] = {(cuuint64_t)d->C, (cuuint64_t)d->SW, (cuuint64_t)d->SH, (cuuint64_t)d->B};
-        const cuuint64_t strides[3] = {(cuuint64_t)d->C * 4, (cuuint64_t)d->SW * d->C * 4, (cuuint64_t)d->SH * d->SW * d->C * 4};
-        const cuuint32_t box[4] = {32, (cuuint32_t)(g.bw * d->x_mul), (cuuint32_t)(g.box_rows * d->y_mul), 1};
-        const cuuint32_t estr[4] = {1, (cuuint32_t)d->x_mul, (cuuint32_t)d->y_mul, 1};
+        // (C, W, H, B) with one image per box, or (C, W, B, H) with nb images per box row: shared-memory rows (py, image, px)
+        const bool span = g.nb > 1;
+        const cuuint64_t row_stride = (cuuint64_t)d->SW * d->C * 4, img_stride = (cuuint64_t)d->SH * d->SW * d->C * 4;
+        const cuuint32_t box_y = (cuuint32_t)(g.box_rows * d->y_mul);
+        const cuuint64_t dims[4] = {(cuuint64_t)d->C, (cuuint64_t)d->SW, (cuuint64_t)(span ? d->B : d->SH), (cuuint64_t)(span ? d->SH : d->B)};
+        const cuuint64_t strides[3] = {(cuuint64_t)d->C * 4, span ? img_stride : row_stride, span ? row_stride : img_stride};
+        const cuuint32_t box[4] = {32, (cuuint32_t)(g.bw * d->x_mul), span ? (cuuint32_t)g.nb : box_y, span ? box_y : 1u};
+        const cuuint32_t estr[4] = {1, (cuuint32_t)d->x_mul, span ? 1u : (cuuint32_t)d->y_mul, span ? (cuuint32_t)d->y_mul : 1u};
         const CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(d->src), dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -565,12 +662,20 @@ bool sdt_tc_conv_ytap_shape_ok(const sdt_conv_desc* d) {
     return make_plan(d).ok;
 }
 
-int sdt_tc_conv_ytap_row_tiles(const sdt_conv_desc* d) { return make_plan(d).g.subtiles; }
+// statistics rows: one per (image, patch position), image-major
+int sdt_tc_conv_ytap_row_tiles(const sdt_conv_desc* d) {
+    const Plan pl = make_plan(d);
+    return d->B * pl.g.tiles_x * pl.g.tiles_y;
+}
 
 // profiling aids (not part of the public header)
 extern "C" int sdt_debug_conv_flags(int flags) {
     SDT_CUDA_OK(cudaMemcpyToSymbol(g_dbg_flags, &flags, sizeof(flags)));
     g_host_debug = flags != 0;
+    return SDT_OK;
+}
+extern "C" int sdt_debug_conv_force(int bn, int mt, int bw, int nb) {
+    g_force[0] = bn; g_force[1] = mt; g_force[2] = bw; g_force[3] = nb;
     return SDT_OK;
 }
 // per-CTA timeline buffer of 8 x int64 records, or NULL to switch off
@@ -585,7 +690,7 @@ extern "C" int sdt_debug_conv_timeline(void* buf, int ctas) {
 int sdt_tc_conv_ytap_describe(const sdt_conv_desc* d, int32_t* out10) {
     const Plan pl = make_plan(d);
     if (!pl.ok) return 0;
-    out10[1] = pl.bn; out10[2] = pl.mt; out10[3] = pl.g.bh; out10[4] = pl.g.bw; out10[5] = pl.g.box_rows;
+    out10[1] = pl.bn; out10[2] = pl.mt; out10[3] = pl.g.bh | (pl.g.nb << 8); out10[4] = pl.g.bw; out10[5] = pl.g.box_rows;
     out10[6] = pl.g.a_stages; out10[7] = pl.g.b_stages; out10[8] = pl.smem;
     out10[9] = pl.tiles;
     return 1;

@@ -13,6 +13,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from speechdrivestemplates_b200 import _lib, ops  # noqa: E402
 
+if os.environ.get("SDT_DIAG_LIB"):          # A/B against another build of the library (diagnostic only)
+    _lib.LIB_PATH = os.environ["SDT_DIAG_LIB"]
+
 LAYERS = [(64, 64, 4, 4, 2, 1, 80, 427), (64, 128, 3, 3, 1, 1, 40, 213), (128, 128, 4, 4, 2, 1, 40, 213),
           (128, 256, 3, 3, 1, 1, 20, 106), (256, 256, 4, 4, 2, 1, 20, 106), (256, 256, 3, 3, 1, 1, 10, 53),
           (256, 256, 6, 3, 1, 0, 10, 53)]
@@ -57,6 +60,26 @@ def main():
             ms = e0.elapsed_time(e1) / 10
             line = "L %3d->%3d %dx%d s%d %3dx%3d mode %d: %.1f us  %.0f TFLOP/s  plan %s" % (
                 cin, cout, kh, kw, s, H, W, mode, ms * 1e3, flops / ms / 1e9, list(plan))
+            d.stat_partial = None
+            for _ in range(3):
+                ops.conv_gemm(d)
+            e0.record()
+            for _ in range(10):
+                ops.conv_gemm(d)
+            e1.record()
+            torch.cuda.synchronize()
+            line += " | no stats %.1f us" % (e0.elapsed_time(e1) * 100)
+            dy = torch.randn(B, oh, ow, cout, device=dev)
+            dx = torch.empty(B, H, W, cin, device=dev)
+            for _ in range(3):
+                ops.conv_dgrad(dy, w, g, H, W, out=dx)
+            e0.record()
+            for _ in range(5):
+                ops.conv_dgrad(dy, w, g, H, W, out=dx)
+            e1.record()
+            torch.cuda.synchronize()
+            line += " | dgrad (incl. weight prep) %.1f us" % (e0.elapsed_time(e1) * 200)
+            d.stat_partial = partial.data_ptr()
             for fl in (flags_list if (mode == 3 and plan[0] == 3 and len(sys.argv) > 3) else []):
                 lib.sdt_debug_conv_flags(fl)
                 for _ in range(2):

@@ -175,16 +175,18 @@ def test_conv_plan_for_the_encoder_layers(B):
             d, oh, ow = _fake_fwd_desc(ops, *cfg, B)
             out = (ctypes.c_int32 * 10)()
             assert lib.sdt_conv_plan(ctypes.byref(d), out) == 0
-            kind, bn, mt, bh, bw, box_rows, a_st, b_st, smem, tiles = list(out)
+            kind, bn, mt, bh_nb, bw, box_rows, a_st, b_st, smem, tiles = list(out)
+            bh, nb = bh_nb & 255, bh_nb >> 8                     # patch rows, images per patch
             assert kind == 3, (cfg, list(out))
             assert bn in (64, 128) and mt in (1, 2, 4) and 2 * mt * bn <= 512
-            assert bh * bw == 128 and bw % 8 == 0
+            assert bh * bw * nb == 128 and bw % 8 == 0 and nb in (1, 2, 4, 8, 16) and nb < 2 * B
             assert smem <= 227 * 1024 and a_st >= 2 and b_st >= 2
-            assert bw * cfg[4] <= 256 and box_rows * cfg[4] <= 256
-            sub = B * (-(-oh // bh)) * (-(-ow // bw))
+            assert bw * cfg[4] <= 256 and box_rows * cfg[4] <= 256 and box_rows >= bh
+            tpi = (-(-oh // bh)) * (-(-ow // bw))
+            sub = -(-B // nb) * tpi
             assert tiles == -(-sub // mt) * (cfg[1] // bn)
             if torch.cuda.is_available():                        # needs the driver's cuTensorMapEncodeTiled to be eligible
-                assert lib.sdt_conv_row_tiles(ctypes.byref(d)) == sub      # one statistics row per sub-tile
+                assert lib.sdt_conv_row_tiles(ctypes.byref(d)) == B * tpi  # one statistics row per (image, patch position)
     finally:
         lib.sdt_set_conv_math(0)
 
@@ -207,7 +209,7 @@ def test_conv_plan_falls_back_outside_mode_3_and_remaps_1d():
         d1.y_mul, d1.ty_mul, d1.y_off, d1.x_mul, d1.tx_mul, d1.x_off = 1, 1, 0, 1, 1, -1
         d1.N, d1.DH, d1.DW, d1.dy_mul, d1.dx_mul = 256, 1, 64, 1, 1
         if os.environ.get("SDT_REMAP_1D") == "1":           # experimental switch (slower at B = 32, see conv_gemm.cu)
-            assert lib.sdt_conv_plan(ctypes.byref(d1), out) == 0 and out[0] == 3 and out[3] * out[4] == 128 and out[5] == out[3]
+            assert lib.sdt_conv_plan(ctypes.byref(d1), out) == 0 and out[0] == 3 and (out[3] & 255) * (out[3] >> 8) * out[4] == 128
         else:
             assert lib.sdt_conv_plan(ctypes.byref(d1), out) == 0 and out[0] != 3
         d1.B = 1                                             # a single clip has nothing to stack: TMA kernel of mode 2

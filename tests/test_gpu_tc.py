@@ -247,6 +247,70 @@ def test_reuse_forward_and_dgrad_odd_geometries(cfg):
     assert rel(ps[:, 1], (got * got).sum((2, 3))) < 1e-4
 
 
+def _reuse_case(cfg, seed=41):
+    """Forward (+ statistics partials) and data gradient of one layer in math mode 3 against float64 torch."""
+    from speechdrivestemplates_b200 import ops
+    cin, cout, kh, kw, s, p, H, W, B = cfg
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, cin, H, W, generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(cout, cin, kh, kw, generator=g, dtype=torch.float64) / math.sqrt(cin * kh * kw)
+    y = F.conv2d(x, w, None, s, p)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(dy)
+    geom = ops.ConvGeom.conv2d(cin, cout, kh, kw, s, p)
+    n0 = tc_launches()
+    yk, partial = ops.conv_forward(to_cl(x.detach().float()).to(dev()), w.float().to(dev()).contiguous(), geom, want_stats=True,
+                                   per_image=True)
+    dx = ops.conv_dgrad(to_cl(dy.float()).to(dev()), w.float().to(dev()).contiguous(), geom, H, W)
+    torch.cuda.synchronize()
+    assert tc_launches() > n0
+    assert rel(from_cl(yk), y) < TF32_TOL
+    assert rel(from_cl(dx), x.grad) < TF32_TOL
+    tiles = partial.shape[0] // B
+    ps = partial.view(B, tiles, 2, cout).double().sum(1).cpu()
+    got = from_cl(yk).double().cpu()
+    assert rel(ps[:, 0], got.sum((2, 3))) < 1e-4
+    assert rel(ps[:, 1], (got * got).sum((2, 3))) < 1e-4
+
+
+SPAN_CASES = [
+    # (cin, cout, kh, kw, s, p, H, W, B), forced (N tile, accumulators, patch width, images per patch)
+    ((64, 128, 3, 3, 1, 1, 10, 53, 9), (0, 0, 8, 8)),          # 16 statistics runs per patch, B not a multiple of nb
+    ((64, 128, 3, 3, 1, 1, 10, 53, 9), (128, 2, 8, 4)),
+    ((64, 64, 4, 4, 2, 1, 20, 106, 6), (64, 2, 8, 8)),         # stride 2: two y phases; dgrad = 4 parity classes
+    ((64, 64, 4, 4, 2, 1, 20, 106, 6), (64, 2, 16, 4)),        # 8 runs per patch
+    ((128, 64, 3, 3, 1, 1, 20, 26, 5), (0, 0, 32, 2)),         # runs of 32 rows: one image per epilogue warp
+    ((64, 64, 6, 3, 1, 0, 10, 53, 4), (64, 1, 32, 2)),         # six vertical taps, no padding
+    ((64, 64, 3, 3, 1, 1, 5, 13, 21), (0, 0, 8, 16)),          # bh = 1, 16 images per patch
+    ((64, 64, 5, 5, 1, 2, 19, 21, 3), (0, 0, 8, 2)),
+]
+
+
+@pytest.mark.parametrize("cfg,force", SPAN_CASES)
+def test_reuse_image_spanning_patches(cfg, force):
+    """Patches that take their pixels from several consecutive images (tensor map ordered (C, W, B, H)): results, masking of
+    the images past the batch, and the per-image statistics rows."""
+    import ctypes
+    from speechdrivestemplates_b200 import _lib, ops
+    lib = _lib.load()
+    ops.set_conv_math(3)
+    lib.sdt_debug_conv_force(*force)
+    try:
+        cin, cout, kh, kw, s, p, H, W, B = cfg
+        geom = ops.ConvGeom.conv2d(cin, cout, kh, kw, s, p)
+        x = torch.zeros(B, H, W, cin, device=dev())
+        oh, ow = geom.out_hw(H, W)
+        d = ops.fwd_desc(geom, x, torch.empty(geom.k, cout, device=dev()), torch.empty(B, oh, ow, cout, device=dev()), B, H, W,
+                         None, 1.0, None, None, True, wt_nk=torch.empty(cout, geom.k, device=dev()))
+        plan = (ctypes.c_int32 * 10)()
+        assert lib.sdt_conv_plan(ctypes.byref(d), plan) == 0
+        assert plan[0] == 3 and plan[3] >> 8 == force[3] and plan[4] == force[2], list(plan)
+        _reuse_case(cfg, seed=43)
+    finally:
+        lib.sdt_debug_conv_force(0, 0, 0, 0)
+        ops.set_conv_math(0)
+
+
 def test_reuse_matches_tma_mode_bitwise_products():
     """Modes 2 and 3 multiply the same TF32-rounded operands; only the fp32 accumulation order differs."""
     from speechdrivestemplates_b200 import ops

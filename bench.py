@@ -220,7 +220,15 @@ class EventProfiler:
         e0 = torch.cuda.Event(enable_timing=True)
         e0.record()
         flops = 0.0
-        if name in ("sdt_conv_gemm", "sdt_conv_wgrad"):
+        if name == "sdt_conv_gemm_multi":             # the parity classes of one data gradient (one launch in math mode 3)
+            import ctypes as C
+            from speechdrivestemplates_b200 import _lib
+            ds = [args[0][i] for i in range(args[1])]
+            flops = sum(2.0 * d.B * d.GH * d.GW * d.N * d.TH * d.TW * d.C for d in ds)
+            plan = (C.c_int32 * 10)()
+            _lib.load().sdt_conv_plan(C.byref(ds[0]), plan)
+            name = "sdt_conv_gemm[tc_conv_ytap_kernel]" if plan[0] in (3, 4) else "sdt_conv_gemm"
+        elif name in ("sdt_conv_gemm", "sdt_conv_wgrad"):
             d = args[0]._obj
             flops = 2.0 * d.B * d.GH * d.GW * d.N * d.TH * d.TW * d.C
             if name == "sdt_conv_gemm":

@@ -109,6 +109,11 @@ int sdt_conv_gemm(const sdt_conv_desc* d, void* stream);
  * out10[1..9] = N tile, accumulators per CTA, patch rows | images per patch << 8, patch cols, box rows, A stages, B stages,
  * shared memory, tiles */
 int sdt_conv_plan(const sdt_conv_desc* d, int32_t* out10);
+/* n (1..16) independent problems in stream order -- the stride-parity classes of a strided layer's data gradient
+ * (reference: one cuDNN dgrad call behind `loss.backward()`, core/networks/building_blocks.py:15-21).  Equivalent to n calls of
+ * sdt_conv_gemm; in math mode 3, problems that share source, destination and shapes and differ in grid / offsets / weight
+ * operand only run as ONE persistent launch.  *launched (may be NULL) receives the number of kernels launched. */
+int sdt_conv_gemm_multi(const sdt_conv_desc* descs, int n, void* stream, int* launched);
 /* wgrad: contractions with K = TH*TW*C <= 16 and N <= 64 (first encoder layer) use a streaming kernel whose CTA count
  * equals `splits`; otherwise split-K GEMM tiles (FFMA, or tcgen05 in math mode 1 when C % 32 == 0, N in {64,128,256}). */
 int sdt_conv_wgrad(const sdt_conv_desc* d, void* stream);

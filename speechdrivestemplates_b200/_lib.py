@@ -42,6 +42,7 @@ SIGNATURES = {
     "sdt_conv_row_tiles": [_P],
     "sdt_conv_gemm": [_P, c_ptr],
     "sdt_conv_plan": [_P, c_ptr],
+    "sdt_conv_gemm_multi": [_P, i32, c_ptr, c_ptr],
     "sdt_conv_wgrad": [_P, c_ptr],
     "sdt_conv_wgrad_reduce": [c_ptr, i32, i32, i32, i32, c_ptr, i32, c_ptr],
     "sdt_weight_prep": [c_ptr, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, c_ptr, c_ptr],

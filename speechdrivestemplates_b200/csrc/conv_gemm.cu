@@ -769,6 +769,30 @@ extern "C" int sdt_conv_gemm(const sdt_conv_desc* d, void* stream) {
     return SDT_OK;
 }
 
+// n independent convolution problems in stream order.  In math mode >= 3, problems that differ in their grids and offsets
+// only (the stride-parity classes of one data gradient) run as ONE persistent launch; anything else is n launches.
+// returns in *launched (may be NULL) the number of kernels launched
+extern "C" int sdt_conv_gemm_multi(const sdt_conv_desc* descs, int n, void* stream, int* launched) {
+    SDT_REQUIRE(descs != nullptr && n >= 1 && n <= 16, "sdt_conv_gemm_multi: %d problems (1..16)", n);
+    if (launched) *launched = 0;
+    if (sdt_get_conv_math() == 3 && n >= 2 && n <= 4) {
+        bool ok = true;
+        for (int c = 0; c < n && ok; ++c) {
+            if (int rc = check_desc(descs + c, "sdt_conv_gemm_multi")) return rc;
+            ok = descs[c].dst && descs[c].wt_nk && use_ytap(descs + c);
+        }
+        if (ok && sdt_tc_conv_ytap_multi_ok(descs, n)) {
+            if (launched) *launched = 1;
+            return sdt_tc_conv_ytap_launch_multi(descs, n, sdt::as_stream(stream));
+        }
+    }
+    for (int c = 0; c < n; ++c) {
+        if (int rc = sdt_conv_gemm(descs + c, stream)) return rc;
+        if (launched) ++*launched;
+    }
+    return SDT_OK;
+}
+
 extern "C" int sdt_conv_wgrad(const sdt_conv_desc* d, void* stream) {
     if (int rc = check_desc(d, "sdt_conv_wgrad")) return rc;
     SDT_REQUIRE(d->dy && d->wpart, "sdt_conv_wgrad: null dy/wpart");

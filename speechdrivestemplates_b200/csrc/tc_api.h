@@ -16,6 +16,9 @@ bool sdt_tc_conv_ytap_shape_ok(const sdt_conv_desc* d);
 int sdt_tc_conv_ytap_row_tiles(const sdt_conv_desc* d);
 int sdt_tc_conv_ytap_describe(const sdt_conv_desc* d, int32_t* out10);
 int sdt_tc_conv_ytap_launch(const sdt_conv_desc* d, cudaStream_t st);
+// several problems (stride-parity classes of one data gradient) as one persistent launch
+bool sdt_tc_conv_ytap_multi_ok(const sdt_conv_desc* ds, int n);
+int sdt_tc_conv_ytap_launch_multi(const sdt_conv_desc* ds, int n, cudaStream_t st);
 bool sdt_tc_conv_pair_eligible(const sdt_conv_desc* d);
 bool sdt_tc_conv_pair_shape_ok(const sdt_conv_desc* d);
 int sdt_tc_conv_pair_row_tiles(const sdt_conv_desc* d);

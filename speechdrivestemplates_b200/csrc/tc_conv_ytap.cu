@@ -74,6 +74,24 @@ struct YGeom {
     // tap j of a group reads the box shifted by j patch rows
     unsigned long long groups;
 };
+// Up to four problems that share source, destination, weights' shape and patch geometry and differ in their grid and offsets
+// only -- the stride-parity classes of one data gradient -- run as ONE launch: four 140-tile launches of a 2 x 2-tap
+// problem each paid their own pipeline fill and an epilogue that nothing overlapped; as one 560-tile launch the persistent
+// CTAs drain the accumulators of one class while the tensor pipe works on the next.  A single problem is the n == 1 case.
+constexpr int MAX_CLASSES = 4;
+struct YClasses {
+    int n;
+    int unit_start[MAX_CLASSES + 1];      // prefix sums of ceil(subtiles / MT): a CTA's MT sub-tiles share the weight boxes
+    int subtiles[MAX_CLASSES], tiles_x[MAX_CLASSES], tpi[MAX_CLASSES];
+    int GH[MAX_CLASSES], GW[MAX_CLASSES];
+    int y_off[MAX_CLASSES], x_off[MAX_CLASSES], dy_off[MAX_CLASSES], dx_off[MAX_CLASSES];
+};
+struct YMaps {
+    CUtensorMap b[MAX_CLASSES];           // the weight operand of each class
+};
+// (kernel parameters: select without dynamic indexing, which would copy the struct to local memory)
+__device__ __forceinline__ int sel4(const int (&a)[MAX_CLASSES], int c) { return c == 0 ? a[0] : c == 1 ? a[1] : c == 2 ? a[2] : a[3]; }
+
 __host__ __device__ __forceinline__ int grp_y_add(unsigned long long p, int gi) { return (int)((p >> (16 * gi)) & 15u) - 8; }
 __host__ __device__ __forceinline__ int grp_taps(unsigned long long p, int gi) { return (int)((p >> (16 * gi + 4)) & 15u); }
 __host__ __device__ __forceinline__ int grp_ty0(unsigned long long p, int gi) { return (int)((p >> (16 * gi + 8)) & 15u); }
@@ -97,8 +115,8 @@ __device__ __forceinline__ long long gtimer() {
 
 template <int BN, int MT, bool DBG>
 __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                const __grid_constant__ CUtensorMap tmB,
-                                                                const sdt_conv_desc d, const YGeom g) {
+                                                                const __grid_constant__ YMaps tmBs,
+                                                                const sdt_conv_desc d, const YGeom g, const YClasses cl) {
     constexpr int B_BYTES = BN * 128;
     constexpr int ACC_COLS = MT * BN;                 // one accumulator set; two sets (double buffer) are allocated
     constexpr int N_ISS = MT >= 2 ? 2 : 1;            // MMA-issuing warps; issuer i owns sub-tiles i, i + N_ISS, ...
@@ -132,8 +150,16 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = d.N;
     const int n_ntiles = N / BN;
-    const int n_tiles = ((g.subtiles + MT - 1) / MT) * n_ntiles;
-    const int tpi = g.tiles_x * g.tiles_y;
+    const int n_tiles = (cl.n == 1 ? cl.unit_start[1] : cl.n == 2 ? cl.unit_start[2] : cl.n == 3 ? cl.unit_start[3] : cl.unit_start[4]) * n_ntiles;
+    // tile -> class, first sub-tile within the class
+    auto class_of = [&](int unit) {
+        int c = 0;
+#pragma unroll
+        for (int k = 1; k < MAX_CLASSES; ++k)
+            if (k < cl.n && unit >= cl.unit_start[k]) c = k;
+        return c;
+    };
+    auto unit_base = [&](int c) { return c == 0 ? 0 : c == 1 ? cl.unit_start[1] : c == 2 ? cl.unit_start[2] : cl.unit_start[3]; };
     const int chunks = d.C / BKF;
     const int dbg = DBG ? g_dbg_flags : 0;
     long long* tl = nullptr;
@@ -177,17 +203,21 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
         for (int tile = blockIdx.x; tile < n_tiles && !(dbg & 1); tile += gridDim.x) {
             const int grp_idx = tile / n_ntiles;
             const int n0 = (tile - grp_idx * n_ntiles) * BN;
-            const int t0 = grp_idx * MT;
-            const int nvalid = min(MT, g.subtiles - t0);
+            const int cls = class_of(grp_idx);
+            const int t0 = (grp_idx - unit_base(cls)) * MT;
+            const int c_sub = sel4(cl.subtiles, cls), tpi = sel4(cl.tpi, cls), c_tx = sel4(cl.tiles_x, cls);
+            const int c_yoff = sel4(cl.y_off, cls), c_xoff = sel4(cl.x_off, cls);
+            const CUtensorMap* tmB = &tmBs.b[0] + cls;
+            const int nvalid = min(MT, c_sub - t0);
             int sb[MT], sy[MT], sx[MT];
 #pragma unroll
             for (int m = 0; m < MT; ++m) {
-                const int t = min(t0 + m, g.subtiles - 1);
+                const int t = min(t0 + m, c_sub - 1);
                 sb[m] = t / tpi;
                 const int rem = t - sb[m] * tpi;
                 sb[m] <<= g.lnb;                               // first image of the patch
-                sy[m] = (rem / g.tiles_x) * g.bh * d.y_mul + d.y_off;
-                sx[m] = (rem % g.tiles_x) * g.bw * d.x_mul + d.x_off;
+                sy[m] = (rem / c_tx) * g.bh * d.y_mul + c_yoff;
+                sx[m] = (rem % c_tx) * g.bw * d.x_mul + c_xoff;
             }
             for (int ch = 0; ch < chunks; ++ch) {
                 const int c0 = ch * BKF;
@@ -219,7 +249,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
                             if (DBG && tl) wait_empty += clock64() - tw;
                             if (elect_one()) {
                                 mbar_expect_tx(fullB(sbi), B_BYTES);
-                                tma_load_2d(smB + sbi * B_BYTES, &tmB, (ty * d.TW + tx) * d.C + c0, n0, fullB(sbi));
+                                tma_load_2d(smB + sbi * B_BYTES, tmB, (ty * d.TW + tx) * d.C + c0, n0, fullB(sbi));
                             }
                             __syncwarp();
                             if (++sbi == g.b_stages) { sbi = 0; pb ^= 1; }
@@ -241,7 +271,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int grp_idx = tile / n_ntiles;
-            const int nvalid = min(MT, g.subtiles - grp_idx * MT);
+            const int cls = class_of(grp_idx);
+            const int nvalid = min(MT, sel4(cl.subtiles, cls) - (grp_idx - unit_base(cls)) * MT);
             const int acc = it & 1;
             const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * ACC_COLS);
             long long tw = 0;
@@ -304,7 +335,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
         const int py = r >> (g.lbw + g.lnb), pn = (r >> g.lbw) & (g.nb - 1), px = r & (g.bw - 1);
         const bool per_m = slots > 4;                        // one set of statistics partials, reduced after every sub-tile
         // column sums of one sub-tile: the runs of each image, in row order -> partial rows [B][tiles_x * tiles_y][2][N]
-        auto reduce_stats = [&](const float* red, int b0, int rem, int n0) {
+        auto reduce_stats = [&](const float* red, int b0, int rem, int n0, int tpi) {
             for (int i = tid; i < BN << g.lnb; i += EPI_THREADS) {
                 const int c = i % BN, n = i / BN;
                 if (b0 + n >= d.B) continue;
@@ -326,8 +357,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int grp_idx = tile / n_ntiles;
             const int n0 = (tile - grp_idx * n_ntiles) * BN;
-            const int t0 = grp_idx * MT;
-            const int nvalid = min(MT, g.subtiles - t0);
+            const int cls = class_of(grp_idx);
+            const int t0 = (grp_idx - unit_base(cls)) * MT;
+            const int tpi = sel4(cl.tpi, cls), c_tx = sel4(cl.tiles_x, cls);
+            const int c_GH = sel4(cl.GH, cls), c_GW = sel4(cl.GW, cls), c_dyoff = sel4(cl.dy_off, cls), c_dxoff = sel4(cl.dx_off, cls);
+            const int nvalid = min(MT, sel4(cl.subtiles, cls) - t0);
             const int acc = it & 1;
             long long tw = 0;
             if (DBG && tl) tw = clock64();
@@ -339,8 +373,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
                 const int ib = t / tpi;
                 const int rem = t - ib * tpi;
                 const int b0 = ib << g.lnb;
-                const int ty0 = (rem / g.tiles_x) * g.bh, tx0 = (rem % g.tiles_x) * g.bw;
-                const bool ok = (ty0 + py) < d.GH && (tx0 + px) < d.GW && (b0 + pn) < d.B;
+                const int ty0 = (rem / c_tx) * g.bh, tx0 = (rem % c_tx) * g.bw;
+                const bool ok = (ty0 + py) < c_GH && (tx0 + px) < c_GW && (b0 + pn) < d.B;
                 float* red_m = s_red + (per_m ? 0 : m * 2 * slots * BN);
                 const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
                 // destination of the 8 rows this lane writes back (rows sub, sub+4, ... of the warp's 32), column n0
@@ -350,7 +384,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
                     const int rr = q * 32 + 4 * k + sub;
                     const int gy = ty0 + (rr >> (g.lbw + g.lnb)), gx = tx0 + (rr & (g.bw - 1));
                     const int b = b0 + ((rr >> g.lbw) & (g.nb - 1));
-                    rowp[k] = d.dst + (((long long)b * d.DH + (gy * d.dy_mul + d.dy_off)) * d.DW + (gx * d.dx_mul + d.dx_off)) * N + n0 + col4 * 4;
+                    rowp[k] = d.dst + (((long long)b * d.DH + (gy * d.dy_mul + c_dyoff)) * d.DW + (gx * d.dx_mul + c_dxoff)) * N + n0 + col4 * 4;
                 }
                 for (int c = 0; c < BN / 32; ++c) {
                     float v[32];
@@ -423,7 +457,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
                 }
                 if (d.stat_partial != nullptr && per_m) {
                     asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps
-                    reduce_stats(s_red, b0, rem, n0);
+                    reduce_stats(s_red, b0, rem, n0, tpi);
                     asm volatile("bar.sync 1, 128;" ::: "memory");          // s_red is reused by the next sub-tile
                 }
             }
@@ -431,7 +465,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 for (int m = 0; m < nvalid; ++m) {
                     const int ib = (t0 + m) / tpi;
-                    reduce_stats(s_red + m * 2 * slots * BN, ib << g.lnb, t0 + m - ib * tpi, n0);
+                    reduce_stats(s_red + m * 2 * slots * BN, ib << g.lnb, t0 + m - ib * tpi, n0, tpi);
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
@@ -524,7 +558,8 @@ bool spanning_maps_ok() {
 int env_int(const char* name) { return getenv(name) ? atoi(getenv(name)) : 0; }
 int g_force[4] = {env_int("SDT_YTAP_BN"), env_int("SDT_YTAP_MT"), env_int("SDT_YTAP_BW"), env_int("SDT_YTAP_NB")};
 
-Plan make_plan(const sdt_conv_desc* d) {
+// n_classes problems of (nearly) d's size share the launch: the tile count that fills the machine is the sum
+Plan make_plan(const sdt_conv_desc* d, int n_classes = 1) {
     Plan best{};
     best.ok = false;
     if (d->N % 64 != 0 || d->C % 32 != 0) return best;
@@ -555,7 +590,7 @@ Plan make_plan(const sdt_conv_desc* d) {
                 g.tiles_x = (d->GW + bw - 1) / bw;
                 g.tiles_y = (d->GH + g.bh - 1) / g.bh;
                 g.subtiles = ((d->B + nb - 1) / nb) * g.tiles_x * g.tiles_y;
-                const long long tiles = (long long)((g.subtiles + mt - 1) / mt) * (d->N / bn);
+                const long long tiles = (long long)((g.subtiles + mt - 1) / mt) * (d->N / bn) * n_classes;
                 const int budget = SMEM_MAX - epi_bytes(bn, mt, slots) - TAIL_BYTES;
                 const int a_stage = mt * g.a_box_bytes, b_stage = bn * 128;
                 int as = 2, bs = 2;
@@ -595,7 +630,7 @@ Plan make_plan(const sdt_conv_desc* d) {
 bool g_host_debug = false;       // set by sdt_debug_conv_timeline / sdt_debug_conv_flags: launch the DBG instantiation
 
 template <int BN, int MT, bool DBG>
-int launch_ytap2(const sdt_conv_desc* d, const Plan& pl, const CUtensorMap& tmA, const CUtensorMap& tmB, cudaStream_t st) {
+int launch_ytap2(const sdt_conv_desc* d, const Plan& pl, const CUtensorMap& tmA, const YMaps& tmB, const YClasses& cl, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         SDT_CUDA_OK(cudaFuncSetAttribute(tc_conv_ytap_kernel<BN, MT, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
@@ -607,19 +642,24 @@ int launch_ytap2(const sdt_conv_desc* d, const Plan& pl, const CUtensorMap& tmA,
         SDT_CUDA_OK(cudaGetDevice(&dev));
         SDT_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
-    const int grid = pl.tiles < sm_count ? pl.tiles : sm_count;      // persistent: one CTA per SM, static round-robin tiles
-    sdt::launch(tc_conv_ytap_kernel<BN, MT, DBG>, dim3(grid), dim3(THREADS), pl.smem, st, tmA, tmB, *d, pl.g);
+    const int tiles = cl.unit_start[cl.n] * (d->N / BN);
+    const int grid = tiles < sm_count ? tiles : sm_count;      // persistent: one CTA per SM, static round-robin tiles
+    sdt::launch(tc_conv_ytap_kernel<BN, MT, DBG>, dim3(grid), dim3(THREADS), pl.smem, st, tmA, tmB, *d, pl.g, cl);
     SDT_LAUNCH_OK("tc_conv_ytap_kernel");
     sdt_note_tc_launch();
     return SDT_OK;
 }
 
+// ds[0..n): the problems of one launch (n == 1: a plain convolution; n > 1: compatible parity classes, see multi_ok)
 template <int BN, int MT>
-int launch_ytap(const sdt_conv_desc* d, const Plan& pl, cudaStream_t st) {
+int launch_ytap(const sdt_conv_desc* ds, int n, const Plan& pl, cudaStream_t st) {
     EncodeTiledFn enc = get_encode();
     SDT_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    const sdt_conv_desc* d = ds;
     const YGeom& g = pl.g;
-    alignas(64) CUtensorMap tmA, tmB;
+    alignas(64) CUtensorMap tmA;
+    alignas(64) YMaps tmB;
+    YClasses cl{};
     {
         // (C, W, H, B) with one image per box, or (C, W, B, H) with nb images per box row: shared-memory rows (py, image, px)
         const bool span = g.nb > 1;
@@ -634,19 +674,37 @@ int launch_ytap(const sdt_conv_desc* d, const Plan& pl, cudaStream_t st) {
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SDT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A, y-tap) failed with %d", (int)r);
     }
-    {
-        const int K = d->TH * d->TW * d->C;
-        const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)d->N};
+    cl.n = n;
+    for (int c = 0; c < MAX_CLASSES; ++c) {
+        const sdt_conv_desc* dc = ds + (c < n ? c : n - 1);       // unused entries repeat the last class
+        const int K = dc->TH * dc->TW * dc->C;
+        const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)dc->N};
         const cuuint64_t strides[1] = {(cuuint64_t)K * 4};
         const cuuint32_t box[2] = {32, (cuuint32_t)BN};
         const cuuint32_t estr[2] = {1, 1};
-        const CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(d->wt_nk), dims, strides, box, estr,
+        const CUresult r = enc(&tmB.b[c], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(dc->wt_nk), dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SDT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B, y-tap) failed with %d", (int)r);
+        cl.tiles_x[c] = (dc->GW + g.bw - 1) / g.bw;
+        cl.tpi[c] = cl.tiles_x[c] * ((dc->GH + g.bh - 1) / g.bh);
+        cl.subtiles[c] = ((dc->B + g.nb - 1) / g.nb) * cl.tpi[c];
+        cl.GH[c] = dc->GH; cl.GW[c] = dc->GW;
+        cl.y_off[c] = dc->y_off; cl.x_off[c] = dc->x_off; cl.dy_off[c] = dc->dy_off; cl.dx_off[c] = dc->dx_off;
+        cl.unit_start[c + 1] = cl.unit_start[c] + (c < n ? (cl.subtiles[c] + MT - 1) / MT : 0);
     }
-    if (g_host_debug) return launch_ytap2<BN, MT, true>(d, pl, tmA, tmB, st);
-    return launch_ytap2<BN, MT, false>(d, pl, tmA, tmB, st);
+    if (g_host_debug) return launch_ytap2<BN, MT, true>(d, pl, tmA, tmB, cl, st);
+    return launch_ytap2<BN, MT, false>(d, pl, tmA, tmB, cl, st);
+}
+
+int launch_planned(const sdt_conv_desc* ds, int n, const Plan& pl, cudaStream_t st) {
+    if (pl.bn == 128) {
+        if (pl.mt == 2) return launch_ytap<128, 2>(ds, n, pl, st);
+        return launch_ytap<128, 1>(ds, n, pl, st);
+    }
+    if (pl.mt == 4) return launch_ytap<64, 4>(ds, n, pl, st);
+    if (pl.mt == 2) return launch_ytap<64, 2>(ds, n, pl, st);
+    return launch_ytap<64, 1>(ds, n, pl, st);
 }
 
 }  // namespace
@@ -699,11 +757,27 @@ int sdt_tc_conv_ytap_describe(const sdt_conv_desc* d, int32_t* out10) {
 int sdt_tc_conv_ytap_launch(const sdt_conv_desc* d, cudaStream_t st) {
     const Plan pl = make_plan(d);
     SDT_REQUIRE(pl.ok, "sdt_tc_conv_ytap_launch: no plan for this descriptor");
-    if (pl.bn == 128) {
-        if (pl.mt == 2) return launch_ytap<128, 2>(d, pl, st);
-        return launch_ytap<128, 1>(d, pl, st);
+    return launch_planned(d, 1, pl, st);
+}
+
+// Can ds[0..n) run as one launch?  Same source / destination / shapes / tap structure; only grids and offsets differ, and
+// no statistics epilogue (its partial rows are per problem).
+bool sdt_tc_conv_ytap_multi_ok(const sdt_conv_desc* ds, int n) {
+    if (n < 2 || n > MAX_CLASSES) return false;
+    for (int c = 0; c < n; ++c) {
+        const sdt_conv_desc& a = ds[0];
+        const sdt_conv_desc& b = ds[c];
+        if (!sdt_tc_conv_ytap_eligible(&b) || b.stat_partial != nullptr) return false;
+        if (b.src != a.src || b.dst != a.dst || b.bias != a.bias || b.accumulate != a.accumulate) return false;
+        if (b.B != a.B || b.SH != a.SH || b.SW != a.SW || b.C != a.C || b.N != a.N || b.TH != a.TH || b.TW != a.TW) return false;
+        if (b.y_mul != a.y_mul || b.ty_mul != a.ty_mul || b.x_mul != a.x_mul || b.tx_mul != a.tx_mul) return false;
+        if (b.DH != a.DH || b.DW != a.DW || b.dy_mul != a.dy_mul || b.dx_mul != a.dx_mul) return false;
+        if (b.GH > a.GH || b.GW > a.GW || ((uintptr_t)b.wt_nk & 15) != 0) return false;      // planned on the largest (first) class
     }
-    if (pl.mt == 4) return launch_ytap<64, 4>(d, pl, st);
-    if (pl.mt == 2) return launch_ytap<64, 2>(d, pl, st);
-    return launch_ytap<64, 1>(d, pl, st);
+    return make_plan(ds, n).ok;
+}
+
+int sdt_tc_conv_ytap_launch_multi(const sdt_conv_desc* ds, int n, cudaStream_t st) {
+    SDT_REQUIRE(sdt_tc_conv_ytap_multi_ok(ds, n), "sdt_tc_conv_ytap_launch_multi: the problems cannot share a launch");
+    return launch_planned(ds, n, make_plan(ds, n), st);
 }

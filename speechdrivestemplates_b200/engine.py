@@ -456,8 +456,8 @@ def _wgrad_now(self, g, x, dy, B, H, W, grad_out, xf=None, slope=1.0):
 
 def _dgrad(self, name, g, dy, w, dx, B, H, W, accumulate=False):
     # stride-parity classes with their weight operands, prepared at the start of the step by the batched launch
-    for cls, wt, wt_nk in self.wprep.dgrad[name]:
-        ops.conv_gemm(ops.dgrad_desc(g, cls, dy, wt, dx, B, H, W, accumulate, wt_nk=wt_nk))
+    ops.conv_gemm_multi([ops.dgrad_desc(g, cls, dy, wt, dx, B, H, W, accumulate, wt_nk=wt_nk)
+                         for cls, wt, wt_nk in self.wprep.dgrad[name]])
 
 
 def _gen_backward(self, g_pred, grads, g_code=None):

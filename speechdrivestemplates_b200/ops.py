@@ -217,6 +217,17 @@ def wgrad_splits(g, B, oh, ow, target_ctas=444):
     return max(1, min(-(-target_ctas // tiles), -(-pixels // 256)))
 
 
+def conv_gemm_multi(descs):
+    """Several convolution problems in stream order (the stride-parity classes of one data gradient): one persistent launch
+    in math mode 3 when they are compatible, else one launch each (csrc/conv_gemm.cu: sdt_conv_gemm_multi)."""
+    if len(descs) == 1:
+        return conv_gemm(descs[0])
+    arr = (ConvDesc * len(descs))(*descs)
+    launched = C.c_int(0)
+    call("sdt_conv_gemm_multi", arr, len(descs), _stream(), C.byref(launched))
+    _lib.launch_count += launched.value - 1          # call() counted one kernel
+
+
 def row_tiles(desc):
     n = call("sdt_conv_row_tiles", C.byref(desc))
     if n < 0:
@@ -295,6 +306,7 @@ def conv_dgrad(dy, w, g, H, W, out=None, accumulate=False):
     dx = out if out is not None else torch.empty(B, H, W, g.cin, device=dy.device)
     if g.sh * g.sw > 1 and out is None and not accumulate:
         pass  # every input position belongs to exactly one parity class -> fully written
+    descs, keep = [], []
     for cls in g.dgrad_classes(H, W):
         wt = torch.empty(cls["th"] * cls["tw"] * g.cout, g.cin, device=dy.device)
         weight_prep_dgrad(w, g, cls, wt)
@@ -302,7 +314,9 @@ def conv_dgrad(dy, w, g, H, W, out=None, accumulate=False):
         if get_conv_math() >= 1 and tc_eligible(g.cout, g.cin):
             wt_nk = torch.empty(g.cin, cls["th"] * cls["tw"] * g.cout, device=dy.device)
             weight_prep_dgrad_nk(w, g, cls, wt_nk)
-        conv_gemm(dgrad_desc(g, cls, dy, wt, dx, B, H, W, accumulate, wt_nk=wt_nk))
+        descs.append(dgrad_desc(g, cls, dy, wt, dx, B, H, W, accumulate, wt_nk=wt_nk))
+        keep.append((wt, wt_nk))
+    conv_gemm_multi(descs)
     return dx
 
 

@@ -214,6 +214,7 @@ REUSE_GEOMS = [
     (64, 256, 6, 3, 1, 0, 10, 53, 3),
     (128, 256, 3, 3, 1, 1, 17, 23, 2),
     (64, 64, 5, 5, 1, 2, 19, 21, 2),
+    (64, 64, 4, 4, 2, 1, 21, 27, 3),          # odd input: the four parity classes of the data gradient have different grids
 ]
 
 
@@ -309,6 +310,39 @@ def test_reuse_image_spanning_patches(cfg, force):
     finally:
         lib.sdt_debug_conv_force(0, 0, 0, 0)
         ops.set_conv_math(0)
+
+
+@pytest.mark.parametrize("cfg", [(128, 64, 4, 4, 2, 1, 30, 62, 5), (64, 64, 4, 4, 2, 1, 21, 27, 3), (256, 256, 4, 4, 2, 1, 20, 106, 8)])
+def test_parity_classes_in_one_launch_match_separate_launches(cfg):
+    """sdt_conv_gemm_multi: the four stride-parity classes of a data gradient as ONE persistent launch give bit-identical
+    results to four launches (same K order per output element), with one kernel instead of four."""
+    from speechdrivestemplates_b200 import _lib, ops
+    cin, cout, kh, kw, s, p, H, W, B = cfg
+    g = torch.Generator().manual_seed(45)
+    geom = ops.ConvGeom.conv2d(cin, cout, kh, kw, s, p)
+    oh, ow = geom.out_hw(H, W)
+    dy = torch.randn(B, oh, ow, cout, generator=g).to(dev())
+    w = (torch.randn(cout, cin, kh, kw, generator=g) / math.sqrt(cin * kh * kw)).to(dev())
+    ops.set_conv_math(3)
+    try:
+        descs, keep = [], []
+        for cls in geom.dgrad_classes(H, W):
+            wt_nk = torch.empty(geom.cin, cls["th"] * cls["tw"] * geom.cout, device=dev())
+            ops.weight_prep_dgrad_nk(w, geom, cls, wt_nk)
+            keep.append(wt_nk)
+            descs.append((cls, wt_nk))
+        dx1 = torch.full((B, H, W, cin), float("nan"), device=dev())
+        for cls, wt_nk in descs:
+            ops.conv_gemm(ops.dgrad_desc(geom, cls, dy, None, dx1, B, H, W, wt_nk=wt_nk))
+        dx2 = torch.full((B, H, W, cin), float("nan"), device=dev())
+        n0, k0 = tc_launches(), _lib.launch_count
+        ops.conv_gemm_multi([ops.dgrad_desc(geom, cls, dy, None, dx2, B, H, W, wt_nk=wt_nk) for cls, wt_nk in descs])
+        torch.cuda.synchronize()
+        assert tc_launches() - n0 == 1 and _lib.launch_count - k0 == 1
+    finally:
+        ops.set_conv_math(0)
+    assert torch.isfinite(dx2).all()
+    assert torch.equal(dx1, dx2)
 
 
 def test_reuse_matches_tma_mode_bitwise_products():

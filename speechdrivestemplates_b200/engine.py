@@ -64,7 +64,7 @@ class WeightPrep:
         scale/shift per CTA, so layers whose loader transform spans a batch-wide statistic stay on the FFMA kernel)."""
         import numpy as np
         tc = ops.get_conv_math() >= 1
-        key = (tc, with_dgrad, tuple(l[6] if len(l) > 6 else 0 for l in layers)) + tuple(params[l[1]].data_ptr() for l in layers)
+        key = (tc, with_dgrad, tuple(tuple(l[6:]) for l in layers)) + tuple(params[l[1]].data_ptr() for l in layers)
         if key == self.key:
             return
         self.key = key
@@ -83,8 +83,11 @@ class WeightPrep:
             name, wkey, g, (H, W), needs_dgrad = layer[:5]
             tc_ok = layer[5] if len(layer) > 5 else True
             cin_pad = layer[6] if len(layer) > 6 else 0    # forward-only layers: input channels zero-padded (242 -> 256)
+            dgrad_only = len(layer) > 7 and layer[7]       # zero-padded copy of a layer for its data gradient (TMA kernels: N % 64 == 0)
             w = params[wkey]
-            if tc and tc_ok and cin_pad and ops.tc_eligible(cin_pad, g.cout):
+            if dgrad_only:
+                pass
+            elif tc and tc_ok and cin_pad and ops.tc_eligible(cin_pad, g.cout):
                 assert not needs_dgrad
                 nk = A.get("wt_fnk:" + name, (g.cout, g.kh * g.kw * cin_pad))
                 add(w, nk, g, 2, 0, 0, g.kh, g.kw, cin_pad)
@@ -99,7 +102,7 @@ class WeightPrep:
                 self.fwd[name] = (kn, None)
             if with_dgrad and needs_dgrad:
                 lst = []
-                dtc = tc and tc_ok and ops.tc_eligible(g.cout, g.cin)
+                dtc = tc and tc_ok and (ops.tc_eligible(g.cout, g.cin) or dgrad_only)
                 for ci, cls in enumerate(g.dgrad_classes(H, W)):
                     kd = cls["th"] * cls["tw"] * g.cout
                     if dtc:
@@ -233,6 +236,10 @@ class GeneratorEngine:
             else:                                   # up(prev)+skip: resampled to the skip's (== this layer's) length
                 lin = self.seq_len[name]
             out.append((name, name + ".conv.weight", g, (1, lin), True))
+        if self._x0_pad():
+            g0 = self.seq_layers()[0][1]
+            out.append(("unet.e0:dpad", "unet.e0.conv.weight_dpad", ConvGeom.conv1d(self._x0_pad(), g0.cout, g0.kw, g0.sw, g0.pw),
+                        (1, self.F), True, True, 0, True))
         if self._head_pad():
             out.append(("decoder.4", "decoder.4.weight_pad", ConvGeom.conv1d(256, self._head_pad(), 1, 1, 0), (1, self.F), True))
         else:
@@ -247,18 +254,34 @@ class GeneratorEngine:
             return -(-self.kp2 // 64) * 64
         return 0
 
+    def _x0_pad(self):
+        """The first UNet layer reads 256 encoder channels + the clip code (288 with a 32-d code): its data gradient is a GEMM
+        with N = 288, which no 64-wide tensor-core tile divides (it ran 74 us on the FFMA kernel, on the critical path).  In the
+        TMA math modes the gradient is computed with a zero-padded copy of the weight (input channels 288 -> 320) into a
+        320-channel buffer whose tail is zero; the resize / code adjoint reads it as 256 + 64 channels.  0 = no padding."""
+        cin = 256 + self.code_dim
+        if ops.get_conv_math() >= 2 and cin % 64 != 0:
+            return -(-cin // 64) * 64
+        return 0
+
     def _padded_head_params(self, params):
         """params + zero-padded copies of decoder.4.weight / .bias (refreshed from the parameters every step)."""
-        npad = self._head_pad()
-        if not npad:
+        npad, cpad = self._head_pad(), self._x0_pad()
+        if not npad and not cpad:
             return params
         A = self.arena
-        wp = A.get("head_w_pad", (npad, 256, 1), zero=True)
-        bp = A.get("head_b_pad", (npad,), zero=True)
-        wp[:self.kp2].copy_(params["decoder.4.weight"])
-        bp[:self.kp2].copy_(params["decoder.4.bias"])
         out = dict(params)
-        out["decoder.4.weight_pad"], out["decoder.4.bias_pad"] = wp, bp
+        if npad:
+            wp = A.get("head_w_pad", (npad, 256, 1), zero=True)
+            bp = A.get("head_b_pad", (npad,), zero=True)
+            wp[:self.kp2].copy_(params["decoder.4.weight"])
+            bp[:self.kp2].copy_(params["decoder.4.bias"])
+            out["decoder.4.weight_pad"], out["decoder.4.bias_pad"] = wp, bp
+        if cpad:
+            w0 = params["unet.e0.conv.weight"]
+            wp0 = A.get("x0_w_dpad", (w0.shape[0], cpad, w0.shape[2]), zero=True)
+            wp0[:, :w0.shape[1]].copy_(w0)
+            out["unet.e0.conv.weight_dpad"] = wp0
         return out
 
     # ---- forward ----------------------------------------------------------------------------------
@@ -506,7 +529,12 @@ def _gen_backward(self, g_pred, grads, g_code=None):
         L_in = xin.shape[1]
         _wgrad(self, g, xin, g_raw, B, 1, L_in, grads[name + ".conv.weight"])
         w = params[name + ".conv.weight"]
-        if kind == "x0":
+        if kind == "x0" and self._x0_pad():
+            cpad = self._x0_pad()
+            g_x0 = A.get("g_x0_pad", (B, L_in, cpad))
+            _dgrad(self, name + ":dpad", ConvGeom.conv1d(cpad, g.cout, g.kw, g.sw, g.pw), g_raw, params[name + ".conv.weight_dpad"],
+                   g_x0, B, 1, L_in)
+        elif kind == "x0":
             g_x0 = A.get("g_x0", tuple(xin.shape))
             _dgrad(self, name, g, g_raw, w, g_x0, B, 1, L_in)
         elif kind.startswith("act:"):
@@ -527,7 +555,15 @@ def _gen_backward(self, g_pred, grads, g_code=None):
     h7, w7 = self.enc_hw[8]
     g_enc = A.get("g_enc:7", (B, h7, w7, 256))
     D = self.code_dim
-    ops.enc_to_seq_bwd(g_x0, h7, w7, 256, D, g_act=g_enc, g_code=g_code if D > 0 else None)
+    if self._x0_pad():
+        # the padded gradient buffer reads as 256 encoder channels + (D + zero tail) code channels
+        Dp = self._x0_pad() - 256
+        gc_pad = A.get("g_code_pad", (B, Dp))
+        ops.enc_to_seq_bwd(g_x0, h7, w7, 256, Dp, g_act=g_enc, g_code=gc_pad)
+        if D > 0 and g_code is not None:
+            g_code.copy_(gc_pad[:, :D])
+    else:
+        ops.enc_to_seq_bwd(g_x0, h7, w7, 256, D, g_act=g_enc, g_code=g_code if D > 0 else None)
     # ---- 2-D encoder in reverse
     groups = self._groups()
     for l in range(7, -1, -1):

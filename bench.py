@@ -373,9 +373,9 @@ def run_own(args):
         roofline = {
             "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
             "frac": achieved / pk["tf_sustained"],
-            # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the 8 launches of one `ncu --set full` capture of
-            # this command (profiles/r1_ncu_tc_conv_mode3.txt)
-            "traffic": 102.3e6,
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the 14 launches of one step in one `ncu --set full`
+            # capture of this command (profiles/r1_ncu_tc_conv_mode3_final.txt: 1762.6 MB over 14 launches)
+            "traffic": 125.9e6,
             "kernel": "tc_conv_ytap_kernel (tcgen05 kind::tf32, TMA operands, persistent, double-buffered TMEM): 2-D encoder "
                       "convolutions forward + data gradient",
             "algorithmic_flops_per_launch": dom[2] / max(dom[1], 1),
@@ -383,7 +383,7 @@ def run_own(args):
             "launches_per_step": dom[1] // reps, "avg_launch_ms": dom[0] / max(dom[1], 1),
             "peak_source": pk["src"] + " bf16 dense, sustained (kernel timed inside a long step); the kernel computes in TF32, whose "
                                        "nominal dense rate is half of bf16 (1.1 vs 2.25 PFLOP/s)",
-            "ncu_tensor_pipe_active_pct": "57-85 (Cout >= 128), 41 (64->64 stride 2): profiles/r1_ncu_tc_conv_mode3.txt",
+            "ncu_tensor_pipe_active_pct": "51-85 (Cout >= 128), 32-51 (64-channel stride-2 layer): profiles/r1_ncu_tc_conv_mode3_final.txt",
             # the same measured peak scaled to the arithmetic type the kernel uses (TF32 = half the bf16 rate)
             "frac_of_tf32_equivalent_peak": achieved / (0.5 * pk["tf_sustained"]),
         }

@@ -268,6 +268,8 @@ def run_own(args):
     dev = torch.device("cuda", local)
     pg = None
     if world > 1:
+        # stdout carries the ONE JSON line: NCCL's own banner / debug lines (NCCL_DEBUG=VERSION|WARN|INFO in the environment) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
     B, K, W = args.batch, args.steps, max(args.warmup, 3)

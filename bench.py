@@ -206,10 +206,28 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries the ONE JSON line.  Keep the real stdout for it and point fd 1 at stderr, so that nothing a library writes
+    to stdout (NCCL's version banner, a C-level printf) can end up next to it."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 class EventProfiler:
     """Brackets every C-ABI kernel call of one eager step with CUDA events on the launching (current) stream."""
 
@@ -438,7 +456,7 @@ def run_own(args):
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "last_losses": last,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -455,6 +473,7 @@ def main():
                     help="convolution math: fp32 FFMA kernels or tcgen05 TF32 tensor-core kernels (fp32 accumulate)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

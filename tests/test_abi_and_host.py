@@ -191,6 +191,20 @@ def test_conv_plan_for_the_encoder_layers(B):
         lib.sdt_set_conv_math(0)
 
 
+def test_conv_gemm_multi_rejects_bad_arguments_without_launching():
+    """sdt_conv_gemm_multi (the parity classes of one data gradient as one launch): argument errors are reported through the
+    status code + sdt_last_error(), before anything touches the GPU."""
+    _built()
+    from speechdrivestemplates_b200 import _lib, ops
+    with pytest.raises(_lib.SdtError, match="sdt_conv_gemm_multi"):
+        _lib.call("sdt_conv_gemm_multi", None, 2, None, None)
+    arr = (ops.ConvDesc * 17)()
+    with pytest.raises(_lib.SdtError, match="17 problems"):
+        _lib.call("sdt_conv_gemm_multi", arr, 17, None, None)
+    with pytest.raises(_lib.SdtError):
+        _lib.call("sdt_conv_gemm_multi", arr, 0, None, None)
+
+
 def test_conv_plan_falls_back_outside_mode_3_and_remaps_1d():
     _built()
     from speechdrivestemplates_b200 import _lib, ops

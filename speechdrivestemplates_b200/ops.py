@@ -304,9 +304,8 @@ def conv_dgrad(dy, w, g, H, W, out=None, accumulate=False):
     _chk(dy, name="dy")
     B = dy.shape[0]
     dx = out if out is not None else torch.empty(B, H, W, g.cin, device=dy.device)
-    if g.sh * g.sw > 1 and out is None and not accumulate:
-        pass  # every input position belongs to exactly one parity class -> fully written
-    descs, keep = [], []
+    # every input position belongs to exactly one stride-parity class, so the classes together write all of dx
+    descs, keep = [], []          # keep: the operand tensors must outlive the (asynchronous) launch
     for cls in g.dgrad_classes(H, W):
         wt = torch.empty(cls["th"] * cls["tw"] * g.cout, g.cin, device=dy.device)
         weight_prep_dgrad(w, g, cls, wt)

@@ -399,7 +399,11 @@ def run_own(args):
             "kernel": "tc_conv_ytap_kernel (tcgen05 kind::tf32, TMA operands, persistent, double-buffered TMEM): 2-D encoder "
                       "convolutions forward + data gradient",
             "algorithmic_flops_per_launch": dom[2] / max(dom[1], 1),
+            # share of the serial sum of event-bracketed launches; every bracket around one of the ~250 small launches also
+            # holds a few us of launch latency, so this reads lower than the share in the ncu launch list of the same command
+            # (profiles/r1_step_breakdown_mode3.txt: 1.081 of 4.039 ms)
             "share_of_step": dom[0] / total_ms if total_ms else None,
+            "share_of_step_ncu_launch_list": 0.268,
             "launches_per_step": dom[1] // reps, "avg_launch_ms": dom[0] / max(dom[1], 1),
             "peak_source": pk["src"] + " bf16 dense, sustained (kernel timed inside a long step); the kernel computes in TF32, whose "
                                        "nominal dense rate is half of bf16 (1.1 vs 2.25 PFLOP/s)",

@@ -191,6 +191,50 @@ def test_conv_plan_for_the_encoder_layers(B):
         lib.sdt_set_conv_math(0)
 
 
+def test_conv_plan_invariants_on_random_layers():
+    """Property test of the mode-3 planner (host only): whatever layer it accepts, the plan respects the hardware limits
+    (shared memory of one CTA per SM, 512 TMEM columns for two accumulator sets, TMA box extents <= 256) and tiles the
+    whole output grid; image-spanning patches never leave more than one half-empty group of images."""
+    _built()
+    import random
+    from speechdrivestemplates_b200 import _lib, ops
+    lib = _lib.load()
+    rng = random.Random(7)
+    assert lib.sdt_set_conv_math(3) == 0
+    planned = spanning = 0
+    try:
+        for _ in range(300):
+            cin, cout = rng.choice([32, 64, 96, 128, 256]), rng.choice([64, 128, 192, 256])
+            k, s = rng.choice([(3, 1), (4, 2), (5, 1), (1, 1), (2, 2), (6, 1)])
+            kh, kw = k, rng.choice([k, 3]) if s == 1 else k
+            p = rng.choice([0, 1, k // 2])
+            H, W, B = rng.randint(max(kh, 2), 90), rng.randint(max(kw, 2), 450), rng.choice([1, 2, 3, 7, 32, 33, 128])
+            if (H + 2 * p - kh) // s + 1 < 2 or (W + 2 * p - kw) // s + 1 < 1:
+                continue
+            d, oh, ow = _fake_fwd_desc(ops, cin, cout, kh, kw, s, p, H, W, B)
+            out = (ctypes.c_int32 * 10)()
+            assert lib.sdt_conv_plan(ctypes.byref(d), out) == 0
+            kind, bn, mt, bh_nb, bw, box_rows, a_st, b_st, smem, tiles = list(out)
+            if kind != 3:
+                continue
+            planned += 1
+            bh, nb = bh_nb & 255, bh_nb >> 8
+            spanning += nb > 1
+            assert cout % bn == 0 and bn in (64, 128) and mt in (1, 2, 4) and 2 * mt * bn <= 512
+            assert bh * bw * nb == 128 and bw % 8 == 0 and (nb == 1 or nb // 2 < B)
+            assert smem <= 227 * 1024 and 2 <= a_st <= 4 and 2 <= b_st <= 6
+            assert bw * s <= 256 and box_rows * s <= 256 and box_rows >= bh
+            sub = -(-B // nb) * (-(-oh // bh)) * (-(-ow // bw))
+            assert tiles == -(-sub // mt) * (cout // bn)
+            # ring + epilogue scratch as the kernel lays them out
+            slots = 4 if (nb == 1 or bw >= 32) else 128 // bw
+            epi = 4 * 32 * 36 * 4 + (1 if slots > 4 else mt) * 2 * slots * bn * 4
+            assert smem == a_st * mt * box_rows * nb * bw * 128 + b_st * bn * 128 + epi + (2 * 4 + 2 * 6 + 4) * 8 + 16
+    finally:
+        lib.sdt_set_conv_math(0)
+    assert planned > 100 and spanning > 10
+
+
 def test_conv_gemm_multi_rejects_bad_arguments_without_launching():
     """sdt_conv_gemm_multi (the parity classes of one data gradient as one launch): argument errors are reported through the
     status code + sdt_last_error(), before anything touches the GPU."""

@@ -128,7 +128,8 @@ class ConvGeom:
 
 def set_conv_math(mode):
     """0 = fp32 FFMA kernels, 1 = tcgen05 TF32 tensor-core kernels where a layer is eligible, 2 = 1 with TMA-delivered
-    operands, 3 = 2 with shared-memory operand reuse across vertical taps / accumulators (process-wide)."""
+    operands, 3 = 2 with the persistent kernel (shared-memory operand reuse across vertical taps / accumulators, image-spanning
+    patches, parity classes in one launch), 4 = 3 with CTA pairs (experimental).  Process-wide."""
     call("sdt_set_conv_math", int(mode))
 
 

@@ -32,7 +32,9 @@ extern "C" {
 /* ---- library ---------------------------------------------------------------------------------- */
 const char* sdt_last_error(void);
 int sdt_version(void);
-/* math mode of the dense convolutions (process-wide, default 0):
+/* math mode of the dense convolutions.  The PROCESS DEFAULT below applies to descriptors whose `math` field is 0; it starts at
+ * 3 (this library runs on sm_100a only, and TF32 is the reference's own GPU default: torch.backends.cudnn.allow_tf32) unless the
+ * environment variable SDT_CONV_MATH=0..4 says otherwise.  Engines pass their own mode per descriptor (sdt_conv_desc.math).
  *   0 = fp32 FFMA (SIMT);
  *   1 = tcgen05 tensor cores, TF32 operands, fp32 accumulation in TMEM, operand tiles built by producer warps
  *       (supports the loader transform) -- for shapes with C % 32 == 0 and N in {64,128,256}, FFMA otherwise;
@@ -99,6 +101,8 @@ typedef struct sdt_conv_desc {
     int32_t accumulate;        /* conv: dst += result */
     int32_t per_image_tiles;   /* conv: row tiles never straddle images (needed for per-(b,c) statistics) */
     int32_t splits;            /* wgrad: number of K splits (== gridDim.z) */
+    int32_t math;              /* 0 = the process default (sdt_get_conv_math()); m + 1 = math mode m for THIS problem, so every
+                                * engine / model of a process carries its own mode and no call depends on shared mutable state */
 } sdt_conv_desc;
 
 /* number of row tiles sdt_conv_gemm will use for this descriptor (size of stat_partial's first dim) */

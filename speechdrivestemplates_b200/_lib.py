@@ -25,7 +25,7 @@ class ConvDesc(C.Structure):
         ("N", i32),
         ("DH", i32), ("DW", i32), ("dy_mul", i32), ("dy_off", i32), ("dx_mul", i32), ("dx_off", i32),
         ("xf_bstride", i32), ("xf_slope", f32),
-        ("accumulate", i32), ("per_image_tiles", i32), ("splits", i32),
+        ("accumulate", i32), ("per_image_tiles", i32), ("splits", i32), ("math", i32),
     ]
 
 

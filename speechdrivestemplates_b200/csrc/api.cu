@@ -8,7 +8,13 @@
 
 namespace {
 thread_local char g_err[512] = "";
-std::atomic<int> g_conv_math{0};
+// process default of the convolution math mode: 3 (tcgen05 TF32, TMA operands, persistent kernel) unless SDT_CONV_MATH=0..4
+int initial_conv_math() {
+    const char* e = getenv("SDT_CONV_MATH");
+    if (e != nullptr && e[0] >= '0' && e[0] <= '4' && e[1] == '\0') return e[0] - '0';
+    return 3;
+}
+std::atomic<int> g_conv_math{initial_conv_math()};
 std::atomic<long long> g_tc_launches{0};
 }  // namespace
 

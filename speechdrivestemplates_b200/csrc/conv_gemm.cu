@@ -659,6 +659,7 @@ int check_desc(const sdt_conv_desc* d, const char* who) {
                 d->C, d->GH, d->GW, d->TH, d->TW, d->N);
     SDT_REQUIRE((d->xf_scale == nullptr) == (d->xf_shift == nullptr), "%s: xf_scale and xf_shift must come together", who);
     SDT_REQUIRE(d->xf_scale == nullptr || d->xf_bstride == 0 || d->xf_bstride == d->C, "%s: xf_bstride must be 0 or C", who);
+    SDT_REQUIRE(d->math >= 0 && d->math <= 5, "%s: math must be 0 (process default) or mode + 1 (1..5), got %d", who, d->math);
     return SDT_OK;
 }
 
@@ -684,9 +685,12 @@ inline int pick_bm(const sdt_conv_desc* d) {
 // TMA's out-of-bounds fill in x.  There are no vertical taps (TH == 1), so rows never mix clips.
 // Measured (B = 32): the 36 small 1-D launches of a step are 0.1 ms SLOWER this way than on tc_conv_tma.cu (a persistent CTA with
 // the whole shared memory and 512 TMEM columns per SM is a heavy vehicle for 16-64 tiles), so it is off unless SDT_REMAP_1D=1.
+// math mode of one problem: its own (`math` = mode + 1) or the process default
+inline int mode_of(const sdt_conv_desc* d) { return d->math > 0 ? d->math - 1 : sdt_get_conv_math(); }
+
 inline bool remap_1d(const sdt_conv_desc* d, sdt_conv_desc* out) {
     static const bool on = getenv("SDT_REMAP_1D") != nullptr && getenv("SDT_REMAP_1D")[0] == '1';
-    if (!on || sdt_get_conv_math() < 3) return false;
+    if (!on || mode_of(d) < 3) return false;
     if (!(d->SH == 1 && d->GH == 1 && d->DH == 1 && d->TH == 1 && d->B > 1 && d->per_image_tiles == 0)) return false;
     *out = *d;
     out->SH = out->GH = out->DH = d->B;
@@ -699,10 +703,10 @@ inline bool remap_1d(const sdt_conv_desc* d, sdt_conv_desc* out) {
     return true;
 }
 
-inline bool use_pair(const sdt_conv_desc* d) { return sdt_get_conv_math() == 4 && sdt_tc_conv_pair_eligible(d); }
-inline bool use_ytap(const sdt_conv_desc* d) { return sdt_get_conv_math() >= 3 && sdt_tc_conv_ytap_eligible(d); }
-inline bool use_tma(const sdt_conv_desc* d) { return sdt_get_conv_math() >= 2 && sdt_tc_conv_tma_eligible(d); }
-inline bool use_tc(const sdt_conv_desc* d) { return sdt_get_conv_math() >= 1 && sdt_tc_conv_eligible(d); }
+inline bool use_pair(const sdt_conv_desc* d) { return mode_of(d) == 4 && sdt_tc_conv_pair_eligible(d); }
+inline bool use_ytap(const sdt_conv_desc* d) { return mode_of(d) >= 3 && sdt_tc_conv_ytap_eligible(d); }
+inline bool use_tma(const sdt_conv_desc* d) { return mode_of(d) >= 2 && sdt_tc_conv_tma_eligible(d); }
+inline bool use_tc(const sdt_conv_desc* d) { return mode_of(d) >= 1 && sdt_tc_conv_eligible(d); }
 
 extern "C" int sdt_conv_row_tiles(const sdt_conv_desc* d) {
     if (check_desc(d, "sdt_conv_row_tiles") != SDT_OK) return -1;
@@ -722,10 +726,10 @@ extern "C" int sdt_conv_plan(const sdt_conv_desc* d, int32_t* out10) {
     if (remap_1d(d, &r1) && sdt_tc_conv_ytap_shape_ok(&r1)) {
         out10[0] = 3;
         sdt_tc_conv_ytap_describe(&r1, out10);
-    } else if (sdt_get_conv_math() == 4 && sdt_tc_conv_pair_shape_ok(d)) {
+    } else if (mode_of(d) == 4 && sdt_tc_conv_pair_shape_ok(d)) {
         out10[0] = 4;
         sdt_tc_conv_pair_describe(d, out10);
-    } else if (sdt_get_conv_math() >= 3 && sdt_tc_conv_ytap_shape_ok(d)) {
+    } else if (mode_of(d) >= 3 && sdt_tc_conv_ytap_shape_ok(d)) {
         out10[0] = 3;
         sdt_tc_conv_ytap_describe(d, out10);
     } else if (use_tma(d)) {
@@ -775,11 +779,11 @@ extern "C" int sdt_conv_gemm(const sdt_conv_desc* d, void* stream) {
 extern "C" int sdt_conv_gemm_multi(const sdt_conv_desc* descs, int n, void* stream, int* launched) {
     SDT_REQUIRE(descs != nullptr && n >= 1 && n <= 16, "sdt_conv_gemm_multi: %d problems (1..16)", n);
     if (launched) *launched = 0;
-    if (sdt_get_conv_math() == 3 && n >= 2 && n <= 4) {
+    if (mode_of(descs) == 3 && n >= 2 && n <= 4) {
         bool ok = true;
         for (int c = 0; c < n && ok; ++c) {
             if (int rc = check_desc(descs + c, "sdt_conv_gemm_multi")) return rc;
-            ok = descs[c].dst && descs[c].wt_nk && use_ytap(descs + c);
+            ok = descs[c].dst && descs[c].wt_nk && descs[c].math == descs[0].math && use_ytap(descs + c);
         }
         if (ok && sdt_tc_conv_ytap_multi_ok(descs, n)) {
             if (launched) *launched = 1;
@@ -800,9 +804,9 @@ extern "C" int sdt_conv_wgrad(const sdt_conv_desc* d, void* stream) {
     const int Kc = d->TH * d->TW * d->C;
     const bool veca = (d->N % 4) == 0, vecb = (d->C % 4) == 0;
     cudaStream_t st = sdt::as_stream(stream);
-    if (sdt_get_conv_math() >= 3 && sdt_tc_wgrad_ytap_eligible(d)) return sdt_tc_wgrad_ytap_launch(d, st);   // + vertical-tap reuse
-    if (sdt_get_conv_math() >= 2 && sdt_tc_wgrad_tma_eligible(d)) return sdt_tc_wgrad_tma_launch(d, st);   // tcgen05 + TMA
-    if (sdt_get_conv_math() >= 1 && sdt_tc_wgrad_eligible(d)) return sdt_tc_wgrad_launch(d, st);   // tcgen05 TF32
+    if (mode_of(d) >= 3 && sdt_tc_wgrad_ytap_eligible(d)) return sdt_tc_wgrad_ytap_launch(d, st);   // + vertical-tap reuse
+    if (mode_of(d) >= 2 && sdt_tc_wgrad_tma_eligible(d)) return sdt_tc_wgrad_tma_launch(d, st);   // tcgen05 + TMA
+    if (mode_of(d) >= 1 && sdt_tc_wgrad_eligible(d)) return sdt_tc_wgrad_launch(d, st);   // tcgen05 TF32
     if (Kc <= 16 && d->N <= 64) {       // tiny contraction: streaming kernel, one partial per CTA (gridDim.x == splits)
         sdt::launch(conv_wgrad_smallk_kernel, dim3(d->splits), dim3(256), 0, st, *d);
         SDT_LAUNCH_OK("conv_wgrad_smallk_kernel");

@@ -51,8 +51,9 @@ class WeightPrep:
     table is built and uploaded once and rebuilt only if a parameter moved or the math mode changed.
     """
 
-    def __init__(self, arena):
+    def __init__(self, arena, math):
         self.arena = arena
+        self.math = math
         self.key = None
         self.fwd = {}       # name -> (wt or None, wt_nk or None)
         self.dgrad = {}     # name -> [(cls, wt or None, wt_nk or None)]
@@ -63,7 +64,7 @@ class WeightPrep:
         tc_ok=False keeps a layer on the FFMA operands even in math mode 1 (the tcgen05 kernel stages one image's
         scale/shift per CTA, so layers whose loader transform spans a batch-wide statistic stay on the FFMA kernel)."""
         import numpy as np
-        tc = ops.get_conv_math() >= 1
+        tc = self.math >= 1
         key = (tc, with_dgrad, tuple(tuple(l[6:]) for l in layers)) + tuple(params[l[1]].data_ptr() for l in layers)
         if key == self.key:
             return
@@ -141,7 +142,7 @@ class GeneratorEngine:
     (e.g. 'audio_encoder.specgram_encoder_2d.0.0.conv.weight', 'unet.e0.conv.weight', 'decoder.4.bias').
     """
 
-    def __init__(self, norm, leaky, code_dim, n_landmarks, device):
+    def __init__(self, norm, leaky, code_dim, n_landmarks, device, math=None):
         if norm not in ("IN", "BN"):
             raise NotImplementedError(norm)                # building_blocks.py:27-28
         self.norm = norm
@@ -153,7 +154,8 @@ class GeneratorEngine:
         self.enc_geoms = [ConvGeom.conv2d(ci, co, kh, kw, s, p) for (_n, co, ci, kh, kw, s, p) in ENC2D]
         self.shape_key = None
         self.fwd_id = 0
-        self.wprep = WeightPrep(self.arena)
+        self.math = ops.resolve_math(math)      # this engine's convolution math mode (every descriptor carries it)
+        self.wprep = WeightPrep(self.arena, self.math)
 
     # ---- static layer tables -------------------------------------------------------------------
     def seq_layers(self):
@@ -250,7 +252,7 @@ class GeneratorEngine:
         """The pose head is a 1x1 convolution to 2*K = 242 channels, which no tensor-core tile divides.  In the TMA math modes it runs
         as a 256 -> 256 layer on zero-padded copies (weight rows / bias entries / gradient channels 242..255 are zero, 0.3 MB) so that
         its forward, data gradient and weight gradient use the tcgen05 kernels instead of three ~50 us FFMA launches.  0 = no padding."""
-        if ops.get_conv_math() >= 2 and self.kp2 % 64 != 0:
+        if self.math >= 2 and self.kp2 % 64 != 0:
             return -(-self.kp2 // 64) * 64
         return 0
 
@@ -260,7 +262,7 @@ class GeneratorEngine:
         TMA math modes the gradient is computed with a zero-padded copy of the weight (input channels 288 -> 320) into a
         320-channel buffer whose tail is zero; the resize / code adjoint reads it as 256 + 64 channels.  0 = no padding."""
         cin = 256 + self.code_dim
-        if ops.get_conv_math() >= 2 and cin % 64 != 0:
+        if self.math >= 2 and cin % 64 != 0:
             return -(-cin // 64) * 64
         return 0
 
@@ -303,7 +305,7 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
     self.fwd_id += 1
     self._mel = mel
     self._params = params
-    self.materialize = ops.get_conv_math() >= 2
+    self.materialize = self.math >= 2
     # math mode 2 with InstanceNorm and an invertible activation: the 1 -> 64 first block runs as the single-pass special
     # case (csrc/first_layer.cu): no raw map, no separate normalisation pass, closed-form weight gradient
     self.fused_first = self.materialize and self.norm == "IN" and slope > 0.0
@@ -346,7 +348,7 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
         wt, wt_nk = self._prep_weight(name, params[name + ".conv.weight"], g)
         raw = A.get("raw:" + name, (B, oh, ow, co))
         use_batch_stats = self.norm == "IN" or training
-        d = ops.fwd_desc(g, src, wt, raw, B, H, W, xf, slope, per_image=True, wt_nk=wt_nk)
+        d = ops.fwd_desc(g, src, wt, raw, B, H, W, xf, slope, per_image=True, wt_nk=wt_nk, math=self.math)
         if use_batch_stats:
             partial = A.get("partial:" + name, (ops.row_tiles(d), 2, co))
             d.stat_partial = partial.data_ptr()
@@ -394,7 +396,7 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
         acts["in:" + name] = xin
         wt, wt_nk = self._prep_weight(name, params[name + ".conv.weight"], g)
         raw = A.get("raw:" + name, (B, L_out, 256))
-        d = ops.fwd_desc(g, xin, wt, raw, B, 1, L_in, wt_nk=wt_nk)
+        d = ops.fwd_desc(g, xin, wt, raw, B, 1, L_in, wt_nk=wt_nk, math=self.math)
         act = A.get("act:" + name, (B, L_out, 256))
         if self.norm == "IN":
             ops.conv_gemm(d)
@@ -424,12 +426,12 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
         gl = ConvGeom.conv1d(256, npad, 1, 1, 0)
         wt, wt_nk = self._prep_weight("decoder.4", params["decoder.4.weight_pad"], gl)
         pred_pad = A.get("pred_pad", (B, num_frames, npad))
-        ops.conv_gemm(ops.fwd_desc(gl, acts["decoder.3"], wt, pred_pad, B, 1, num_frames, bias=params["decoder.4.bias_pad"], wt_nk=wt_nk))
+        ops.conv_gemm(ops.fwd_desc(gl, acts["decoder.3"], wt, pred_pad, B, 1, num_frames, bias=params["decoder.4.bias_pad"], wt_nk=wt_nk, math=self.math))
         pred.copy_(pred_pad[..., :self.kp2])
         return pred
     gl = ConvGeom.conv1d(256, self.kp2, 1, 1, 0)
     wt, wt_nk = self._prep_weight("decoder.4", params["decoder.4.weight"], gl)
-    ops.conv_gemm(ops.fwd_desc(gl, acts["decoder.3"], wt, pred, B, 1, num_frames, bias=params["decoder.4.bias"], wt_nk=wt_nk))
+    ops.conv_gemm(ops.fwd_desc(gl, acts["decoder.3"], wt, pred, B, 1, num_frames, bias=params["decoder.4.bias"], wt_nk=wt_nk, math=self.math))
     return pred
 
 
@@ -469,17 +471,17 @@ def _wgrad_join(self):
 
 def _wgrad_now(self, g, x, dy, B, H, W, grad_out, xf=None, slope=1.0):
     oh, ow = g.out_hw(H, W)
-    splits = ops.wgrad_splits(g, B, oh, ow)
+    splits = ops.wgrad_splits(g, B, oh, ow, math=self.math)
     need = splits * g.cout * g.k
     ws = self.arena.get("wgrad_ws", (max(need, getattr(self, "_ws_elems", 0)),))
     self._ws_elems = ws.numel()
-    ops.conv_wgrad(ops.wgrad_desc(g, x, dy, ws, B, H, W, splits, xf, slope))
+    ops.conv_wgrad(ops.wgrad_desc(g, x, dy, ws, B, H, W, splits, xf, slope, math=self.math))
     ops.wgrad_reduce(ws, splits, g, grad_out)
 
 
 def _dgrad(self, name, g, dy, w, dx, B, H, W, accumulate=False):
     # stride-parity classes with their weight operands, prepared at the start of the step by the batched launch
-    ops.conv_gemm_multi([ops.dgrad_desc(g, cls, dy, wt, dx, B, H, W, accumulate, wt_nk=wt_nk)
+    ops.conv_gemm_multi([ops.dgrad_desc(g, cls, dy, wt, dx, B, H, W, accumulate, wt_nk=wt_nk, math=self.math)
                          for cls, wt, wt_nk in self.wprep.dgrad[name]])
 
 
@@ -614,14 +616,15 @@ class PoseEncoderEngine:
     """PoseSeqEncoder (autoencoder.py:8-35), forward only: BatchNorm in train mode (batch statistics, running-stat
     update) or eval mode.  Raw conv outputs + per-channel (scale, shift); activations never materialised."""
 
-    def __init__(self, n_landmarks, code_dim, leaky, device):
+    def __init__(self, n_landmarks, code_dim, leaky, device, math=None):
         self.kp2 = n_landmarks * 2
         self.code2 = code_dim * 2
         self.slope = 0.2 if leaky else 0.0
+        self.math = ops.resolve_math(math)
         self.arena = Arena(device)
         self.geoms = ([ConvGeom.conv1d(self.kp2, 256, 3, 1, 1), ConvGeom.conv1d(256, 256, 3, 1, 1)]
                       + [ConvGeom.conv1d(256, 256, 4, 2, 1)] * 4 + [ConvGeom.conv1d(256, self.code2, 4, 2, 1)])
-        self.wprep = WeightPrep(self.arena)
+        self.wprep = WeightPrep(self.arena, self.math)
 
     def param_shapes(self):
         shapes = {}
@@ -638,7 +641,7 @@ class PoseEncoderEngine:
         src, xf = poses.view(B, 1, L, self.kp2), None
         # TMA-fed tensor-core path (math modes 2, 3): the 242 input channels are zero-padded to 256 (K-block = 32 channels)
         # and every block's activation is materialised (2 MB), because TMA delivers plain tensors only
-        tma = ops.get_conv_math() >= 2
+        tma = self.math >= 2
         cpad = -(-self.kp2 // 32) * 32 if tma else 0
         if tag in ("", "/pred"):        # the two FGD passes of a step share one weight refresh
             self.wprep.ensure([("blocks.%d" % i, "blocks.%d.conv.weight" % i, g, (1, 1), False, True, cpad if i == 0 else 0)
@@ -656,7 +659,7 @@ class PoseEncoderEngine:
                 g = ConvGeom.conv1d(src.shape[-1], g.cout, g.kw, g.sw, g.pw)
             raw = A.get("raw%s:%s" % (tag, name), (B, 1, lo, g.cout))
             # BN statistics span the batch (row tiles may straddle clips); scale/shift are per channel (bstride 0)
-            d = ops.fwd_desc(g, src, wt, raw, B, 1, L, xf, self.slope, wt_nk=wt_nk)
+            d = ops.fwd_desc(g, src, wt, raw, B, 1, L, xf, self.slope, wt_nk=wt_nk, math=self.math)
             sc = A.get("scale%s:%s" % (tag, name), (1, g.cout))
             sh = A.get("shift%s:%s" % (tag, name), (1, g.cout))
             if training:

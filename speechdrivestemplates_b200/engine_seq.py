@@ -28,7 +28,7 @@ class SeqBlock:
         wt, wt_nk = self.o.wprep.fwd[name]
         raw = A.get("raw%s:%s" % (tag, name), (B, L_out, g.cout))
         bias = params.get(name + ".bias") if self.norm is None else None
-        d = ops.fwd_desc(g, xin, wt, raw, B, 1, L_in, bias=bias, wt_nk=wt_nk)
+        d = ops.fwd_desc(g, xin, wt, raw, B, 1, L_in, bias=bias, wt_nk=wt_nk, math=self.o.math)
         if self.norm == "BN":
             sc = A.get("scale%s:%s" % (tag, name), (1, g.cout))
             sh = A.get("shift%s:%s" % (tag, name), (1, g.cout))
@@ -68,26 +68,27 @@ class SeqBlock:
             ops.colsum(g_act, grads[name + ".bias"], accumulate_params)
         g_raw = g_act
         oh, ow = g.out_hw(1, L_in)
-        splits = ops.wgrad_splits(g, B, oh, ow)
+        splits = ops.wgrad_splits(g, B, oh, ow, math=self.o.math)
         need = splits * g.cout * g.k
         ws = A.get("wgrad_ws", (max(need, getattr(self.o, "_ws_elems", 0)),))
         self.o._ws_elems = ws.numel()
-        ops.conv_wgrad(ops.wgrad_desc(g, xin, g_raw, ws, B, 1, L_in, splits))
+        ops.conv_wgrad(ops.wgrad_desc(g, xin, g_raw, ws, B, 1, L_in, splits, math=self.o.math))
         ops.wgrad_reduce(ws, splits, g, grads[self.wkey], accumulate_params)
         if not need_dx:
             return None
         if dx is None:
             dx = A.get("dx%s:%s" % (tag, name), (B, L_in, g.cin))
         for cls, wt, wt_nk in self.o.wprep.dgrad[name]:
-            ops.conv_gemm(ops.dgrad_desc(g, cls, g_raw, wt, dx, B, 1, L_in, accumulate_dx, wt_nk=wt_nk))
+            ops.conv_gemm(ops.dgrad_desc(g, cls, g_raw, wt, dx, B, 1, L_in, accumulate_dx, wt_nk=wt_nk, math=self.o.math))
         return dx
 
 
 class _SeqEngine:
-    def __init__(self, device):
+    def __init__(self, device, math=None):
         self.arena = Arena(device)
         self.device = device
-        self.wprep = WeightPrep(self.arena)
+        self.math = ops.resolve_math(math)       # this engine's convolution math mode (every descriptor carries it)
+        self.wprep = WeightPrep(self.arena, self.math)
         self.blocks = []
 
     def _prep(self, params, lengths, with_dgrad=True):
@@ -100,8 +101,8 @@ class AutoencoderEngine(_SeqEngine):
     """Autoencoder (autoencoder.py:71-92): PoseSeqEncoder -> reparameterisation -> PoseSeqDecoder; parameter names are
     relative to the Autoencoder module ('encoder.blocks.0.conv.weight', 'decoder.d5.norm.bias', 'decoder.blocks.4.bias')."""
 
-    def __init__(self, n_landmarks, code_dim, leaky, device):
-        super().__init__(device)
+    def __init__(self, n_landmarks, code_dim, leaky, device, math=None):
+        super().__init__(device, math)
         self.kp2, self.D = n_landmarks * 2, code_dim
         self.slope = 0.2 if leaky else 0.0
         s = self.slope
@@ -213,8 +214,8 @@ class AutoencoderEngine(_SeqEngine):
 class DiscriminatorEngine(_SeqEngine):
     """PoseSequenceDiscriminator (discriminator.py:6-23) on channels-last motion sequences (B,T,2K) -> scores (B,T')."""
 
-    def __init__(self, n_landmarks, leaky, device):
-        super().__init__(device)
+    def __init__(self, n_landmarks, leaky, device, math=None):
+        super().__init__(device, math)
         self.kp2 = n_landmarks * 2
         self.slope = 0.2 if leaky else 0.0
         s = self.slope

@@ -70,7 +70,22 @@ def _seq(*mods):
 
 
 class _EngineModule(nn.Module):
-    """Shared plumbing: lazily built engine, name-ordered parameter / buffer views."""
+    """Shared plumbing: lazily built engine, name-ordered parameter / buffer views.
+
+    ``conv_math`` (class default None = the process default at the time the engine is built, ``ops.set_conv_math``) is the math
+    mode of THIS module's engine; set it before the first forward (the fused trainers do, from their ``conv_math`` argument)."""
+
+    conv_math = None
+
+    def set_conv_math(self, mode):
+        """Math mode of this module's engine (and of its sub-engines); rebuilds the engine on the next call."""
+        self.conv_math = None if mode is None else int(mode)
+        for attr in ("_eng", "_ae_eng", "_d_eng"):
+            if hasattr(self, attr):
+                setattr(self, attr, None)
+        for child in self.children():
+            if isinstance(child, _EngineModule):
+                child.set_conv_math(mode)
 
     def _device(self):
         return next(self.parameters()).device
@@ -133,7 +148,7 @@ class SequenceGeneratorCNN(_EngineModule):
     def engine(self):
         dev = self._device()
         if self._eng is None or self._eng.device != dev:
-            self._eng = E.GeneratorEngine(self.norm_kind, self.leaky, self.code_dim, self.n_landmarks, dev)
+            self._eng = E.GeneratorEngine(self.norm_kind, self.leaky, self.code_dim, self.n_landmarks, dev, self.conv_math)
         return self._eng
 
     def forward(self, x, num_frames, code=None):
@@ -198,7 +213,7 @@ class PoseSeqEncoder(_EngineModule):
     def engine(self):
         dev = self._device()
         if self._eng is None or self._eng.arena.device != dev:
-            self._eng = E.PoseEncoderEngine(self.n_landmarks, self.code_dim, self.leaky, dev)
+            self._eng = E.PoseEncoderEngine(self.n_landmarks, self.code_dim, self.leaky, dev, self.conv_math)
         return self._eng
 
     def forward(self, x):
@@ -250,7 +265,7 @@ class Autoencoder(_EngineModule):
         from .engine_seq import AutoencoderEngine
         dev = self._device()
         if self._ae_eng is None or self._ae_eng.device != dev:
-            self._ae_eng = AutoencoderEngine(self.n_landmarks, self.code_dim, self.leaky, dev)
+            self._ae_eng = AutoencoderEngine(self.n_landmarks, self.code_dim, self.leaky, dev, self.conv_math)
         return self._ae_eng
 
     def forward(self, x, num_frames, mel=None, external_code=None):
@@ -320,7 +335,7 @@ class PoseSequenceDiscriminator(_EngineModule):
         from .engine_seq import DiscriminatorEngine
         dev = self._device()
         if self._d_eng is None or self._d_eng.device != dev:
-            self._d_eng = DiscriminatorEngine(self.n_landmarks, self.leaky, dev)
+            self._d_eng = DiscriminatorEngine(self.n_landmarks, self.leaky, dev, self.conv_math)
         return self._d_eng
 
     def forward(self, x):

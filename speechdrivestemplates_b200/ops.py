@@ -127,14 +127,27 @@ class ConvGeom:
 
 
 def set_conv_math(mode):
-    """0 = fp32 FFMA kernels, 1 = tcgen05 TF32 tensor-core kernels where a layer is eligible, 2 = 1 with TMA-delivered
-    operands, 3 = 2 with the persistent kernel (shared-memory operand reuse across vertical taps / accumulators, image-spanning
-    patches, parity classes in one launch), 4 = 3 with CTA pairs (experimental).  Process-wide."""
+    """PROCESS DEFAULT of the convolution math mode: 0 = fp32 FFMA kernels, 1 = tcgen05 TF32 tensor-core kernels where a layer
+    is eligible, 2 = 1 with TMA-delivered operands, 3 = 2 with the persistent kernel (shared-memory operand reuse across
+    vertical taps / accumulators, image-spanning patches, parity classes in one launch), 4 = 3 with CTA pairs (experimental).
+
+    The default starts at 3 (SDT_CONV_MATH in the environment overrides it).  It is what an engine built without an explicit
+    ``conv_math`` captures at construction and what the single-shot helpers of this module use; every engine then passes ITS
+    mode per descriptor (``sdt_conv_desc.math``), so changing the default never changes a live engine."""
     call("sdt_set_conv_math", int(mode))
 
 
 def get_conv_math():
     return call("sdt_get_conv_math")
+
+
+def resolve_math(math):
+    """An explicit mode, or the process default when ``math`` is None."""
+    return get_conv_math() if math is None else int(math)
+
+
+def _set_math(d, math):
+    d.math = 0 if math is None else int(math) + 1          # 0 = process default (include/sdt_b200.h)
 
 
 def tc_eligible(cin, cout):
@@ -143,9 +156,10 @@ def tc_eligible(cin, cout):
 
 
 def fwd_desc(g, x, wt, dst, B, H, W, xf=None, slope=1.0, bias=None, stat_partial=None, per_image=False, accumulate=False,
-             wt_nk=None):
+             wt_nk=None, math=None):
     oh, ow = g.out_hw(H, W)
     d = ConvDesc()
+    _set_math(d, math)
     d.src, d.bias, d.dst = x.data_ptr(), bias.data_ptr() if bias is not None else None, dst.data_ptr()
     d.wt = wt.data_ptr() if wt is not None else None
     d.wt_nk = wt_nk.data_ptr() if wt_nk is not None else None
@@ -165,10 +179,11 @@ def fwd_desc(g, x, wt, dst, B, H, W, xf=None, slope=1.0, bias=None, stat_partial
     return d
 
 
-def dgrad_desc(g, cls, dy, wt_cls, dx, B, H, W, accumulate=False, wt_nk=None):
+def dgrad_desc(g, cls, dy, wt_cls, dx, B, H, W, accumulate=False, wt_nk=None, math=None):
     """Data gradient for one stride-parity class: dx[b, q*s+py, ...] = sum_taps dy[...] * W."""
     oh, ow = g.out_hw(H, W)
     d = ConvDesc()
+    _set_math(d, math)
     d.src, d.dst = dy.data_ptr(), dx.data_ptr()
     d.wt = wt_cls.data_ptr() if wt_cls is not None else None
     d.wt_nk = wt_nk.data_ptr() if wt_nk is not None else None
@@ -186,9 +201,10 @@ def dgrad_desc(g, cls, dy, wt_cls, dx, B, H, W, accumulate=False, wt_nk=None):
     return d
 
 
-def wgrad_desc(g, x, dy, wpart, B, H, W, splits, xf=None, slope=1.0):
+def wgrad_desc(g, x, dy, wpart, B, H, W, splits, xf=None, slope=1.0, math=None):
     oh, ow = g.out_hw(H, W)
     d = ConvDesc()
+    _set_math(d, math)
     d.src, d.dy, d.wpart = x.data_ptr(), dy.data_ptr(), wpart.data_ptr()
     if xf is not None:
         d.xf_scale, d.xf_shift, d.xf_bstride = xf[0].data_ptr(), xf[1].data_ptr(), xf[2]
@@ -202,13 +218,13 @@ def wgrad_desc(g, x, dy, wpart, B, H, W, splits, xf=None, slope=1.0):
     return d
 
 
-def wgrad_splits(g, B, oh, ow, target_ctas=444):
+def wgrad_splits(g, B, oh, ow, target_ctas=444, math=None):
     """Number of K (pixel) splits so that the weight-gradient GEMM fills the 148 SMs ~3 times over -- but never fewer than
     256 pixels (8 k-blocks of the tensor-core kernel) per split: every split writes, and the reduction re-reads, a full
     copy of the layer's gradient, which for the 1-D stacks (2048 pixels, 0.8 MB of weights) used to be 32 copies per layer."""
     if g.k <= 16 and g.cout <= 64:          # streaming small-K kernel: one partial per CTA, 4 CTAs per SM
         return min(148 * 4, max(1, -(-(B * oh * ow) // 64)))
-    if get_conv_math() >= 3 and g.cin % 128 == 0 and g.cout % 128 == 0 and g.kh >= 2 and oh >= 2:
+    if resolve_math(math) >= 3 and g.cin % 128 == 0 and g.cout % 128 == 0 and g.kh >= 2 and oh >= 2:
         # csrc/tc_wgrad_ytap.cu: one CTA per SM and per (128-channel block, kernel column, group of <= 3 vertical taps, N tile)
         groups = sum(-(-(-(-(g.kh - p) // g.sh)) // 3) for p in range(min(g.sh, g.kh)))
         tiles = (g.cin // 128) * g.kw * groups * (g.cout // 128)

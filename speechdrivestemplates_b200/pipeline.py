@@ -266,6 +266,13 @@ class Voice2PoseModel(nn.Module):
             self._step_engine = Voice2PoseStepEngine(self)
         return self._step_engine
 
+    def set_conv_math(self, mode):
+        """Convolution math mode of every engine of this model (networks._EngineModule.set_conv_math)."""
+        for name in ("netG", "pose_encoder", "netD_pose"):
+            mod = getattr(self, name, None)
+            if mod is not None:
+                mod.set_conv_math(mode)
+
     def _p2g_stats(self, batch, dataset, device):
         """Parted and global statistics of the batch's (single) speaker as fp32 device tensors (gesture_dataset.py:228-229)."""
         if "stat_parted" in batch and batch["stat_parted"] is not None:
@@ -399,14 +406,16 @@ class Voice2PoseTrainer:
     def __init__(self, cfg, num_train_samples, device, use_cuda_graph=True, process_group=None, seed=0, conv_math=None):
         self.cfg = cfg
         self.device = torch.device(device)
-        if conv_math is not None:          # 0 = fp32 FFMA, 1 = tcgen05 TF32 (the reference's own GPU default: cudnn.allow_tf32)
-            ops.set_conv_math(conv_math)
+        # convolution math mode of THIS trainer's engines (None = the process default, 3 = tcgen05 TF32 unless SDT_CONV_MATH /
+        # ops.set_conv_math say otherwise); 0 = fp32 FFMA.  TF32 is the reference's own GPU default (cudnn.allow_tf32)
+        self.conv_math = ops.resolve_math(conv_math)
         self.has_d = cfg.VOICE2POSE.POSE_DISCRIMINATOR.NAME is not None
         if self.has_d and cfg.VOICE2POSE.POSE_DISCRIMINATOR.WHITE_LIST is not None:
             raise NotImplementedError("the fused trainer feeds the discriminator all keypoints (POSE_DISCRIMINATOR.WHITE_LIST=None); "
                                       "a white list trains through the drop-in Voice2PoseModel (tests/test_gpu_step.py)")
         torch.manual_seed(seed)                                       # main.py:37
         self.model = Voice2PoseModel(cfg, num_train_samples=num_train_samples).to(self.device)
+        self.model.set_conv_math(self.conv_math)
         ae_ckpt = cfg.VOICE2POSE.POSE_ENCODER.AE_CHECKPOINT
         if cfg.VOICE2POSE.POSE_ENCODER.NAME is not None and ae_ckpt is not None:      # voice2pose.py:234-242
             ckpt = torch.load(ae_ckpt, map_location="cpu")
@@ -791,10 +800,10 @@ class Pose2PoseTrainer:
     def __init__(self, cfg, num_train_samples, device, use_cuda_graph=True, process_group=None, seed=0, conv_math=None):
         self.cfg = cfg
         self.device = torch.device(device)
-        if conv_math is not None:
-            ops.set_conv_math(conv_math)
+        self.conv_math = ops.resolve_math(conv_math)
         torch.manual_seed(seed)
         self.model = Pose2PoseModel(cfg, num_train_samples=num_train_samples).to(self.device)
+        self.model.ae.set_conv_math(self.conv_math)
         self.model.train()
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1

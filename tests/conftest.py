@@ -7,6 +7,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+# The library's process-default convolution math mode is 3 (tcgen05 TF32).  The suite pins the default to the fp32 FFMA
+# mode (tight 1e-4 tolerances); every TF32 test asks for its mode explicitly (conv_math=... / ops.set_conv_math).
+os.environ["SDT_CONV_MATH"] = "0"
 
 
 def pytest_configure(config):

@@ -149,13 +149,29 @@ def test_sdt_bp_step_matches_oracle_fp64_and_shards():
     assert rel_err(out1["poses_pred_batch"].cpu().numpy(), out["poses_pred_batch"][2:3].cpu().numpy()) < 1e-5
 
 
-def test_generator_backward_smooth_activation_vs_fp64_oracle():
+# per math mode: (prediction rel. to its range, max gradient error / rms, gradient rel. L2 error, code-gradient rel.)
+# mode 0 = fp32 FFMA: the fp32 noise floor of the earliest layers is ~1e-3 of rms.  modes 3 / 4 = tcgen05 kind::tf32: both
+# operands of every product keep 10 mantissa bits (relative rounding 2^-11 = 4.9e-4 each, fp32 accumulation), and the error
+# random-walks through the 24 convolutions of the backward chain -- stated TF32 bound: 3e-3 of rms in the L2 sense per
+# tensor, 2e-2 of rms for the worst single element (measured 1.7e-3 / 1.2e-2, profiles/r2_parity_tf32.txt).
+SMOOTH_TOL = {0: (1e-4, 5e-3, 2e-3, 1e-3), 3: (3e-3, 2e-2, 3e-3, 5e-3), 4: (3e-3, 2e-2, 3e-3, 5e-3)}
+
+
+@pytest.mark.parametrize("mode", [0, 3, 4])
+def test_generator_backward_smooth_activation_vs_fp64_oracle(mode):
     """Backward wiring of the whole generator at a tight tolerance: with negative slope 1.0 (identity activation) the
     network stays non-linear through its IN2d / channel-LayerNorm layers but has no derivative discontinuity, so the
-    fp32 CUDA gradients must agree with the fp64 oracle to the fp32 noise floor."""
-    from speechdrivestemplates_b200 import engine, pipeline
+    CUDA gradients must agree with the fp64 oracle to the noise floor of the arithmetic: fp32 in mode 0, TF32 operands
+    in modes 3 / 4 (the benchmarked tcgen05 forward / data-gradient / weight-gradient kernels, every layer).
+
+    Mode 0 back-propagates the L1 loss itself.  In the TF32 modes the loss is the linear functional sum(pred * G) with a
+    fixed random G: the gradient of L1 is sign(pred - gt), and the 1e-3 TF32 deviation of the prediction flips ~2.5e-4 of
+    those signs, which alone moves EVERY gradient (even the bias column sums) by 3e-2 in the L2 sense (measured,
+    profiles/r2_parity_tf32.txt) and hides the arithmetic under test."""
+    from speechdrivestemplates_b200 import _lib, engine, pipeline
     from oracle import sdt_oracle as O
     B = 4
+    tol_pred, tol_max, tol_l2, tol_code = SMOOTH_TOL[mode]
     cfgo = O.make_cfg("voice2pose_sdt_bp", g_leaky=1.0)
     torch.manual_seed(0)
     sd = O.init_generator(cfgo)
@@ -167,26 +183,78 @@ def test_generator_backward_smooth_activation_vs_fp64_oracle():
     code64 = code.double().requires_grad_(True)
     mel64 = O.mel_spectrogram(audio, dtype=torch.float64)
     pred64 = O.generator_forward(mel64, 64, code64, sd64, cfgo, True, "netG.")
-    loss = torch.abs(pred64 - gt.double()).mean()
+    G = torch.randn(B, 64, 2, 121, generator=g) / gt.numel()
+    loss = torch.abs(pred64 - gt.double()).mean() if mode == 0 else (pred64 * G.double()).sum()
     names = list(sd64)
     gr = torch.autograd.grad(loss, [sd64[k] for k in names] + [code64])
-    eng = engine.GeneratorEngine("IN", 1.0, 32, 121, dev())
+    eng = engine.GeneratorEngine("IN", 1.0, 32, 121, dev(), math=mode)
     params = {k[len("netG."):]: v.to(dev()).contiguous() for k, v in sd.items()}
     mel = pipeline.MelSpectrogram().to(dev())(audio.to(dev()))
+    n_tc = _lib.call("sdt_tc_launches")
     pred = eng.forward(mel, 64, code.to(dev()).contiguous(), params)
-    assert rel_err(pred.view(B, 64, 2, 121).cpu().numpy(), pred64.detach().numpy()) < 1e-4
+    assert rel_err(pred.view(B, 64, 2, 121).cpu().numpy(), pred64.detach().numpy()) < tol_pred
     from speechdrivestemplates_b200 import ops
     g_pred = torch.empty(B, 64, 242, device=dev())
     ops.l1_loss(pred, gt.to(dev()).view(B, 64, 242).contiguous(), 1.0, torch.empty(1, device=dev()), g_pred, torch.empty(1024, device=dev()))
+    if mode != 0:
+        g_pred = G.to(dev()).view(B, 64, 242).contiguous()
     grads = {k: torch.empty_like(v) for k, v in params.items()}
     g_code = torch.empty(B, 32, device=dev())
     eng.backward(g_pred, grads, g_code)
+    torch.cuda.synchronize()
+    if mode >= 3:          # 7 encoder forwards + 7 data gradients + 8 weight gradients + the 1-D stacks ran on tcgen05 kernels
+        assert _lib.call("sdt_tc_launches") - n_tc >= 60
+    else:
+        assert _lib.call("sdt_tc_launches") == n_tc
+    table = []
     for k, ref in zip(names, gr[:-1]):
         ref = ref.numpy()
+        got = grads[k[len("netG."):]].cpu().numpy().astype(np.float64)
         rms = float(np.sqrt((ref ** 2).mean())) + 1e-30
-        err = np.abs(grads[k[len("netG."):]].cpu().numpy() - ref).max() / rms
-        assert err < 5e-3, (k, err)          # fp32 noise floor of the earliest layers is ~1e-3 of rms
-    assert rel_err(g_code.cpu().numpy(), gr[-1].numpy()) < 1e-3
+        table.append((k, np.abs(got - ref).max() / rms, np.linalg.norm((got - ref).ravel()) / (np.linalg.norm(ref.ravel()) + 1e-30)))
+    print("smooth-activation backward, math mode %d: gradient max-err/rms, rel-L2 per tensor" % mode)
+    for k, err, l2 in table:
+        print("  %-60s %.2e %.2e" % (k, err, l2))
+    for k, err, l2 in table:
+        assert err < tol_max and l2 < tol_l2, (mode, k, err, l2)
+    assert rel_err(g_code.cpu().numpy(), gr[-1].numpy()) < tol_code
+
+
+def test_sdt_bp_step_batch32_tf32_vs_cpu_oracle():
+    """BASELINE configs[1] exactly as bench.py runs it -- batch 32, math mode 3 (tcgen05 TF32, the tile plans of the full
+    80 x 427 maps: image-spanning patches, 560 / 140-tile persistent grids, fused parity classes) -- against the fp32 CPU
+    oracle on the same seeded inputs.  Stated TF32 tolerance: losses 1e-3 (relative to max(1, |loss|)), prediction 5e-3 of
+    its range, f64 final results 5e-3; the clip-code gradient (a short path: L1 -> 1-D stacks -> code) 2e-2 of its max;
+    every generator gradient within 0.25 relative L2 and cosine > 0.97 of the oracle's (TF32 rounding moves ~0.1 % of the
+    LeakyReLU units across zero, tests/diag_grad_noise.py; the tight TF32 gradient check is the smooth-activation test)."""
+    from speechdrivestemplates_b200 import _lib, pipeline
+    from oracle import sdt_oracle as O
+    n_train, bs = 4096, 32
+    orc = O.Voice2PoseOracle(O.make_cfg("voice2pose_sdt_bp"), n_train, seed=0)
+    code0 = 0.1 * torch.randn(n_train, 32, generator=torch.Generator().manual_seed(11))
+    orc.sd["clips_code"] = code0.clone()
+    batch = O.synthetic_batch(bs, n_train, oliver_stat(True), seed=1000)
+    losses, results, grads = orc.train_step(batch)
+    tr = pipeline.Voice2PoseTrainer(_cfg("voice2pose_sdt_bp"), n_train, dev(), use_cuda_graph=False, seed=0, conv_math=3)
+    tr.model.clips_code.data.copy_(code0)
+    n_tc = _lib.call("sdt_tc_launches")
+    out = tr.train_step(_to_host_batch(batch))
+    host = tr.losses_to_host(out)
+    assert _lib.call("sdt_tc_launches") - n_tc >= 60
+    for k in ("G_reg_loss", "G_loss", "G_clipcode_kl_loss"):
+        ref = float(losses[k])
+        assert abs(host[k] - ref) <= 1e-3 * max(1.0, abs(ref)), (k, host[k], ref)
+    assert rel_err(out["poses_pred_batch"].cpu().numpy(), results["poses_pred_batch"].detach().numpy()) < 5e-3
+    assert rel_err(out["final_pred"].cpu().numpy(), results["final_pred"]) < 5e-3
+    assert np.array_equal(out["final_gt"].cpu().numpy(), results["final_gt"])           # f64 path on identical f32 input
+    assert rel_err(out["mu_gt"].cpu().numpy(), results["mu_gt"].detach().numpy()) < 5e-3
+    ref = grads["clips_code"].numpy()
+    assert np.abs(tr.g_table.cpu().numpy() - ref).max() <= 2e-2 * np.abs(ref).max()
+    for n, t in tr.grads.items():
+        a, b = t.double().flatten().cpu(), grads["netG." + n].double().flatten()
+        err = float((a - b).norm() / (b.norm() + 1e-30))
+        cos = float((a * b).sum() / (a.norm() * b.norm() + 1e-30))
+        assert err < 0.25 and cos > 0.97, (n, err, cos)
 
 
 def test_cuda_graph_replay_equals_eager_and_dropin_autograd():

@@ -276,14 +276,15 @@ int sdt_pose_parted2global(const float* poses, int64_t n_rows, const float* mean
 int sdt_pose_metrics(const double* pred, const double* gt, int B, int T, double* partial, double* out, void* stream);
 
 /* ---- optimizer ----------------------------------------------------------------------------------
- * torch.optim.Adam (voice2pose.py:249,263,274; pose2pose.py:114), wd = 0, over a flat fp32 buffer.
+ * torch.optim.Adam (voice2pose.py:249,263,274; pose2pose.py:114) over a flat fp32 buffer; weight_decay is Adam's L2 term
+ * (grad += weight_decay * param, cfg.TRAIN.WD at voice2pose.py:250; 0 in every shipped config).
  * state_host-free: scalars (step count -> bias corrections) live in `scalars` (device, 4 floats + 1 i64 as 8 floats):
  *   sdt_adam_advance bumps the step and recomputes them on device so that a captured CUDA graph can replay
  *   (lr < 0: take the learning rate from scalars[3], so a schedule can change it between replays);
  *   grad_scale multiplies the gradient first (1/world_size after the NCCL sum). */
 int sdt_adam_advance(float* scalars, float lr, double beta1, double beta2, void* stream);
 int sdt_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* scalars,
-                  double beta1, double beta2, double eps, float grad_scale, void* stream);
+                  double beta1, double beta2, double eps, float grad_scale, float weight_decay, void* stream);
 
 #ifdef __cplusplus
 }

@@ -579,20 +579,36 @@ class Voice2PoseOracle:
             st["t"] += 1
             adam_update(self.sd[n], g, st["m"], st["v"], st["t"], lr)
 
-    def forward(self, batch, taps=None):
-        """Voice2PoseModel.forward in training mode with return_loss=True."""
+    def forward(self, batch, taps=None, training=True, code=None):
+        """Voice2PoseModel.forward with return_loss=True (voice2pose.py:84-210).
+
+        training=True: ``model.train()`` -- clip codes gathered from the table (:94), BatchNorm layers on batch statistics.
+        training=False: ``model.eval()`` (Voice2Pose.test_step, :333-352) -- BatchNorm from running statistics; the code is
+        ``code`` if given, else mu of the ground-truth poses when cfg['test_with_gt_code'] (:100-106); the reference's other
+        eval-time selections are random draws and have to be passed in as ``code``.  The loss terms are the same either way."""
         cfg, sd = self.cfg, self.sd
         audio = batch["audio"].to(self.dtype)
         gt = batch["poses"].to(self.dtype)
         nf = int(batch["num_frames"][0])
-        code = None
-        if cfg["code_dim"] is not None:
-            table = batch["external_code_table"] if cfg["external_code"] else sd["clips_code"]
-            code = table[batch["clip_index"]].to(self.dtype)               # voice2pose.py:94
+
+        def fgd_input(x):
+            if cfg["hierarchical"]:
+                return x
+            return transform_normalized_parted2global(x, batch["stat_parted"], batch["stat_global"])
+
+        if cfg["code_dim"] is not None and code is None:
+            if training:
+                table = batch["external_code_table"] if cfg["external_code"] else sd["clips_code"]
+                code = table[batch["clip_index"]].to(self.dtype)               # voice2pose.py:94
+            elif cfg.get("test_with_gt_code"):
+                with torch.no_grad():
+                    code, _ = pose_encoder_forward(fgd_input(gt), sd, cfg, False)
+            else:
+                raise ValueError("eval forward: pass the (randomly selected) condition code explicitly")
         mel = mel_spectrogram(audio, sd["mel_transfm.spectrogram.window"], sd["mel_transfm.mel_scale.fb"], self.dtype)
         if taps is not None:
             taps["mel"] = mel
-        pred = generator_forward(mel, nf, code, sd, cfg, True, "netG.", taps)
+        pred = generator_forward(mel, nf, code, sd, cfg, training, "netG.", taps)
         losses = OrderedDict()
         reg = (torch.abs(pred - gt) * cfg["lambda_reg"]).mean()           # voice2pose.py:141-142
         losses["G_reg_loss"] = reg
@@ -605,21 +621,17 @@ class Voice2PoseOracle:
         losses["G_loss"] = g_loss
         results = {"poses_pred_batch": pred, "poses_gt_batch": gt, "condition_code": code}
         if cfg["pose_encoder"]:
-            with torch.no_grad():       # voice2pose.py:162-176; BN in train mode
-                pe_pred, pe_gt = pred.detach(), gt
-                if not cfg["hierarchical"]:
-                    pe_pred = transform_normalized_parted2global(pe_pred, batch["stat_parted"], batch["stat_global"])
-                    pe_gt = transform_normalized_parted2global(pe_gt, batch["stat_parted"], batch["stat_global"])
-                results["mu_pred"], results["logvar_pred"] = pose_encoder_forward(pe_pred, sd, cfg, True)
-                results["mu_gt"], results["logvar_gt"] = pose_encoder_forward(pe_gt, sd, cfg, True)
+            with torch.no_grad():       # voice2pose.py:162-176; BN follows the model's mode (train in a train step)
+                results["mu_pred"], results["logvar_pred"] = pose_encoder_forward(fgd_input(pred.detach()), sd, cfg, training)
+                results["mu_gt"], results["logvar_gt"] = pose_encoder_forward(fgd_input(gt), sd, cfg, training)
         if cfg["disc"]:                 # voice2pose.py:179-208
             real, fake = gt, pred
             if cfg["d_motion"]:
                 real = real[:, 1:] - real[:, :-1]
                 fake = fake[:, 1:] - fake[:, :-1]
-            s_real = discriminator_forward(real, sd, cfg, True)
-            s_fake = discriminator_forward(fake, sd, cfg, True)
-            s_fake_d = discriminator_forward(fake.detach(), sd, cfg, True)
+            s_real = discriminator_forward(real, sd, cfg, training)
+            s_fake = discriminator_forward(fake, sd, cfg, training)
+            s_fake_d = discriminator_forward(fake.detach(), sd, cfg, training)
             g_gan = F.mse_loss(s_fake, torch.ones_like(s_fake)) * cfg["lambda_gan"]
             losses["G_pose_gan_loss"] = g_gan
             losses["G_loss"] = g_loss + g_gan

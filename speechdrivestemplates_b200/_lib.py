@@ -78,7 +78,7 @@ SIGNATURES = {
     "sdt_pose_parted2global": [c_ptr, i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     "sdt_pose_metrics": [c_ptr, c_ptr, i32, i32, c_ptr, c_ptr, c_ptr],
     "sdt_adam_advance": [c_ptr, f32, f64, f64, c_ptr],
-    "sdt_adam_flat": [c_ptr, c_ptr, c_ptr, c_ptr, i64, c_ptr, f64, f64, f64, f32, c_ptr],
+    "sdt_adam_flat": [c_ptr, c_ptr, c_ptr, c_ptr, i64, c_ptr, f64, f64, f64, f32, f32, c_ptr],
 }
 _RESTYPES = {"sdt_last_error": C.c_char_p, "sdt_tc_launches": C.c_int64}
 # entry points whose int return value is a result, not a status

@@ -113,4 +113,45 @@ def load_voice2pose(trainer, ckpt, strict=True):
         d_params = [p for _, p in m.netD_pose.named_parameters()]
         _load_optimizer_state(trainer, ckpt["optimizerD_pose_state_dict"], trainer.d_names, d_params, trainer.off_d, trainer.adam_d)
     trainer.set_lr(lr)
+    trainer._graphs = None          # captured graphs hold the old mel band tables / weight-operand tables: re-capture
+    if hasattr(m.mel_transfm, "_tables_key"):
+        m.mel_transfm._tables_key = None
+    return int(ckpt["epoch"]), int(ckpt["step"])
+
+
+def pose2pose_checkpoint(trainer, epoch, step):
+    """The dict ``Trainer.save_checkpoint`` would ``torch.save`` for a ``pipeline.Pose2PoseTrainer`` (trainer.py:305-321 with
+    the single optimizer named 'optimizer', pose2pose.py:114): ``module.clip_code_mu`` / ``module.clip_code_logvar`` /
+    ``module.mel_transfm.*`` / ``module.ae.*`` + ``optimizer_state_dict``.  This is the file VOICE2POSE.POSE_ENCODER.AE_CHECKPOINT
+    and CLIP_CODE.EXTERNAL_CODE of voice2pose_sdt_vae read (voice2pose.py:40-55,234-242)."""
+    m = trainer.model
+    params = [p for _, p in m.ae.named_parameters()]
+    return {"epoch": int(epoch), "step": int(step),
+            "model_state_dict": OrderedDict(("module." + k, v.detach().clone().cpu()) for k, v in m.state_dict().items()),
+            "optimizer_state_dict": _optimizer_state(trainer, trainer.names, params, 0, trainer.adam, trainer.lr,
+                                                     float(trainer.cfg.TRAIN.WD))}
+
+
+def save_pose2pose(trainer, path, epoch, step):
+    assert str(path).split(".")[-1] == "pth", "file type not supported: %s" % path        # trainer.py:173
+    torch.save(pose2pose_checkpoint(trainer, epoch, step), path)
+
+
+def load_pose2pose(trainer, ckpt):
+    """Resume a ``pipeline.Pose2PoseTrainer`` (pose2pose.py:104-119: strict state-dict load + optimizer state).  Returns (epoch, step)."""
+    if not isinstance(ckpt, dict):
+        ckpt = torch.load(ckpt, map_location="cpu")
+    m = trainer.model
+    sd = OrderedDict((k[len("module."):] if k.startswith("module.") else k, v) for k, v in ckpt["model_state_dict"].items())
+    own = m.state_dict()
+    missing = [k for k in own if k not in sd]
+    unexpected = [k for k in sd if k not in own]
+    if missing or unexpected:
+        raise RuntimeError("Error(s) in loading state_dict: missing %s, unexpected %s" % (missing, unexpected))
+    with torch.no_grad():
+        for k, v in sd.items():
+            own[k].copy_(v)
+    params = [p for _, p in m.ae.named_parameters()]
+    trainer.set_lr(_load_optimizer_state(trainer, ckpt["optimizer_state_dict"], trainer.names, params, 0, trainer.adam))
+    trainer._graphs = None
     return int(ckpt["epoch"]), int(ckpt["step"])

@@ -402,7 +402,7 @@ __global__ void adam_advance_kernel(float* scalars, float lr, double beta1, doub
 __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                         float* __restrict__ m, float* __restrict__ v, long long n,
                                                         const float* __restrict__ scalars, float beta1, float beta2,
-                                                        float omb1, float omb2, float eps, float grad_scale) {
+                                                        float omb1, float omb2, float eps, float grad_scale, float wd) {
     sdt::pdl_wait();
     sdt::pdl_launch_dependents();
     // omb1/omb2 = (float)(1 - beta) evaluated in double on the host, as torch does for add_(alpha=1-beta1)
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
         float mm[4] = {mv.x, mv.y, mv.z, mv.w}, vq[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float gq = gg[q] * grad_scale;
+            const float gq = wd != 0.f ? gg[q] * grad_scale + wd * pp[q] : gg[q] * grad_scale;   // grad.add(param, alpha=wd)
             mm[q] = beta1 * mm[q] + omb1 * gq;
             vq[q] = beta2 * vq[q] + omb2 * gq * gq;
             const float denom = sqrtf(vq[q]) * inv_sqrt_bc2 + eps;
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
     // tail
     if (blockIdx.x == 0) {
         for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
-            const float gq = g[i] * grad_scale;
+            const float gq = wd != 0.f ? g[i] * grad_scale + wd * p[i] : g[i] * grad_scale;
             const float mq = beta1 * m[i] + omb1 * gq;
             const float vq = beta2 * v[i] + omb2 * gq * gq;
             m[i] = mq; v[i] = vq;
@@ -560,15 +560,17 @@ extern "C" int sdt_adam_advance(float* scalars, float lr, double beta1, double b
 }
 
 extern "C" int sdt_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
-                             const float* scalars, double beta1, double beta2, double eps, float grad_scale, void* stream) {
+                             const float* scalars, double beta1, double beta2, double eps, float grad_scale, float weight_decay,
+                             void* stream) {
     SDT_REQUIRE(param && grad && exp_avg && exp_avg_sq && scalars && n > 0, "sdt_adam_flat: bad arguments");
+    SDT_REQUIRE(weight_decay >= 0.f, "sdt_adam_flat: negative weight_decay");
     SDT_REQUIRE((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0,
                 "sdt_adam_flat: buffers must be 16-byte aligned");
     int blocks = sdt::ceil_div(n / 4 + 1, 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     sdt::launch(adam_flat_kernel, dim3(blocks), dim3(256), 0, sdt::as_stream(stream), param, grad, exp_avg, exp_avg_sq, n, scalars, (float)beta1,
                                                                  (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2),
-                                                                 (float)eps, grad_scale);
+                                                                 (float)eps, grad_scale, weight_decay);
     SDT_LAUNCH_OK("adam_flat_kernel");
     return SDT_OK;
 }

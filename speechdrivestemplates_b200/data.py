@@ -55,9 +55,11 @@ class DeviceBatchBuilder:
                           poses=torch.empty(self.B, self.T, 2, 121, device=self.device)) for _ in range(2)]
         self._copy = torch.cuda.Stream(device=self.device)
         self._done = [torch.cuda.Event(), torch.cuda.Event()]       # upload + preprocessing of slot i finished
-        self._free = [torch.cuda.Event(), torch.cuda.Event()]       # consumer finished with slot i
-        for e in self._free:
+        self._free = [torch.cuda.Event(), torch.cuda.Event()]       # the H2D copies that read pinned set i have finished
+        self._consumed = [torch.cuda.Event(), torch.cuda.Event()]   # the consumer's last read of device set i (release())
+        for e in self._free + self._consumed:
             e.record(torch.cuda.current_stream(self.device))
+        self._handed = [False, False]                               # batch(i) handed out and not released yet
         self._slot = 0
 
     def pack(self, clips):
@@ -84,6 +86,11 @@ class DeviceBatchBuilder:
         """H2D on the copy stream + the keypoint pipeline (gather 122 of 137, neck-relative, parted, normalise) in one launch."""
         h, d = self._host[slot], self._dev[slot]
         cs = self._copy
+        if self._handed[slot]:
+            # the previous batch of this slot was never released: fall back to "everything enqueued on the consumer's
+            # stream so far" (correct for any consumer on the current stream, but serialises the upload behind the step in flight)
+            self.release(slot)
+        cs.wait_event(self._consumed[slot])                # the device set is overwritten only after its last reader
         with torch.cuda.stream(cs):
             for k in ("audio", "pose", "idx"):
                 d[k].copy_(h[k], non_blocking=True)
@@ -93,11 +100,22 @@ class DeviceBatchBuilder:
             self._done[slot].record(cs)
 
     def batch(self, slot):
-        """The reference's collated batch dict with device tensors; valid until the slot is packed again (two calls later)."""
+        """The reference's collated batch dict with device tensors.  The consumer calls ``batch["_release"]()`` (or
+        ``builder.release(slot)``) on the stream of its LAST read of these tensors -- ``Voice2PoseTrainer`` does so right after
+        its device-to-device staging copies -- and the next upload into this slot (two calls later) waits for exactly that
+        point.  Without a release the next upload waits for everything enqueued on the current stream at that time."""
         torch.cuda.current_stream(self.device).wait_event(self._done[slot])
         d = self._dev[slot]
+        self._handed[slot] = True
         return {"audio": d["audio"], "poses": d["poses"], "clip_index": d["idx"],
-                "num_frames": torch.full((self.B,), self.num_frames, dtype=torch.long), "speaker_stat": self.stat_dev}
+                "num_frames": torch.full((self.B,), self.num_frames, dtype=torch.long), "speaker_stat": self.stat_dev,
+                "_release": lambda stream=None, _s=slot: self.release(_s, stream)}
+
+    def release(self, slot, stream=None):
+        """The consumer is done reading the device tensors of ``slot`` once the work enqueued so far on ``stream`` (default: the
+        current stream) has run."""
+        self._consumed[slot].record(stream if stream is not None else torch.cuda.current_stream(self.device))
+        self._handed[slot] = False
 
     def __call__(self, clips):
         s = self.pack(clips)

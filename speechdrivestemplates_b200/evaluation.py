@@ -22,7 +22,7 @@ from . import ops
 def mutiply_batch(batch, multiple):
     """trainer.py:343-353 (the reference's spelling): every sample repeated `multiple` times, whole batch tiled."""
     if isinstance(batch, dict):
-        return {k: mutiply_batch(v, multiple) for k, v in batch.items()}
+        return {k: mutiply_batch(v, multiple) for k, v in batch.items() if not callable(v)}   # (drops data.py's "_release" hook)
     if isinstance(batch, list):
         return batch * multiple
     if isinstance(batch, torch.Tensor):

@@ -607,6 +607,6 @@ def adam_advance(scalars, lr, beta1=0.9, beta2=0.999):
     call("sdt_adam_advance", _p(scalars), lr, beta1, beta2, _stream())
 
 
-def adam_flat(param, grad, exp_avg, exp_avg_sq, scalars, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+def adam_flat(param, grad, exp_avg, exp_avg_sq, scalars, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, weight_decay=0.0):
     call("sdt_adam_flat", _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), _p(scalars), beta1, beta2, eps,
-         grad_scale, _stream())
+         grad_scale, float(weight_decay), _stream())

@@ -249,7 +249,10 @@ class Voice2PoseModel(nn.Module):
                     assert state_dict is not None, "No state_dict available, while no dataset is configured."
                     num_train_samples = state_dict["module.clips_code"].shape[0]
                 if ccfg.FRAME_VARIANT:
-                    raise NotImplementedError("CLIP_CODE.FRAME_VARIANT")
+                    # the reference builds an (N, D, NUM_FRAMES) table (voice2pose.py:66-67) but its own generator then fails:
+                    # generator.py:110 does code.unsqueeze(2).repeat([1, 1, T]) on the 3-D code -> a 4-D tensor repeated with 3
+                    # factors, a RuntimeError in torch.  The option cannot run in the reference either; refuse it up front.
+                    raise NotImplementedError("CLIP_CODE.FRAME_VARIANT (unusable in the reference too: generator.py:110)")
                 self.clips_code = nn.Parameter(torch.zeros(num_train_samples, ccfg.DIMENSION), requires_grad=bool(ccfg.TRAIN))
         else:
             self.clips_code = None
@@ -284,7 +287,7 @@ class Voice2PoseModel(nn.Module):
         f32 = lambda a: torch.as_tensor(a, dtype=torch.float64).float().to(device).contiguous()
         return (f32(sp["mean"]), f32(sp["std"]), f32(sg["mean"]), f32(sg["std"]))
 
-    def _condition_code(self, batch, clip_indices, audio, poses_gt, return_loss, interpolation_coeff):
+    def _condition_code(self, batch, dataset, clip_indices, audio, poses_gt, return_loss, interpolation_coeff):
         """Eval-time code selection (voice2pose.py:96-120)."""
         cfg = self.cfg
         ccfg = cfg.VOICE2POSE.GENERATOR.CLIP_CODE
@@ -294,7 +297,7 @@ class Voice2PoseModel(nn.Module):
         if ccfg.TEST_WITH_GT_CODE:
             assert cfg.VOICE2POSE.POSE_ENCODER.NAME is not None
             with torch.no_grad():
-                mu_gt, _ = self.pose_encoder(poses_gt)
+                mu_gt, _ = self.pose_encoder(self._fgd_input(poses_gt, batch, dataset))     # voice2pose.py:102-105
             return mu_gt
         table = self.clips_code.to(dev)
         if cfg.DEMO.CODE_INDEX is not None:
@@ -307,6 +310,35 @@ class Voice2PoseModel(nn.Module):
                 code = code * (1 - interpolation_coeff) + code_b * interpolation_coeff
             return code
         return table[torch.randint(table.size(0), (len(audio),)).to(dev)]
+
+    def _fgd_input(self, poses, batch, dataset):
+        """Input of the FGD feature extractor: the poses as they are (hierarchical statistics) or
+        ``dataset.transform_normalized_parted2global`` of them (voice2pose.py:102-105,164-169) as one kernel."""
+        if self.cfg.DATASET.HIERARCHICAL_POSE:
+            return poses
+        p2g = self._p2g_stats(batch, dataset, poses.device)
+        return ops.pose_parted2global(poses.detach().contiguous().float(), *p2g)
+
+    def _discriminator_losses(self, losses, g_loss, poses_gt, pred):
+        """voice2pose.py:179-208: three discriminator passes (each with its own BatchNorm statistics in train mode) + LSGAN terms."""
+        dcfg = self.cfg.VOICE2POSE.POSE_DISCRIMINATOR
+        real_batch, fake_batch = poses_gt, pred
+        if dcfg.WHITE_LIST is not None:
+            real_batch, fake_batch = real_batch[..., dcfg.WHITE_LIST], fake_batch[..., dcfg.WHITE_LIST]
+        if dcfg.MOTION:
+            real_batch = real_batch[:, 1:, ...] - real_batch[:, :-1, ...]
+            fake_batch = fake_batch[:, 1:, ...] - fake_batch[:, :-1, ...]
+        score_real = self.netD_pose(real_batch)
+        score_fake = self.netD_pose(fake_batch)
+        score_fake_detach = self.netD_pose(fake_batch.detach())
+        g_gan = self.pose_gan_criterion(score_fake, torch.ones_like(score_fake)) * dcfg.LAMBDA_GAN
+        losses["G_pose_gan_loss"] = g_gan
+        losses["G_loss"] = g_loss + g_gan
+        d_fake = self.pose_gan_criterion(score_fake_detach, torch.zeros_like(score_fake_detach))
+        d_real = self.pose_gan_criterion(score_real, torch.ones_like(score_real))
+        losses["D_pose_gan_loss"] = (d_real + d_fake) * dcfg.LAMBDA_GAN
+        losses["pose_score_fake"] = score_fake.mean()
+        losses["pose_score_real"] = score_real.mean()
 
     def forward(self, batch, dataset=None, return_loss=True, interpolation_coeff=None):
         cfg = self.cfg
@@ -336,30 +368,14 @@ class Voice2PoseModel(nn.Module):
                 if k in res:
                     results[k] = res[k].clone()
             if hasattr(self, "netD_pose"):                                           # voice2pose.py:179-208
-                dcfg = cfg.VOICE2POSE.POSE_DISCRIMINATOR
-                real_batch, fake_batch = poses_gt, pred
-                if dcfg.WHITE_LIST is not None:
-                    real_batch, fake_batch = real_batch[..., dcfg.WHITE_LIST], fake_batch[..., dcfg.WHITE_LIST]
-                if dcfg.MOTION:
-                    real_batch = real_batch[:, 1:, ...] - real_batch[:, :-1, ...]
-                    fake_batch = fake_batch[:, 1:, ...] - fake_batch[:, :-1, ...]
-                score_real = self.netD_pose(real_batch)
-                score_fake = self.netD_pose(fake_batch)
-                score_fake_detach = self.netD_pose(fake_batch.detach())
-                g_gan = self.pose_gan_criterion(score_fake, torch.ones_like(score_fake)) * dcfg.LAMBDA_GAN
-                losses["G_pose_gan_loss"] = g_gan
-                losses["G_loss"] = g_loss + g_gan
-                d_fake = self.pose_gan_criterion(score_fake_detach, torch.zeros_like(score_fake_detach))
-                d_real = self.pose_gan_criterion(score_real, torch.ones_like(score_real))
-                losses["D_pose_gan_loss"] = (d_real + d_fake) * dcfg.LAMBDA_GAN
-                losses["pose_score_fake"] = score_fake.mean()
-                losses["pose_score_real"] = score_real.mean()
+                self._discriminator_losses(losses, g_loss, poses_gt, pred)
             return losses, results
 
-        # eval / demo: code selection then a plain generator forward
+        # eval / demo: code selection (voice2pose.py:96-120), then the same loss graph without gradients.  (In the reference
+        # `self.training` only switches the code selection and the BatchNorm mode; the loss terms are computed either way.)
         code = None
         if D is not None:
-            code = self._condition_code(batch, clip_indices, audio, poses_gt, return_loss, interpolation_coeff)
+            code = self._condition_code(batch, dataset, clip_indices, audio, poses_gt, return_loss, interpolation_coeff)
         with torch.no_grad():
             mel = self.mel_transfm(audio)
             pred = self.netG(mel, num_frames, code)
@@ -368,13 +384,25 @@ class Voice2PoseModel(nn.Module):
             return results
         results["poses_gt_batch"] = poses_gt
         losses = OrderedDict()
-        reg = (torch.abs(pred - poses_gt) * cfg.VOICE2POSE.GENERATOR.LAMBDA_REG).mean()   # eval-time logging only
-        losses["G_reg_loss"] = reg
-        losses["G_loss"] = reg.clone()
-        if cfg.VOICE2POSE.POSE_ENCODER.NAME is not None:
-            with torch.no_grad():
-                results["mu_pred"], results["logvar_pred"] = self.pose_encoder(pred)
-                results["mu_gt"], results["logvar_gt"] = self.pose_encoder(poses_gt)
+        with torch.no_grad():
+            gt32 = poses_gt.contiguous().float()
+            reg = torch.empty(1, device=pred.device)
+            ops.l1_loss(pred.contiguous(), gt32, float(cfg.VOICE2POSE.GENERATOR.LAMBDA_REG), reg, None,
+                        torch.empty(1024, device=pred.device))                                # voice2pose.py:141-142
+            losses["G_reg_loss"] = reg.squeeze(0)
+            g_loss = losses["G_reg_loss"].clone()
+            if code is not None:                                                               # voice2pose.py:147-157, (B, D) glue
+                mu, var = code.mean(dim=0), code.var(dim=0)
+                if bool((var != 0).all()):
+                    kl = 0.5 * (-torch.log(var) + mu ** 2 + var - 1).mean() * cfg.VOICE2POSE.GENERATOR.LAMBDA_CLIP_KL
+                    losses["G_clipcode_kl_loss"] = kl
+                    g_loss = g_loss + kl
+            losses["G_loss"] = g_loss
+            if cfg.VOICE2POSE.POSE_ENCODER.NAME is not None:                                   # voice2pose.py:162-176
+                results["mu_pred"], results["logvar_pred"] = self.pose_encoder(self._fgd_input(pred, batch, dataset))
+                results["mu_gt"], results["logvar_gt"] = self.pose_encoder(self._fgd_input(gt32, batch, dataset))
+            if hasattr(self, "netD_pose"):
+                self._discriminator_losses(losses, g_loss, gt32, pred)
         return losses, results
 
 
@@ -393,6 +421,27 @@ def _V2PLossFn_last_results(model):
 # ------------------------------------------------------------------------------------------------
 # fused train step
 # ------------------------------------------------------------------------------------------------
+def _cuda_device(device):
+    d = torch.device(device)
+    if d.type != "cuda":
+        raise RuntimeError("the fused trainers run only on CUDA devices (libsdt_b200 has no CPU fallback), got %s" % d)
+    return torch.device("cuda", torch.cuda.current_device() if d.index is None else d.index)
+
+
+def _on_device(fn):
+    """Run a trainer method with the trainer's device current: streams, events and ``ops._stream()`` all follow torch's
+    current device, so ``Trainer(cfg, n, 'cuda:1')`` must not depend on the caller having called ``torch.cuda.set_device``."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kwargs):
+        if torch.cuda.current_device() == self.device.index:
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+    return wrapped
+
+
 class Voice2PoseTrainer:
     """The numeric part of Voice2Pose.train_step (voice2pose.py:281-312) for the SDT configs as a fused device program.
 
@@ -405,7 +454,12 @@ class Voice2PoseTrainer:
 
     def __init__(self, cfg, num_train_samples, device, use_cuda_graph=True, process_group=None, seed=0, conv_math=None):
         self.cfg = cfg
-        self.device = torch.device(device)
+        self.device = _cuda_device(device)
+        with torch.cuda.device(self.device):
+            self._init(num_train_samples, use_cuda_graph, process_group, seed, conv_math)
+
+    def _init(self, num_train_samples, use_cuda_graph, process_group, seed, conv_math):
+        cfg = self.cfg
         # convolution math mode of THIS trainer's engines (None = the process default, 3 = tcgen05 TF32 unless SDT_CONV_MATH /
         # ops.set_conv_math say otherwise); 0 = fp32 FFMA.  TF32 is the reference's own GPU default (cudnn.allow_tf32)
         self.conv_math = ops.resolve_math(conv_math)
@@ -478,7 +532,7 @@ class Voice2PoseTrainer:
         self.adam_d = torch.zeros(8, device=self.device)
         self.set_lr(self.lr)
         self.engine = m.step_engine()
-        self._wg_stream = torch.cuda.Stream()                # weight gradients overlap the dgrad chain (engine._wgrad)
+        self._wg_stream = torch.cuda.Stream(device=self.device)                # weight gradients overlap the dgrad chain (engine._wgrad)
         m.netG.engine().wg_stream = self._wg_stream
         self._overlap = True
         self._aux = None
@@ -492,6 +546,7 @@ class Voice2PoseTrainer:
         self.kernels_per_step = 0
         self.steps_done = 0
 
+    @_on_device
     def set_overlap(self, on):
         """Multi-stream overlap of the step (FGD/metrics and weight gradients beside the dgrad chain). bench.py switches
         it off for the per-kernel roofline pass so that every launch is timed alone."""
@@ -535,8 +590,12 @@ class Voice2PoseTrainer:
         s["mean"].copy_(torch.as_tensor(st["mean"]), non_blocking=True)
         s["std"].copy_(torch.as_tensor(st["std"]), non_blocking=True)
         s["scale"].copy_(torch.as_tensor(st["scale_factor"]), non_blocking=True)
+        release = batch.get("_release")
+        if release is not None:                         # data.DeviceBatchBuilder: its device buffers may be refilled from here on
+            release()
         return s
 
+    @_on_device
     def prefetch(self, batch):
         """Start the host->device copy of a FUTURE batch on a copy stream, overlapping the step in flight.  The next
         ``train_step(batch)`` with this very object picks the device copy up (one inbox: prefetch one batch ahead)."""
@@ -547,15 +606,22 @@ class Voice2PoseTrainer:
         if self._inbox is None or any(self._inbox[k].shape != v.shape for k, v in src.items()):
             dt = dict(audio=torch.float32, poses=torch.float32, idx=torch.long, mean=torch.float64, std=torch.float64, scale=torch.float64)
             self._inbox = {k: torch.empty(tuple(v.shape), device=dev, dtype=dt[k]) for k, v in src.items()}
-            self._copy_stream = torch.cuda.Stream()
+            self._copy_stream = torch.cuda.Stream(device=self.device)
             self._inbox_ready, self._inbox_free = torch.cuda.Event(), torch.cuda.Event()
             self._inbox_free.record(torch.cuda.current_stream())
         cs = self._copy_stream
         cs.wait_event(self._inbox_free)                 # the previous occupant has been handed over to the step's staging
+        if any(v.is_cuda for v in src.values()):
+            # device-resident sources (data.DeviceBatchBuilder): their producer (upload + sdt_pose_preprocess) was ordered
+            # before the CURRENT stream by builder.batch(); the copy stream has to see that order too
+            cs.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(cs):
             for k, v in src.items():
                 self._inbox[k].copy_(v, non_blocking=True)
             self._inbox_ready.record(cs)
+            release = batch.get("_release")
+            if release is not None:
+                release(cs)
         self._prefetched = batch
 
     def set_p2g_stats(self, stat_parted, stat_global):
@@ -633,7 +699,7 @@ class Voice2PoseTrainer:
         # fork: FGD features + f64 results/metrics on a second stream while the backward pass runs on this one
         main = torch.cuda.current_stream()
         if self._aux is None:
-            self._aux = torch.cuda.Stream()
+            self._aux = torch.cuda.Stream(device=self.device)
         fork, join = torch.cuda.Event(), torch.cuda.Event()
         fork.record(main)
         with torch.cuda.stream(self._aux):
@@ -649,7 +715,8 @@ class Voice2PoseTrainer:
         gs = 1.0 / self.world
         ops.adam_advance(self.adam_g, -1.0)
         ops.adam_flat(self.flat_p[:self.n_g_pad], self.flat_g[:self.n_g_pad], self.exp_avg[:self.n_g_pad],
-                      self.exp_avg_sq[:self.n_g_pad], self.adam_g, grad_scale=gs)
+                      self.exp_avg_sq[:self.n_g_pad], self.adam_g, grad_scale=gs,
+                      weight_decay=float(self.cfg.TRAIN.WD))            # optimizerG only (voice2pose.py:249-250)
         if self.train_code:
             ops.adam_advance(self.adam_c, -1.0)
             sl = slice(self.n_g_pad, self.n_g_pad + self.n_code_pad)
@@ -663,6 +730,7 @@ class Voice2PoseTrainer:
         if self.world > 1:
             parallel.allreduce_flat_(self.flat_g, self.pg)             # ONE flat NCCL all-reduce per step
 
+    @_on_device
     def run_staged(self):
         """Run one step on the already-staged device batch (bench.py's device-resident timing)."""
         if self.use_graph and self._graphs is None and self._warm >= 2:
@@ -681,9 +749,10 @@ class Voice2PoseTrainer:
         self.steps_done += 1
         return self.out
 
+    @_on_device
     def _capture(self):
         torch.cuda.synchronize()
-        side = torch.cuda.Stream()
+        side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.stream(side):
@@ -695,6 +764,7 @@ class Voice2PoseTrainer:
         torch.cuda.synchronize()
         self._graphs = (g1, g2)
 
+    @_on_device
     def train_step(self, batch):
         """batch: the reference's batch dict (host tensors; pinned memory recommended). Returns a dict of device
         tensors: G_reg_loss, [G_clipcode_kl_loss], G_loss, L2_dist, lip_sync_error_n, poses_pred_batch, mu_*/logvar_*."""
@@ -716,10 +786,12 @@ class Voice2PoseTrainer:
             d.pop("G_clipcode_kl_loss", None)
         return d
 
+    @_on_device
     def losses_to_host(self, out=None):
         """One small D2H read of the last step's scalars (the reference logs these every LOG_INTERVAL steps). Blocking."""
         return self._scalars_dict(self._scal.cpu().tolist())
 
+    @_on_device
     def post_losses(self, slot):
         """Asynchronous variant: enqueue the D2H of the last step's scalars into pinned slot 0/1; collect_losses(slot)
         waits for exactly that copy, so the host can run one step ahead of the device."""
@@ -730,6 +802,7 @@ class Voice2PoseTrainer:
         self._scal_ev[slot].synchronize()
         return self._scalars_dict(self._scal_host[slot].tolist())
 
+    @_on_device
     def run_epoch(self, batches, on_losses=None):
         """The reference's inner loop (trainer.py: ``for batch in dataloader: train_step; log``) as a software pipeline:
         batch k+1 is uploaded on a copy stream while step k runs, and the scalars of step k are read while step k+1 is
@@ -799,7 +872,12 @@ class Pose2PoseTrainer:
 
     def __init__(self, cfg, num_train_samples, device, use_cuda_graph=True, process_group=None, seed=0, conv_math=None):
         self.cfg = cfg
-        self.device = torch.device(device)
+        self.device = _cuda_device(device)
+        with torch.cuda.device(self.device):
+            self._init(num_train_samples, use_cuda_graph, process_group, seed, conv_math)
+
+    def _init(self, num_train_samples, use_cuda_graph, process_group, seed, conv_math):
+        cfg = self.cfg
         self.conv_math = ops.resolve_math(conv_math)
         torch.manual_seed(seed)
         self.model = Pose2PoseModel(cfg, num_train_samples=num_train_samples).to(self.device)
@@ -886,12 +964,14 @@ class Pose2PoseTrainer:
 
     def _optim(self):
         ops.adam_advance(self.adam, -1.0)
-        ops.adam_flat(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, self.adam, grad_scale=1.0 / self.world)
+        ops.adam_flat(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, self.adam, grad_scale=1.0 / self.world,
+                      weight_decay=float(self.cfg.TRAIN.WD))            # pose2pose.py:114-115
 
+    @_on_device
     def run_staged(self):
         if self.use_graph and self._graphs is None and self._warm >= 2:
             torch.cuda.synchronize()
-            side = torch.cuda.Stream()
+            side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream())
             g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.stream(side):
@@ -917,10 +997,12 @@ class Pose2PoseTrainer:
             self._warm += 1
         return self.out
 
+    @_on_device
     def train_step(self, batch):
         self._stage(batch)
         return self.run_staged()
 
+    @_on_device
     def losses_to_host(self, out):
         keys = ["reg_loss", "kl_loss", "loss", "L2_dist", "lip_sync_error_n"]
         vals = torch.cat([out[k].double().view(1) for k in keys]).cpu().tolist()

@@ -216,6 +216,48 @@ def golden_s2g_forward(stats):
     np.savez_compressed(os.path.join(HERE, "s2g_forward_golden.npz"), **out)
 
 
+def golden_eval(stats):
+    """Validation forward (``model.eval()``, return_loss=True: Voice2Pose.test_step, voice2pose.py:333-352) of the UNMODIFIED
+    reference for the two configurations whose eval path differs from training beyond the BatchNorm mode:
+      s2g     -- BatchNorm generator / discriminator / FGD extractor from running statistics, HIERARCHICAL_POSE=False so the FGD
+                 input goes through dataset.transform_normalized_parted2global (:164-169), LSGAN terms in the losses;
+      gtcode  -- voice2pose_sdt_bp with CLIP_CODE.TEST_WITH_GT_CODE: condition_code = mu of the ground-truth poses (:100-106),
+                 clip-code KL on that code (:147-157).
+    Parameters come from torch.manual_seed(0) + the reference constructors (reproduced by the drop-in modules / the oracle);
+    the BatchNorm buffers after a few training-mode forwards are stored in full (they are small)."""
+    from core.pipelines.voice2pose import Voice2PoseModel
+    out = {}
+    for tag, name, opts, bs in (("s2g", "voice2pose_s2g", [], 3),
+                                ("gtcode", "voice2pose_sdt_bp", ["VOICE2POSE.GENERATOR.CLIP_CODE.TEST_WITH_GT_CODE", True], 3)):
+        cfg = refshim.get_cfg(name, opts)
+        ocfg = O.make_cfg(name)
+        n_train = 8
+        torch.manual_seed(0)
+        model = Voice2PoseModel(cfg, num_train_samples=n_train)
+        ds = refshim.make_dataset_stub(cfg)
+        st = stat_of(stats, ocfg["hierarchical"])
+        model.train()
+        with torch.no_grad():                      # move every BatchNorm's running statistics off their initial values
+            for s in range(2):
+                model(to_ref_batch(O.synthetic_batch(bs, n_train, st, seed=400 + s)), ds)
+        model.eval()
+        batch = O.synthetic_batch(bs, n_train, st, seed=410)
+        with torch.no_grad():
+            losses, results = model(to_ref_batch(batch), ds)
+        for k, v in losses.items():
+            out["%s/loss/%s" % (tag, k)] = np.float64(v.item())
+        out[tag + "/pred"] = results["poses_pred_batch"].numpy().astype(np.float32)
+        for k in ("mu_pred", "mu_gt", "logvar_pred", "logvar_gt", "condition_code"):
+            if results.get(k) is not None:
+                out["%s/%s" % (tag, k)] = results[k].numpy()
+        out[tag + "/batch_size"], out[tag + "/n_train"] = np.int64(bs), np.int64(n_train)
+        for k, v in model.state_dict().items():
+            if "running_" in k or "num_batches" in k:
+                out["%s/buf/%s" % (tag, k)] = v.numpy()
+        print("eval", tag, {k: float(v) for k, v in losses.items()})
+    np.savez_compressed(os.path.join(HERE, "eval_golden.npz"), **out)
+
+
 def golden_pose2pose(stats, batch_size=4, n_train=16, steps=2):
     from core.pipelines.pose2pose import Pose2PoseModel
     import core.networks.poses_reconstruction.autoencoder as ae_mod
@@ -265,10 +307,15 @@ def main():
     run_voice2pose("voice2pose_sdt_bp", stats, 2, 16, 1, False, "sdt_bp_zero_code_golden")
     run_voice2pose("voice2pose_s2g", stats, 2, 16, 2, False, "s2g_step_golden")
     golden_pose2pose(stats)
+    golden_eval(stats)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print("%-32s %8.1f KB" % (f, os.path.getsize(os.path.join(HERE, f)) / 1024))
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "eval":        # only the (round-2) eval fixture
+        torch.set_num_threads(8)
+        golden_eval(speaker_stats())
+    else:
+        main()

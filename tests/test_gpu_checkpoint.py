@@ -75,3 +75,48 @@ def test_state_dict_keys_strip_and_strictness():
     with pytest.raises(RuntimeError, match="missing"):
         C.load_voice2pose(tr, bad)
     C.load_voice2pose(tr, bad, strict=False)
+
+
+def test_pose2pose_checkpoint_resume_and_handoff_to_sdt_vae(tmp_path):
+    """Pose2PoseTrainer checkpoints in the reference layout (trainer.py:305-321 with the single 'optimizer', pose2pose.py:114):
+    (a) a resumed trainer continues bit for bit; (b) the file is what voice2pose_sdt_vae reads as VOICE2POSE.POSE_ENCODER.AE_CHECKPOINT
+    -- external clip codes from module.clip_code_mu (voice2pose.py:40-55) and the FGD encoder from module.ae.encoder.* (:234-242)."""
+    from speechdrivestemplates_b200 import checkpoint as C, config, pipeline
+    n_train = 16
+    dev = torch.device("cuda:0")
+
+    def p2p():
+        tr = pipeline.Pose2PoseTrainer(config.get_cfg("pose2pose"), n_train, dev, use_cuda_graph=False, seed=3)
+        return tr
+
+    a = p2p()
+    eps = [torch.randn(4, 32, generator=torch.Generator().manual_seed(50 + s)).to(dev) for s in range(5)]
+    for s in range(3):
+        a.eps_override = eps[s]
+        a.train_step(_batch(4, n_train, 900 + s))
+    path = str(tmp_path / "checkpoint_epoch-2_step-3.pth")
+    C.save_pose2pose(a, path, epoch=2, step=3)
+    ck = torch.load(path, map_location="cpu")
+    assert set(ck) == {"epoch", "step", "model_state_dict", "optimizer_state_dict"}
+    keys = set(ck["model_state_dict"])
+    assert {"module.clip_code_mu", "module.clip_code_logvar", "module.mel_transfm.spectrogram.window",
+            "module.ae.encoder.blocks.0.conv.weight", "module.ae.decoder.blocks.4.bias"} <= keys
+    assert ck["optimizer_state_dict"]["state"][0]["exp_avg"].shape == ck["model_state_dict"]["module.ae.encoder.blocks.0.conv.weight"].shape
+    b = p2p()
+    assert C.load_pose2pose(b, path) == (2, 3)
+    for s in range(3, 5):
+        a.eps_override = b.eps_override = eps[s]
+        oa = a.train_step(_batch(4, n_train, 900 + s))
+        ob = b.train_step(_batch(4, n_train, 900 + s))
+    assert a.losses_to_host(oa) == b.losses_to_host(ob)
+    assert torch.equal(a.flat_p, b.flat_p) and torch.equal(a.exp_avg_sq, b.exp_avg_sq)
+    assert torch.equal(a.model.clip_code_mu, b.model.clip_code_mu)
+    # (b) hand-off
+    cfg = config.get_cfg("voice2pose_sdt_vae", ["VOICE2POSE.POSE_ENCODER.AE_CHECKPOINT", path])
+    v = pipeline.Voice2PoseTrainer(cfg, n_train, dev, use_cuda_graph=False, seed=0)
+    assert not isinstance(v.model.clips_code, torch.nn.Parameter)
+    assert torch.equal(v.model.clips_code.cpu(), ck["model_state_dict"]["module.clip_code_mu"])
+    enc = ck["model_state_dict"]["module.ae.encoder.blocks.3.norm.running_var"]
+    assert torch.equal(v.model.pose_encoder.state_dict()["blocks.3.norm.running_var"].cpu(), enc)
+    out = v.train_step(_batch(4, n_train, 950))
+    assert np.isfinite(v.losses_to_host(out)["G_loss"])

@@ -343,6 +343,25 @@ def test_colsum_and_adam(ops):
     assert rel(mk, mo) < 1e-6 and rel(vk, vo) < 1e-6
 
 
+def test_adam_weight_decay_matches_torch_adam(ops):
+    """cfg.TRAIN.WD (voice2pose.py:250, pose2pose.py:115): Adam's L2 term grad += wd * param, against torch.optim.Adam itself."""
+    g = torch.Generator().manual_seed(12)
+    n = 257 * 4 + 1
+    p0 = torch.randn(n, generator=g)
+    ref = torch.nn.Parameter(p0.clone().to(dev()))
+    opt = torch.optim.Adam([ref], lr=1e-3, weight_decay=0.05)
+    pk, mk, vk = p0.clone().to(dev()), torch.zeros(n, device=dev()), torch.zeros(n, device=dev())
+    scalars = torch.zeros(8, device=dev())
+    for _ in range(4):
+        gr = (torch.randn(n, generator=g) * 1e-2).to(dev())
+        ref.grad = gr.clone()
+        opt.step()
+        ops.adam_advance(scalars, 1e-3)
+        ops.adam_flat(pk, gr, mk, vk, scalars, weight_decay=0.05)
+    assert float((pk - ref.detach()).abs().max()) < 2e-7
+    assert float((pk - p0.to(dev())).abs().max()) > 1e-3          # the steps moved the parameters
+
+
 # ---------------------------------------------------------------- keypoints (bit-exact gates)
 @pytest.mark.parametrize("parted", [True, False])
 def test_pose_kernels_bit_exact(ops, parted):

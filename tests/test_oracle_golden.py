@@ -178,3 +178,30 @@ def test_pose2pose_step_matches_reference():
         _check_digests(g, p + "/grad", grads, rtol=1e-3 if s == 0 else 3e-2, what="grad", outlier_frac=0.0 if s == 0 else 0.02)
         orc.apply_optimizers(grads)
         _check_digests(g, p + "/state", orc.sd, rtol=1e-4, atol=2.5e-4 * (s + 1), what="state")
+
+
+@pytest.mark.parametrize("tag,name,over", [("s2g", "voice2pose_s2g", {}), ("gtcode", "voice2pose_sdt_bp", {"test_with_gt_code": True})])
+def test_eval_forward_matches_reference(tag, name, over):
+    """Validation forward (model.eval(), return_loss=True) of the reference: BatchNorm from running statistics, the FGD input
+    through transform_normalized_parted2global (s2g), the ground-truth code + its KL (TEST_WITH_GT_CODE), LSGAN terms."""
+    g = golden("eval_golden")
+    cfg = O.make_cfg(name, **over)
+    n_train, bs = int(g[tag + "/n_train"]), int(g[tag + "/batch_size"])
+    orc = O.Voice2PoseOracle(cfg, n_train, seed=0)
+    for k in g.files:
+        if k.startswith(tag + "/buf/"):
+            orc.sd[k[len(tag) + 5:]] = torch.from_numpy(g[k])
+    batch = O.synthetic_batch(bs, n_train, oliver_stat(cfg["hierarchical"]), seed=410, stat_parted=oliver_stat(True),
+                              stat_global=oliver_stat(False))
+    with torch.no_grad():
+        losses, results = orc.forward(batch, training=False)
+    ref_keys = {k.split("/")[-1] for k in g.files if k.startswith(tag + "/loss/")}
+    assert set(losses) == ref_keys
+    for k, v in losses.items():
+        ref = float(g["%s/loss/%s" % (tag, k)])
+        assert abs(float(v) - ref) <= 1e-4 * max(1.0, abs(ref)), (k, float(v), ref)
+    assert rel_err(results["poses_pred_batch"].numpy(), g[tag + "/pred"]) < 1e-4
+    for k in ("mu_pred", "mu_gt", "logvar_pred", "logvar_gt"):
+        assert rel_err(results[k].numpy(), g["%s/%s" % (tag, k)]) < 1e-3, k
+    if tag == "gtcode":
+        assert rel_err(results["condition_code"].numpy(), g[tag + "/condition_code"]) < 1e-4

@@ -130,7 +130,8 @@ int sdt_conv_wgrad_reduce(const float* wpart, int splits, int N, int C, int T, f
  *   mode 1 dgrad   : taps ky = ky0 + kstep*jy (jy < TH), kx likewise:
  *                    out[((jy*TW+jx)*Cout + co)*Cin + ci] = w[co,ci,ky0+kstep*jy,kx0+kstep*jx]
  *   mode 2 / 3     : the transposes of mode 0 / 1, i.e. (N, K) with K contiguous -- the K-major tensor-core operand:
- *                    mode 2 out[co*K + (ky*KW+kx)*Cin + ci], mode 3 out[ci*K' + (jy*TW+jx)*Cout + co]           */
+ *                    mode 2 out[co*K + (ky*KW+kx)*Cin + ci], mode 3 out[ci*K' + (jy*TW+jx)*Cout + co];
+ *                    values are rounded to nearest TF32 (see "out_tf32" below) because only the tcgen05 kernels read them */
 int sdt_weight_prep(const float* w, int Cout, int Cin, int KH, int KW, int mode, int ky0, int kx0, int kstep,
                     int TH, int TW, float* out, void* stream);
 
@@ -145,6 +146,15 @@ typedef struct sdt_prep_item {
     int32_t pad1;
 } sdt_prep_item;
 int sdt_weight_prep_batch(const sdt_prep_item* items_device, int n_items, long long max_elems, void* stream);
+
+/* ---- "out_tf32" ------------------------------------------------------------------------------------
+ * tcgen05.mma kind::tf32 reads fp32 operands and ignores their low 13 mantissa bits: it TRUNCATES, so every product is low by
+ * ~7e-4 on average.  Normalisation on batch / instance statistics cancels that scale bias layer by layer; BatchNorm in eval
+ * mode (validation, demo: voice2pose.py:333-410) does not, and 25 layers of it drift by 1.6e-2 (profiles/
+ * r2_tf32_truncation_bias.txt).  Every entry point that PRODUCES a tensor-core operand (activations, input gradients, GEMM
+ * weight copies) therefore takes `out_tf32`: non-zero = store the result rounded to the nearest TF32 value (cvt.rna.tf32.f32),
+ * which makes the MMA's view of it exact and its rounding error unbiased -- what cuDNN's TF32 convolutions, the reference's own
+ * GPU default, do.  Callers pass 0 in the fp32 math mode. */
 
 /* ---- normalisation -----------------------------------------------------------------------------
  * nn.InstanceNorm2d / nn.BatchNorm{1,2}d inside ConvNormRelu (building_blocks.py:23-27,38-43,53) with
@@ -174,16 +184,16 @@ int sdt_norm_bwd_finalize(const float* partial, int groups, int tiles_per_group,
                           float* m2, float* dgamma, float* dbeta, int accumulate, void* stream);
 int sdt_norm_bwd_apply(float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
                        const float* beta, const float* m1, const float* m2, int B, int P, int C, int groups, float slope,
-                       void* stream);
+                       int out_tf32, void* stream);
 /* InstanceNorm1d on the permuted tensor == LayerNorm over channels per (b,t), no affine
  * (building_blocks.py:50-51) + activation, on rows of a (R, C) channels-last matrix. */
 int sdt_rownorm_act_fwd(const float* x, int R, int C, float eps, float slope, float* y, float* mean, float* rstd,
-                        void* stream);
+                        int out_tf32, void* stream);
 int sdt_rownorm_act_bwd(const float* g_y, const float* x, const float* mean, const float* rstd, int R, int C,
-                        float slope, float* g_x, void* stream);
+                        float slope, float* g_x, int out_tf32, void* stream);
 /* y = act(x*scale[g,c] + shift[g,c]) materialised (used at module boundaries only). */
 int sdt_scale_shift_act(const float* x, const float* scale, const float* shift, int B, int P, int C, int bstride,
-                        float slope, float* y, void* stream);
+                        float slope, float* y, int out_tf32, void* stream);
 
 /* ---- first block of the audio encoder, special-cased ------------------------------------------------
  * Conv2d(1 -> 64, 3x3, s1, p1, no bias) + InstanceNorm2d + LeakyReLU (generator.py:17 via building_blocks.py
@@ -194,7 +204,8 @@ int sdt_scale_shift_act(const float* x, const float* scale, const float* shift, 
  * -mean*rstd.  mom_partial: (B, sdt_first_layer_units(H,W), 54) f64 scratch. */
 int sdt_first_layer_units(int H, int W);
 int sdt_first_layer_fwd(const float* x, const float* w, int B, int H, int W, int C, float eps, float slope,
-                        double* mom_partial, double* moments, float* scale, float* shift, float* act, void* stream);
+                        double* mom_partial, double* moments, float* scale, float* shift, float* act, int out_tf32,
+                        void* stream);
 /* Weight gradient of that block from g_act = dLoss/d act in ONE pass over (g_act, act): the InstanceNorm + LeakyReLU
  * backward is folded into per-(image, channel) sums and combined in closed form (f64) with the forward's moments; the
  * block's input needs no gradient (it is the mel spectrogram).  Requires slope > 0 (the pre-activation is recovered
@@ -208,13 +219,14 @@ int sdt_first_layer_bwd(const float* g_act, const float* act, const float* x, co
  * concat (generator.py:109-111): reads the last encoder block's raw output (B,H,W,C) through its
  * scale/shift/activation, writes the UNet input (B, F, C + D) channels-last; code (B, D) or NULL. */
 int sdt_enc_to_seq_fwd(const float* x, const float* scale, const float* shift, int xf_bstride, float slope, int B, int H,
-                       int W, int C, const float* code, int D, int F, float* out, void* stream);
+                       int W, int C, const float* code, int D, int F, float* out, int out_tf32, void* stream);
 /* adjoint: g_out (B,F,C+D) -> g_act (B,H,W,C) (zero outside the sampled row) and g_code (B,D) = sum_t. */
 int sdt_enc_to_seq_bwd(const float* g_out, int B, int H, int W, int C, int D, int F, float* g_act, float* g_code,
                        void* stream);
 /* F.interpolate(x, Lout, mode='linear') + skip (generator.py:79-83; autoencoder.py:62-66 with skip NULL):
  * out (B,Lout,C) = lerp(x (B,Lin,C)) [+ skip]. */
-int sdt_upsample_add_fwd(const float* x, const float* skip, int B, int Lin, int Lout, int C, float* out, void* stream);
+int sdt_upsample_add_fwd(const float* x, const float* skip, int B, int Lin, int Lout, int C, float* out, int out_tf32,
+                         void* stream);
 /* adjoint of the lerp: g_x (B,Lin,C) (+)= A^T g_out. */
 int sdt_upsample_bwd(const float* g_out, int B, int Lin, int Lout, int C, float* g_x, int accumulate, void* stream);
 
@@ -232,6 +244,10 @@ int sdt_code_gather_kl(const float* table, const int64_t* idx, int B, int D, flo
  * g_table must be zeroed by the caller. */
 int sdt_code_scatter_grad(const float* g_code_a, const float* g_code_b, const int64_t* idx, int B, int D,
                           float* g_table, void* stream);
+/* Pose2Pose.train_step's buffer scatter (pose2pose.py:135-137): table_a[idx[b]] = src_a[b] (and table_b / src_b likewise when
+ * given), rows of D floats.  Duplicate indices in a batch: the last occurrence wins (the sequential CPU semantics). */
+int sdt_code_store_rows(const float* src_a, float* table_a, const float* src_b, float* table_b, const int64_t* idx, int B,
+                        int D, void* stream);
 /* column sums of a (R, C) matrix: bias gradient of the final Conv1d (generator.py:103). */
 int sdt_colsum(const float* g, int R, int C, float* out, int accumulate, void* stream);
 /* LSGAN terms, nn.MSELoss vs a constant target (voice2pose.py:82,195-202): out[0] = lambda*mean((s-target)^2),

@@ -51,20 +51,21 @@ SIGNATURES = {
     "sdt_bn_eval_scale_shift": [c_ptr, c_ptr, c_ptr, c_ptr, f32, i32, c_ptr, c_ptr, c_ptr],
     "sdt_norm_bwd_reduce": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, i32, i32, f32, c_ptr, i32, c_ptr],
     "sdt_norm_bwd_finalize": [c_ptr, i32, i32, i32, f64, c_ptr, c_ptr, c_ptr, c_ptr, i32, c_ptr],
-    "sdt_norm_bwd_apply": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, i32, i32, f32, c_ptr],
-    "sdt_rownorm_act_fwd": [c_ptr, i32, i32, f32, f32, c_ptr, c_ptr, c_ptr, c_ptr],
-    "sdt_rownorm_act_bwd": [c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, f32, c_ptr, c_ptr],
-    "sdt_scale_shift_act": [c_ptr, c_ptr, c_ptr, i32, i32, i32, i32, f32, c_ptr, c_ptr],
+    "sdt_norm_bwd_apply": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, i32, i32, f32, i32, c_ptr],
+    "sdt_rownorm_act_fwd": [c_ptr, i32, i32, f32, f32, c_ptr, c_ptr, c_ptr, i32, c_ptr],
+    "sdt_rownorm_act_bwd": [c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, f32, c_ptr, i32, c_ptr],
+    "sdt_scale_shift_act": [c_ptr, c_ptr, c_ptr, i32, i32, i32, i32, f32, c_ptr, i32, c_ptr],
     "sdt_first_layer_units": [i32, i32],
-    "sdt_first_layer_fwd": [c_ptr, c_ptr, i32, i32, i32, i32, f32, f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
+    "sdt_first_layer_fwd": [c_ptr, c_ptr, i32, i32, i32, i32, f32, f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, i32, c_ptr],
     "sdt_first_layer_bwd": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, i32, i32, f32, c_ptr, c_ptr, c_ptr],
-    "sdt_enc_to_seq_fwd": [c_ptr, c_ptr, c_ptr, i32, f32, i32, i32, i32, i32, c_ptr, i32, i32, c_ptr, c_ptr],
+    "sdt_enc_to_seq_fwd": [c_ptr, c_ptr, c_ptr, i32, f32, i32, i32, i32, i32, c_ptr, i32, i32, c_ptr, i32, c_ptr],
     "sdt_enc_to_seq_bwd": [c_ptr, i32, i32, i32, i32, i32, i32, c_ptr, c_ptr, c_ptr],
-    "sdt_upsample_add_fwd": [c_ptr, c_ptr, i32, i32, i32, i32, c_ptr, c_ptr],
+    "sdt_upsample_add_fwd": [c_ptr, c_ptr, i32, i32, i32, i32, c_ptr, i32, c_ptr],
     "sdt_upsample_bwd": [c_ptr, i32, i32, i32, i32, c_ptr, i32, c_ptr],
     "sdt_l1_loss": [c_ptr, c_ptr, i64, f32, c_ptr, c_ptr, c_ptr, c_ptr],
     "sdt_code_gather_kl": [c_ptr, c_ptr, i32, i32, f32, c_ptr, c_ptr, c_ptr, c_ptr],
     "sdt_code_scatter_grad": [c_ptr, c_ptr, c_ptr, i32, i32, c_ptr, c_ptr],
+    "sdt_code_store_rows": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, c_ptr],
     "sdt_colsum": [c_ptr, i32, i32, c_ptr, i32, c_ptr],
     "sdt_mse_const_loss": [c_ptr, i64, f32, f32, c_ptr, c_ptr, c_ptr],
     "sdt_motion_diff_fwd": [c_ptr, i32, i32, i32, c_ptr, c_ptr],

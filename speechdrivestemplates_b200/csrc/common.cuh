@@ -73,6 +73,18 @@ __device__ __forceinline__ float leaky(float v, float slope) { return v > 0.f ? 
 // derivative of LeakyReLU/ReLU from the sign of the (pre- or post-)activation value; 0 -> slope
 __device__ __forceinline__ float leaky_grad(float v, float slope) { return v > 0.f ? 1.f : slope; }
 
+// round-to-nearest (ties away) to TF32's 10 mantissa bits.  tcgen05 kind::tf32 ignores the low 13 bits of its fp32 operands,
+// i.e. TRUNCATES: every product comes out low by ~7e-4 on average, a bias that normalisation layers on batch / instance
+// statistics cancel but BatchNorm in eval mode does not (1.6e-2 over the 25 layers of the s2g generator, profiles/
+// r2_tf32_truncation_bias.txt).  Producers of tensor-core operands therefore store RN-rounded values when asked (out_tf32):
+// the MMA then sees exactly representable operands and its error is unbiased.
+__device__ __forceinline__ float tf32_rna(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float out_round(float v, int out_tf32) { return out_tf32 ? tf32_rna(v) : v; }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

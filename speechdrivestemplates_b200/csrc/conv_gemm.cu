@@ -541,7 +541,8 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, int Cout, int Ci
         jy = tap / TW; jx = tap % TW;
     }
     const int ky = ky0 + kstep * jy, kx = kx0 + kstep * jx;
-    out[e] = w[(((size_t)co * Cin + ci) * KH + ky) * KW + kx];
+    // modes 2 / 3 are tensor-core operands: stored RN-rounded to TF32 (the MMA would truncate, common.cuh: tf32_rna)
+    out[e] = sdt::out_round(w[(((size_t)co * Cin + ci) * KH + ky) * KW + kx], mode >= 2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -647,7 +648,7 @@ __global__ void weight_prep_batch_kernel(const PrepItem* __restrict__ items) {
         else { ci = (int)(e % it.Cin); co = (int)((e / it.Cin) % it.Cout); tap = (int)(e / ((long long)it.Cout * it.Cin)); }
         const int jy = tap / it.TW, jx = tap % it.TW;
         const int ky = it.ky0 + it.kstep * jy, kx = it.kx0 + it.kstep * jx;
-        it.out[e] = it.w[(((size_t)co * it.Cin + ci) * it.KH + ky) * it.KW + kx];
+        it.out[e] = sdt::out_round(it.w[(((size_t)co * it.Cin + ci) * it.KH + ky) * it.KW + kx], it.mode >= 2);
     }
 }
 

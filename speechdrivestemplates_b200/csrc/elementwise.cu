@@ -19,7 +19,7 @@ __device__ __forceinline__ void lerp_coeff(int j, int in_size, int out_size, int
 // ---- F.interpolate(x,(1,F),'bilinear').squeeze(2) + cat(code) : generator.py:41-42,109-111 ----------------------------
 __global__ void enc_to_seq_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                       const float* __restrict__ shift, int bstride, float slope, int B, int H, int W, int C,
-                                      const float* __restrict__ code, int D, int F, float* __restrict__ out) {
+                                      const float* __restrict__ code, int D, int F, float* __restrict__ out, int out_tf32) {
     sdt::pdl_wait();
     sdt::pdl_launch_dependents();
     const long long total = (long long)B * F * (C + D);
@@ -29,7 +29,7 @@ __global__ void enc_to_seq_fwd_kernel(const float* __restrict__ x, const float* 
     const int j = (int)((e / (C + D)) % F);
     const int b = (int)(e / ((long long)(C + D) * F));
     if (ch >= C) {
-        out[e] = code[b * D + (ch - C)];
+        out[e] = sdt::out_round(code[b * D + (ch - C)], out_tf32);
         return;
     }
     int y0, y1, x0, x1;
@@ -39,7 +39,7 @@ __global__ void enc_to_seq_fwd_kernel(const float* __restrict__ x, const float* 
     const float sc = scale[b * bstride + ch], sh = shift[b * bstride + ch];
     auto at = [&](int yy, int xx) { return sdt::leaky(fmaf(x[(((size_t)b * H + yy) * W + xx) * C + ch], sc, sh), slope); };
     // ATen: w_y0*(w_x0*v00 + w_x1*v01) + w_y1*(w_x0*v10 + w_x1*v11)
-    out[e] = wy0 * (wx0 * at(y0, x0) + wx1 * at(y0, x1)) + wy1 * (wx0 * at(y1, x0) + wx1 * at(y1, x1));
+    out[e] = sdt::out_round(wy0 * (wx0 * at(y0, x0) + wx1 * at(y0, x1)) + wy1 * (wx0 * at(y1, x0) + wx1 * at(y1, x1)), out_tf32);
 }
 
 // adjoint in gather form (deterministic): every (b, y, x, c) sums the output frames that sampled it
@@ -93,7 +93,7 @@ __global__ void code_grad_from_seq_kernel(const float* __restrict__ g_out, int B
 
 // ---- F.interpolate(x, Lout, 'linear') (+ skip): generator.py:79-83, autoencoder.py:62-66 ----------------------------
 __global__ void upsample_add_fwd_kernel(const float* __restrict__ x, const float* __restrict__ skip, int B, int Lin,
-                                        int Lout, int C, float* __restrict__ out) {
+                                        int Lout, int C, float* __restrict__ out, int out_tf32) {
     sdt::pdl_wait();
     sdt::pdl_launch_dependents();
     const long long total = (long long)B * Lout * C;
@@ -107,7 +107,7 @@ __global__ void upsample_add_fwd_kernel(const float* __restrict__ x, const float
     lerp_coeff(j, Lin, Lout, i0, i1, w0, w1);
     float v = w0 * x[((size_t)b * Lin + i0) * C + c] + w1 * x[((size_t)b * Lin + i1) * C + c];
     if (skip != nullptr) v += skip[e];
-    out[e] = v;
+    out[e] = sdt::out_round(v, out_tf32);
 }
 
 __global__ void upsample_bwd_kernel(const float* __restrict__ g_out, int B, int Lin, int Lout, int C,
@@ -237,6 +237,22 @@ __global__ void code_scatter_grad_kernel(const float* __restrict__ ga, const flo
     for (int p = b; p < B; ++p)
         if (idx[p] == row) s += (ga ? ga[p * D + dd] : 0.f) + (gb ? gb[p * D + dd] : 0.f);
     g_table[(size_t)row * D + dd] += s;
+}
+
+// buffer scatter table[idx[b]] = src[b] (pose2pose.py:135-137).  Duplicate indices: the LAST occurrence wins, which is what the
+// sequential CPU index_put does; torch's CUDA index_put_ leaves the winner unspecified.
+__global__ void code_store_rows_kernel(const float* __restrict__ src_a, float* __restrict__ table_a, const float* __restrict__ src_b,
+                                       float* __restrict__ table_b, const int64_t* __restrict__ idx, int B, int D) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B * D) return;
+    const int b = e / D, dd = e % D;
+    const int64_t row = idx[b];
+    for (int p = b + 1; p < B; ++p)
+        if (idx[p] == row) return;   // a later occurrence owns this row
+    table_a[(size_t)row * D + dd] = src_a[e];
+    if (src_b != nullptr) table_b[(size_t)row * D + dd] = src_b[e];
 }
 
 __global__ void __launch_bounds__(1024) colsum_kernel(const float* __restrict__ g, int R, int C, float* __restrict__ out,
@@ -443,11 +459,11 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
 #define GRID1D(total) sdt::ceil_div((long long)(total), 256), 256, 0, sdt::as_stream(stream)
 
 extern "C" int sdt_enc_to_seq_fwd(const float* x, const float* scale, const float* shift, int xf_bstride, float slope, int B,
-                                  int H, int W, int C, const float* code, int D, int F, float* out, void* stream) {
+                                  int H, int W, int C, const float* code, int D, int F, float* out, int out_tf32, void* stream) {
     SDT_REQUIRE(x && scale && shift && out, "sdt_enc_to_seq_fwd: null pointer");
     SDT_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && F > 0 && D >= 0, "sdt_enc_to_seq_fwd: bad extents");
     SDT_REQUIRE(D == 0 || code != nullptr, "sdt_enc_to_seq_fwd: D > 0 needs code");
-    sdt::launch(enc_to_seq_fwd_kernel, dim3(sdt::ceil_div((long long)((long long)B * F * (C + D)), 256)), dim3(256), 0, sdt::as_stream(stream), x, scale, shift, xf_bstride, slope, B, H, W, C, code, D, F, out);
+    sdt::launch(enc_to_seq_fwd_kernel, dim3(sdt::ceil_div((long long)((long long)B * F * (C + D)), 256)), dim3(256), 0, sdt::as_stream(stream), x, scale, shift, xf_bstride, slope, B, H, W, C, code, D, F, out, out_tf32);
     SDT_LAUNCH_OK("enc_to_seq_fwd_kernel");
     return SDT_OK;
 }
@@ -466,9 +482,9 @@ extern "C" int sdt_enc_to_seq_bwd(const float* g_out, int B, int H, int W, int C
 }
 
 extern "C" int sdt_upsample_add_fwd(const float* x, const float* skip, int B, int Lin, int Lout, int C, float* out,
-                                    void* stream) {
+                                    int out_tf32, void* stream) {
     SDT_REQUIRE(x && out && B > 0 && Lin > 0 && Lout > 0 && C > 0, "sdt_upsample_add_fwd: bad arguments");
-    sdt::launch(upsample_add_fwd_kernel, dim3(sdt::ceil_div((long long)((long long)B * Lout * C), 256)), dim3(256), 0, sdt::as_stream(stream), x, skip, B, Lin, Lout, C, out);
+    sdt::launch(upsample_add_fwd_kernel, dim3(sdt::ceil_div((long long)((long long)B * Lout * C), 256)), dim3(256), 0, sdt::as_stream(stream), x, skip, B, Lin, Lout, C, out, out_tf32);
     SDT_LAUNCH_OK("upsample_add_fwd_kernel");
     return SDT_OK;
 }
@@ -504,6 +520,15 @@ extern "C" int sdt_code_scatter_grad(const float* g_code_a, const float* g_code_
     SDT_REQUIRE(idx && g_table && (g_code_a || g_code_b), "sdt_code_scatter_grad: null pointer");
     sdt::launch(code_scatter_grad_kernel, dim3(sdt::ceil_div((long long)(B * D), 256)), dim3(256), 0, sdt::as_stream(stream), g_code_a, g_code_b, idx, B, D, g_table);
     SDT_LAUNCH_OK("code_scatter_grad_kernel");
+    return SDT_OK;
+}
+
+extern "C" int sdt_code_store_rows(const float* src_a, float* table_a, const float* src_b, float* table_b, const int64_t* idx,
+                                   int B, int D, void* stream) {
+    SDT_REQUIRE(src_a && table_a && idx && B > 0 && D > 0, "sdt_code_store_rows: bad arguments");
+    SDT_REQUIRE((src_b == nullptr) == (table_b == nullptr), "sdt_code_store_rows: src_b and table_b come together");
+    sdt::launch(code_store_rows_kernel, dim3(sdt::ceil_div((long long)(B * D), 256)), dim3(256), 0, sdt::as_stream(stream), src_a, table_a, src_b, table_b, idx, B, D);
+    SDT_LAUNCH_OK("code_store_rows_kernel");
     return SDT_OK;
 }
 

@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(128) fl_stats_kernel(const double* __restrict_
 // 256 threads: 16 channel quads x 16 pixel lanes; a warp stores 2 adjacent pixels = 512 contiguous bytes
 __global__ void __launch_bounds__(256) fl_act_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                      const float* __restrict__ scale, const float* __restrict__ shift, int H,
-                                                     int W, float slope, float* __restrict__ act) {
+                                                     int W, float slope, float* __restrict__ act, int out_tf32) {
     sdt::pdl_wait();
     sdt::pdl_launch_dependents();
     __shared__ float s_rows[3 * kPitch];
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256) fl_act_kernel(const float* __restrict__ x
             float a = sh[j];
 #pragma unroll
             for (int k = 0; k < kTaps; ++k) a = fmaf(wq[j][k], t[k], a);
-            v[j] = sdt::leaky(a, slope);
+            v[j] = sdt::out_round(sdt::leaky(a, slope), out_tf32);
         }
         out[(size_t)px * (kC / 4)] = make_float4(v[0], v[1], v[2], v[3]);
     }
@@ -292,7 +292,7 @@ extern "C" int sdt_first_layer_units(int H, int W) { return H * ((W + kChunk - 1
 
 extern "C" int sdt_first_layer_fwd(const float* x, const float* w, int B, int H, int W, int C, float eps, float slope,
                                    double* mom_partial, double* moments, float* scale, float* shift, float* act,
-                                   void* stream) {
+                                   int out_tf32, void* stream) {
     SDT_REQUIRE(x && w && mom_partial && moments && scale && shift && act, "sdt_first_layer_fwd: null pointer");
     SDT_REQUIRE(C == kC, "sdt_first_layer_fwd: the block has %d output channels (got %d)", kC, C);
     SDT_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535, "sdt_first_layer_fwd: bad extents");
@@ -302,7 +302,7 @@ extern "C" int sdt_first_layer_fwd(const float* x, const float* w, int B, int H,
     SDT_LAUNCH_OK("fl_moments_kernel");
     sdt::launch(fl_stats_kernel, dim3(B), dim3(128), 0, st, mom_partial, w, units, (double)H * W, eps, moments, scale, shift);
     SDT_LAUNCH_OK("fl_stats_kernel");
-    sdt::launch(fl_act_kernel, dim3(units, B), dim3(256), 0, st, x, w, scale, shift, H, W, slope, act);
+    sdt::launch(fl_act_kernel, dim3(units, B), dim3(256), 0, st, x, w, scale, shift, H, W, slope, act, out_tf32);
     SDT_LAUNCH_OK("fl_act_kernel");
     return SDT_OK;
 }

@@ -162,7 +162,8 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(float* __restrict__
                                                              const float* __restrict__ mean, const float* __restrict__ rstd,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              const float* __restrict__ m1, const float* __restrict__ m2,
-                                                             long long total4, int P, int C, int groups_is_batch, float slope) {
+                                                             long long total4, int P, int C, int groups_is_batch, float slope,
+                                                             int out_tf32) {
     sdt::pdl_wait();
     sdt::pdl_launch_dependents();
     const long long e4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(float* __restrict__
         const float xh = (xx[q] - mean[so + q]) * rs;
         const float y = fmaf(xh, ga, be);
         const float gp = gg[q] * sdt::leaky_grad(y, slope);
-        gg[q] = rs * ga * (gp - m1[so + q] - xh * m2[so + q]);
+        gg[q] = sdt::out_round(rs * ga * (gp - m1[so + q] - xh * m2[so + q]), out_tf32);
     }
     *reinterpret_cast<float4*>(g + e) = make_float4(gg[0], gg[1], gg[2], gg[3]);
 }
@@ -249,7 +250,8 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_pow2_kernel(float* __restr
                                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                   const float* __restrict__ m1, const float* __restrict__ m2,
-                                                                  long long per_image4, int C, int groups_is_batch, float slope) {
+                                                                  long long per_image4, int C, int groups_is_batch, float slope,
+                                                                  int out_tf32) {
     sdt::pdl_wait();
     sdt::pdl_launch_dependents();
     const int b = blockIdx.y;
@@ -278,7 +280,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_pow2_kernel(float* __restr
             const float xh = (xx[q] - mu_[q]) * rs_[q];
             const float y = fmaf(xh, ga_[q], be_[q]);
             const float gp = gg[q] * sdt::leaky_grad(y, slope);
-            gg[q] = rs_[q] * ga_[q] * (gp - a1_[q] - xh * a2_[q]);
+            gg[q] = sdt::out_round(rs_[q] * ga_[q] * (gp - a1_[q] - xh * a2_[q]), out_tf32);
         }
         gi[e] = make_float4(gg[0], gg[1], gg[2], gg[3]);
     }
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(256) norm_bwd_apply_pow2_kernel(float* __restr
 template <int MAXV>
 __global__ void __launch_bounds__(256) rownorm_fwd_kernel(const float* __restrict__ x, int R, int C, float eps, float slope,
                                                           float* __restrict__ y, float* __restrict__ mean,
-                                                          float* __restrict__ rstd) {
+                                                          float* __restrict__ rstd, int out_tf32) {
     sdt::pdl_wait();
     sdt::pdl_launch_dependents();
     const int row = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(256) rownorm_fwd_kernel(const float* __restric
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
         const int c = lane + 32 * i;
-        if (c < C) yr[c] = sdt::leaky((v[i] - mu) * rs, slope);
+        if (c < C) yr[c] = sdt::out_round(sdt::leaky((v[i] - mu) * rs, slope), out_tf32);
     }
     if (lane == 0) {
         mean[row] = mu;
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(256) rownorm_fwd_kernel(const float* __restric
 template <int MAXV>
 __global__ void __launch_bounds__(256) rownorm_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x,
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                          int R, int C, float slope, float* __restrict__ gx) {
+                                                          int R, int C, float slope, float* __restrict__ gx, int out_tf32) {
     sdt::pdl_wait();
     sdt::pdl_launch_dependents();
     const int row = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -353,13 +355,13 @@ __global__ void __launch_bounds__(256) rownorm_bwd_kernel(const float* __restric
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
         const int c = lane + 32 * i;
-        if (c < C) o[c] = rs * (gp[i] - m1 - xh[i] * m2);
+        if (c < C) o[c] = sdt::out_round(rs * (gp[i] - m1 - xh[i] * m2), out_tf32);
     }
 }
 
 __global__ void scale_shift_act_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                        const float* __restrict__ shift, long long total, int P, int C, int bstride,
-                                       float slope, float* __restrict__ y) {
+                                       float slope, float* __restrict__ y, int out_tf32) {
     sdt::pdl_wait();
     sdt::pdl_launch_dependents();
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -367,13 +369,13 @@ __global__ void scale_shift_act_kernel(const float* __restrict__ x, const float*
     const int c = (int)(e % C);
     const int b = (int)(e / ((long long)P * C));
     const int so = b * bstride + c;
-    y[e] = sdt::leaky(fmaf(x[e], scale[so], shift[so]), slope);
+    y[e] = sdt::out_round(sdt::leaky(fmaf(x[e], scale[so], shift[so]), slope), out_tf32);
 }
 
 // C % 4 == 0: one float4 per thread, image index from the block (gridDim.y = B)
 __global__ void __launch_bounds__(256) scale_shift_act_v4_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                                                  const float* __restrict__ shift, long long per_image4, int C,
-                                                                 int bstride, float slope, float* __restrict__ y) {
+                                                                 int bstride, float slope, float* __restrict__ y, int out_tf32) {
     sdt::pdl_wait();
     sdt::pdl_launch_dependents();
     const int b = blockIdx.y;
@@ -387,10 +389,10 @@ __global__ void __launch_bounds__(256) scale_shift_act_v4_kernel(const float* __
         const float4 v = xi[e];
         const float4 s4 = *reinterpret_cast<const float4*>(sc + c), h4 = *reinterpret_cast<const float4*>(sh + c);
         float4 o;
-        o.x = sdt::leaky(fmaf(v.x, s4.x, h4.x), slope);
-        o.y = sdt::leaky(fmaf(v.y, s4.y, h4.y), slope);
-        o.z = sdt::leaky(fmaf(v.z, s4.z, h4.z), slope);
-        o.w = sdt::leaky(fmaf(v.w, s4.w, h4.w), slope);
+        o.x = sdt::out_round(sdt::leaky(fmaf(v.x, s4.x, h4.x), slope), out_tf32);
+        o.y = sdt::out_round(sdt::leaky(fmaf(v.y, s4.y, h4.y), slope), out_tf32);
+        o.z = sdt::out_round(sdt::leaky(fmaf(v.z, s4.z, h4.z), slope), out_tf32);
+        o.w = sdt::out_round(sdt::leaky(fmaf(v.w, s4.w, h4.w), slope), out_tf32);
         yi[e] = o;
     }
 }
@@ -449,7 +451,7 @@ extern "C" int sdt_norm_bwd_finalize(const float* partial, int groups, int tiles
 
 extern "C" int sdt_norm_bwd_apply(float* g, const float* x, const float* mean, const float* rstd, const float* gamma,
                                   const float* beta, const float* m1, const float* m2, int B, int P, int C, int groups,
-                                  float slope, void* stream) {
+                                  float slope, int out_tf32, void* stream) {
     SDT_REQUIRE(g && x && mean && rstd && m1 && m2, "sdt_norm_bwd_apply: null pointer");
     SDT_REQUIRE(C % 4 == 0, "sdt_norm_bwd_apply: need C %% 4 == 0 (C=%d)", C);
     SDT_REQUIRE(groups == B || groups == 1, "sdt_norm_bwd_apply: groups must be B or 1");
@@ -458,52 +460,52 @@ extern "C" int sdt_norm_bwd_apply(float* g, const float* x, const float* mean, c
         const long long per_image4 = (long long)P * C / 4;
         const int gx = (int)std::min<long long>(sdt::ceil_div(per_image4, 256 * 4), 4096);
         sdt::launch(norm_bwd_apply_pow2_kernel, dim3(gx, B), dim3(256), 0, sdt::as_stream(stream), g, x, mean, rstd, gamma, beta, m1, m2,
-                                                                                  per_image4, C, groups == B ? 1 : 0, slope);
+                                                                                  per_image4, C, groups == B ? 1 : 0, slope, out_tf32);
     } else
         sdt::launch(norm_bwd_apply_kernel, dim3(sdt::ceil_div(total4, 256)), dim3(256), 0, sdt::as_stream(stream), g, x, mean, rstd, gamma, beta, m1, m2,
-                                                                                             total4, P, C, groups == B ? 1 : 0, slope);
+                                                                                             total4, P, C, groups == B ? 1 : 0, slope, out_tf32);
     SDT_LAUNCH_OK("norm_bwd_apply_kernel");
     return SDT_OK;
 }
 
 extern "C" int sdt_rownorm_act_fwd(const float* x, int R, int C, float eps, float slope, float* y, float* mean, float* rstd,
-                                   void* stream) {
+                                   int out_tf32, void* stream) {
     SDT_REQUIRE(x && y && mean && rstd && R > 0 && C > 0, "sdt_rownorm_act_fwd: bad arguments");
     SDT_REQUIRE(C <= 1024, "sdt_rownorm_act_fwd: C=%d > 1024 unsupported", C);
     cudaStream_t st = sdt::as_stream(stream);
     const int grid = sdt::ceil_div(R, 8);
-    if (C <= 256) sdt::launch(rownorm_fwd_kernel<8>, dim3(grid), dim3(256), 0, st, x, R, C, eps, slope, y, mean, rstd);
-    else sdt::launch(rownorm_fwd_kernel<32>, dim3(grid), dim3(256), 0, st, x, R, C, eps, slope, y, mean, rstd);
+    if (C <= 256) sdt::launch(rownorm_fwd_kernel<8>, dim3(grid), dim3(256), 0, st, x, R, C, eps, slope, y, mean, rstd, out_tf32);
+    else sdt::launch(rownorm_fwd_kernel<32>, dim3(grid), dim3(256), 0, st, x, R, C, eps, slope, y, mean, rstd, out_tf32);
     SDT_LAUNCH_OK("rownorm_fwd_kernel");
     return SDT_OK;
 }
 
 extern "C" int sdt_rownorm_act_bwd(const float* g_y, const float* x, const float* mean, const float* rstd, int R, int C,
-                                   float slope, float* g_x, void* stream) {
+                                   float slope, float* g_x, int out_tf32, void* stream) {
     SDT_REQUIRE(g_y && x && mean && rstd && g_x && R > 0 && C > 0, "sdt_rownorm_act_bwd: bad arguments");
     SDT_REQUIRE(C <= 1024, "sdt_rownorm_act_bwd: C=%d > 1024 unsupported", C);
     cudaStream_t st = sdt::as_stream(stream);
     const int grid = sdt::ceil_div(R, 8);
-    if (C <= 256) sdt::launch(rownorm_bwd_kernel<8>, dim3(grid), dim3(256), 0, st, g_y, x, mean, rstd, R, C, slope, g_x);
-    else sdt::launch(rownorm_bwd_kernel<32>, dim3(grid), dim3(256), 0, st, g_y, x, mean, rstd, R, C, slope, g_x);
+    if (C <= 256) sdt::launch(rownorm_bwd_kernel<8>, dim3(grid), dim3(256), 0, st, g_y, x, mean, rstd, R, C, slope, g_x, out_tf32);
+    else sdt::launch(rownorm_bwd_kernel<32>, dim3(grid), dim3(256), 0, st, g_y, x, mean, rstd, R, C, slope, g_x, out_tf32);
     SDT_LAUNCH_OK("rownorm_bwd_kernel");
     return SDT_OK;
 }
 
 extern "C" int sdt_scale_shift_act(const float* x, const float* scale, const float* shift, int B, int P, int C, int bstride,
-                                   float slope, float* y, void* stream) {
+                                   float slope, float* y, int out_tf32, void* stream) {
     SDT_REQUIRE(x && scale && shift && y && B > 0 && P > 0 && C > 0, "sdt_scale_shift_act: bad arguments");
     const long long total = (long long)B * P * C;
     if (C % 4 == 0 && B <= 65535 && ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)scale | (uintptr_t)shift) & 15) == 0)) {
         const long long per_image4 = (long long)P * C / 4;
         int gx = sdt::ceil_div(per_image4, 256 * 2);
         if (gx > 2048) gx = 2048;
-        sdt::launch(scale_shift_act_v4_kernel, dim3(gx, B), dim3(256), 0, sdt::as_stream(stream), x, scale, shift, per_image4, C, bstride, slope, y);
+        sdt::launch(scale_shift_act_v4_kernel, dim3(gx, B), dim3(256), 0, sdt::as_stream(stream), x, scale, shift, per_image4, C, bstride, slope, y, out_tf32);
         SDT_LAUNCH_OK("scale_shift_act_v4_kernel");
         return SDT_OK;
     }
     sdt::launch(scale_shift_act_kernel, dim3(sdt::ceil_div(total, 256)), dim3(256), 0, sdt::as_stream(stream), x, scale, shift, total, P, C, bstride,
-                                                                                         slope, y);
+                                                                                         slope, y, out_tf32);
     SDT_LAUNCH_OK("scale_shift_act_kernel");
     return SDT_OK;
 }

@@ -306,6 +306,8 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
     self._mel = mel
     self._params = params
     self.materialize = self.math >= 2
+    # tensor-core math: every producer of a convolution operand stores TF32-rounded values (include/sdt_b200.h "out_tf32")
+    tf32 = self.math >= 1
     # math mode 2 with InstanceNorm and an invertible activation: the 1 -> 64 first block runs as the single-pass special
     # case (csrc/first_layer.cu): no raw map, no separate normalisation pass, closed-form weight gradient
     self.fused_first = self.materialize and self.norm == "IN" and slope > 0.0
@@ -339,7 +341,7 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
             act = A.get("act2d:" + name, (B, oh, ow, co))
             ops.first_layer_fwd(mel, params[name + ".conv.weight"], slope,
                                 out=(act, sc, sh, A.get("mom:" + name, (B, 54), torch.float64)),
-                                scratch=A.get("mom_partial:" + name, (B, ops.first_layer_units(H, W), 54), torch.float64))
+                                scratch=A.get("mom_partial:" + name, (B, ops.first_layer_units(H, W), 54), torch.float64), tf32=tf32)
             src, xf = act, None
             continue
         if wprep_ready is not None:
@@ -371,7 +373,7 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
             # math mode 2: the TMA-fed tensor-core kernels take plain tensors, so the normalised + activated map is written
             # once (HBM is at ~10 % utilisation; the SM-side operand path is the bottleneck)
             act = A.get("act2d:" + name, (B, oh, ow, co))
-            ops.scale_shift_act(raw, sc, sh, self._bstride(co), slope, out=act)
+            ops.scale_shift_act(raw, sc, sh, self._bstride(co), slope, out=act, tf32=tf32)
             src, xf = act, None
         else:
             src, xf = last_raw, last_xf
@@ -379,7 +381,7 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
     D = self.code_dim
     h7, w7 = self.enc_hw[8]
     x0 = A.get("x0", (B, num_frames, 256 + D))
-    ops.enc_to_seq_fwd(last_raw, last_xf[0], last_xf[1], last_xf[2], slope, code if D > 0 else None, num_frames, out=x0)
+    ops.enc_to_seq_fwd(last_raw, last_xf[0], last_xf[1], last_xf[2], slope, code if D > 0 else None, num_frames, out=x0, tf32=tf32)
     # ---- 1-D stack
     acts = {"x0": x0}
     for name, g, kind in self.seq_layers():
@@ -391,7 +393,7 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
         else:
             prev, skip = kind[3:].split("+")
             xin = A.get("xin:" + name, (B, L_out, 256))
-            ops.upsample_add_fwd(acts[prev], acts[skip], L_out, out=xin)
+            ops.upsample_add_fwd(acts[prev], acts[skip], L_out, out=xin, tf32=tf32)
         L_in = xin.shape[1]
         acts["in:" + name] = xin
         wt, wt_nk = self._prep_weight(name, params[name + ".conv.weight"], g)
@@ -400,7 +402,7 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
         act = A.get("act:" + name, (B, L_out, 256))
         if self.norm == "IN":
             ops.conv_gemm(d)
-            ops.rownorm_act_fwd(raw, slope, out=(act, A.get("rmean:" + name, (B * L_out,)), A.get("rrstd:" + name, (B * L_out,))))
+            ops.rownorm_act_fwd(raw, slope, out=(act, A.get("rmean:" + name, (B * L_out,)), A.get("rrstd:" + name, (B * L_out,))), tf32=tf32)
         else:
             sc = A.get("scale:" + name, (1, 256))
             sh = A.get("shift:" + name, (1, 256))
@@ -416,7 +418,7 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
                 ops.conv_gemm(d)
                 ops.bn_eval_scale_shift(buffers[name + ".norm.running_mean"], buffers[name + ".norm.running_var"],
                                         params[name + ".norm.weight"], params[name + ".norm.bias"], out=(sc, sh))
-            ops.scale_shift_act(raw, sc, sh, 0, slope, out=act)
+            ops.scale_shift_act(raw, sc, sh, 0, slope, out=act, tf32=tf32)
         acts[name] = act
     self._acts = acts
     # ---- final 1x1 conv + bias (generator.py:103); channels-last output IS (B,F,2,K) (generator.py:116)
@@ -493,6 +495,7 @@ def _gen_backward(self, g_pred, grads, g_code=None):
     """
     A, B, F, slope = self.arena, self.B, self.F, self.slope
     bn = self.norm == "BN"
+    tf32 = self.math >= 1
     params, acts = self._params, self._acts
     # ---- final conv
     ops.colsum(g_pred, grads["decoder.4.bias"])
@@ -522,11 +525,11 @@ def _gen_backward(self, g_pred, grads, g_code=None):
             scratch = (A.get("nb_partial:" + name, (B * tpi, 2, 256)), A.get("nb_m1:" + name, (1, 256)), A.get("nb_m2:" + name, (1, 256)))
             g_raw = ops.norm_backward(g_act[name], raw, A.get("mean:" + name, (1, 256)), A.get("rstd:" + name, (1, 256)), 1, slope,
                                       params[name + ".norm.weight"], params[name + ".norm.bias"],
-                                      grads[name + ".norm.weight"], grads[name + ".norm.bias"], scratch=scratch)
+                                      grads[name + ".norm.weight"], grads[name + ".norm.bias"], scratch=scratch, tf32=tf32)
         else:
             g_raw = A.get("g_raw:" + name, (B, L_out, 256))          # per layer: its wgrad may still be in flight
             ops.rownorm_act_bwd(g_act[name], raw, A.get("rmean:" + name, (B * L_out,)), A.get("rrstd:" + name, (B * L_out,)), slope,
-                                out=g_raw)
+                                out=g_raw, tf32=tf32)
         xin = acts["in:" + name]
         L_in = xin.shape[1]
         _wgrad(self, g, xin, g_raw, B, 1, L_in, grads[name + ".conv.weight"])
@@ -586,10 +589,10 @@ def _gen_backward(self, g_pred, grads, g_code=None):
         if bn:
             ops.norm_backward(g_enc, raw, A.get("mean:" + name, (groups, co)), A.get("rstd:" + name, (groups, co)), groups, slope,
                               params[name + ".norm.weight"], params[name + ".norm.bias"],
-                              grads[name + ".norm.weight"], grads[name + ".norm.bias"], scratch=scratch)
+                              grads[name + ".norm.weight"], grads[name + ".norm.bias"], scratch=scratch, tf32=tf32)
         else:
             ops.norm_backward(g_enc, raw, A.get("mean:" + name, (groups, co)), A.get("rstd:" + name, (groups, co)), groups, slope,
-                              scratch=scratch)
+                              scratch=scratch, tf32=tf32)
         if l == 0:
             src, xf = self._mel.view(B, 80, self.T, 1), None
         else:
@@ -676,7 +679,7 @@ class PoseEncoderEngine:
                                         params[name + ".norm.weight"], params[name + ".norm.bias"], out=(sc, sh))
             if tma and i + 1 < len(self.geoms):
                 act = A.get("act%s:%s" % (tag, name), (B, 1, lo, g.cout))
-                ops.scale_shift_act(raw.view(B, lo, g.cout), sc, sh, 0, self.slope, out=act.view(B, lo, g.cout))
+                ops.scale_shift_act(raw.view(B, lo, g.cout), sc, sh, 0, self.slope, out=act.view(B, lo, g.cout), tf32=True)
                 src, xf, L = act, None, lo
             else:
                 src, xf, L = raw, (sc, sh, 0), lo

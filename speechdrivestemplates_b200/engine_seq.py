@@ -46,7 +46,7 @@ class SeqBlock:
                 ops.bn_eval_scale_shift(buffers[name + ".norm.running_mean"], buffers[name + ".norm.running_var"], gamma, beta,
                                         out=(sc, sh))
             act = A.get("act%s:%s" % (tag, name), (B, L_out, g.cout))
-            ops.scale_shift_act(raw, sc, sh, 0, self.slope, out=act)
+            ops.scale_shift_act(raw, sc, sh, 0, self.slope, out=act, tf32=self.o.math >= 1)
         else:
             ops.conv_gemm(d)
             act = raw
@@ -63,7 +63,8 @@ class SeqBlock:
             scratch = (A.get("nb_partial:" + name, (B * tpi, 2, g.cout)), A.get("nb_m1:" + name, (1, g.cout)), A.get("nb_m2:" + name, (1, g.cout)))
             ops.norm_backward(g_act, raw, A.get("mean%s:%s" % (tag, name), (1, g.cout)), A.get("rstd%s:%s" % (tag, name), (1, g.cout)), 1,
                               self.slope, params[name + ".norm.weight"], params[name + ".norm.bias"],
-                              grads[name + ".norm.weight"], grads[name + ".norm.bias"], accumulate_params, scratch=scratch)
+                              grads[name + ".norm.weight"], grads[name + ".norm.bias"], accumulate_params, scratch=scratch,
+                              tf32=self.o.math >= 1)
         elif name + ".bias" in grads:
             ops.colsum(g_act, grads[name + ".bias"], accumulate_params)
         g_raw = g_act
@@ -157,7 +158,7 @@ class AutoencoderEngine(_SeqEngine):
         L = 2
         for b in self.dec_up:
             up = A.get("up:" + b.name, (B, 2 * L, b.g.cin))
-            ops.upsample_add_fwd(x, None, 2 * L, out=up)           # F.interpolate(..., mode='linear') x2 (autoencoder.py:62-66)
+            ops.upsample_add_fwd(x, None, 2 * L, out=up, tf32=self.math >= 1)           # F.interpolate(..., mode='linear') x2 (autoencoder.py:62-66)
             x = b.forward(up, B, 2 * L, params, buffers, training)
             L *= 2
         for b in self.dec_tail:

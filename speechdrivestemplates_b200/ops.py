@@ -382,8 +382,9 @@ def bwd_tiles(P, B):
 
 
 def norm_backward(g, x, mean, rstd, groups, slope, gamma=None, beta=None, dgamma=None, dbeta=None, accumulate=False,
-                  scratch=None):
-    """In place: g (B,P,C) := d loss / d x for [normalise(groups) -> affine -> act]; returns g."""
+                  scratch=None, tf32=False):
+    """In place: g (B,P,C) := d loss / d x for [normalise(groups) -> affine -> act]; returns g.
+    tf32: store the result rounded to TF32 (it is the next data / weight gradient's tensor-core operand, sdt_b200.h "out_tf32")."""
     B = g.shape[0]
     Cc = g.shape[-1]
     P = g.numel() // (B * Cc)
@@ -399,11 +400,11 @@ def norm_backward(g, x, mean, rstd, groups, slope, gamma=None, beta=None, dgamma
     call("sdt_norm_bwd_finalize", _p(partial), groups, (B * tpi) // groups, Cc, float(P * (B // groups)), _p(m1), _p(m2),
          _p(dgamma), _p(dbeta), int(accumulate), _stream())
     call("sdt_norm_bwd_apply", _p(g), _p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(m1), _p(m2), B, P, Cc, groups, slope,
-         _stream())
+         int(tf32), _stream())
     return g
 
 
-def rownorm_act_fwd(x, slope, out=None):
+def rownorm_act_fwd(x, slope, out=None, tf32=False):
     """x (..., C) -> (y, mean (R), rstd (R)): channel LayerNorm (the reference's 1-D 'IN') + activation."""
     Cc = x.shape[-1]
     R = x.numel() // Cc
@@ -413,23 +414,23 @@ def rownorm_act_fwd(x, slope, out=None):
         rstd = torch.empty(R, device=x.device)
     else:
         y, mean, rstd = out
-    call("sdt_rownorm_act_fwd", _p(x), R, Cc, EPS_NORM, slope, _p(y), _p(mean), _p(rstd), _stream())
+    call("sdt_rownorm_act_fwd", _p(x), R, Cc, EPS_NORM, slope, _p(y), _p(mean), _p(rstd), int(tf32), _stream())
     return y, mean, rstd
 
 
-def rownorm_act_bwd(g_y, x, mean, rstd, slope, out=None):
+def rownorm_act_bwd(g_y, x, mean, rstd, slope, out=None, tf32=False):
     Cc = x.shape[-1]
     R = x.numel() // Cc
     g_x = out if out is not None else torch.empty_like(x)
-    call("sdt_rownorm_act_bwd", _p(g_y), _p(x), _p(mean), _p(rstd), R, Cc, slope, _p(g_x), _stream())
+    call("sdt_rownorm_act_bwd", _p(g_y), _p(x), _p(mean), _p(rstd), R, Cc, slope, _p(g_x), int(tf32), _stream())
     return g_x
 
 
-def scale_shift_act(x, scale, shift, bstride, slope, out=None):
+def scale_shift_act(x, scale, shift, bstride, slope, out=None, tf32=False):
     B, Cc = x.shape[0], x.shape[-1]
     P = x.numel() // (B * Cc)
     y = out if out is not None else torch.empty_like(x)
-    call("sdt_scale_shift_act", _p(x), _p(scale), _p(shift), B, P, Cc, bstride, slope, _p(y), _stream())
+    call("sdt_scale_shift_act", _p(x), _p(scale), _p(shift), B, P, Cc, bstride, slope, _p(y), int(tf32), _stream())
     return y
 
 
@@ -437,7 +438,7 @@ def first_layer_units(H, W):
     return call("sdt_first_layer_units", H, W)
 
 
-def first_layer_fwd(x, w, slope, eps=None, out=None, scratch=None):
+def first_layer_fwd(x, w, slope, eps=None, out=None, scratch=None, tf32=False):
     """x (B,H,W) one-channel image, w (64,1,3,3) -> (act (B,H,W,64), scale (B,64), shift (B,64), moments (B,54) f64):
     Conv2d(1,64,3,1,1) + InstanceNorm2d + LeakyReLU in one pass over the output (generator.py:17)."""
     B, H, W = x.shape
@@ -448,7 +449,7 @@ def first_layer_fwd(x, w, slope, eps=None, out=None, scratch=None):
                torch.empty(B, Cc, device=x.device), torch.empty(B, 54, device=x.device, dtype=torch.float64))
     act, sc, sh, mom = out
     part = scratch if scratch is not None else torch.empty(B, units, 54, device=x.device, dtype=torch.float64)
-    call("sdt_first_layer_fwd", _p(x), _p(w), B, H, W, Cc, EPS_NORM if eps is None else eps, slope, _p(part), _p(mom), _p(sc), _p(sh), _p(act), _stream())
+    call("sdt_first_layer_fwd", _p(x), _p(w), B, H, W, Cc, EPS_NORM if eps is None else eps, slope, _p(part), _p(mom), _p(sc), _p(sh), _p(act), int(tf32), _stream())
     return act, sc, sh, mom
 
 
@@ -467,11 +468,11 @@ def first_layer_bwd(g_act, act, x, w, mom, sc, sh, slope, dw, scratch=None):
 # resampling / losses / heads / optimizer
 # ------------------------------------------------------------------------------------------------
 
-def enc_to_seq_fwd(x, scale, shift, bstride, slope, code, F, out=None):
+def enc_to_seq_fwd(x, scale, shift, bstride, slope, code, F, out=None, tf32=False):
     B, H, W, Cc = x.shape
     D = 0 if code is None else code.shape[1]
     y = out if out is not None else torch.empty(B, F, Cc + D, device=x.device)
-    call("sdt_enc_to_seq_fwd", _p(x), _p(scale), _p(shift), bstride, slope, B, H, W, Cc, _p(code), D, F, _p(y), _stream())
+    call("sdt_enc_to_seq_fwd", _p(x), _p(scale), _p(shift), bstride, slope, B, H, W, Cc, _p(code), D, F, _p(y), int(tf32), _stream())
     return y
 
 
@@ -485,10 +486,10 @@ def enc_to_seq_bwd(g_out, H, W, Cc, D, g_act=None, g_code=None):
     return g_act, g_code
 
 
-def upsample_add_fwd(x, skip, Lout, out=None):
+def upsample_add_fwd(x, skip, Lout, out=None, tf32=False):
     B, Lin, Cc = x.shape
     y = out if out is not None else torch.empty(B, Lout, Cc, device=x.device)
-    call("sdt_upsample_add_fwd", _p(x), _p(skip), B, Lin, Lout, Cc, _p(y), _stream())
+    call("sdt_upsample_add_fwd", _p(x), _p(skip), B, Lin, Lout, Cc, _p(y), int(tf32), _stream())
     return y
 
 
@@ -512,6 +513,12 @@ def code_scatter_grad(ga, gb, idx, g_table):
     B = idx.numel()
     D = g_table.shape[1]
     call("sdt_code_scatter_grad", _p(ga), _p(gb), _p(idx), B, D, _p(g_table), _stream())
+
+
+def code_store_rows(src_a, table_a, idx, src_b=None, table_b=None):
+    """table_a[idx[b]] = src_a[b] (and table_b / src_b): pose2pose.py:135-137, last duplicate wins."""
+    B, D = src_a.shape
+    call("sdt_code_store_rows", _p(src_a), _p(table_a), _p(src_b), _p(table_b), _p(idx), B, D, _stream())
 
 
 def colsum(g, out, accumulate=False):

@@ -955,8 +955,7 @@ class Pose2PoseTrainer:
         fp = ops.pose_final_results(pred.view(B, F, 2, -1), s["mean"], s["std"], s["scale"], hier, out=A.get("final_pred", (B, F, 2, K2 // 2), torch.float64))
         fg = ops.pose_final_results(s["poses"], s["mean"], s["std"], s["scale"], hier, out=A.get("final_gt", (B, F, 2, K2 // 2), torch.float64))
         met = ops.pose_metrics(fp, fg, A.get("met_partial", (2 * B,), torch.float64), A.get("met_out", (2,), torch.float64))
-        m.clip_code_mu[s["idx"]] = mu                                   # pose2pose.py:135-137
-        m.clip_code_logvar[s["idx"]] = logvar
+        ops.code_store_rows(mu, m.clip_code_mu, s["idx"], logvar, m.clip_code_logvar)      # pose2pose.py:135-137
         eng.backward(g_pred, self.grads, include_kl=True)
         self.out = OrderedDict(reg_loss=reg, kl_loss=kl, loss=loss, L2_dist=met[0:1], lip_sync_error_n=met[1:2],
                                poses_pred_batch=pred.view(B, F, 2, -1), clip_code_mu=mu, clip_code_logvar=logvar,

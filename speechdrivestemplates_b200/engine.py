@@ -156,6 +156,8 @@ class GeneratorEngine:
         self.fwd_id = 0
         self.math = ops.resolve_math(math)      # this engine's convolution math mode (every descriptor carries it)
         self.wprep = WeightPrep(self.arena, self.math)
+        self.grad_marks = None                  # {layer name: event recorded behind that layer's weight gradient} (multi-GPU buckets)
+        self.on_mark = None                     # callback(name, event), called when a mark has been recorded
 
     # ---- static layer tables -------------------------------------------------------------------
     def seq_layers(self):
@@ -440,12 +442,17 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
 _DIAG_SKIP_WGRAD = bool(__import__("os").environ.get("SDT_DIAG_SKIP_WGRAD"))
 
 
-def _wgrad(self, g, x, dy, B, H, W, grad_out, xf=None, slope=1.0, post=None):
+def _wgrad(self, g, x, dy, B, H, W, grad_out, xf=None, slope=1.0, post=None, name=None):
     """Weight gradient of one layer.  Nothing downstream in the backward pass depends on it, so when the engine has a
-    `wg_stream` it is enqueued there (after an event marking dy ready) and overlaps the dgrad chain on the main stream."""
+    `wg_stream` it is enqueued there (after an event marking dy ready) and overlaps the dgrad chain on the main stream.
+
+    `name` in self.grad_marks: an event is recorded right behind this layer's gradient (weight gradients are produced in
+    reverse layer order on one stream, so the event also covers every layer after it) -- the fused trainer starts the
+    all-reduce of a gradient bucket on it (pipeline.Voice2PoseTrainer._start_buckets)."""
     if _DIAG_SKIP_WGRAD:              # diagnostic only (wrong gradients): how much of the step do the weight gradients cost?
         return
     wg = getattr(self, "wg_stream", None)
+    marks = getattr(self, "grad_marks", None)
     if wg is not None:
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
@@ -454,11 +461,21 @@ def _wgrad(self, g, x, dy, B, H, W, grad_out, xf=None, slope=1.0, post=None):
             _wgrad_now(self, g, x, dy, B, H, W, grad_out, xf, slope)
             if post is not None:
                 post()
+            if marks is not None and name in marks:
+                marks[name] = torch.cuda.Event()
+                marks[name].record(wg)
+                if self.on_mark is not None:
+                    self.on_mark(name, marks[name])
         self._wg_pending = True
         return
     _wgrad_now(self, g, x, dy, B, H, W, grad_out, xf, slope)
     if post is not None:
         post()
+    if marks is not None and name in marks:
+        marks[name] = torch.cuda.Event()
+        marks[name].record(torch.cuda.current_stream())
+        if self.on_mark is not None:
+            self.on_mark(name, marks[name])
 
 
 def _wgrad_join(self):
@@ -532,7 +549,7 @@ def _gen_backward(self, g_pred, grads, g_code=None):
                                 out=g_raw, tf32=tf32)
         xin = acts["in:" + name]
         L_in = xin.shape[1]
-        _wgrad(self, g, xin, g_raw, B, 1, L_in, grads[name + ".conv.weight"])
+        _wgrad(self, g, xin, g_raw, B, 1, L_in, grads[name + ".conv.weight"], name=name)
         w = params[name + ".conv.weight"]
         if kind == "x0" and self._x0_pad():
             cpad = self._x0_pad()
@@ -603,7 +620,7 @@ def _gen_backward(self, g_pred, grads, g_code=None):
             else:
                 src = A.get("raw:" + pname, (B, H, W, pc))
                 xf = (A.get("scale:" + pname, (groups, pc)), A.get("shift:" + pname, (groups, pc)), self._bstride(pc))
-        _wgrad(self, g, src, g_enc, B, H, W, grads[name + ".conv.weight"], xf, slope)
+        _wgrad(self, g, src, g_enc, B, H, W, grads[name + ".conv.weight"], xf, slope, name=name)
         if l > 0:
             g_prev = A.get("g_enc:%d" % (l - 1), (B, H, W, ci))
             _dgrad(self, name, g, g_enc, params[name + ".conv.weight"], g_prev, B, H, W)

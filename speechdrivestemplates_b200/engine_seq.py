@@ -192,6 +192,8 @@ class AutoencoderEngine(_SeqEngine):
             L //= 2
             g = A.get("g_pre:" + b.name, (B, L, b.g.cin))
             ops.upsample_bwd(g_up, L, out=g)
+        if getattr(self, "on_decoder_done", None) is not None:     # every decoder.* gradient is final (multi-GPU: first bucket)
+            self.on_decoder_done()
         g_code = A.get("g_code", (B, self.D))
         torch.add(g[:, 0, :], g[:, 1, :], out=g_code)              # adjoint of the nearest x2 duplicate
         mu, logvar = A.get("mu", (B, self.D)), A.get("logvar", (B, self.D))

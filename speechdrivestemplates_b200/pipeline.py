@@ -14,6 +14,9 @@ import os
 import torch
 from torch import nn
 
+# diagnostic switch (wrong results: the FGD / metrics side stream is skipped); bench.py refuses to run with it set
+_DIAG_SKIP_SIDE = bool(os.environ.get("SDT_DIAG_SKIP_SIDE"))
+
 from . import _lib, ops, parallel
 from .networks import PoseSeqEncoder, SequenceGeneratorCNN, get_model
 
@@ -535,6 +538,12 @@ class Voice2PoseTrainer:
         self._wg_stream = torch.cuda.Stream(device=self.device)                # weight gradients overlap the dgrad chain (engine._wgrad)
         m.netG.engine().wg_stream = self._wg_stream
         self._overlap = True
+        # multi-GPU: "overlap" = gradient buckets all-reduced on a communication stream while the backward pass still runs, the
+        # clip-code gradient exchanged as B x (index, 32) rows, NCCL captured inside the step's CUDA graph; "serial" = one flat
+        # all-reduce between two graphs (round-1 behaviour; also the fallback when NCCL cannot be captured on this stack)
+        self.comm_mode = os.environ.get("SDT_COMM", "overlap") if self.world > 1 else "none"
+        self._comm = torch.cuda.Stream(device=self.device) if self.world > 1 else None
+        self._works = []
         self._aux = None
         self._inbox, self._prefetched = None, None
         self._scal = torch.zeros(12, device=self.device, dtype=torch.float64)
@@ -685,15 +694,77 @@ class Voice2PoseTrainer:
         return g_total
 
     # ---- the device program, in two halves around the all-reduce
+    # ---- multi-GPU: gradient buckets in the order the backward pass completes them (SURVEY C3: still ONE logical exchange of the
+    # flat gradient per step, cut where the weight-gradient stream passes two layers so that the wire overlaps the remaining math)
+    def _buckets(self):
+        """[(engine mark or None, start, end)] over flat_g.  A mark names the layer whose weight gradient completes the bucket."""
+        n = self.flat_g.numel()
+        if self.has_d or self.comm_mode != "overlap" or not self._overlap:
+            return [(None, 0, n)]
+        from .engine import ENC_PREFIX
+        tail = self.n_g_pad if self.train_code else n          # the dense clip-code gradient never goes on the wire (rows do)
+        plan = parallel.bucket_plan([(k, p.numel()) for k, p in self.model.netG.named_parameters()],
+                                    ["unet.e0.conv.weight", ENC_PREFIX + "2.0.conv.weight"], n, tail)
+        return [(m[:-len(".conv.weight")] if m else None, lo, hi) for m, lo, hi in plan]      # engine marks are layer names
+
+    def _reduce_async(self, ready, lo, hi):
+        """all-reduce(sum) of flat_g[lo:hi] on the communication stream, starting when `ready` (event) has happened."""
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(ready)
+            self._works.append(torch.distributed.all_reduce(self.flat_g[lo:hi], op=torch.distributed.ReduceOp.SUM, group=self.pg,
+                                                            async_op=True))
+
+    def _exchange(self, g_code):
+        """Everything of the step that crosses GPUs and is not a marked bucket: the last bucket, the clip-code gradient rows and
+        (C5, trainer.py:323-327) the loss / metric scalars.  Ends with the main stream waiting for all of the step's collectives."""
+        dist = torch.distributed
+        main = torch.cuda.current_stream()
+        done = torch.cuda.Event()
+        done.record(main)
+        A = self.engine._arena(self.device)
+        rows_all = idx_all = None
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(done)
+            for mark, lo, hi in self._bucket_plan:
+                if mark is None:
+                    self._works.append(dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+            if self.train_code and self.comm_mode == "overlap" and not self.has_d:
+                B, D = g_code.shape
+                rows = A.get("xchg_rows", (B, D))
+                torch.add(g_code, A.get("g_code_kl", (B, D)), out=rows)
+                rows_all, idx_all, works = parallel.gather_rows(
+                    rows, self.engine._clip_index, self.pg, async_op=True,
+                    out=(A.get("xchg_rows_all", (self.world * B, D)), A.get("xchg_idx_all", (self.world * B,), torch.long)))
+                self._works += works
+            self._works.append(dist.all_reduce(self._scal, op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        for w in self._works:
+            w.wait()                                    # the main stream waits; nothing blocks the host
+        self._works = []
+        main.wait_stream(self._comm)
+        if rows_all is not None:                        # dense clip-code gradient = sum over ranks of the scattered rows (K12)
+            ops.code_scatter_grad(rows_all, None, idx_all, self.g_table)
+
     def _fwd_bwd(self):
         s = self._staging
         if self.train_code:
             self.g_table.zero_()                                       # optimizerClipCode.zero_grad(); dense grad (K12)
         p2g = getattr(self, "_p2g", None)
+        multi = self.world > 1 and self.comm_mode == "overlap"
+        sparse_code = multi and self.train_code and not self.has_d
+        eng = self.model.netG.engine()
+        if multi:
+            self._bucket_plan = self._buckets()
+            ranges = {m: (lo, hi) for m, lo, hi in self._bucket_plan if m is not None}
+            eng.grad_marks = {m: None for m in ranges}
+            eng.on_mark = lambda name, ev: self._reduce_async(ev, *ranges[name])
+        else:
+            eng.grad_marks, eng.on_mark = None, None
         if not self._overlap:
             self.out = self.engine.forward(s["audio"], s["poses"], s["idx"], (s["mean"], s["std"], s["scale"]), p2g_stats=p2g)
-            self.engine.backward(self.grads, self.g_table, g_pred=self._gan() if self.has_d else None)
+            g_code = self.engine.backward(self.grads, None if sparse_code else self.g_table, g_pred=self._gan() if self.has_d else None)
             self._pack_scalars()
+            if multi:
+                self._exchange(g_code)
             return
         self.out = self.engine.forward(s["audio"], s["poses"], s["idx"], (s["mean"], s["std"], s["scale"]), p2g_stats=p2g, defer_side=True)
         # fork: FGD features + f64 results/metrics on a second stream while the backward pass runs on this one
@@ -704,12 +775,14 @@ class Voice2PoseTrainer:
         fork.record(main)
         with torch.cuda.stream(self._aux):
             self._aux.wait_event(fork)
-            if not os.environ.get("SDT_DIAG_SKIP_SIDE"):       # diagnostic only: cost of the FGD / metrics side stream
+            if not _DIAG_SKIP_SIDE:                            # diagnostic only: cost of the FGD / metrics side stream
                 self.engine.run_side()
             join.record(self._aux)
-        self.engine.backward(self.grads, self.g_table, g_pred=self._gan() if self.has_d else None)
+        g_code = self.engine.backward(self.grads, None if sparse_code else self.g_table, g_pred=self._gan() if self.has_d else None)
         main.wait_event(join)
         self._pack_scalars()
+        if multi:
+            self._exchange(g_code)
 
     def _optim(self):
         gs = 1.0 / self.world
@@ -727,8 +800,16 @@ class Voice2PoseTrainer:
             ops.adam_flat(self.flat_p[sl], self.flat_g[sl], self.exp_avg[sl], self.exp_avg_sq[sl], self.adam_d, grad_scale=gs)
 
     def _allreduce(self):
-        if self.world > 1:
-            parallel.allreduce_flat_(self.flat_g, self.pg)             # ONE flat NCCL all-reduce per step
+        """comm_mode "serial": ONE flat NCCL all-reduce of the whole gradient buffer between the two graphs + the scalars (C5)."""
+        if self.world > 1 and self.comm_mode != "overlap":
+            parallel.allreduce_flat_(self.flat_g, self.pg)
+            torch.distributed.all_reduce(self._scal, group=self.pg)
+
+    def _step(self):
+        """The whole device program of one step in stream order (collectives included in comm_mode "overlap")."""
+        self._fwd_bwd()
+        self._allreduce()
+        self._optim()
 
     @_on_device
     def run_staged(self):
@@ -737,13 +818,12 @@ class Voice2PoseTrainer:
             self._capture()
         if self._graphs is not None:
             self._graphs[0].replay()
-            self._allreduce()
-            self._graphs[1].replay()
+            if len(self._graphs) == 2:
+                self._allreduce()
+                self._graphs[1].replay()
         else:
             n0 = _lib.launch_count
-            self._fwd_bwd()
-            self._allreduce()
-            self._optim()
+            self._step()
             self.kernels_per_step = _lib.launch_count - n0
             self._warm += 1
         self.steps_done += 1
@@ -751,18 +831,39 @@ class Voice2PoseTrainer:
 
     @_on_device
     def _capture(self):
+        """world 1 and comm_mode "overlap": ONE graph holds the step (NCCL collectives are captured with it, on the streams
+        torch's process group gives them).  comm_mode "serial": two graphs around the eager all-reduce.  If capturing NCCL fails
+        on this software stack the trainer drops to "serial" and says so."""
         torch.cuda.synchronize()
+        if self.world > 1:
+            torch.distributed.barrier(group=self.pg)
+            torch.cuda.synchronize()
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
-        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        with torch.cuda.stream(side):
-            with torch.cuda.graph(g1, stream=side):
-                self._fwd_bwd()
-            with torch.cuda.graph(g2, stream=side):
-                self._optim()
+        if self.world == 1 or self.comm_mode == "overlap":
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.stream(side):
+                    with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+                        self._step()
+                self._graphs = (g,)
+            except Exception as e:                      # noqa: BLE001 - NCCL capture unsupported: fall back, loudly
+                if self.world == 1:
+                    raise
+                import warnings
+                warnings.warn("capturing NCCL inside the step graph failed (%s: %s); falling back to SDT_COMM=serial" % (type(e).__name__, e))
+                self.comm_mode, self._works = "serial", []
+                torch.cuda.synchronize()
+        if self._graphs is None:
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g1, stream=side):
+                    self._fwd_bwd()
+                with torch.cuda.graph(g2, stream=side):
+                    self._optim()
+            self._graphs = (g1, g2)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self._graphs = (g1, g2)
 
     @_on_device
     def train_step(self, batch):
@@ -781,6 +882,8 @@ class Voice2PoseTrainer:
                 self._scal[i:i + 1].copy_(self.out[k])
 
     def _scalars_dict(self, vals):
+        if self.world > 1:              # the all-reduced sums -> means over ranks (reduce_tensor_dict, trainer.py:323-327)
+            vals = [v / self.world for v in vals]
         d = {k: v for k, v in zip(self._SCALARS, vals) if k in self.out}
         if "kl_applied" in d and d.pop("kl_applied") == 0.0:          # the reference's guard (voice2pose.py:154)
             d.pop("G_clipcode_kl_loss", None)
@@ -908,6 +1011,11 @@ class Pose2PoseTrainer:
         self._staging, self._graphs, self._warm = None, None, 0
         self.kernels_per_step = 0
         self.eps_override = None          # tests inject the N(0,1) draw here
+        self.comm_mode = os.environ.get("SDT_COMM", "overlap") if self.world > 1 else "none"
+        self._comm = torch.cuda.Stream(device=self.device) if self.world > 1 else None
+        self._works, self._reduce_scalars = [], False
+        self._scal = torch.zeros(len(self._SCALARS), device=self.device, dtype=torch.float64)
+        self._dec_off = sum(p.numel() for nme, p in zip(self.names, params) if nme.startswith("encoder."))
 
     def set_lr(self, lr):
         self.lr = float(lr)
@@ -966,32 +1074,77 @@ class Pose2PoseTrainer:
         ops.adam_flat(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, self.adam, grad_scale=1.0 / self.world,
                       weight_decay=float(self.cfg.TRAIN.WD))            # pose2pose.py:114-115
 
+    # ---- multi-GPU (pose2pose.py:101-102: DDP over `ae`): two gradient buckets, decoder first (its gradients are final when the
+    # backward pass enters the encoder), all-reduced on a communication stream inside the step's graph
+    def _reduce_async(self, lo, hi):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(ev)
+            self._works.append(torch.distributed.all_reduce(self.flat_g[lo:hi], op=torch.distributed.ReduceOp.SUM, group=self.pg,
+                                                            async_op=True))
+
+    def _step(self):
+        multi = self.world > 1 and self.comm_mode == "overlap"
+        eng = self.model.ae.engine()
+        eng.on_decoder_done = (lambda: self._reduce_async(self._dec_off, self.flat_g.numel())) if multi else None
+        self._fwd_bwd()
+        if multi:
+            self._reduce_async(0, self._dec_off)
+            self._scal.copy_(torch.cat([self.out[k].double().view(1) for k in self._SCALARS]))
+            self._reduce_scalars = True
+            with torch.cuda.stream(self._comm):
+                self._works.append(torch.distributed.all_reduce(self._scal, group=self.pg, async_op=True))
+            for w in self._works:
+                w.wait()
+            self._works = []
+            torch.cuda.current_stream().wait_stream(self._comm)
+        elif self.world > 1:
+            parallel.allreduce_flat_(self.flat_g, self.pg)
+        self._optim()
+
     @_on_device
     def run_staged(self):
         if self.use_graph and self._graphs is None and self._warm >= 2:
             torch.cuda.synchronize()
+            if self.world > 1:
+                torch.distributed.barrier(group=self.pg)
+                torch.cuda.synchronize()
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream())
-            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.stream(side):
-                with torch.cuda.graph(g1, stream=side):
-                    self._fwd_bwd()
-                with torch.cuda.graph(g2, stream=side):
-                    self._optim()
+            if self.world == 1 or self.comm_mode == "overlap":
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.stream(side):
+                        with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+                            self._step()
+                    self._graphs = (g,)
+                except Exception as e:                      # noqa: BLE001
+                    if self.world == 1:
+                        raise
+                    import warnings
+                    warnings.warn("capturing NCCL inside the step graph failed (%s: %s); falling back to SDT_COMM=serial" % (type(e).__name__, e))
+                    self.comm_mode, self._works = "serial", []
+                    torch.cuda.synchronize()
+            if self._graphs is None:
+                g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.stream(side):
+                    with torch.cuda.graph(g1, stream=side):
+                        self._fwd_bwd()
+                    with torch.cuda.graph(g2, stream=side):
+                        self._optim()
+                self._graphs = (g1, g2)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            self._graphs = (g1, g2)
         if self._graphs is not None:
             self._graphs[0].replay()
-            if self.world > 1:
-                parallel.allreduce_flat_(self.flat_g, self.pg)
-            self._graphs[1].replay()
+            if len(self._graphs) == 2:
+                if self.world > 1:
+                    parallel.allreduce_flat_(self.flat_g, self.pg)
+                self._graphs[1].replay()
         else:
             n0 = _lib.launch_count
-            self._fwd_bwd()
-            if self.world > 1:
-                parallel.allreduce_flat_(self.flat_g, self.pg)
-            self._optim()
+            self._step()
             self.kernels_per_step = _lib.launch_count - n0
             self._warm += 1
         return self.out
@@ -1001,8 +1154,13 @@ class Pose2PoseTrainer:
         self._stage(batch)
         return self.run_staged()
 
+    _SCALARS = ("reg_loss", "kl_loss", "loss", "L2_dist", "lip_sync_error_n")
+
     @_on_device
     def losses_to_host(self, out):
-        keys = ["reg_loss", "kl_loss", "loss", "L2_dist", "lip_sync_error_n"]
-        vals = torch.cat([out[k].double().view(1) for k in keys]).cpu().tolist()
-        return dict(zip(keys, vals))
+        """One small D2H read of the step's scalars; with several ranks in comm_mode "overlap" these are the means over ranks
+        (the all-reduce rode along with the gradient exchange: reduce_tensor_dict, trainer.py:323-327)."""
+        if self._reduce_scalars:
+            return dict(zip(self._SCALARS, (self._scal / self.world).cpu().tolist()))
+        vals = torch.cat([out[k].double().view(1) for k in self._SCALARS]).cpu().tolist()
+        return dict(zip(self._SCALARS, vals))

@@ -1,0 +1,152 @@
+"""Multi-GPU correctness of the fused trainers on real hardware (not a pytest test: needs N GPUs and torchrun).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/multi_gpu_check.py [--out gpurun_out/multi_gpu_check.json]
+
+Checks, for voice2pose_sdt_bp (reference: DDP wrap + per-step gradient all-reduce, voice2pose.py:222-223,298-309) and pose2pose
+(pose2pose.py:101-102,145-147):
+  1. the reduced gradient of W ranks with B clips each equals the gradient of ONE rank on the W*B-clip batch (per-sample norms
+     make the generator shard-invariant); fp32 math mode, clip codes at zero so that the per-rank batch-statistics KL
+     term (which legitimately differs) is skipped; the exchanged clip-code rows scatter to the dense single-rank gradient;
+  2. after K steps through the CUDA-graph path every rank holds bit-identical parameters and Adam state (max - min over ranks);
+  3. comm modes "overlap" (buckets on a comm stream + code rows, NCCL inside the graph) and "serial" (one flat all-reduce between
+     two graphs) land on the same parameters;
+  4. the loss scalars read on every rank are the means over ranks (C5, trainer.py:323-327).
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def host_batch(b):
+    out = dict(b)
+    out["speaker_stat"] = {k: torch.from_numpy(np.asarray(v)) for k, v in b["speaker_stat"].items()}
+    return out
+
+
+def shard(batch, rank, per):
+    sl = slice(rank * per, (rank + 1) * per)
+    out = {k: (v[sl] if torch.is_tensor(v) else v) for k, v in batch.items()}
+    out["speaker"] = batch["speaker"][sl]
+    out["speaker_stat"] = {k: v[sl] for k, v in batch["speaker_stat"].items()}
+    return host_batch(out)
+
+
+def spread(t, group):
+    hi, lo = t.clone(), t.clone()
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    return float((hi - lo).abs().max())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "multi_gpu_check.json"))
+    ap.add_argument("--steps", type=int, default=6)
+    args = ap.parse_args()
+    from oracle import sdt_oracle as O                    # seeded synthetic batches only
+    from util import oliver_stat
+    from speechdrivestemplates_b200 import config, pipeline
+
+    world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    pg = dist.group.WORLD
+    res = {"world": world}
+    per, n_train = 2, 64
+    stat = oliver_stat(True)
+    full = O.synthetic_batch(per * world, n_train, stat, seed=4321)
+
+    # ---- 1. reduced gradient == full-batch gradient (fp32 mode, eager)
+    cfg = config.get_cfg("voice2pose_sdt_bp")
+    tr = pipeline.Voice2PoseTrainer(cfg, n_train, dev, use_cuda_graph=False, process_group=pg, seed=0, conv_math=0)
+    out = tr.train_step(shard(full, rank, per))
+    torch.cuda.synchronize()
+    got = (tr.flat_g / world).clone()                     # Adam applies the 1/W (grad_scale)
+    mean_losses = tr.losses_to_host(out)
+    if rank == 0:
+        one = pipeline.Voice2PoseTrainer(cfg, n_train, dev, use_cuda_graph=False, seed=0, conv_math=0)
+        one_out = one.train_step(host_batch(full))
+        ref = one.flat_g
+        worst = 0.0
+        off = 0
+        for name, p in one.model.netG.named_parameters():
+            a, b = got[off:off + p.numel()].double(), ref[off:off + p.numel()].double()
+            worst = max(worst, float((a - b).abs().max() / (b.pow(2).mean().sqrt() + 1e-30)))
+            off += p.numel()
+        code_a, code_b = got[one.n_g_pad:one.n_g_pad + one.n_code], ref[one.n_g_pad:one.n_g_pad + one.n_code]
+        res["reduced_vs_full_batch_grad_max_err_over_rms"] = worst
+        res["code_grad_max_abs_err"] = float((code_a - code_b).abs().max())
+        res["code_grad_max_abs"] = float(code_b.abs().max())
+        full_losses = one.losses_to_host(one_out)
+        res["mean_of_rank_losses"] = mean_losses
+        res["full_batch_losses"] = full_losses
+        # L1 'mean' over equal shards: the mean over ranks of the per-rank loss IS the full-batch loss
+        res["loss_mean_err"] = abs(mean_losses["G_reg_loss"] - full_losses["G_reg_loss"])
+    # every rank read the same (reduced) scalars
+    t = torch.tensor([mean_losses["G_loss"], mean_losses["L2_dist"]], device=dev, dtype=torch.float64)
+    res["scalar_spread_over_ranks"] = spread(t, pg)
+
+    # ---- 2./3. K graph-replayed steps in both comm modes, benchmarked math mode
+    finals = {}
+    for mode in ("overlap", "serial"):
+        os.environ["SDT_COMM"] = mode
+        tr = pipeline.Voice2PoseTrainer(cfg, n_train, dev, use_cuda_graph=True, process_group=pg, seed=0, conv_math=3)
+        tr.model.clips_code.data.copy_(0.1 * torch.randn(n_train, 32, generator=torch.Generator().manual_seed(11)))
+        for s in range(args.steps):
+            b = O.synthetic_batch(per * world, n_train, stat, seed=5000 + s)
+            out = tr.train_step(shard(b, rank, per))
+        torch.cuda.synchronize()
+        res["sdt_bp/%s/comm_mode_in_effect" % mode] = tr.comm_mode
+        res["sdt_bp/%s/graphs" % mode] = len(tr._graphs) if tr._graphs is not None else 0
+        res["sdt_bp/%s/rank_param_spread" % mode] = spread(tr.flat_p, pg)
+        res["sdt_bp/%s/rank_adam_state_spread" % mode] = max(spread(tr.exp_avg, pg), spread(tr.exp_avg_sq, pg))
+        res["sdt_bp/%s/losses" % mode] = tr.losses_to_host(out)
+        finals[mode] = tr.flat_p.clone()
+    d = (finals["overlap"] - finals["serial"]).abs().max()
+    res["sdt_bp/overlap_vs_serial_param_max_abs_diff"] = float(d)
+
+    # ---- pose2pose
+    pcfg = config.get_cfg("pose2pose")
+    finals = {}
+    for mode in ("overlap", "serial"):
+        os.environ["SDT_COMM"] = mode
+        tr = pipeline.Pose2PoseTrainer(pcfg, n_train, dev, use_cuda_graph=True, process_group=pg, seed=0, conv_math=3)
+        for s in range(args.steps):
+            b = O.synthetic_batch(4 * world, n_train, stat, seed=6000 + s)
+            tr.eps_override = torch.randn(4, 32, generator=torch.Generator().manual_seed(7000 + 10 * s + rank)).to(dev)
+            out = tr.train_step(shard(b, rank, 4))
+        torch.cuda.synchronize()
+        res["pose2pose/%s/comm_mode_in_effect" % mode] = tr.comm_mode
+        res["pose2pose/%s/rank_param_spread" % mode] = spread(tr.flat_p, pg)
+        res["pose2pose/%s/losses" % mode] = tr.losses_to_host(out)
+        finals[mode] = tr.flat_p.clone()
+    res["pose2pose/overlap_vs_serial_param_max_abs_diff"] = float((finals["overlap"] - finals["serial"]).abs().max())
+
+    ok = (res["scalar_spread_over_ranks"] == 0.0
+          and all(v == 0.0 for k, v in res.items() if k.endswith("rank_param_spread") or k.endswith("rank_adam_state_spread")))
+    if rank == 0:
+        ok = ok and res["reduced_vs_full_batch_grad_max_err_over_rms"] < 1e-3 and res["loss_mean_err"] < 1e-5 \
+            and res["code_grad_max_abs_err"] <= 1e-5 * max(res["code_grad_max_abs"], 1e-30) + 1e-9
+        res["ok"] = bool(ok)
+        os.makedirs(os.path.dirname(args.out), exist_ok=True)
+        with open(args.out, "w") as f:
+            json.dump(res, f, indent=1)
+        print(json.dumps(res, indent=1))
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

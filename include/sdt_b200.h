@@ -169,6 +169,13 @@ int sdt_norm_finalize(const float* partial, int groups, int tiles_per_group, int
                       const float* beta, float eps, float* scale, float* shift, float* mean, float* rstd,
                       float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
                       void* stream);
+/* Column sums / sums of squares of the window [w0, w1) of a channels-last map x (B, H, W, C), in the partial layout
+ * sdt_norm_finalize reads: partial (B, n_parts, 2, C), part p = positions [p*rows_per_part, (p+1)*rows_per_part) of the
+ * window's H*(w1-w0) positions (parts past the end are written as zeros).  Time-tiled long-audio inference
+ * (trainer.py:459-484 / voice2pose.py:386-410 run the whole utterance in one forward): InstanceNorm2d statistics span the
+ * utterance, a tile contributes its OWNED columns only (the receptive-field halo is excluded). */
+int sdt_chan_stats(const float* x, int B, int H, int W, int C, int w0, int w1, int rows_per_part, float* partial,
+                   int n_parts, void* stream);
 /* BatchNorm eval mode: scale/shift from running statistics (C). */
 int sdt_bn_eval_scale_shift(const float* running_mean, const float* running_var, const float* gamma, const float* beta,
                             float eps, int C, float* scale, float* shift, void* stream);

@@ -249,10 +249,10 @@ def mel_spectrogram(audio, window=None, fb=None, dtype=torch.float32):
     one-sided rFFT, |X|^2, then P^T . fb.
     """
     audio = audio.to(dtype)
-    w = (hann_window_periodic() if window is None else window).to(dtype)
-    fbm = (mel_filterbank() if fb is None else fb).to(dtype)
+    w = (hann_window_periodic() if window is None else window).to(device=audio.device, dtype=dtype)
+    fbm = (mel_filterbank() if fb is None else fb).to(device=audio.device, dtype=dtype)
     lpad = (N_FFT - WIN_LENGTH) // 2
-    wfull = torch.zeros(N_FFT, dtype=dtype)
+    wfull = torch.zeros(N_FFT, dtype=dtype, device=audio.device)
     wfull[lpad:lpad + WIN_LENGTH] = w
     x = F.pad(audio.unsqueeze(1), (N_FFT // 2, N_FFT // 2), mode="reflect").squeeze(1)
     frames = x.unfold(-1, N_FFT, HOP)                     # (B, T, 512)

@@ -30,6 +30,44 @@ __device__ __forceinline__ void sum_partials_32ch(const float* __restrict__ p, i
     }
 }
 
+// ---- statistics of a column window of a channels-last map (time-tiled inference) ------------------------------------
+// x (B, H, W, C); positions p = h * (w1 - w0) + (w - w0) over the window; part `blockIdx.x` sums rows_per_part positions.
+// lane = channel (coalesced), the row groups of the CTA are combined in shared memory in fixed order.
+__global__ void chan_stats_kernel(const float* __restrict__ x, int H, int W, int C, int w0, int w1, int rows_per_part,
+                                  float* __restrict__ partial, int n_parts) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
+    extern __shared__ float s_cs[];                     // (rgroups, 2, C)
+    const int part = blockIdx.x, b = blockIdx.y;
+    const int rgroups = blockDim.x / C, rg = threadIdx.x / C, c = threadIdx.x % C;
+    const int ww = w1 - w0;
+    const long long P = (long long)H * ww;
+    const long long p0 = (long long)part * rows_per_part;
+    const long long p1 = p0 + rows_per_part < P ? p0 + rows_per_part : P;
+    float s = 0.f, q = 0.f;
+    if (rg < rgroups)
+        for (long long p = p0 + rg; p < p1; p += rgroups) {
+            const int h = (int)(p / ww), w = w0 + (int)(p % ww);
+            const float v = __ldg(x + (((size_t)b * H + h) * W + w) * C + c);
+            s += v;
+            q += v * v;
+        }
+    if (rg < rgroups) {
+        s_cs[(rg * 2 + 0) * C + c] = s;
+        s_cs[(rg * 2 + 1) * C + c] = q;
+    }
+    __syncthreads();
+    if (rg == 0) {
+        for (int r = 1; r < rgroups; ++r) {
+            s += s_cs[(r * 2 + 0) * C + c];
+            q += s_cs[(r * 2 + 1) * C + c];
+        }
+        float* o = partial + ((size_t)b * n_parts + part) * 2 * C;
+        o[c] = s;
+        o[C + c] = q;
+    }
+}
+
 __global__ void norm_finalize_kernel(const float* __restrict__ partial, int groups, int tiles_per_group, int C,
                                      double count, const float* __restrict__ gamma, const float* __restrict__ beta,
                                      float eps, float* __restrict__ scale, float* __restrict__ shift,
@@ -410,6 +448,18 @@ extern "C" int sdt_norm_finalize(const float* partial, int groups, int tiles_per
     sdt::launch(norm_finalize_kernel, dim3(groups * sdt::ceil_div(C, 32)), dim3(256), 0, sdt::as_stream(stream), partial, groups, tiles_per_group, C, count, gamma, beta, eps, scale, shift, mean, rstd, running_mean, running_var,
         num_batches_tracked, momentum);
     SDT_LAUNCH_OK("norm_finalize_kernel");
+    return SDT_OK;
+}
+
+extern "C" int sdt_chan_stats(const float* x, int B, int H, int W, int C, int w0, int w1, int rows_per_part, float* partial,
+                              int n_parts, void* stream) {
+    SDT_REQUIRE(x && partial, "sdt_chan_stats: null pointer");
+    SDT_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C <= 256 && 256 % C == 0, "sdt_chan_stats: need C dividing 256 (C=%d)", C);
+    SDT_REQUIRE(w0 >= 0 && w1 >= w0 && w1 <= W && rows_per_part > 0 && n_parts > 0, "sdt_chan_stats: bad window [%d, %d) of %d", w0, w1, W);
+    SDT_REQUIRE((long long)n_parts * rows_per_part >= (long long)H * (w1 - w0), "sdt_chan_stats: %d parts of %d rows do not cover the window", n_parts, rows_per_part);
+    sdt::launch(chan_stats_kernel, dim3(n_parts, B), dim3(256), (size_t)(256 / C) * 2 * C * sizeof(float), sdt::as_stream(stream), x, H, W, C, w0,
+                w1, rows_per_part, partial, n_parts);
+    SDT_LAUNCH_OK("chan_stats_kernel");
     return SDT_OK;
 }
 

@@ -298,7 +298,13 @@ class GeneratorEngine:
         raise NotImplementedError  # replaced below (kept for doc ordering)
 
 
-def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=None):
+def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=None, upto=None, from_x0=None):
+    """upto='encoder': stop after the 2-D encoder + resize/concat and return the UNet input x0 (B, F, 256 + D) -- lets bench.py
+    time the fused mel + encoder forward of the north-star roofline on its own.
+    from_x0: the UNet input (B, F, 256 + D) computed by the caller (inference.StreamingGenerator runs the 2-D encoder in time
+    tiles): only the 1-D stack runs here; the caller has set the engine up (``prepare``) and refreshed the weight operands."""
+    if from_x0 is not None:
+        return _gen_forward_seq(self, from_x0, num_frames, params, training, buffers)
     B, _, T = mel.shape
     self._setup(B, T, num_frames)
     A = self.arena
@@ -384,6 +390,29 @@ def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=Non
     h7, w7 = self.enc_hw[8]
     x0 = A.get("x0", (B, num_frames, 256 + D))
     ops.enc_to_seq_fwd(last_raw, last_xf[0], last_xf[1], last_xf[2], slope, code if D > 0 else None, num_frames, out=x0, tf32=tf32)
+    if upto == "encoder":
+        return x0
+    return _gen_forward_seq(self, x0, num_frames, params, training, buffers)
+
+
+def _gen_prepare(self, B, T, num_frames, params, training=False):
+    """Engine set-up + ONE weight-operand refresh for callers that sequence the layers themselves (time-tiled inference)
+    -> params with the padded head copies."""
+    self._setup(B, T, num_frames)
+    self.fwd_id += 1
+    self.materialize = self.math >= 2
+    self.fused_first = False
+    params = self._padded_head_params(params)
+    self._params = params
+    self.wprep.ensure(self._all_layers(), params, with_dgrad=training)
+    self.wprep.run()
+    return params
+
+
+def _gen_forward_seq(self, x0, num_frames, params, training, buffers):
+    """1-D stack (UNet_1D generator.py:53-84 + decoder :98-104) on the UNet input x0 (B, F, 256 + D)."""
+    A, B, slope = self.arena, x0.shape[0], self.slope
+    tf32 = self.math >= 1
     # ---- 1-D stack
     acts = {"x0": x0}
     for name, g, kind in self.seq_layers():
@@ -629,6 +658,7 @@ def _gen_backward(self, g_pred, grads, g_code=None):
 
 
 GeneratorEngine.forward = _gen_forward
+GeneratorEngine.prepare = _gen_prepare
 GeneratorEngine.backward = _gen_backward
 
 

@@ -365,6 +365,14 @@ def norm_finalize(partial, groups, C, count, gamma=None, beta=None, running=None
     return scale, shift, mean, rstd
 
 
+def chan_stats(x, w0, w1, rows_per_part, partial):
+    """x (B, H, W, C) channels-last; partial (B, n_parts, 2, C) <- sums / sums of squares over the columns [w0, w1) (include/sdt_b200.h)."""
+    B, H, W, Cc = x.shape
+    n_parts = partial.shape[1]
+    call("sdt_chan_stats", _p(x), B, H, W, Cc, int(w0), int(w1), int(rows_per_part), _p(partial), n_parts, _stream())
+    return partial
+
+
 def bn_eval_scale_shift(rm, rv, gamma, beta, out=None):
     Cc = rm.numel()
     scale, shift = out if out is not None else (torch.empty(1, Cc, device=rm.device), torch.empty(1, Cc, device=rm.device))

@@ -556,6 +556,12 @@ class Voice2PoseTrainer:
         self.steps_done = 0
 
     @_on_device
+    def close(self):
+        """Drop the captured graphs and pending collectives (call before tearing the process group down: NCCL communicators
+        cannot be destroyed while graphs that hold their kernels are alive)."""
+        self._graphs, self._works = None, []
+        torch.cuda.synchronize(self.device)
+
     def set_overlap(self, on):
         """Multi-stream overlap of the step (FGD/metrics and weight gradients beside the dgrad chain). bench.py switches
         it off for the per-kernel roofline pass so that every launch is timed alone."""
@@ -1016,6 +1022,10 @@ class Pose2PoseTrainer:
         self._works, self._reduce_scalars = [], False
         self._scal = torch.zeros(len(self._SCALARS), device=self.device, dtype=torch.float64)
         self._dec_off = sum(p.numel() for nme, p in zip(self.names, params) if nme.startswith("encoder."))
+
+    def close(self):
+        self._graphs, self._works = None, []
+        torch.cuda.synchronize(self.device)
 
     def set_lr(self, lr):
         self.lr = float(lr)

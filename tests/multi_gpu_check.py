@@ -113,6 +113,7 @@ def main():
         res["sdt_bp/%s/rank_adam_state_spread" % mode] = max(spread(tr.exp_avg, pg), spread(tr.exp_avg_sq, pg))
         res["sdt_bp/%s/losses" % mode] = tr.losses_to_host(out)
         finals[mode] = tr.flat_p.clone()
+        tr.close()
     d = (finals["overlap"] - finals["serial"]).abs().max()
     res["sdt_bp/overlap_vs_serial_param_max_abs_diff"] = float(d)
 
@@ -131,6 +132,7 @@ def main():
         res["pose2pose/%s/rank_param_spread" % mode] = spread(tr.flat_p, pg)
         res["pose2pose/%s/losses" % mode] = tr.losses_to_host(out)
         finals[mode] = tr.flat_p.clone()
+        tr.close()
     res["pose2pose/overlap_vs_serial_param_max_abs_diff"] = float((finals["overlap"] - finals["serial"]).abs().max())
 
     ok = (res["scalar_spread_over_ranks"] == 0.0
@@ -144,8 +146,10 @@ def main():
             json.dump(res, f, indent=1)
         print(json.dumps(res, indent=1))
     dist.barrier()
-    dist.destroy_process_group()
-    sys.exit(0 if ok else 1)
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    # no destroy_process_group(): tearing NCCL down after graph capture has been seen to hang at exit; the OS reclaims everything
+    os._exit(0 if ok else 1)
 
 
 if __name__ == "__main__":

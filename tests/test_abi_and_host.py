@@ -140,6 +140,64 @@ def test_plugin_registers_into_reference_registries():
     assert sorted(m.state_dict().keys()) == ref_keys
     m2 = ref_p2p.Pose2PoseModel(refshim.get_cfg("pose2pose"), num_train_samples=4)
     assert "clip_code_mu" in m2.state_dict() and "ae.decoder.blocks.4.bias" in m2.state_dict()
+    # the pipeline registry (core/pipelines/__init__.py:5-16): get_pipeline resolves to subclasses of the reference's own classes
+    # that override exactly the three methods the fused trainers replace; registering twice does not stack subclasses
+    import core.pipelines as ref_pipelines
+    assert {"pipeline:Voice2Pose", "pipeline:Pose2Pose"} <= set(done)
+    for name, base in (("Voice2Pose", ref_v2p.Voice2Pose), ("Pose2Pose", ref_p2p.Pose2Pose)):
+        cls = ref_pipelines.get_pipeline(name)
+        assert cls is not base and issubclass(cls, base) and cls.__mro__[1] is base
+        assert {k for k in vars(cls) if not k.startswith("_") and callable(vars(cls)[k])} == {"setup_model", "setup_optimizer", "train_step"}
+        import inspect
+        for meth in ("setup_model", "setup_optimizer", "train_step"):
+            assert inspect.signature(getattr(cls, meth)) == inspect.signature(getattr(base, meth)), (name, meth)
+    plugin.register()
+    assert ref_pipelines.get_pipeline("Voice2Pose").__mro__[1] is ref_v2p.Voice2Pose
+    with pytest.raises(KeyError, match="Unknown pipeline"):
+        ref_pipelines.get_pipeline("Nope")
+
+
+def test_multistep_handle_follows_torch_multisteplr():
+    """pipelines.MultiStepHandle == torch.optim.lr_scheduler.MultiStepLR on the reference's milestones (voice2pose.py:251-257)."""
+    from speechdrivestemplates_b200 import pipelines
+
+    class FakeTrainer:
+        lr = None
+
+        def set_lr(self, lr):
+            self.lr = lr
+    epochs, base = 14, 1e-4
+    ms = [epochs - 10, epochs - 2]
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.Adam([p], lr=base)
+    ref = torch.optim.lr_scheduler.MultiStepLR(opt, ms, gamma=0.1, last_epoch=-1)
+    tr = FakeTrainer()
+    h = pipelines.MultiStepHandle(tr, base, ms, 0.1, -1)
+    follower = pipelines.MultiStepHandle(tr, base, ms, 0.1, -1, drives=False)
+    assert tr.lr == pytest.approx(opt.param_groups[0]["lr"])
+    for _ in range(epochs):
+        opt.step()
+        ref.step()
+        h.step()
+        follower.step()
+        assert tr.lr == pytest.approx(opt.param_groups[0]["lr"], rel=1e-12)
+        assert h.get_last_lr()[0] == pytest.approx(ref.get_last_lr()[0], rel=1e-12)
+    assert tr.lr == pytest.approx(base * 1e-2)
+    # resume at epoch 5 (setup_experiment passes last_epoch=epoch, trainer.py:184): already past the first milestone
+    tr2 = FakeTrainer()
+    pipelines.MultiStepHandle(tr2, base, ms, 0.1, last_epoch=5)
+    assert tr2.lr == pytest.approx(base * 0.1)
+
+
+def test_default_conv_math_precedence(monkeypatch):
+    from speechdrivestemplates_b200 import config, pipelines
+    cfg = config.get_cfg("voice2pose_sdt_bp")
+    monkeypatch.delenv("SDT_CONV_MATH", raising=False)
+    assert pipelines.default_conv_math(cfg) == 3
+    cfg.SYS["SDT_CONV_MATH"] = 0
+    assert pipelines.default_conv_math(cfg) == 0
+    monkeypatch.setenv("SDT_CONV_MATH", "2")
+    assert pipelines.default_conv_math(cfg) == 2
 
 
 # ---------------------------------------------------------------- tile planner of the mode-3 convolution (host only)

@@ -125,6 +125,16 @@ int sdt_conv_wgrad(const sdt_conv_desc* d, void* stream);
  * grad[(n*C + c)*T + t] (+)= sum_z wpart[z][n][(t*C + c)],  T = TH*TW  -> (Cout, Cin, kh, kw) */
 int sdt_conv_wgrad_reduce(const float* wpart, int splits, int N, int C, int T, float* grad, int accumulate,
                           void* stream);
+/* The same reduction for several layers in ONE launch (the fused trainers defer the reductions of a gradient bucket to its end:
+ * 24 launches of ~10 us each per step become 2-3).  items_device: device array of n_items records, every item with C % 32 == 0
+ * and T <= max_T <= 256; max_ctas = the largest N * (C / 32) among them. */
+typedef struct sdt_reduce_item {
+    const float* wpart;        /* (splits, N, T*C) partials of sdt_conv_wgrad */
+    float* grad;               /* (N, C, T) reference-layout gradient */
+    int32_t splits, N, C, T, accumulate;
+    int32_t pad0;
+} sdt_reduce_item;
+int sdt_conv_wgrad_reduce_batch(const sdt_reduce_item* items_device, int n_items, int max_ctas, int max_T, void* stream);
 /* reference-layout weight (Cout, Cin, KH, KW) -> GEMM operand (K, N):
  *   mode 0 forward : out[((ky*KW+kx)*Cin + ci)*Cout + co] = w[co,ci,ky,kx]
  *   mode 1 dgrad   : taps ky = ky0 + kstep*jy (jy < TH), kx likewise:

@@ -511,6 +511,47 @@ __global__ void __launch_bounds__(256) wgrad_reduce_tiled_kernel(const float* __
     }
 }
 
+// All split-K reductions of a group of layers in ONE launch (the fused trainers defer them to the end of a gradient bucket):
+// blockIdx.y = item, blockIdx.x = (output channel, 32-channel chunk) of that item, same tiling as wgrad_reduce_tiled_kernel.
+struct ReduceItem {     // mirrors sdt_reduce_item
+    const float* wpart;
+    float* grad;
+    int32_t splits, N, C, T, accumulate, pad0;
+};
+
+__global__ void __launch_bounds__(256) wgrad_reduce_batch_kernel(const ReduceItem* __restrict__ items) {
+    sdt::pdl_wait();
+    sdt::pdl_launch_dependents();
+    extern __shared__ float s_t[];          // [T][33]
+    const ReduceItem it = items[blockIdx.y];
+    const int cchunks = it.C >> 5;
+    if ((int)blockIdx.x >= it.N * cchunks) return;
+    const int C = it.C, T = it.T, splits = it.splits;
+    const int n = blockIdx.x / cchunks, c0 = (blockIdx.x - n * cchunks) << 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t stride = (size_t)it.N * T * C;
+    for (int t = warp; t < T; t += 8) {
+        const float* p = it.wpart + ((size_t)n * T + t) * C + c0 + lane;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int z = 0;
+        for (; z + 4 <= splits; z += 4) {
+            s0 += __ldg(p + (size_t)z * stride);
+            s1 += __ldg(p + (size_t)(z + 1) * stride);
+            s2 += __ldg(p + (size_t)(z + 2) * stride);
+            s3 += __ldg(p + (size_t)(z + 3) * stride);
+        }
+        for (; z < splits; ++z) s0 += __ldg(p + (size_t)z * stride);
+        s_t[t * 33 + lane] = (s0 + s1) + (s2 + s3);
+    }
+    __syncthreads();
+    float* out = it.grad + ((size_t)n * C + c0) * T;
+    for (int i = threadIdx.x; i < 32 * T; i += 256) {
+        const int c = i / T, t = i - c * T;
+        const float v = s_t[t * 33 + c];
+        out[i] = it.accumulate ? out[i] + v : v;
+    }
+}
+
 __global__ void weight_prep_kernel(const float* __restrict__ w, int Cout, int Cin, int KH, int KW, int mode, int ky0,
                                    int kx0, int kstep, int TH, int TW, float* __restrict__ out) {
     sdt::pdl_wait();
@@ -634,21 +675,24 @@ __global__ void weight_prep_batch_kernel(const PrepItem* __restrict__ items) {
     sdt::pdl_wait();
     sdt::pdl_launch_dependents();
     const PrepItem it = items[blockIdx.y];
-    const int cin_p = (it.mode == 2 && it.pad0 > it.Cin) ? it.pad0 : it.Cin;      // mode 2: input channels zero-padded to pad0
-    const long long total = (long long)it.TH * it.TW * cin_p * it.Cout;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        int co, ci, tap;
-        const int T = it.TH * it.TW;
+    // 32-bit index arithmetic (an operand has < 2^31 elements; the 64-bit divisions of the first version were most of its time)
+    const unsigned Cin = it.Cin, Cout = it.Cout, T = it.TH * it.TW, TW = it.TW;
+    const unsigned cin_p = (it.mode == 2 && it.pad0 > it.Cin) ? it.pad0 : Cin;      // mode 2: input channels zero-padded to pad0
+    const unsigned total = T * cin_p * Cout;
+    const unsigned KHW = it.KH * it.KW;
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        unsigned co, ci, tap;
         if (it.mode == 2) {
-            ci = (int)(e % cin_p); tap = (int)((e / cin_p) % T); co = (int)(e / ((long long)cin_p * T));
-            if (ci >= it.Cin) { it.out[e] = 0.f; continue; }
+            const unsigned q = e / cin_p;
+            ci = e - q * cin_p; co = q / T; tap = q - co * T;
+            if (ci >= Cin) { it.out[e] = 0.f; continue; }
         }
-        else if (it.mode == 3) { co = (int)(e % it.Cout); tap = (int)((e / it.Cout) % T); ci = (int)(e / ((long long)it.Cout * T)); }
-        else if (it.mode == 0) { co = (int)(e % it.Cout); ci = (int)((e / it.Cout) % it.Cin); tap = (int)(e / ((long long)it.Cout * it.Cin)); }
-        else { ci = (int)(e % it.Cin); co = (int)((e / it.Cin) % it.Cout); tap = (int)(e / ((long long)it.Cout * it.Cin)); }
-        const int jy = tap / it.TW, jx = tap % it.TW;
-        const int ky = it.ky0 + it.kstep * jy, kx = it.kx0 + it.kstep * jx;
-        it.out[e] = sdt::out_round(it.w[(((size_t)co * it.Cin + ci) * it.KH + ky) * it.KW + kx], it.mode >= 2);
+        else if (it.mode == 3) { const unsigned q = e / Cout; co = e - q * Cout; ci = q / T; tap = q - ci * T; }
+        else if (it.mode == 0) { const unsigned q = e / Cout; co = e - q * Cout; tap = q / Cin; ci = q - tap * Cin; }
+        else { const unsigned q = e / Cin; ci = e - q * Cin; tap = q / Cout; co = q - tap * Cout; }
+        const unsigned jy = tap / TW, jx = tap - jy * TW;
+        const unsigned ky = it.ky0 + it.kstep * jy, kx = it.kx0 + it.kstep * jx;
+        it.out[e] = sdt::out_round(__ldg(it.w + ((size_t)co * Cin + ci) * KHW + ky * it.KW + kx), it.mode >= 2);
     }
 }
 
@@ -840,6 +884,16 @@ extern "C" int sdt_conv_wgrad_reduce(const float* wpart, int splits, int N, int 
     else
         sdt::launch(wgrad_reduce_kernel, dim3(sdt::ceil_div(total, 256)), dim3(256), 0, sdt::as_stream(stream), wpart, splits, N, C, T, grad, accumulate);
     SDT_LAUNCH_OK("wgrad_reduce_kernel");
+    return SDT_OK;
+}
+
+extern "C" int sdt_conv_wgrad_reduce_batch(const sdt_reduce_item* items_device, int n_items, int max_ctas, int max_T, void* stream) {
+    SDT_REQUIRE(items_device && n_items > 0 && max_ctas > 0, "sdt_conv_wgrad_reduce_batch: bad arguments");
+    SDT_REQUIRE(max_T > 0 && max_T <= 256, "sdt_conv_wgrad_reduce_batch: taps per item must be in [1, 256] (max_T=%d)", max_T);
+    static_assert(sizeof(ReduceItem) == sizeof(sdt_reduce_item), "sdt_reduce_item layout");
+    sdt::launch(wgrad_reduce_batch_kernel, dim3(max_ctas, n_items), dim3(256), (size_t)max_T * 33 * sizeof(float), sdt::as_stream(stream),
+                reinterpret_cast<const ReduceItem*>(items_device));
+    SDT_LAUNCH_OK("wgrad_reduce_batch_kernel");
     return SDT_OK;
 }
 

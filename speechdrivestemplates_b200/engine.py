@@ -471,36 +471,38 @@ def _gen_forward_seq(self, x0, num_frames, params, training, buffers):
 _DIAG_SKIP_WGRAD = bool(__import__("os").environ.get("SDT_DIAG_SKIP_WGRAD"))
 
 
-def _wgrad(self, g, x, dy, B, H, W, grad_out, xf=None, slope=1.0, post=None, name=None):
+def _wgrad(self, g, x, dy, B, H, W, grad_out, xf=None, slope=1.0, post=None, name=None, key=None):
     """Weight gradient of one layer.  Nothing downstream in the backward pass depends on it, so when the engine has a
     `wg_stream` it is enqueued there (after an event marking dy ready) and overlaps the dgrad chain on the main stream.
 
     `name` in self.grad_marks: an event is recorded right behind this layer's gradient (weight gradients are produced in
     reverse layer order on one stream, so the event also covers every layer after it) -- the fused trainer starts the
-    all-reduce of a gradient bucket on it (pipeline.Voice2PoseTrainer._start_buckets)."""
+    all-reduce of a gradient bucket on it (pipeline.Voice2PoseTrainer._start_buckets).
+
+    `self.defer_reduce` (set by the fused trainers, whose gradient buffers are static): the split-K reduction of the layer is not
+    launched here but collected and run as ONE batched launch per gradient bucket / at the join (_wgrad_flush)."""
     if _DIAG_SKIP_WGRAD:              # diagnostic only (wrong gradients): how much of the step do the weight gradients cost?
         return
     wg = getattr(self, "wg_stream", None)
     marks = getattr(self, "grad_marks", None)
+    key = key or name
     if wg is not None:
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
         with torch.cuda.stream(wg):
             wg.wait_event(ev)
-            _wgrad_now(self, g, x, dy, B, H, W, grad_out, xf, slope)
-            if post is not None:
-                post()
+            _wgrad_now(self, g, x, dy, B, H, W, grad_out, xf, slope, post, key)
             if marks is not None and name in marks:
+                _wgrad_flush(self)
                 marks[name] = torch.cuda.Event()
                 marks[name].record(wg)
                 if self.on_mark is not None:
                     self.on_mark(name, marks[name])
         self._wg_pending = True
         return
-    _wgrad_now(self, g, x, dy, B, H, W, grad_out, xf, slope)
-    if post is not None:
-        post()
+    _wgrad_now(self, g, x, dy, B, H, W, grad_out, xf, slope, post, key)
     if marks is not None and name in marks:
+        _wgrad_flush(self)
         marks[name] = torch.cuda.Event()
         marks[name].record(torch.cuda.current_stream())
         if self.on_mark is not None:
@@ -508,23 +510,58 @@ def _wgrad(self, g, x, dy, B, H, W, grad_out, xf=None, slope=1.0, post=None, nam
 
 
 def _wgrad_join(self):
-    """Main stream waits for the weight gradients enqueued on wg_stream."""
+    """Main stream waits for the weight gradients enqueued on wg_stream (the deferred reductions are flushed first)."""
     wg = getattr(self, "wg_stream", None)
     if wg is not None and getattr(self, "_wg_pending", False):
+        with torch.cuda.stream(wg):
+            _wgrad_flush(self)
         ev = torch.cuda.Event()
         ev.record(wg)
         torch.cuda.current_stream().wait_event(ev)
         self._wg_pending = False
+    else:
+        _wgrad_flush(self)
 
 
-def _wgrad_now(self, g, x, dy, B, H, W, grad_out, xf=None, slope=1.0):
+def _wgrad_flush(self):
+    """One batched launch for the split-K reductions collected since the last flush (on the current stream = the stream the
+    weight gradients ran on).  The item tables are cached by their (static) pointers: built during the eager warm-up steps,
+    replayed from the CUDA graph afterwards."""
+    pending = getattr(self, "_reduce_pending", None)
+    if not pending:
+        return
+    self._reduce_pending = []
+    items = [p[0] for p in pending]
+    key = tuple((wp.data_ptr(), gr.data_ptr(), sp, n, c, t, acc) for (wp, gr, sp, n, c, t, acc) in items)
+    tables = self.__dict__.setdefault("_reduce_tables", {})
+    if key not in tables:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("weight-gradient reduction table missing during graph capture (buffers moved since the warm-up step)")
+        tables[key] = ops.reduce_item_table(items, self.arena.device)
+    table, max_ctas, max_T = tables[key]
+    ops.wgrad_reduce_batch(table, len(items), max_ctas, max_T)
+    for p in pending:
+        if p[1] is not None:
+            p[1]()
+
+
+def _wgrad_now(self, g, x, dy, B, H, W, grad_out, xf=None, slope=1.0, post=None, key=None):
     oh, ow = g.out_hw(H, W)
     splits = ops.wgrad_splits(g, B, oh, ow, math=self.math)
     need = splits * g.cout * g.k
-    ws = self.arena.get("wgrad_ws", (max(need, getattr(self, "_ws_elems", 0)),))
-    self._ws_elems = ws.numel()
+    defer = getattr(self, "defer_reduce", False) and key is not None and g.cin % 32 == 0 and g.kh * g.kw <= 256
+    if defer:
+        ws = self.arena.get("wgrad_ws:" + key, (need,))            # per layer: it lives until the bucket's batched reduction
+    else:
+        ws = self.arena.get("wgrad_ws", (max(need, getattr(self, "_ws_elems", 0)),))
+        self._ws_elems = ws.numel()
     ops.conv_wgrad(ops.wgrad_desc(g, x, dy, ws, B, H, W, splits, xf, slope, math=self.math))
+    if defer:
+        self.__dict__.setdefault("_reduce_pending", []).append(((ws, grad_out, splits, g.cout, g.cin, g.kh * g.kw, False), post))
+        return
     ops.wgrad_reduce(ws, splits, g, grad_out)
+    if post is not None:
+        post()
 
 
 def _dgrad(self, name, g, dy, w, dx, B, H, W, accumulate=False):
@@ -554,11 +591,11 @@ def _gen_backward(self, g_pred, grads, g_code=None):
         g_pad[..., :self.kp2].copy_(g_pred.view(B, F, self.kp2))
         gw_pad = A.get("head_gw_pad", (npad, 256, 1))
         dst = grads["decoder.4.weight"]
-        _wgrad(self, gl, acts["decoder.3"], g_pad, B, 1, F, gw_pad, post=lambda: dst.copy_(gw_pad[:self.kp2]))
+        _wgrad(self, gl, acts["decoder.3"], g_pad, B, 1, F, gw_pad, post=lambda: dst.copy_(gw_pad[:self.kp2]), key="decoder.4")
         _dgrad(self, "decoder.4", gl, g_pad, params["decoder.4.weight_pad"], g_act["decoder.3"], B, 1, F)
     else:
         gl = ConvGeom.conv1d(256, self.kp2, 1, 1, 0)
-        _wgrad(self, gl, acts["decoder.3"], g_pred, B, 1, F, grads["decoder.4.weight"])
+        _wgrad(self, gl, acts["decoder.3"], g_pred, B, 1, F, grads["decoder.4.weight"], key="decoder.4")
         _dgrad(self, "decoder.4", gl, g_pred, params["decoder.4.weight"], g_act["decoder.3"], B, 1, F)
     # ---- 1-D stack in reverse
     layers = self.seq_layers()

@@ -264,6 +264,24 @@ def wgrad_reduce(wpart, splits, g, grad, accumulate=False):
     call("sdt_conv_wgrad_reduce", _p(wpart), splits, g.cout, g.cin, g.kh * g.kw, _p(grad), int(accumulate), _stream())
 
 
+def wgrad_reduce_batch(table, n_items, max_ctas, max_T):
+    """table: device uint8 tensor holding n_items sdt_reduce_item records (include/sdt_b200.h)."""
+    call("sdt_conv_wgrad_reduce_batch", C.c_void_p(table.data_ptr()), n_items, max_ctas, max_T, _stream())
+
+
+def reduce_item_table(items, device):
+    """items: [(wpart, grad, splits, N, C, T, accumulate)] -> (device table, max_ctas, max_T)."""
+    import numpy as np
+    dt = np.dtype([("wpart", "<u8"), ("grad", "<u8"), ("i", "<i4", (6,))])
+    arr = np.zeros(len(items), dtype=dt)
+    max_ctas = max_T = 1
+    for k, (wp, gr, splits, N, Cc, T, acc) in enumerate(items):
+        assert Cc % 32 == 0 and T <= 256
+        arr[k] = (wp.data_ptr(), gr.data_ptr(), (splits, N, Cc, T, int(acc), 0))
+        max_ctas, max_T = max(max_ctas, N * (Cc // 32)), max(max_T, T)
+    return torch.from_numpy(arr.view(np.uint8).copy()).to(device), max_ctas, max_T
+
+
 def weight_prep_fwd(w, g, out):
     """(Cout,Cin,kh,kw) reference-layout parameter -> (K, Cout) forward GEMM operand."""
     call("sdt_weight_prep", _p(w), g.cout, g.cin, g.kh, g.kw, 0, 0, 0, 1, g.kh, g.kw, _p(out), _stream())

@@ -537,6 +537,7 @@ class Voice2PoseTrainer:
         self.engine = m.step_engine()
         self._wg_stream = torch.cuda.Stream(device=self.device)                # weight gradients overlap the dgrad chain (engine._wgrad)
         m.netG.engine().wg_stream = self._wg_stream
+        m.netG.engine().defer_reduce = os.environ.get("SDT_DEFER_REDUCE", "1") != "0"   # gradient buffers are static: batch the split-K reductions
         self._overlap = True
         # multi-GPU: "overlap" = gradient buckets all-reduced on a communication stream while the backward pass still runs, the
         # clip-code gradient exchanged as B x (index, 32) rows, NCCL captured inside the step's CUDA graph; "serial" = one flat

@@ -667,7 +667,7 @@ def _gen_backward(self, g_pred, grads, g_code=None):
                                 scratch=A.get("fl_partial:" + name, (B, ops.first_layer_units(H, W), 11, co)))
             break
         raw = A.get("raw:" + name, (B, oh, ow, co))
-        tpi = ops.bwd_tiles(oh * ow, B)
+        tpi = ops.bwd_partial_tiles(oh * ow, B, co)
         scratch = (A.get("nb_partial:" + name, (B * tpi, 2, co)), A.get("nb_m1:" + name, (groups, co)), A.get("nb_m2:" + name, (groups, co)))
         if bn:
             ops.norm_backward(g_enc, raw, A.get("mean:" + name, (groups, co)), A.get("rstd:" + name, (groups, co)), groups, slope,

@@ -407,10 +407,27 @@ def bwd_tiles(P, B):
     return max(-(-P // BWD_ROWS), min(-(-P // 32), -(-600 // max(B, 1))))
 
 
+NORM_BWD_L2_BYTES = int(float(__import__("os").environ.get("SDT_NORM_BWD_L2_MB", "64")) * 1e6)
+
+
+def bwd_partial_tiles(P, B, Cc):
+    """Tiles per image to ALLOCATE for norm_backward's partial sums: the image-group path uses more tiles per image than the
+    whole-batch path (fewer images per launch, same ~600 CTAs)."""
+    per_image = 2 * P * Cc * 4
+    nb = max(1, min(B, NORM_BWD_L2_BYTES // per_image)) if NORM_BWD_L2_BYTES > 0 else B
+    return max(bwd_tiles(P, B), min(bwd_tiles(P, nb), P))
+
+
+
+
 def norm_backward(g, x, mean, rstd, groups, slope, gamma=None, beta=None, dgamma=None, dbeta=None, accumulate=False,
                   scratch=None, tf32=False):
     """In place: g (B,P,C) := d loss / d x for [normalise(groups) -> affine -> act]; returns g.
-    tf32: store the result rounded to TF32 (it is the next data / weight gradient's tensor-core operand, sdt_b200.h "out_tf32")."""
+    tf32: store the result rounded to TF32 (it is the next data / weight gradient's tensor-core operand, sdt_b200.h "out_tf32").
+
+    Two passes over g and x (reduce, apply).  With per-image statistics (groups == B) the images are independent, so maps larger
+    than L2 are processed in image groups of <= NORM_BWD_L2_BYTES (g + x): the apply pass of a group then reads what its reduce
+    pass just brought into the 126 MB L2 instead of streaming 2 x 140 MB from HBM a second time."""
     B = g.shape[0]
     Cc = g.shape[-1]
     P = g.numel() // (B * Cc)
@@ -421,6 +438,21 @@ def norm_backward(g, x, mean, rstd, groups, slope, gamma=None, beta=None, dgamma
         m2 = torch.empty(groups, Cc, device=g.device)
     else:
         partial, m1, m2 = scratch
+    per_image = 2 * P * Cc * 4
+    if groups == B and B > 1 and NORM_BWD_L2_BYTES > 0 and B * per_image > NORM_BWD_L2_BYTES and gamma is None:
+        nb = max(1, min(B, NORM_BWD_L2_BYTES // per_image))
+        nb = -(-B // -(-B // nb))                      # balanced groups
+        st = _stream()
+        for b0 in range(0, B, nb):
+            n = min(nb, B - b0)
+            tg = max(1, min(bwd_tiles(P, nb), partial.shape[0] // B, P))
+            gs, xs = g[b0:b0 + n], x[b0:b0 + n]
+            ps = partial[b0 * tg:(b0 + n) * tg]
+            call("sdt_norm_bwd_reduce", _p(gs), _p(xs), _p(mean[b0:b0 + n]), _p(rstd[b0:b0 + n]), None, None, n, P, Cc, n, slope, _p(ps), tg, st)
+            call("sdt_norm_bwd_finalize", _p(ps), n, tg, Cc, float(P), _p(m1[b0:b0 + n]), _p(m2[b0:b0 + n]), None, None, 0, st)
+            call("sdt_norm_bwd_apply", _p(gs), _p(xs), _p(mean[b0:b0 + n]), _p(rstd[b0:b0 + n]), None, None, _p(m1[b0:b0 + n]), _p(m2[b0:b0 + n]),
+                 n, P, Cc, n, slope, int(tf32), st)
+        return g
     call("sdt_norm_bwd_reduce", _p(g), _p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), B, P, Cc, groups, slope, _p(partial),
          tpi, _stream())
     call("sdt_norm_bwd_finalize", _p(partial), groups, (B * tpi) // groups, Cc, float(P * (B // groups)), _p(m1), _p(m2),

@@ -346,3 +346,48 @@ def test_wgrad_splits_keep_at_least_256_pixels_per_split():
     assert 1 <= s <= 32 * 40 * 213 // 256 and s * 5 >= 400   # ~3 CTAs per SM
     assert ops.bwd_tiles(255, 32) >= 8 and ops.bwd_tiles(255, 32) * 32 >= 255 // 8
     assert ops.bwd_tiles(40 * 213, 32) == -(-40 * 213 // 256)
+
+
+@pytest.mark.parametrize("name", ["voice2pose_sdt_bp", "voice2pose_s2g", "pose2pose"])
+def test_checkpoint_layout_loads_into_the_reference_classes_strictly(name):
+    """a model_state_dict in the layout checkpoint.py writes ('module.' + the drop-in's state-dict keys) loads into
+    the REFERENCE's own step model with strict=True, the reference's state dict loads back into the drop-in, and the parameter ORDER
+    (which indexes torch.optim.Adam's per-parameter state in the checkpoint, trainer.py:318-319) is the same on both sides."""
+    if not os.path.isdir("/root/reference/core/pipelines"):
+        pytest.skip("reference tree not present")
+    import importlib
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import refshim
+    from speechdrivestemplates_b200 import pipeline
+    cfg = refshim.get_cfg(name)
+    import core.networks as ref_networks
+    import core.pipelines.pose2pose as ref_p2p
+    import core.pipelines.voice2pose as ref_v2p
+    importlib.reload(ref_networks)                 # undo a plugin.register() of an earlier test: the reference's own classes
+    importlib.reload(ref_v2p)
+    importlib.reload(ref_p2p)
+    if name == "pose2pose":
+        RefModel, Own = ref_p2p.Pose2PoseModel, pipeline.Pose2PoseModel
+    else:
+        RefModel, Own = ref_v2p.Voice2PoseModel, pipeline.Voice2PoseModel
+    assert RefModel.__module__.startswith("core.pipelines")
+    torch.manual_seed(1)
+    ref = RefModel(cfg, None, 6, 0)
+    torch.manual_seed(2)
+    own = Own(cfg, num_train_samples=6)
+    written = {"module." + k: v.detach().clone() for k, v in own.state_dict().items()}         # checkpoint.voice2pose_checkpoint's layout
+    # (no GPU here, so no DataParallel wrapper around the reference model: strip the prefix by hand)
+    missing, unexpected = ref.load_state_dict({k[len("module."):]: v for k, v in written.items()}, strict=True)
+    assert not missing and not unexpected
+    for k, v in ref.state_dict().items():
+        assert torch.equal(v, own.state_dict()[k]), k
+    torch.manual_seed(3)
+    ref2 = RefModel(cfg, None, 6, 0)
+    own.load_state_dict(ref2.state_dict(), strict=True)
+    for k, v in own.state_dict().items():
+        assert torch.equal(v, ref2.state_dict()[k]), k
+    sub = "ae" if name == "pose2pose" else "netG"
+    assert [n for n, _ in getattr(own, sub).named_parameters()] == [n for n, _ in getattr(ref, sub).named_parameters()]
+    if name == "voice2pose_s2g":
+        assert [n for n, _ in own.netD_pose.named_parameters()] == [n for n, _ in ref.netD_pose.named_parameters()]

@@ -299,7 +299,25 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int grp_idx = unit_of(tile / n_ntiles);
             const int cls = class_of(grp_idx);
-            const int nvalid = min(MT, sel4(cl.subtiles, cls) - (grp_idx - unit_base(cls)) * MT);
+            const int t0i = (grp_idx - unit_base(cls)) * MT;
+            const int c_subi = sel4(cl.subtiles, cls);
+            const int nvalid = min(MT, c_subi - t0i);
+            // Vertical taps that fall outside the source for EVERY row of a sub-tile contribute zeros (TMA's out-of-bounds fill): skip
+            // their MMAs.  The 6 x 3 / no-padding layer's data gradient walks a 10-row grid over a 5-row source: half of its taps.
+            // yb = source row of patch row 0 at tap shift 0 (before the group's y_add); rows_m = patch rows inside the grid.
+            int yb[MT / N_ISS], rows_m[MT / N_ISS];
+            {
+                const int tpi_i = sel4(cl.tpi, cls), c_txi = sel4(cl.tiles_x, cls), c_GHi = sel4(cl.GH, cls), c_yoffi = sel4(cl.y_off, cls);
+#pragma unroll
+                for (int mm = 0; mm < MT / N_ISS; ++mm) {
+                    const int t = min(t0i + iss + mm * N_ISS, c_subi - 1);
+                    const int rem = t - (t / tpi_i) * tpi_i;
+                    const int y0 = (rem / c_txi) * g.bh;
+                    yb[mm] = y0 * d.y_mul + c_yoffi;
+                    rows_m[mm] = min(g.bh, c_GHi - y0);
+                }
+            }
+            uint32_t started_m = 0;                  // bit mm: accumulator of sub-tile iss + mm * N_ISS has received an MMA
             const int acc = it & 1;
             const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * ACC_COLS);
             long long tw = 0;
@@ -307,11 +325,12 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
             mbar_wait_spin(tmem_empty(acc), (uint32_t)(((it >> 1) & 1) ^ 1));     // the epilogue has drained this accumulator set
             if (DBG && tl) wait_acc += clock64() - tw;
             tc_fence_after();
-            uint32_t started = 0;
             for (int ch = 0; ch < chunks; ++ch) {
                 for (int tx = 0; tx < d.TW; ++tx) {
                     for (int gi = 0; gi < g.n_groups; ++gi) {
                         const int taps = grp_taps(g.groups, gi);
+                        const int y_add = grp_y_add(g.groups, gi);
+                        const bool first_box = (ch | tx | gi) == 0;
                         if (DBG && tl) tw = clock64();
                         if (!(dbg & 1)) mbar_wait_spin(fullA(sa), (uint32_t)pa);
                         if (DBG && tl) wait_full += clock64() - tw;
@@ -326,17 +345,22 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
 #pragma unroll
                                 for (int mm = 0; mm < MT / N_ISS; ++mm) {
                                     const int m = iss + mm * N_ISS;
-                                    if (m < nvalid && !(dbg & 4)) {
+                                    // source rows of this tap: ys + py * y_mul, py < rows_m; the very first tap is always issued (it
+                                    // initialises the accumulator, zeros are harmless)
+                                    const int ys = yb[mm] + y_add + j * d.y_mul;
+                                    const bool live = (first_box && j == 0) || (ys + (rows_m[mm] - 1) * d.y_mul >= 0 && ys < d.SH);
+                                    if (m < nvalid && live && !(dbg & 4)) {
+                                        const uint32_t st = (started_m >> mm) & 1u;
 #pragma unroll
                                         for (int k4 = 0; k4 < 4; ++k4)
                                             mma_tf32_lo(tmem_acc + (uint32_t)(m * BN), a_lo + m * box_lo + 2u * k4, b_lo + 2u * k4, idesc,
-                                                        started | (uint32_t)k4);
+                                                        st | (uint32_t)k4);
+                                        started_m |= 1u << mm;
                                     }
                                 }
                                 if (!(dbg & 8)) mma_commit(emptyB(sbi));
                             }
                             if (!(dbg & 64)) __syncwarp();
-                            started = 1;
                             if (++sbi == g.b_stages) { sbi = 0; pb ^= 1; }
                         }
                         if (!(dbg & 32) && elect_one()) mma_commit(emptyA(sa));
@@ -586,6 +610,21 @@ bool spanning_maps_ok() {
 int env_int(const char* name) { return getenv(name) ? atoi(getenv(name)) : 0; }
 int g_force[4] = {env_int("SDT_YTAP_BN"), env_int("SDT_YTAP_MT"), env_int("SDT_YTAP_BW"), env_int("SDT_YTAP_NB")};
 
+// Fraction of the (tile row, vertical tap) pairs whose source rows are not all outside the source: the MMA issuers skip the rest.
+double live_tap_fraction(const sdt_conv_desc* d, const YGeom& g) {
+    long long live = 0, all = 0;
+    for (int ty = 0; ty < g.tiles_y; ++ty) {
+        const int y0 = ty * g.bh, rows = std::min(g.bh, d->GH - y0);
+        for (int gi = 0; gi < g.n_groups; ++gi)
+            for (int j = 0; j < grp_taps(g.groups, gi); ++j) {
+                const int ys = y0 * d->y_mul + d->y_off + grp_y_add(g.groups, gi) + j * d->y_mul;
+                live += (ys + (rows - 1) * d->y_mul >= 0 && ys < d->SH) ? 1 : 0;
+                ++all;
+            }
+    }
+    return all ? (double)live / (double)all : 1.0;
+}
+
 // n_classes problems of (nearly) d's size share the launch: the tile count that fills the machine is the sum
 Plan make_plan(const sdt_conv_desc* d, int n_classes = 1) {
     Plan best{};
@@ -633,8 +672,9 @@ Plan make_plan(const sdt_conv_desc* d, int n_classes = 1) {
                 // cost model (clocks per tile): shared-memory traffic (TMA fill + tensor-core operand reads, 128 B/clk) against
                 // tensor-pipe clocks; the persistent CTAs (one per SM) run ceil(tiles / 148) tiles each
                 const double fill = (double)(d->C / BKF) * d->TW * g.n_groups * g.a_box_bytes * mt + (double)K * bn * 4.0;
-                const double reads = (double)mt * (K / 8) * (128 + bn) * 32.0;
-                const double mma_clk = (double)mt * (K / 8) * (bn / 2.0);
+                const double live = live_tap_fraction(d, g);         // skipped taps neither read their operands nor use the tensor pipe
+                const double reads = (double)mt * (K / 8) * (128 + bn) * 32.0 * live;
+                const double mma_clk = (double)mt * (K / 8) * (bn / 2.0) * live;
                 const double smem_clk = (fill + reads) / 128.0;
                 const double rounds = (double)((tiles + 147) / 148);
                 // a single issuing warp (MT == 1) exposes its loop overhead: measured ~1.5x slower per MMA than two issuers

@@ -407,7 +407,10 @@ def bwd_tiles(P, B):
     return max(-(-P // BWD_ROWS), min(-(-P // 32), -(-600 // max(B, 1))))
 
 
-NORM_BWD_L2_BYTES = int(float(__import__("os").environ.get("SDT_NORM_BWD_L2_MB", "64")) * 1e6)
+# 0 = off (default).  Measured at B = 32 (profiles/r2_ablation_classminor_normbwd_groups.txt): image groups of 40 / 64 / 100 MB make the
+# step 0.08 / 0.04 / 0.02 ms SLOWER than the whole-batch passes -- the extra launches and the smaller grids cost more than the L2 hits
+# of the apply pass save (the whole-batch passes already run at 5.4 / 6.4 TB/s).
+NORM_BWD_L2_BYTES = int(float(__import__("os").environ.get("SDT_NORM_BWD_L2_MB", "0")) * 1e6)
 
 
 def bwd_partial_tiles(P, B, Cc):

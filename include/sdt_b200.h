@@ -223,10 +223,11 @@ int sdt_first_layer_units(int H, int W);
 int sdt_first_layer_fwd(const float* x, const float* w, int B, int H, int W, int C, float eps, float slope,
                         double* mom_partial, double* moments, float* scale, float* shift, float* act, int out_tf32,
                         void* stream);
-/* Weight gradient of that block from g_act = dLoss/d act in ONE pass over (g_act, act): the InstanceNorm + LeakyReLU
- * backward is folded into per-(image, channel) sums and combined in closed form (f64) with the forward's moments; the
- * block's input needs no gradient (it is the mel spectrogram).  Requires slope > 0 (the pre-activation is recovered
- * from act).  partial: (B, units, 11, 64) f32 scratch; dw (64,1,3,3) is overwritten. */
+/* Weight gradient of that block from g_act = dLoss/d act in ONE pass over g_act: the InstanceNorm + LeakyReLU backward is
+ * folded into per-(image, channel) sums and combined in closed form (f64) with the forward's moments; the block's input needs
+ * no gradient (it is the mel spectrogram).  The pre-activation is recomputed from x with the forward's arithmetic, so `act`
+ * is not read (it may be NULL; the parameter stays for ABI stability).  Requires slope > 0.
+ * partial: (B, units, 11, 64) f32 scratch; dw (64,1,3,3) is overwritten. */
 int sdt_first_layer_bwd(const float* g_act, const float* act, const float* x, const float* w, const double* moments,
                         const float* scale, const float* shift, int B, int H, int W, int C, float slope, float* partial,
                         float* dw, void* stream);

@@ -1,0 +1,13 @@
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r2q_pytest.log 2>&1; echo "pytest rc=$?"
+tail -3 gpurun_out/r2q_pytest.log
+timeout 600 python bench.py > gpurun_out/r2q_bench.json 2> gpurun_out/r2q_bench.err; echo "bench rc=$?"
+timeout 300 python bench.py --steps 2000 --no-cpu --no-gpu-torch --no-b128 --no-segments > gpurun_out/r2q_sustained.json 2> gpurun_out/r2q_sustained.err; echo "sustained rc=$?"
+F="--steps 2 --warmup 1 --no-graph --no-cpu --no-gpu-torch --no-b128 --no-segments"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/r2q_launches.csv python bench.py $F > gpurun_out/r2q_ncu_bench.log 2>&1; echo "ncu list rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:tc_conv_ytap --launch-skip 70 -c 14 -f -o gpurun_out/r2q_ytap python bench.py $F > gpurun_out/r2q_ncu_full.log 2>&1; echo "ncu full rc=$?"
+python -c "
+import json
+for f in ('r2q_bench','r2q_sustained'):
+    d=json.loads(open('gpurun_out/%s.json'%f).read().strip().splitlines()[-1]);print(f,d['value'],d['ms_per_step'],d['e2e']['value'],d['clocks'])"

@@ -168,9 +168,13 @@ __global__ void __launch_bounds__(256) fl_act_kernel(const float* __restrict__ x
     }
 }
 
-// 256 threads: 32 channel pairs x 8 pixel lanes; one image row per block
-__global__ void __launch_bounds__(256) fl_bwd_kernel(const float* __restrict__ g, const float* __restrict__ act,
-                                                     const float* __restrict__ x, int H, int W, float slope,
+// 256 threads: 32 channel pairs x 8 pixel lanes; one image row per block.  The pre-activation xhat = conv(x) * rstd - mean * rstd
+// is RECOMPUTED from the staged input rows with exactly the forward's arithmetic (fl_act_kernel: shift + sum_k (w_k * rstd) * x_k,
+// same order) instead of being recovered from the stored activation: the pass reads g only (280 MB at B = 32) instead of g + act
+// (560 MB), and xhat is the unrounded fp32 value rather than the TF32-rounded one the activation map holds.
+__global__ void __launch_bounds__(256) fl_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x,
+                                                     const float* __restrict__ w, const float* __restrict__ scale,
+                                                     const float* __restrict__ shift, int H, int W, float slope,
                                                      float* __restrict__ partial) {
     sdt::pdl_wait();
     sdt::pdl_launch_dependents();
@@ -179,32 +183,39 @@ __global__ void __launch_bounds__(256) fl_bwd_kernel(const float* __restrict__ g
     const int b = blockIdx.y;
     const Unit u = unit_of_block(W);
     stage_rows(x, b, u, H, W, s_rows);
-    __syncthreads();
     const int cp = threadIdx.x & 31, pl = threadIdx.x >> 5;
+    float wq[2][kTaps], sh[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int c = cp * 2 + j;
+        const float sc = scale[(size_t)b * kC + c];
+        sh[j] = shift[(size_t)b * kC + c];
+#pragma unroll
+        for (int t = 0; t < kTaps; ++t) wq[j][t] = w[c * kTaps + t] * sc;
+    }
+    __syncthreads();
     const int pitch = kPitch;
-    const float inv_slope = 1.f / slope;
     float acc[2][kBwdQ];
 #pragma unroll
     for (int j = 0; j < 2; ++j)
 #pragma unroll
         for (int q = 0; q < kBwdQ; ++q) acc[j][q] = 0.f;
     const float2* gp = reinterpret_cast<const float2*>(g + (((size_t)b * H + u.y) * W + u.x0) * kC) + cp;
-    const float2* ap = reinterpret_cast<const float2*>(act + (((size_t)b * H + u.y) * W + u.x0) * kC) + cp;
-#pragma unroll 2
+#pragma unroll 4
     for (int px = pl; px < u.n; px += 8) {
         const float2 gv = __ldg(gp + (size_t)px * (kC / 2));
-        const float2 av = __ldg(ap + (size_t)px * (kC / 2));
         float t[kTaps];
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) t[ky * 3 + kx] = s_rows[ky * pitch + px + kx];
-        const float gg[2] = {gv.x, gv.y}, aa[2] = {av.x, av.y};
+        const float gg[2] = {gv.x, gv.y};
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const bool pos = aa[j] > 0.f;
-            const float gh = pos ? gg[j] : gg[j] * slope;
-            const float xh = pos ? aa[j] : aa[j] * inv_slope;
+            float xh = sh[j];
+#pragma unroll
+            for (int k = 0; k < kTaps; ++k) xh = fmaf(wq[j][k], t[k], xh);
+            const float gh = xh > 0.f ? gg[j] : gg[j] * slope;
             acc[j][0] += gh;
             acc[j][1] = fmaf(gh, xh, acc[j][1]);
 #pragma unroll
@@ -310,7 +321,8 @@ extern "C" int sdt_first_layer_fwd(const float* x, const float* w, int B, int H,
 extern "C" int sdt_first_layer_bwd(const float* g_act, const float* act, const float* x, const float* w, const double* moments,
                                    const float* scale, const float* shift, int B, int H, int W, int C, float slope,
                                    float* partial, float* dw, void* stream) {
-    SDT_REQUIRE(g_act && act && x && w && moments && scale && shift && partial && dw, "sdt_first_layer_bwd: null pointer");
+    (void)act;      // not read any more: the pre-activation is recomputed from x (kept in the signature for ABI stability; may be NULL)
+    SDT_REQUIRE(g_act && x && w && moments && scale && shift && partial && dw, "sdt_first_layer_bwd: null pointer");
     SDT_REQUIRE(C == kC, "sdt_first_layer_bwd: the block has %d output channels (got %d)", kC, C);
     SDT_REQUIRE(slope > 0.f, "sdt_first_layer_bwd: needs an invertible activation (slope > 0), got %g", (double)slope);
     SDT_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535, "sdt_first_layer_bwd: bad extents");
@@ -318,7 +330,7 @@ extern "C" int sdt_first_layer_bwd(const float* g_act, const float* act, const f
     const size_t fsmem = (size_t)B * (kBwdQ + kTaps) * sizeof(double);
     SDT_REQUIRE(fsmem <= 40 * 1024, "sdt_first_layer_bwd: batch %d too large for the finalize kernel", B);
     cudaStream_t st = sdt::as_stream(stream);
-    sdt::launch(fl_bwd_kernel, dim3(units, B), dim3(256), 0, st, g_act, act, x, H, W, slope, partial);
+    sdt::launch(fl_bwd_kernel, dim3(units, B), dim3(256), 0, st, g_act, x, w, scale, shift, H, W, slope, partial);
     SDT_LAUNCH_OK("fl_bwd_kernel");
     if (units >= 2) {
         sdt::launch(fl_bwd_colsum_kernel, dim3(B), dim3(kBwdQ * kC), 0, st, partial, units);

@@ -288,18 +288,14 @@ class GeneratorEngine:
             out["unet.e0.conv.weight_dpad"] = wp0
         return out
 
-    # ---- forward ----------------------------------------------------------------------------------
-    def forward(self, mel, code, params, training=True, buffers=None):
-        """mel (B,80,T) f32, code (B,D) or None -> pred (B,F,2K) view of an engine-owned buffer.
-
-        buffers: BN running statistics dict (name -> tensor), updated in training mode, read in eval mode.
-        The number of output frames F must have been set with set_frames()/forward_frames.
-        """
-        raise NotImplementedError  # replaced below (kept for doc ordering)
+    # forward / backward / prepare are attached below (GeneratorEngine.forward = _gen_forward, ...): they are long enough to read
+    # better as module-level functions.
 
 
 def _gen_forward(self, mel, num_frames, code, params, training=True, buffers=None, upto=None, from_x0=None):
-    """upto='encoder': stop after the 2-D encoder + resize/concat and return the UNet input x0 (B, F, 256 + D) -- lets bench.py
+    """GeneratorEngine.forward: mel (B,80,T) f32, code (B,D) or None -> pred (B,F,2K), a view of an engine-owned buffer.
+    buffers: BN running statistics dict (name -> tensor), updated in training mode, read in eval mode.
+    upto='encoder': stop after the 2-D encoder + resize/concat and return the UNet input x0 (B, F, 256 + D) -- lets bench.py
     time the fused mel + encoder forward of the north-star roofline on its own.
     from_x0: the UNet input (B, F, 256 + D) computed by the caller (inference.StreamingGenerator runs the 2-D encoder in time
     tiles): only the 1-D stack runs here; the caller has set the engine up (``prepare``) and refreshed the weight operands."""

@@ -535,7 +535,7 @@ class Voice2PoseTrainer:
         self.adam_d = torch.zeros(8, device=self.device)
         self.set_lr(self.lr)
         self.engine = m.step_engine()
-        self._wg_stream = torch.cuda.Stream(device=self.device)                # weight gradients overlap the dgrad chain (engine._wgrad)
+        self._wg_stream = torch.cuda.Stream(device=self.device, priority=int(os.environ.get("SDT_WG_PRIORITY", "0")))   # weight gradients overlap the dgrad chain (engine._wgrad)
         m.netG.engine().wg_stream = self._wg_stream
         m.netG.engine().defer_reduce = os.environ.get("SDT_DEFER_REDUCE", "1") != "0"   # gradient buffers are static: batch the split-K reductions
         self._overlap = True
@@ -845,11 +845,10 @@ class Voice2PoseTrainer:
         if self.world > 1:
             torch.distributed.barrier(group=self.pg)
             torch.cuda.synchronize()
-        # The step is captured on a HIGH-priority stream: its kernels (forward, data-gradient chain, Adam = the critical path, 2.47 of
-        # 2.95 ms) become high-priority graph nodes, the weight-gradient / FGD / communication streams keep the default (lowest)
-        # priority, so the block scheduler hands freed SMs to the critical path first and the side work fills what is left.
-        prio = int(os.environ.get("SDT_MAIN_PRIORITY", "-1"))
-        side = torch.cuda.Stream(device=self.device, priority=prio)
+        # Stream priorities were measured and rejected (profiles/r2_ablation_stream_priority.txt): capturing the critical path
+        # (forward, data-gradient chain, Adam) on a high-priority stream makes the step 0.27 ms SLOWER -- the weight gradients then
+        # pile up behind it and run alone at the end.  SDT_MAIN_PRIORITY / SDT_WG_PRIORITY remain as tuning aids (default 0 = equal).
+        side = torch.cuda.Stream(device=self.device, priority=int(os.environ.get("SDT_MAIN_PRIORITY", "0")))
         side.wait_stream(torch.cuda.current_stream())
         if self.world == 1 or self.comm_mode == "overlap":
             try:

@@ -29,7 +29,7 @@ from collections import OrderedDict
 import torch
 
 from . import checkpoint as ckpt_io
-from . import ops, pipeline
+from . import pipeline
 
 
 def default_conv_math(cfg=None):
@@ -165,8 +165,15 @@ def make_pipelines(RefVoice2Pose, RefPose2Pose):
                 model.set_conv_math(default_conv_math(cfg))
                 self.model = ModuleHandle(model)
             else:
-                self.fused = pipeline.Voice2PoseTrainer(cfg, self.num_train_samples, torch.device("cuda", rank), process_group=_dist_group(cfg),
-                                                        seed=int(getattr(cfg.SYS, "SEED", 0) or 0), conv_math=default_conv_math(cfg))
+                try:
+                    self.fused = pipeline.Voice2PoseTrainer(cfg, self.num_train_samples, torch.device("cuda", rank), process_group=_dist_group(cfg),
+                                                            seed=int(getattr(cfg.SYS, "SEED", 0) or 0), conv_math=default_conv_math(cfg))
+                except NotImplementedError as e:
+                    # a configuration the fused step does not cover (e.g. POSE_DISCRIMINATOR.WHITE_LIST): the reference's own
+                    # setup_model / setup_optimizer / train_step over the drop-in step model and networks (autograd path)
+                    print("speechdrivestemplates_b200: fused trainer unavailable for this config (%s); using the drop-in modules" % e)
+                    self.fused = None
+                    return super().setup_model(cfg, state_dict)
                 self.model = ModuleHandle(self.fused.model, self.fused)
             if state_dict is not None:
                 self.model.load_state_dict(state_dict, strict=bool(cfg.VOICE2POSE.STRICT_LOADING))
@@ -177,6 +184,8 @@ def make_pipelines(RefVoice2Pose, RefPose2Pose):
                 self.model.module.pose_encoder.load_state_dict(enc)
 
         def setup_optimizer(self, checkpoint=None, last_epoch=-1):
+            if self.fused is None:
+                return super().setup_optimizer(checkpoint, last_epoch)
             tr, cfg, m = self.fused, self.cfg, self.fused.model
             g_params = [p for _, p in m.netG.named_parameters()]
             self.optimizers["optimizerG"] = FusedAdamHandle(tr, tr.g_names, g_params, 0, tr.adam_g, lambda: tr.lr, float(cfg.TRAIN.WD))
@@ -198,6 +207,8 @@ def make_pipelines(RefVoice2Pose, RefPose2Pose):
                     self.schedulers[k.replace("optimizer", "scheduler")] = MultiStepHandle(tr, float(cfg.TRAIN.LR), ms, 0.1, last_epoch, drives=(i == 0))
 
         def train_step(self, batch, t_step, global_step, epoch):
+            if self.fused is None:
+                return super().train_step(batch, t_step, global_step, epoch)
             tag = "TRAIN"
             tr = self.fused
             out = tr.train_step(batch)

@@ -31,7 +31,8 @@
 //     executing (measured: per tap, time = issue-loop overhead + 8 x 64 clk, not the maximum of the two), so a single
 //     issuing thread's loop overhead (~50 clk per MMA) is exposed; two threads hide each other's.
 //
-//   warps 0-3: epilogue (TMEM lane quadrant = warp id)   warp 4: TMA producer   warps 5,6: MMA issuers (5 owns the TMEM allocation)
+//   warps 0-3: epilogue (TMEM lane quadrant = warp % 4)   warp 4: TMA producer   warps 5,6: MMA issuers (5 owns the TMEM allocation)
+//   (EPI_WARPS = 8 shifts the producer / issuers to warps 8 / 9,10)
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -45,8 +46,15 @@ namespace {
 using namespace sdt_tc;
 
 constexpr int BKF = 32;
-constexpr int THREADS = 224;          // 4 epilogue warps, TMA producer, two MMA issuers
-constexpr int EPI_THREADS = 128;
+// Epilogue warps (4 or 8): warp w reads TMEM lane quadrant w % 4 (the hardware's restriction) and takes the 32-column chunks with
+// chunk % (EPI_WARPS / 4) == w / 4.  Eight warps were measured and rejected (profiles/r2_ablation_epilogue_warps.txt): the small-K
+// launches that look epilogue-bound in ncu (64 -> 64 stride 2: tensor pipe 31-40 %, DRAM 30-40 %) did not get faster, and the 18 KB
+// of extra staging cost the deep layers a weight stage: 3.00 instead of 2.97 ms per step.
+constexpr int EPI_WARPS = 4;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int W_TMA = EPI_WARPS;       // warp ids: epilogue 0 .. EPI_WARPS-1, TMA producer, two MMA issuers (highest ids)
+constexpr int W_MMA = EPI_WARPS + 1;
+constexpr int THREADS = EPI_THREADS + 96;
 constexpr int MAX_TH = 8;
 constexpr int MAX_GROUPS = 4;
 constexpr int B_RING_MAX = 6, A_RING_MAX = 4;
@@ -59,7 +67,7 @@ constexpr int STG_PITCH = 36;                 // floats per staged row: 32 colum
 // ones (up to 16).  With 4 slots all MT sub-tiles keep their own partials and the epilogue warps meet once per tile; with more
 // slots one set is reused (two barriers per sub-tile; those are the deep, main-loop-bound layers).
 __host__ __device__ constexpr int epi_bytes(int bn, int mt, int slots) {
-    return 4 * 32 * STG_PITCH * 4 + (slots > 4 ? 1 : mt) * 2 * slots * bn * 4;
+    return EPI_WARPS * 32 * STG_PITCH * 4 + (slots > 4 ? 1 : mt) * 2 * slots * bn * 4;
 }
 
 struct YGeom {
@@ -139,7 +147,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
     }
     const uint32_t smB = smA + g.a_stages * a_stage_bytes;
     float* stg_all = reinterpret_cast<float*>(smem_raw + ring_bytes);              // 4 warps x 32 rows x STG_PITCH floats
-    float* s_red = stg_all + 4 * 32 * STG_PITCH;                                   // [MT or 1][2][slots][BN]
+    float* s_red = stg_all + EPI_WARPS * 32 * STG_PITCH;                                   // [MT or 1][2][slots][BN]
     const uint32_t bars = smA + ring_bytes + epi;
     // barriers: fullA[A_RING_MAX], emptyA[..], fullB[B_RING_MAX], emptyB[..], tmem_full[2], tmem_empty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + ring_bytes + epi + N_BARS * 8);
@@ -208,11 +216,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full(a), N_ISS);
-            mbar_init(tmem_empty(a), 4);            // one arrival per epilogue warp
+            mbar_init(tmem_empty(a), EPI_WARPS);    // one arrival per epilogue warp
         }
         fence_barrier_init();
     }
-    if (warp == 5) tmem_alloc(smem_u32(tmem_slot), 2 * ACC_COLS);
+    if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), 2 * ACC_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -222,7 +230,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
     sdt::pdl_launch_dependents();
     if (DBG && tl && tid == 0) tl[2] = gtimer();
 
-    if (warp == 4) {
+    if (warp == W_TMA) {
         // ================= TMA producer (whole warp walks the loop, one elected lane issues) =================
         int sa = 0, pa = 1, sbi = 0, pb = 1;      // ring slot + parity to wait on the empty barriers (first lap passes)
         long long wait_empty = 0;
@@ -286,9 +294,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
             }
         }
         if (DBG && tl && lane == 0) tl[6] = wait_empty;
-    } else if (warp >= 5) {
+    } else if (warp >= W_MMA) {
         // ================= MMA issuers (whole warp walks the loop, one elected lane issues) =================
-        const int iss = warp - 5;
+        const int iss = warp - W_MMA;
         if (iss < N_ISS) {
         const uint32_t idesc = make_idesc_tf32(BN, 0, 0);
         const uint32_t shift_lo = (uint32_t)(g.bw * g.nb * 128) >> 4;    // one patch row (of all nb images), in descriptor address units
@@ -379,8 +387,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
         }
         }
     } else {
-        // ================= epilogue (warps 0..3 = TMEM lane quadrants), one tile behind the MMA issuer =================
-        const int q = warp;
+        // ================= epilogue (TMEM lane quadrant = warp % 4, column-chunk parity = warp / 4), one tile behind the MMA issuer
+        const int q = warp & 3, half = warp >> 2;
+        constexpr int CH_STEP = EPI_WARPS / 4;                // chunks handled by this warp: half, half + CH_STEP, ...
         const int r = q * 32 + lane;
         // GEMM row -> (py, image, px)
         const int py = r >> (g.lbw + g.lnb), pn = (r >> g.lbw) & (g.nb - 1), px = r & (g.bw - 1);
@@ -401,7 +410,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
                 d.stat_partial[(prow * 2 + 1) * N + n0 + c] = s2;
             }
         };
-        float* stg = stg_all + (size_t)(q * 32) * STG_PITCH;
+        float* stg = stg_all + (size_t)(warp * 32) * STG_PITCH;
         const int sub = lane >> 3, col4 = lane & 7;          // write-back: 8 lanes per 128-byte row segment
         long long wait_tmem = 0;
         int it = 0;
@@ -438,11 +447,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
                     const int b = b0 + ((rr >> g.lbw) & (g.nb - 1));
                     rowp[k] = d.dst + (((long long)b * d.DH + (gy * d.dy_mul + c_dyoff)) * d.DW + (gx * d.dx_mul + c_dxoff)) * N + n0 + col4 * 4;
                 }
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = half; c < BN / 32; c += CH_STEP) {
                     float v[32];
                     if (!(DBG && (dbg & 128)))
                         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + m * BN + c * 32), v);
-                    if (m == nvalid - 1 && c == BN / 32 - 1) {       // last read of this accumulator set: hand it back to the MMA issuer
+                    if (m == nvalid - 1 && c + CH_STEP >= BN / 32) {  // this warp's last read of the accumulator set: hand it back to the MMA issuer
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(tmem_empty(acc));
@@ -508,24 +517,24 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_ytap_kernel(const __grid_c
                     __syncwarp();
                 }
                 if (d.stat_partial != nullptr && per_m) {
-                    asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps
+                    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");          // the epilogue warps
                     reduce_stats(s_red, b0, rem, n0, tpi);
-                    asm volatile("bar.sync 1, 128;" ::: "memory");          // s_red is reused by the next sub-tile
+                    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");          // s_red is reused by the next sub-tile
                 }
             }
             if (d.stat_partial != nullptr && !per_m) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
                 for (int m = 0; m < nvalid; ++m) {
                     const int ib = (t0 + m) / tpi;
                     reduce_stats(s_red + m * 2 * slots * BN, ib << g.lnb, t0 + m - ib * tpi, n0, tpi);
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == W_MMA) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 2 * ACC_COLS);
     }

@@ -286,7 +286,7 @@ def test_conv_plan_invariants_on_random_layers():
             assert tiles == -(-sub // mt) * (cout // bn)
             # ring + epilogue scratch as the kernel lays them out
             slots = 4 if (nb == 1 or bw >= 32) else 128 // bw
-            epi = 4 * 32 * 36 * 4 + (1 if slots > 4 else mt) * 2 * slots * bn * 4
+            epi = 4 * 32 * 36 * 4 + (1 if slots > 4 else mt) * 2 * slots * bn * 4       # 4 epilogue warps x 32 staged rows
             assert smem == a_st * mt * box_rows * nb * bw * 128 + b_st * bn * 128 + epi + (2 * 4 + 2 * 6 + 4) * 8 + 16
     finally:
         lib.sdt_set_conv_math(0)

@@ -103,11 +103,24 @@ typedef struct sdt_conv_desc {
     int32_t splits;            /* wgrad: number of K splits (== gridDim.z) */
     int32_t math;              /* 0 = the process default (sdt_get_conv_math()); m + 1 = math mode m for THIS problem, so every
                                 * engine / model of a process carries its own mode and no call depends on shared mutable state */
+    /* Fused channel-LayerNorm + activation epilogue (the reference's 1-D "IN" block: Conv1d -> InstanceNorm1d on the permuted
+     * tensor -> LeakyReLU, building_blocks.py:31-54): when rn_act != NULL the convolution also writes
+     * rn_act = act((dst - mean_row) * rstd_row) (same shape as dst) and the per-row statistics rn_mean / rn_rstd (B*DH*DW), i.e.
+     * what sdt_rownorm_act_fwd would compute from dst in a second launch.  Only where sdt_conv_rownorm_ok() says so (the TMA
+     * tensor-core kernel with the N = 256 output channels of a row spread over a cluster of four CTAs that exchange the row sums
+     * through distributed shared memory); otherwise leave rn_act NULL and call sdt_rownorm_act_fwd. */
+    float* rn_act;
+    float* rn_mean;
+    float* rn_rstd;
+    float rn_eps, rn_slope;
+    int32_t rn_out_tf32;
 } sdt_conv_desc;
 
 /* number of row tiles sdt_conv_gemm will use for this descriptor (size of stat_partial's first dim) */
 int sdt_conv_row_tiles(const sdt_conv_desc* d);
 int sdt_conv_gemm(const sdt_conv_desc* d, void* stream);
+/* 1 if sdt_conv_gemm can run this problem with the fused row-norm epilogue (rn_* fields), else 0 (host only) */
+int sdt_conv_rownorm_ok(const sdt_conv_desc* d);
 /* which kernel sdt_conv_gemm would launch for this descriptor under the current math mode (host-only, no launch):
  * out10[0] = 0 fp32 FFMA, 1 tcgen05 (producer warps), 2 tcgen05 + TMA, 3 tcgen05 + TMA + shared-memory reuse, 4 CTA pairs; for 3/4 also
  * out10[1..9] = N tile, accumulators per CTA, patch rows | images per patch << 8, patch cols, box rows, A stages, B stages,

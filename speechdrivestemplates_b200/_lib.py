@@ -26,6 +26,7 @@ class ConvDesc(C.Structure):
         ("DH", i32), ("DW", i32), ("dy_mul", i32), ("dy_off", i32), ("dx_mul", i32), ("dx_off", i32),
         ("xf_bstride", i32), ("xf_slope", f32),
         ("accumulate", i32), ("per_image_tiles", i32), ("splits", i32), ("math", i32),
+        ("rn_act", c_ptr), ("rn_mean", c_ptr), ("rn_rstd", c_ptr), ("rn_eps", f32), ("rn_slope", f32), ("rn_out_tf32", i32),
     ]
 
 
@@ -41,6 +42,7 @@ SIGNATURES = {
     "sdt_mel_fwd": [c_ptr, i32, i32, c_ptr, c_ptr, c_ptr, c_ptr, i32, c_ptr, c_ptr],
     "sdt_conv_row_tiles": [_P],
     "sdt_conv_gemm": [_P, c_ptr],
+    "sdt_conv_rownorm_ok": [_P],
     "sdt_conv_plan": [_P, c_ptr],
     "sdt_conv_gemm_multi": [_P, i32, c_ptr, c_ptr],
     "sdt_conv_wgrad": [_P, c_ptr],
@@ -86,7 +88,7 @@ SIGNATURES = {
 _RESTYPES = {"sdt_last_error": C.c_char_p, "sdt_tc_launches": C.c_int64}
 # entry points whose int return value is a result, not a status
 _NOT_STATUS = {"sdt_last_error", "sdt_version", "sdt_get_conv_math", "sdt_conv_row_tiles", "sdt_tc_launches",
-               "sdt_first_layer_units"}
+               "sdt_first_layer_units", "sdt_conv_rownorm_ok"}
 
 _lib = None
 launch_count = 0     # number of CUDA kernels launched through this binding (bench.py's gpu_launches)

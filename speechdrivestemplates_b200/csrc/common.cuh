@@ -66,6 +66,27 @@ inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);      // errors surface through SDT_LAUNCH_OK (cudaPeekAtLastError)
 }
+
+// the same with a thread-block cluster of (cx, cy, cz) CTAs
+template <typename... KArgs, typename... Args>
+inline void launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cx, int cy, int cz,
+                           Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cx;
+    attr[0].val.clusterDim.y = cy;
+    attr[0].val.clusterDim.z = cz;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 #endif
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -763,6 +763,12 @@ extern "C" int sdt_conv_row_tiles(const sdt_conv_desc* d) {
     return row_tiles_for(d, use_tc(d) ? 128 : pick_bm(d));
 }
 
+extern "C" int sdt_conv_rownorm_ok(const sdt_conv_desc* d) {
+    if (check_desc(d, "sdt_conv_rownorm_ok") != SDT_OK) return 0;
+    if (d->GH != 1 || d->SH != 1) return 0;                 // 1-D layers (the 2-D encoder normalises per image, not per row)
+    return (use_tma(d) && sdt_tc_conv_tma_rownorm_ok(d)) ? 1 : 0;
+}
+
 extern "C" int sdt_conv_plan(const sdt_conv_desc* d, int32_t* out10) {
     if (int rc = check_desc(d, "sdt_conv_plan")) return rc;
     SDT_REQUIRE(out10 != nullptr, "sdt_conv_plan: null output");
@@ -791,6 +797,10 @@ extern "C" int sdt_conv_gemm(const sdt_conv_desc* d, void* stream) {
     SDT_REQUIRE(!(d->stat_partial && d->bias), "sdt_conv_gemm: statistics epilogue excludes bias");
     SDT_REQUIRE(!(d->stat_partial && d->accumulate), "sdt_conv_gemm: statistics epilogue excludes accumulate");
     cudaStream_t st = sdt::as_stream(stream);
+    if (d->rn_act != nullptr) {                                                 // fused row-norm epilogue: TMA kernel only
+        SDT_REQUIRE(sdt_conv_rownorm_ok(d), "sdt_conv_gemm: rn_act set but sdt_conv_rownorm_ok() is 0 for this problem");
+        return sdt_tc_conv_tma_launch(d, st);
+    }
     sdt_conv_desc r1;
     if (remap_1d(d, &r1) && use_ytap(&r1)) return sdt_tc_conv_ytap_launch(&r1, st);   // 1-D layers on the persistent kernel
     if (use_pair(d)) return sdt_tc_conv_pair_launch(d, st);                     // math mode 4: CTA pairs (cta_group::2), experimental

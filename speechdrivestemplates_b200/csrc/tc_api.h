@@ -11,6 +11,7 @@ int sdt_tc_wgrad_launch(const sdt_conv_desc* d, cudaStream_t st);
 bool sdt_tc_conv_tma_eligible(const sdt_conv_desc* d);
 int sdt_tc_conv_tma_row_tiles(const sdt_conv_desc* d);
 int sdt_tc_conv_tma_launch(const sdt_conv_desc* d, cudaStream_t st);
+bool sdt_tc_conv_tma_rownorm_ok(const sdt_conv_desc* d);      // fused row-norm epilogue (cluster of N / 64 = 4 CTAs per row tile)
 bool sdt_tc_conv_ytap_eligible(const sdt_conv_desc* d);
 bool sdt_tc_conv_ytap_shape_ok(const sdt_conv_desc* d);
 int sdt_tc_conv_ytap_row_tiles(const sdt_conv_desc* d);

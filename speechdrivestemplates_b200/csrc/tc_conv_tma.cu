@@ -35,19 +35,51 @@ struct TileGeom {
     int tiles_x, tiles_y;  // patches per image
 };
 
+// profiling aid (tests/diag_conv1d_timeline.py): 8 x int64 per CTA -- globaltimer (ns) at CTA start, after the prologue, when the first
+// operand stage has landed, after the last MMA was issued, when the accumulator is complete, at the end of the epilogue, at CTA end
+__device__ long long* g_tma_timeline = nullptr;
+__device__ int g_tma_timeline_ctas = 0;
+__device__ __forceinline__ long long gtimer_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // DEEP: grids of at most one CTA per SM (the 1-D stacks) are latency-bound on the k loop, not on occupancy: give the
 // single resident CTA the whole shared memory as a 6-8 stage ring instead of leaving room for a second CTA.
+constexpr int RN_CL = 4;               // CTAs per cluster of the fused row-norm epilogue: the four 64-column quarters of N = 256
 template <int BN, bool DEEP>
 struct TmaCfg {
     static constexpr int STAGES = DEEP ? (BN == 64 ? 8 : 6) : (BN == 64 ? 4 : 3);
     static constexpr int A_BYTES = BM * 128;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int BAR_BYTES = 256;
-    static constexpr int RED_BYTES = 2 * 4 * BN * 4;
-    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + RED_BYTES + 1024;
+    static constexpr int RED_BYTES = 2 * 4 * BN * 4;              // statistics partials [2][4][BN]; the row-norm epilogue keeps its
+    static constexpr int XCH_BYTES = 2 * RN_CL * BM * 4;          // exchange buffer [2 passes][rank][row] behind them (4 KB)
+    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + BAR_BYTES + RED_BYTES + XCH_BYTES + 1024;
 };
 
-template <int BN, bool DEEP>
+// ---- thread-block cluster helpers (fused row-norm epilogue) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {          // every thread of every CTA of the cluster
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t local_smem_addr, uint32_t rank, float v) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_smem_addr), "r"(rank));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+}
+
+// RN: fused channel-LayerNorm + activation epilogue (sdt_conv_desc.rn_*).  The 256 output channels of a GEMM row are spread over the
+// four CTAs of a cluster (blockIdx.y = 64-column quarter = cluster rank); each epilogue thread owns one row, keeps its 64 accumulators
+// in registers, and the row sums travel through distributed shared memory: pass 1 the sums (-> mean), pass 2 the centred squares
+// (-> rstd), each CTA writing its partial into every member's exchange buffer, a cluster barrier, a fixed-order sum (identical in all
+// four CTAs).  Replaces the separate sdt_rownorm_act_fwd launch behind every 1-D convolution of the generator.
+template <int BN, bool DEEP, bool RN>
 __global__ void __launch_bounds__(THREADS, DEEP ? 1 : 2) tc_conv_tma_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmB,
                                                                  const sdt_conv_desc d, const TileGeom tg) {
@@ -63,6 +95,9 @@ __global__ void __launch_bounds__(THREADS, DEEP ? 1 : 2) tc_conv_tma_kernel(cons
     const uint32_t bars = smB + STAGES * Cfg::B_BYTES;          // full[STAGES], empty[STAGES], tmem_full
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(after + (2 * STAGES + 1) * 8);
     float* s_red = reinterpret_cast<float*>(after + Cfg::BAR_BYTES);   // [2][4][BN]
+    float* s_xch = s_red + 2 * 4 * BN;                                  // [2][RN_CL][BM] (RN only)
+    float rnv[RN ? 64 : 1];                                             // RN: this thread's row of the tile (epilogue warps)
+    long long rn_dst_off = -1;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
     const uint32_t tmem_full_bar = bars + 8u * (2 * STAGES);
@@ -71,6 +106,9 @@ __global__ void __launch_bounds__(THREADS, DEEP ? 1 : 2) tc_conv_tma_kernel(cons
     const int K = d.TH * d.TW * d.C, KB = K / BKF;
     const int N = d.N;
     const int n0 = blockIdx.y * BN;
+    const int cta_lin = blockIdx.y * gridDim.x + blockIdx.x;
+    long long* tl = (g_tma_timeline != nullptr && cta_lin < g_tma_timeline_ctas) ? g_tma_timeline + 8 * cta_lin : nullptr;
+    if (tl && tid == 0) tl[0] = gtimer_ns();
     // patch of this CTA
     const int tpi = tg.tiles_x * tg.tiles_y;
     const int b = blockIdx.x / tpi;
@@ -93,6 +131,7 @@ __global__ void __launch_bounds__(THREADS, DEEP ? 1 : 2) tc_conv_tma_kernel(cons
     // everything above (barrier init, TMEM allocation) overlapped the tail of the preceding kernel; global memory from here on
     sdt::pdl_wait();
     sdt::pdl_launch_dependents();
+    if (tl && tid == 0) tl[1] = gtimer_ns();
 
     // warps 0-3: epilogue (TMEM lane quadrant = warp id); warp 4: TMA producer; warp 5: MMA issuer.  The issuing warps walk
     // their loops as whole warps and elect one lane per instruction (tc_common.cuh: elect_one), and have the highest warp ids.
@@ -126,6 +165,7 @@ __global__ void __launch_bounds__(THREADS, DEEP ? 1 : 2) tc_conv_tma_kernel(cons
         uint32_t started = 0;
         for (int kb = 0; kb < KB; ++kb) {
             mbar_wait_spin(full_bar(s), (uint32_t)par);
+            if (tl && kb == 0 && lane == 0) tl[2] = gtimer_ns();
             tc_fence_after();
             const uint32_t a_lo = desc_lo(smA + s * Cfg::A_BYTES, 16), b_lo = desc_lo(smB + s * Cfg::B_BYTES, 16);
             if (elect_one()) {
@@ -139,6 +179,7 @@ __global__ void __launch_bounds__(THREADS, DEEP ? 1 : 2) tc_conv_tma_kernel(cons
         }
         if (elect_one()) mma_commit(tmem_full_bar);
         __syncwarp();
+        if (tl && lane == 0) tl[3] = gtimer_ns();
     } else {
         // ================= epilogue (warps 2..5; TMEM lane quadrant = warp % 4) =================
         const int q = warp;
@@ -148,7 +189,28 @@ __global__ void __launch_bounds__(THREADS, DEEP ? 1 : 2) tc_conv_tma_kernel(cons
         const bool ok = gy < d.GH && gx < d.GW;
         const long long dst_off = ok ? (((long long)b * d.DH + (gy * d.dy_mul + d.dy_off)) * d.DW + (gx * d.dx_mul + d.dx_off)) * N : -1;
         mbar_wait(tmem_full_bar, 0);
+        if (tl && tid == 0) tl[4] = gtimer_ns();
         tc_fence_after();
+        if constexpr (RN) {
+            // pass 1: the row's 64 accumulators into registers, their sum to every CTA of the cluster
+            static_assert(!RN || BN == 64, "row-norm epilogue: 64-column quarters");
+            float v0[32], v1[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16), v0);
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + 32u, v1);
+            float sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                rnv[i] = v0[i];
+                rnv[32 + i] = v1[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 64; ++i) sum += rnv[i];
+            rn_dst_off = dst_off;
+            const uint32_t rank = cluster_ctarank();
+            const uint32_t slot = smem_u32(s_xch + (0 * RN_CL + rank) * BM + r);
+#pragma unroll
+            for (uint32_t t = 0; t < RN_CL; ++t) st_cluster_f32(slot, t, sum);
+        } else
         for (int c = 0; c < BN / 32; ++c) {
             float v[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
@@ -184,6 +246,47 @@ __global__ void __launch_bounds__(THREADS, DEEP ? 1 : 2) tc_conv_tma_kernel(cons
             }
         }
     }
+    if constexpr (RN) {
+        cluster_sync_all();
+        const int r = (warp & 3) * 32 + lane;
+        float mu = 0.f;
+        if (warp < 4) {
+            mu = ((s_xch[0 * BM + r] + s_xch[1 * BM + r]) + (s_xch[2 * BM + r] + s_xch[3 * BM + r])) * (1.0f / (float)(RN_CL * BN));
+            float qs = 0.f;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+                const float dl = rnv[i] - mu;
+                qs = fmaf(dl, dl, qs);
+            }
+            const uint32_t rank = cluster_ctarank();
+            const uint32_t slot = smem_u32(s_xch + (1 * RN_CL + rank) * BM + r);
+#pragma unroll
+            for (uint32_t t = 0; t < RN_CL; ++t) st_cluster_f32(slot, t, qs);
+        }
+        cluster_sync_all();
+        if (warp < 4 && rn_dst_off >= 0) {
+            const float* x2 = s_xch + RN_CL * BM;
+            const float var = ((x2[0 * BM + r] + x2[1 * BM + r]) + (x2[2 * BM + r] + x2[3 * BM + r])) * (1.0f / (float)(RN_CL * BN));   // biased
+            const float rs = 1.0f / sqrtf(var + d.rn_eps);
+            float4* praw = reinterpret_cast<float4*>(d.dst + rn_dst_off + n0);
+            float4* pact = reinterpret_cast<float4*>(d.rn_act + rn_dst_off + n0);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                praw[j] = make_float4(rnv[4 * j], rnv[4 * j + 1], rnv[4 * j + 2], rnv[4 * j + 3]);
+                float4 o;
+                o.x = sdt::out_round(sdt::leaky((rnv[4 * j] - mu) * rs, d.rn_slope), d.rn_out_tf32);
+                o.y = sdt::out_round(sdt::leaky((rnv[4 * j + 1] - mu) * rs, d.rn_slope), d.rn_out_tf32);
+                o.z = sdt::out_round(sdt::leaky((rnv[4 * j + 2] - mu) * rs, d.rn_slope), d.rn_out_tf32);
+                o.w = sdt::out_round(sdt::leaky((rnv[4 * j + 3] - mu) * rs, d.rn_slope), d.rn_out_tf32);
+                pact[j] = o;
+            }
+            if (n0 == 0) {
+                d.rn_mean[rn_dst_off / N] = mu;
+                d.rn_rstd[rn_dst_off / N] = rs;
+            }
+        }
+    }
+    if (tl && tid == 0) tl[5] = gtimer_ns();
     tc_fence_before();
     __syncthreads();
     if (d.stat_partial != nullptr) {
@@ -201,6 +304,7 @@ __global__ void __launch_bounds__(THREADS, DEEP ? 1 : 2) tc_conv_tma_kernel(cons
     if (warp == 5) {
         tc_fence_after();
         tmem_dealloc(tmem_base, BN);
+        if (tl && lane == 0) tl[6] = gtimer_ns();
     }
 }
 
@@ -235,13 +339,13 @@ TileGeom pick_geom(const sdt_conv_desc* d) {
     return best;
 }
 
-template <int BN, bool DEEP>
+template <int BN, bool DEEP, bool RN = false>
 int launch_tma(const sdt_conv_desc* d, const TileGeom& tg, cudaStream_t st) {
     EncodeTiledFn enc = get_encode();
     SDT_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
     static bool attr_set = false;
     if (!attr_set) {
-        SDT_CUDA_OK(cudaFuncSetAttribute(tc_conv_tma_kernel<BN, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SDT_CUDA_OK(cudaFuncSetAttribute(tc_conv_tma_kernel<BN, DEEP, RN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          TmaCfg<BN, DEEP>::SMEM));
         attr_set = true;
     }
@@ -268,13 +372,24 @@ int launch_tma(const sdt_conv_desc* d, const TileGeom& tg, cudaStream_t st) {
         SDT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed with %d", (int)r);
     }
     dim3 grid(d->B * tg.tiles_x * tg.tiles_y, d->N / BN);
-    sdt::launch(tc_conv_tma_kernel<BN, DEEP>, dim3(grid), dim3(THREADS), TmaCfg<BN, DEEP>::SMEM, st, tmA, tmB, *d, tg);
+    if (RN)
+        sdt::launch_cluster(tc_conv_tma_kernel<BN, DEEP, RN>, dim3(grid), dim3(THREADS), TmaCfg<BN, DEEP>::SMEM, st, 1, RN_CL, 1, tmA, tmB, *d, tg);
+    else
+        sdt::launch(tc_conv_tma_kernel<BN, DEEP, RN>, dim3(grid), dim3(THREADS), TmaCfg<BN, DEEP>::SMEM, st, tmA, tmB, *d, tg);
     SDT_LAUNCH_OK("tc_conv_tma_kernel");
     sdt_note_tc_launch();
     return SDT_OK;
 }
 
 }  // namespace
+
+// per-CTA timeline buffer of 8 x int64 records, or NULL to switch off (diagnostics only)
+extern "C" int sdt_debug_tma_timeline(void* buf, int ctas) {
+    long long* p = static_cast<long long*>(buf);
+    SDT_CUDA_OK(cudaMemcpyToSymbol(g_tma_timeline, &p, sizeof(p)));
+    SDT_CUDA_OK(cudaMemcpyToSymbol(g_tma_timeline_ctas, &ctas, sizeof(ctas)));
+    return SDT_OK;
+}
 
 bool sdt_tc_conv_tma_eligible(const sdt_conv_desc* d) {
     if (d->wt_nk == nullptr || d->xf_scale != nullptr) return false;        // plain (already activated) source only
@@ -289,9 +404,21 @@ int sdt_tc_conv_tma_row_tiles(const sdt_conv_desc* d) {
     return d->B * tg.tiles_x * tg.tiles_y;
 }
 
+bool sdt_tc_conv_tma_rownorm_ok(const sdt_conv_desc* d) {
+    if (!sdt_tc_conv_tma_eligible(d)) return false;
+    if (d->N != RN_CL * 64 || d->bias != nullptr || d->accumulate || d->stat_partial != nullptr) return false;
+    if (d->dy_mul != 1 || d->dx_mul != 1 || d->dy_off != 0 || d->dx_off != 0 || d->DH != d->GH || d->DW != d->GW) return false;   // plain forward
+    return true;
+}
+
 int sdt_tc_conv_tma_launch(const sdt_conv_desc* d, cudaStream_t st) {
     const TileGeom tg = pick_geom(d);
     const long long tiles = (long long)d->B * tg.tiles_x * tg.tiles_y;
+    if (d->rn_act != nullptr) {
+        SDT_REQUIRE(sdt_tc_conv_tma_rownorm_ok(d) && d->rn_mean && d->rn_rstd, "sdt_conv_gemm: the fused row-norm epilogue is not available for this problem");
+        SDT_REQUIRE(((((uintptr_t)d->rn_act) & 15) == 0), "sdt_conv_gemm: rn_act must be 16-byte aligned");
+        return tiles * RN_CL <= 148 ? launch_tma<64, true, true>(d, tg, st) : launch_tma<64, false, true>(d, tg, st);
+    }
     int bn = d->N % 128 == 0 ? 128 : 64;
     if (bn == 128 && tiles * (d->N / 128) < 2 * 148) bn = 64;               // small problems: more CTAs
     const bool deep = tiles * (d->N / bn) <= 148;

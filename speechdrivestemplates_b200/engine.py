@@ -156,6 +156,7 @@ class GeneratorEngine:
         self.fwd_id = 0
         self.math = ops.resolve_math(math)      # this engine's convolution math mode (every descriptor carries it)
         self.wprep = WeightPrep(self.arena, self.math)
+        self.fuse_rownorm = __import__("os").environ.get("SDT_FUSE_ROWNORM", "1") != "0"     # 1-D "IN" blocks: row norm in the conv epilogue
         self.grad_marks = None                  # {layer name: event recorded behind that layer's weight gradient} (multi-GPU buckets)
         self.on_mark = None                     # callback(name, event), called when a mark has been recorded
 
@@ -428,8 +429,13 @@ def _gen_forward_seq(self, x0, num_frames, params, training, buffers):
         d = ops.fwd_desc(g, xin, wt, raw, B, 1, L_in, wt_nk=wt_nk, math=self.math)
         act = A.get("act:" + name, (B, L_out, 256))
         if self.norm == "IN":
-            ops.conv_gemm(d)
-            ops.rownorm_act_fwd(raw, slope, out=(act, A.get("rmean:" + name, (B * L_out,)), A.get("rrstd:" + name, (B * L_out,))), tf32=tf32)
+            rmean, rrstd = A.get("rmean:" + name, (B * L_out,)), A.get("rrstd:" + name, (B * L_out,))
+            if self.fuse_rownorm and ops.conv_rownorm_ok(d):
+                # channel LayerNorm + activation in the convolution's epilogue (cluster of four CTAs per row tile): one launch
+                ops.conv_gemm(ops.set_rownorm(d, act, rmean, rrstd, slope, tf32))
+            else:
+                ops.conv_gemm(d)
+                ops.rownorm_act_fwd(raw, slope, out=(act, rmean, rrstd), tf32=tf32)
         else:
             sc = A.get("scale:" + name, (1, 256))
             sh = A.get("shift:" + name, (1, 256))

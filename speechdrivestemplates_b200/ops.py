@@ -256,6 +256,18 @@ def conv_gemm(desc):
     call("sdt_conv_gemm", C.byref(desc), _stream())
 
 
+def conv_rownorm_ok(desc):
+    """Can sdt_conv_gemm run this (1-D forward) problem with the fused channel-LayerNorm + activation epilogue?"""
+    return bool(call("sdt_conv_rownorm_ok", C.byref(desc)))
+
+
+def set_rownorm(desc, act, mean, rstd, slope, tf32):
+    """Ask sdt_conv_gemm(desc) to also write act = act((dst - mean_row) * rstd_row) and the row statistics (include/sdt_b200.h rn_*)."""
+    desc.rn_act, desc.rn_mean, desc.rn_rstd = act.data_ptr(), mean.data_ptr(), rstd.data_ptr()
+    desc.rn_eps, desc.rn_slope, desc.rn_out_tf32 = EPS_NORM, float(slope), int(tf32)
+    return desc
+
+
 def conv_wgrad(desc):
     call("sdt_conv_wgrad", C.byref(desc), _stream())
 

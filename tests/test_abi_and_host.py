@@ -46,7 +46,7 @@ def test_conv_desc_mirror_matches_header():
         decl = re.sub(r"^(const\s+)?(float\*|int32_t|float)\s*", "", decl)
         names += [n.strip().lstrip("*") for n in decl.split(",")]
     assert names == [f[0] for f in ConvDesc._fields_]
-    assert ctypes.sizeof(ConvDesc) == 10 * 8 + 28 * 4          # 27 ints/floats + tail padding to the 8-byte alignment
+    assert ctypes.sizeof(ConvDesc) == 10 * 8 + 28 * 4 + 3 * 8 + 4 * 4    # 27 scalars + pad, 3 pointers, 3 scalars + tail padding
 
 
 def test_argument_errors_are_reported_not_thrown():

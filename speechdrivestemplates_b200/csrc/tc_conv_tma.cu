@@ -39,6 +39,7 @@ struct TileGeom {
 // operand stage has landed, after the last MMA was issued, when the accumulator is complete, at the end of the epilogue, at CTA end
 __device__ long long* g_tma_timeline = nullptr;
 __device__ int g_tma_timeline_ctas = 0;
+__device__ int g_tma_dbg = 0;            // with a timeline only (results are wrong): 1 = one MMA per k-block instead of four, 2 = no MMAs
 __device__ __forceinline__ long long gtimer_ns() {
     long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -163,6 +164,7 @@ __global__ void __launch_bounds__(THREADS, DEEP ? 1 : 2) tc_conv_tma_kernel(cons
         constexpr uint32_t HI = desc_hi(1024, kSwizzle128B);
         int s = 0, par = 0;
         uint32_t started = 0;
+        const int dbg = tl ? g_tma_dbg : 0;
         for (int kb = 0; kb < KB; ++kb) {
             mbar_wait_spin(full_bar(s), (uint32_t)par);
             if (tl && kb == 0 && lane == 0) tl[2] = gtimer_ns();
@@ -170,7 +172,8 @@ __global__ void __launch_bounds__(THREADS, DEEP ? 1 : 2) tc_conv_tma_kernel(cons
             const uint32_t a_lo = desc_lo(smA + s * Cfg::A_BYTES, 16), b_lo = desc_lo(smB + s * Cfg::B_BYTES, 16);
             if (elect_one()) {
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) mma_tf32_lohi(tmem_base, a_lo + 2u * k4, b_lo + 2u * k4, HI, idesc, started | (uint32_t)k4);
+                for (int k4 = 0; k4 < 4; ++k4)
+                    if (dbg == 0 || (dbg == 1 && k4 == 0)) mma_tf32_lohi(tmem_base, a_lo + 2u * k4, b_lo + 2u * k4, HI, idesc, started | (uint32_t)k4);
                 mma_commit(empty_bar(s));
             }
             __syncwarp();
@@ -384,6 +387,10 @@ int launch_tma(const sdt_conv_desc* d, const TileGeom& tg, cudaStream_t st) {
 }  // namespace
 
 // per-CTA timeline buffer of 8 x int64 records, or NULL to switch off (diagnostics only)
+extern "C" int sdt_debug_tma_flags(int flags) {
+    SDT_CUDA_OK(cudaMemcpyToSymbol(g_tma_dbg, &flags, sizeof(flags)));
+    return SDT_OK;
+}
 extern "C" int sdt_debug_tma_timeline(void* buf, int ctas) {
     long long* p = static_cast<long long*>(buf);
     SDT_CUDA_OK(cudaMemcpyToSymbol(g_tma_timeline, &p, sizeof(p)));

@@ -41,18 +41,22 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 50
-        tlbuf.zero_()
-        lib.sdt_debug_tma_timeline(C.c_void_p(tlbuf.data_ptr()), ncta)
-        ops.conv_gemm(d)
-        torch.cuda.synchronize()
-        lib.sdt_debug_tma_timeline(None, 0)
-        t = tlbuf.cpu().double()
-        t = t[t[:, 0] > 0]
-        base = t[:, 0].min()
-        rel = (t[:, :7] - base) / 1e3
-        names = ["start", "prologue", "1st stage", "MMAs issued", "acc done", "epilogue", "end"]
-        print("L %2d k %d s %d: %d CTAs, %.1f us back to back | mean us since the first CTA start: %s | span %.2f us" % (
-            L, k, s, t.shape[0], us, "  ".join("%s %.2f" % (n, rel[:, i].mean()) for i, n in enumerate(names)), float(rel[:, 6].max())), flush=True)
+        for flags in (0, 1, 2):
+            tlbuf.zero_()
+            lib.sdt_debug_tma_flags(flags)
+            lib.sdt_debug_tma_timeline(C.c_void_p(tlbuf.data_ptr()), ncta)
+            ops.conv_gemm(d)
+            torch.cuda.synchronize()
+            lib.sdt_debug_tma_timeline(None, 0)
+            lib.sdt_debug_tma_flags(0)
+            t = tlbuf.cpu().double()
+            t = t[t[:, 0] > 0]
+            base = t[:, 0].min()
+            rel = (t[:, :7] - base) / 1e3
+            names = ["start", "prologue", "1st stage", "MMAs issued", "acc done", "epilogue", "end"]
+            what = ["", " [1 of 4 MMAs per k-block]", " [no MMAs]"][flags]
+            print("L %2d k %d s %d%s: %d CTAs, %.1f us back to back | mean us since the first CTA start: %s | span %.2f us" % (
+                L, k, s, what, t.shape[0], us, "  ".join("%s %.2f" % (n, rel[:, i].mean()) for i, n in enumerate(names)), float(rel[:, 6].max())), flush=True)
     ops.set_conv_math(0)
 
 

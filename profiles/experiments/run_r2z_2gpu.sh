@@ -1,0 +1,17 @@
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+N=${1:-2}
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+run() { tag=$1; shift; env "$@" timeout 240 $TR --master-port $((29600 + RANDOM % 300)) bench.py --gpus $N --steps 40 --warmup 3 --no-segments > gpurun_out/r2z_${N}gpu_$tag.json 2> gpurun_out/r2z_${N}gpu_$tag.err
+python -c "
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]);print(sys.argv[2],d['value'],d['ms_per_step'],d['e2e']['value'],d.get('rank_param_spread'),d['impl_detail']['comm_mode'])
+except Exception as e: print(sys.argv[2],'FAILED',e)" gpurun_out/r2z_${N}gpu_$tag.json $tag; }
+run overlap SDT_COMM=overlap
+run overlap_cta8_res8 SDT_COMM=overlap NCCL_MAX_CTAS=8 SDT_YTAP_SM_RESERVE=8
+run overlap_cta4_res4 SDT_COMM=overlap NCCL_MAX_CTAS=4 SDT_YTAP_SM_RESERVE=4
+run overlap_cta16_res16 SDT_COMM=overlap NCCL_MAX_CTAS=16 SDT_YTAP_SM_RESERVE=16
+run overlap_cta8 SDT_COMM=overlap NCCL_MAX_CTAS=8
+run serial SDT_COMM=serial
+run serial_cta32 SDT_COMM=serial NCCL_MIN_CTAS=32

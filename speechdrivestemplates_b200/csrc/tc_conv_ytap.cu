@@ -719,8 +719,12 @@ int launch_ytap2(const sdt_conv_desc* d, const Plan& pl, const CUtensorMap& tmA,
         SDT_CUDA_OK(cudaGetDevice(&dev));
         SDT_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
+    // SDT_YTAP_SM_RESERVE=n: the persistent grid leaves n SMs free (multi-GPU: room for the NCCL kernels of the gradient buckets
+    // that run beside the backward pass -- a 148-CTA persistent kernel holding every SM makes them queue behind it)
+    static const int sm_reserve = getenv("SDT_YTAP_SM_RESERVE") ? atoi(getenv("SDT_YTAP_SM_RESERVE")) : 0;
+    const int sm_use = sm_count - sm_reserve > 0 ? sm_count - sm_reserve : sm_count;
     const int tiles = cl.unit_start[cl.n] * (d->N / BN);
-    const int grid = tiles < sm_count ? tiles : sm_count;      // persistent: one CTA per SM, static round-robin tiles
+    const int grid = tiles < sm_use ? tiles : sm_use;          // persistent: one CTA per SM, static round-robin tiles
     sdt::launch(tc_conv_ytap_kernel<BN, MT, DBG>, dim3(grid), dim3(THREADS), pl.smem, st, tmA, tmB, *d, pl.g, cl);
     SDT_LAUNCH_OK("tc_conv_ytap_kernel");
     sdt_note_tc_launch();

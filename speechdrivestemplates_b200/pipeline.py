@@ -16,6 +16,10 @@ from torch import nn
 
 # diagnostic switch (wrong results: the FGD / metrics side stream is skipped); bench.py refuses to run with it set
 _DIAG_SKIP_SIDE = bool(os.environ.get("SDT_DIAG_SKIP_SIDE"))
+# multi-GPU communication mode when SDT_COMM is unset.  Measured at 2 and 8 GPUs (profiles/r2_multi_gpu_modes.txt): the single flat
+# all-reduce between two graphs ("serial") is 0.02-0.04 ms per step FASTER than the gradient buckets overlapped with the backward pass
+# ("overlap"), because an NCCL kernel holding SMs delays the persistent convolution kernel by about its own duration.
+_DEFAULT_COMM = "serial"
 
 from . import _lib, ops, parallel
 from .networks import PoseSeqEncoder, SequenceGeneratorCNN, get_model
@@ -542,7 +546,7 @@ class Voice2PoseTrainer:
         # multi-GPU: "overlap" = gradient buckets all-reduced on a communication stream while the backward pass still runs, the
         # clip-code gradient exchanged as B x (index, 32) rows, NCCL captured inside the step's CUDA graph; "serial" = one flat
         # all-reduce between two graphs (round-1 behaviour; also the fallback when NCCL cannot be captured on this stack)
-        self.comm_mode = os.environ.get("SDT_COMM", "overlap") if self.world > 1 else "none"
+        self.comm_mode = os.environ.get("SDT_COMM", _DEFAULT_COMM) if self.world > 1 else "none"
         self._comm = torch.cuda.Stream(device=self.device) if self.world > 1 else None
         self._works = []
         self._aux = None
@@ -1021,7 +1025,7 @@ class Pose2PoseTrainer:
         self._staging, self._graphs, self._warm = None, None, 0
         self.kernels_per_step = 0
         self.eps_override = None          # tests inject the N(0,1) draw here
-        self.comm_mode = os.environ.get("SDT_COMM", "overlap") if self.world > 1 else "none"
+        self.comm_mode = os.environ.get("SDT_COMM", _DEFAULT_COMM) if self.world > 1 else "none"
         self._comm = torch.cuda.Stream(device=self.device) if self.world > 1 else None
         self._works, self._reduce_scalars = [], False
         self._scal = torch.zeros(len(self._SCALARS), device=self.device, dtype=torch.float64)

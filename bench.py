@@ -497,7 +497,9 @@ def forward_segments(tr, dev_batches, pk, reps=20):
                     "frac_of_hbm": MEL_ENC_BYTES * B / t_enc_net / 1e6 / pk["hbm"],
                     "tflops": MEL_ENC_FLOPS * B / t_enc_net / 1e9, "frac_of_bf16_sustained": MEL_ENC_FLOPS * B / t_enc_net / 1e9 / pk["tf_sustained"],
                     "tighter_roofline": "hbm" if enc_hbm_ms >= enc_tensor_ms else "tensor",
-                    "frac_of_tighter_roofline": max(enc_hbm_ms, enc_tensor_ms) / t_enc_net},
+                    "frac_of_tighter_roofline": max(enc_hbm_ms, enc_tensor_ms) / t_enc_net,
+                    # the kernels compute in TF32: against the MEASURED cuBLAS TF32 peak the tensor roofline is the tighter one
+                    "frac_of_tf32_sustained": (MEL_ENC_FLOPS * B / t_enc_net / 1e9 / pk["tf32_sustained"]) if pk.get("tf32_sustained") else None},
         "decoder": {"ms": t_dec, "what": "UNet_1D + pose decoder forward (generator forward minus mel + encoder)",
                     "hbm_gbs": (DEC_BYTES * B + DEC_WEIGHT_BYTES) / t_dec / 1e6, "tflops": DEC_FLOPS * B / t_dec / 1e9,
                     "tighter_roofline": "hbm" if dec_hbm_ms >= dec_tensor_ms else "tensor",
@@ -831,7 +833,8 @@ def run_demo(args):
     seconds = 600
     alen, nf = data.parse_audio_length(seconds * 16000, 16000, 15)
     torch.manual_seed(0)
-    gen = inference.StreamingGenerator(C.get_cfg("voice2pose_sdt_bp"), dev, conv_math=conv_math, chunk_frames=args.chunk_frames)
+    store = tuple(int(x) for x in args.store_layers.split(",") if x != "")
+    gen = inference.StreamingGenerator(C.get_cfg("voice2pose_sdt_bp"), dev, conv_math=conv_math, chunk_frames=args.chunk_frames, store_layers=store)
     audio = (0.1 * torch.randn(1, alen, generator=torch.Generator().manual_seed(8 + rank))).pin_memory()
     code = 0.1 * torch.randn(1, 32, generator=torch.Generator().manual_seed(9))
     K, W = args.steps, max(args.warmup, 3)
@@ -886,7 +889,8 @@ def run_demo(args):
         "metric": CONFIGS["demo"][0], "value": nf * world * K / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if conv_math == 0 else "tf32",
         "data": "synthetic", "config": config_dict("demo", 1, world),
-        "impl_detail": {"chunk_frames": gen.chunk_frames, "chunks": gen.last_chunks, "peak_mem_GB": torch.cuda.max_memory_allocated() / 1e9,
+        "impl_detail": {"chunk_frames": gen.chunk_frames, "chunks": gen.last_chunks, "store_layers": list(gen.store_layers),
+                        "peak_mem_GB": torch.cuda.max_memory_allocated() / 1e9,
                         "x_realtime": seconds / (ms / K * 1e-3), "out_shape": list(out.shape)},
         "e2e": {"value": nf * world * K / (ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": alen * 4, "d2h_bytes_per_step": nf * 242 * 4,
                 "ms_per_step": ms / K},
@@ -927,7 +931,8 @@ def main():
     ap.add_argument("--no-gpu-torch", action="store_true", help="skip the gpu_torch_baseline leg")
     ap.add_argument("--no-b128", action="store_true", help="skip the batch-128 block")
     ap.add_argument("--no-segments", action="store_true", help="skip the forward-segment sub-rooflines")
-    ap.add_argument("--chunk-frames", type=int, default=0, help="demo: frames per streamed chunk (0 = the module's default)")
+    ap.add_argument("--chunk-frames", type=int, default=0, help="demo: frames per streamed chunk (0 = one-shot forward)")
+    ap.add_argument("--store-layers", default="3,5", help="demo, streamed: encoder layers whose full-length raw map is kept (inference.py)")
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":

@@ -32,8 +32,10 @@ class StreamingGenerator:
     def __init__(self, cfg, device, conv_math=None, chunk_frames=0, netG=None, mel=None, store_layers=(3, 5)):
         self.cfg = cfg
         self.device = torch.device(device)
-        self.netG = (netG if netG is not None else SequenceGeneratorCNN(cfg)).to(self.device).eval()
-        self.netG.set_conv_math(conv_math)
+        own = netG is None
+        self.netG = (SequenceGeneratorCNN(cfg).to(self.device).eval() if own else netG)        # a caller's generator keeps its mode / device
+        if own or self.netG.conv_math != (None if conv_math is None else int(conv_math)):
+            self.netG.set_conv_math(conv_math)
         self.mel = (mel if mel is not None else pipeline.MelSpectrogram()).to(self.device)
         self.math = ops.resolve_math(conv_math)
         self.chunk_frames = int(chunk_frames)
@@ -52,6 +54,8 @@ class StreamingGenerator:
 
     @torch.no_grad()
     def forward_device(self, audio, num_frames, code):
+        if self.netG.training:
+            raise RuntimeError("StreamingGenerator runs the generator in eval mode (call .eval() on the model first)")
         n0 = _lib.launch_count
         mel = self.mel(audio)
         T = mel.shape[-1]

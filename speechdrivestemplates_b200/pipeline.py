@@ -383,6 +383,17 @@ class Voice2PoseModel(nn.Module):
         code = None
         if D is not None:
             code = self._condition_code(batch, dataset, clip_indices, audio, poses_gt, return_loss, interpolation_coeff)
+        chunk = int(getattr(self, "demo_chunk_frames", 0) or os.environ.get("SDT_DEMO_CHUNK_FRAMES", "0"))
+        if not return_loss and chunk > 0 and num_frames > 2 * chunk and audio.shape[0] == 1 and getattr(self.netG, "norm_kind", None) == "IN":
+            # long-audio demo (Trainer.demo -> demo_step, trainer.py:459-484, voice2pose.py:386-410): the time-tiled forward of
+            # inference.StreamingGenerator over THIS model's generator and mel front end -- same result, a fraction of the memory
+            from .inference import StreamingGenerator
+            sg = getattr(self, "_streaming", None)
+            if sg is None or sg.chunk_frames != chunk:
+                sg = StreamingGenerator(self.cfg, audio.device, conv_math=self.netG.conv_math, chunk_frames=chunk, netG=self.netG, mel=self.mel_transfm)
+                object.__setattr__(self, "_streaming", sg)               # not a sub-module: the generator is already registered
+            pred = sg.forward_device(audio.contiguous().float(), num_frames, code)
+            return {"poses_pred_batch": pred, "condition_code": code}
         with torch.no_grad():
             mel = self.mel_transfm(audio)
             pred = self.netG(mel, num_frames, code)
@@ -969,8 +980,14 @@ class Pose2PoseModel(nn.Module):
     def forward(self, batch, return_loss=True, is_testing=False, interpolation_coeff=None):
         cfg = self.cfg
         num_frames = int(batch["num_frames"][0].item())
-        if not return_loss:
-            raise NotImplementedError("Pose2Pose demo path (DEMO.CODE_PATH) is out of the hot-path scope")
+        if not return_loss:                                                                        # pose2pose.py:52-65
+            assert cfg.DEMO.CODE_PATH is not None
+            import numpy as np
+            idx = int((cfg.DEMO.MULTIPLE - 1) * interpolation_coeff)
+            code = np.load(cfg.DEMO.CODE_PATH)["v"][idx] * 10                                        # "10 is empirically selected"
+            code = torch.Tensor(code).cuda().unsqueeze(0)
+            pred, mu, logvar = self.ae(None, cfg.DATASET.NUM_FRAMES, external_code=code)
+            return {"poses_pred_batch": pred, "clip_code_mu": mu, "clip_code_logvar": logvar}
         poses_gt = batch["poses"].cuda()
         pred, mu, logvar = self.ae(poses_gt, num_frames, None)
         losses = OrderedDict()

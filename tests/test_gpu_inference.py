@@ -79,3 +79,23 @@ def test_one_shot_inference_matches_the_oracle_on_8s():
         err = float((out - ref.view_as(out)).abs().max() / ref.abs().max())
         assert err < 2e-4, (chunk, err)
     assert gen.last_chunks >= 2
+
+
+def test_dropin_model_demo_branch_streams_long_audio(monkeypatch):
+    """Voice2PoseModel.forward(return_loss=False) -- what Voice2Pose.demo_step calls (voice2pose.py:386-410) -- switches to the
+    time-tiled forward for long utterances when SDT_DEMO_CHUNK_FRAMES is set, with the same result as the one-shot forward."""
+    from speechdrivestemplates_b200 import config, data, pipeline
+    cfg = config.get_cfg("voice2pose_sdt_bp", ["DEMO.CODE_INDEX", 3])
+    torch.manual_seed(0)
+    model = pipeline.Voice2PoseModel(cfg, num_train_samples=8).cuda().eval()
+    model.clips_code.data.copy_(0.1 * torch.randn(8, 32, generator=torch.Generator().manual_seed(2)))
+    alen, nf = data.parse_audio_length(30 * 16000, 16000, 15)
+    batch = {"audio": 0.1 * torch.randn(1, alen, generator=torch.Generator().manual_seed(4)), "clip_index": torch.zeros(1, dtype=torch.long),
+             "num_frames": torch.tensor([nf])}
+    with torch.no_grad():
+        ref = model(batch, None, return_loss=False)["poses_pred_batch"].clone()
+    monkeypatch.setenv("SDT_DEMO_CHUNK_FRAMES", "64")
+    with torch.no_grad():
+        out = model(batch, None, return_loss=False)["poses_pred_batch"]
+    assert model._streaming.last_chunks >= 5 and out.shape == ref.shape == (1, nf, 2, 121)
+    assert float((out - ref).abs().max() / ref.abs().max()) < 2e-4        # conftest pins the fp32 math mode

@@ -645,3 +645,27 @@ def test_s2g_fused_trainer_graph_replay_equals_eager():
     for k in sums[0][0]:
         assert abs(sums[0][0][k] - sums[1][0][k]) <= 1e-5 * max(1.0, abs(sums[0][0][k])), k
     assert abs(sums[0][1] - sums[1][1]) <= 1e-6 * sums[0][1]
+
+
+def test_pose2pose_demo_forward_decodes_the_external_code(tmp_path):
+    """Pose2PoseModel.forward(return_loss=False) (pose2pose.py:52-65): the clip code comes from DEMO.CODE_PATH['v'][idx] * 10 and only
+    the decoder runs (Autoencoder.forward with external_code, autoencoder.py:80-83); checked against the oracle's decoder in eval mode."""
+    from speechdrivestemplates_b200 import config, pipeline
+    from oracle import sdt_oracle as O
+    codes = np.random.RandomState(3).randn(5, 32).astype(np.float32) * 0.1
+    path = str(tmp_path / "codes.npz")
+    np.savez(path, v=codes)
+    cfg = config.get_cfg("pose2pose", ["DEMO.CODE_PATH", path, "DEMO.MULTIPLE", 5])
+    torch.manual_seed(0)
+    model = pipeline.Pose2PoseModel(cfg, num_train_samples=4).to(dev()).eval()
+    batch = {"audio": torch.zeros(1, 68266), "num_frames": torch.tensor([64])}
+    with torch.no_grad():
+        res = model(batch, return_loss=False, interpolation_coeff=0.5)
+    idx = int((5 - 1) * 0.5)
+    code = torch.from_numpy(codes[idx] * 10).unsqueeze(0)
+    assert torch.equal(res["clip_code_mu"].cpu(), code) and float(res["clip_code_logvar"].abs().max()) == 0.0
+    sd = {"ae." + k: v.detach().cpu() for k, v in model.ae.state_dict().items()}
+    ref = O.pose_decoder_forward(code, sd, O.make_cfg("pose2pose"), False, prefix="ae.decoder.")
+    ref = ref.permute(0, 2, 1).reshape(1, 64, 2, 121)
+    assert tuple(res["poses_pred_batch"].shape) == (1, 64, 2, 121)
+    assert rel_err(res["poses_pred_batch"].cpu().numpy(), ref.numpy()) < 1e-4

@@ -333,6 +333,17 @@ int sdt_adam_advance(float* scalars, float lr, double beta1, double beta2, void*
 int sdt_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, const float* scalars,
                   double beta1, double beta2, double eps, float grad_scale, float weight_decay, void* stream);
 
+/* ---- gradient exchange over peer memory ------------------------------------------------------------------------
+ * All-reduce(sum) of a flat fp32 buffer of n elements (n % 4 == 0) that every rank of one NVSwitch node holds at the same place of
+ * a symmetric allocation -- the DDP gradient all-reduce of voice2pose.py:222-223,298-309 / pose2pose.py:101-102 without NCCL.
+ * peer_ptrs[world]: HOST array of the device addresses of the buffer on rank 0..world-1 (peer-mapped); multicast_ptr: the NVLS
+ * multicast address of the same buffer, or 0 to use peer loads / stores.  Rank r reduces shard r (rank order 0..world-1) and
+ * writes it into every rank's buffer, in place; all ranks end with bit-identical sums.  scal_*: scal_n (<= 512) doubles per rank
+ * (the loss / metric scalars of trainer.py:323-327), read from every rank's scal_peer_ptrs[r], summed into the LOCAL scal_dst.
+ * The caller issues a cross-GPU barrier before (all gradients final) and after (all shards written) this call. */
+int sdt_p2p_allreduce(const uint64_t* peer_ptrs, uint64_t multicast_ptr, int rank, int world, long long n,
+                      const uint64_t* scal_peer_ptrs, double* scal_dst, int scal_n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,7 @@ SIGNATURES = {
     "sdt_weight_prep": [c_ptr, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, c_ptr, c_ptr],
     "sdt_weight_prep_batch": [c_ptr, i32, C.c_longlong, c_ptr],
     "sdt_conv_wgrad_reduce_batch": [c_ptr, i32, i32, i32, c_ptr],
+    "sdt_p2p_allreduce": [c_ptr, C.c_uint64, i32, i32, C.c_longlong, c_ptr, c_ptr, i32, c_ptr],
     "sdt_chan_stats": [c_ptr, i32, i32, i32, i32, i32, i32, i32, c_ptr, i32, c_ptr],
     "sdt_norm_finalize": [c_ptr, i32, i32, i32, f64, c_ptr, c_ptr, f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, f32, c_ptr],
     "sdt_bn_eval_scale_shift": [c_ptr, c_ptr, c_ptr, c_ptr, f32, i32, c_ptr, c_ptr, c_ptr],

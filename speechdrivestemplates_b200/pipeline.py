@@ -16,10 +16,13 @@ from torch import nn
 
 # diagnostic switch (wrong results: the FGD / metrics side stream is skipped); bench.py refuses to run with it set
 _DIAG_SKIP_SIDE = bool(os.environ.get("SDT_DIAG_SKIP_SIDE"))
-# multi-GPU communication mode when SDT_COMM is unset.  Measured at 2 and 8 GPUs (profiles/r2_multi_gpu_modes.txt): the single flat
-# all-reduce between two graphs ("serial") is 0.02-0.04 ms per step FASTER than the gradient buckets overlapped with the backward pass
-# ("overlap"), because an NCCL kernel holding SMs delays the persistent convolution kernel by about its own duration.
-_DEFAULT_COMM = "serial"
+# multi-GPU communication mode when SDT_COMM is unset (profiles/r2_multi_gpu_modes.txt, per step at 2 / 8 GPUs):
+#   "p2p"     3.07 / 3.12 ms  the library's own all-reduce over peer memory (csrc/p2p.cu: peer loads at 2 GPUs, NVLS multicast
+#                             from 3 GPUs up) between two cross-GPU barriers, captured inside the ONE step graph; no NCCL in the step
+#   "serial"  3.08 / 3.19 ms  one flat NCCL all-reduce between two graphs (round 1)
+#   "overlap" 3.11 / 3.23 ms  NCCL all-reduce of three gradient buckets beside the backward pass, inside the step graph
+# p2p falls back to serial (with a warning) where torch's symmetric memory cannot be set up.
+_DEFAULT_COMM = "p2p"
 
 from . import _lib, ops, parallel
 from .networks import PoseSeqEncoder, SequenceGeneratorCNN, get_model
@@ -446,6 +449,23 @@ def _cuda_device(device):
     return torch.device("cuda", torch.cuda.current_device() if d.index is None else d.index)
 
 
+def _peer_exchange(trainer, numel):
+    """parallel.PeerExchange for SDT_COMM=p2p, or None.  If the symmetric allocation cannot be set up on this software / hardware
+    stack the trainer says so and drops to the NCCL all-reduce ("serial")."""
+    if trainer.world <= 1 or trainer.comm_mode != "p2p":
+        return None
+    try:
+        px = parallel.PeerExchange(numel, trainer.device, trainer.pg)
+        if os.environ.get("SDT_P2P_2GRAPHS"):            # tuning aid: two graphs around an eager exchange instead of one graph
+            trainer.comm_mode = "p2p-2graphs"
+        return px
+    except Exception as e:                      # noqa: BLE001 - no symmetric memory / peer access here: fall back, loudly
+        import warnings
+        warnings.warn("SDT_COMM=p2p: symmetric memory is not available (%s: %s); falling back to SDT_COMM=serial" % (type(e).__name__, e))
+        trainer.comm_mode = "serial"
+        return None
+
+
 def _on_device(fn):
     """Run a trainer method with the trainer's device current: streams, events and ``ops._stream()`` all follow torch's
     current device, so ``Trainer(cfg, n, 'cuda:1')`` must not depend on the caller having called ``torch.cuda.set_device``."""
@@ -523,7 +543,9 @@ class Voice2PoseTrainer:
             v = self.flat_p[self.n_g_pad:self.n_g_pad + self.n_code].view(m.clips_code.shape)
             v.copy_(m.clips_code.data)
             m.clips_code.data = v
-        self.flat_g = torch.zeros_like(self.flat_p)
+        self.comm_mode = os.environ.get("SDT_COMM", _DEFAULT_COMM) if self.world > 1 else "none"
+        self._px = _peer_exchange(self, self.flat_p.numel())          # SDT_COMM=p2p: the gradient buffer is a symmetric allocation
+        self.flat_g = self._px.flat if self._px is not None else torch.zeros_like(self.flat_p)
         self.exp_avg = torch.zeros_like(self.flat_p)
         self.exp_avg_sq = torch.zeros_like(self.flat_p)
         self.grads = {}
@@ -557,7 +579,6 @@ class Voice2PoseTrainer:
         # multi-GPU: "overlap" = gradient buckets all-reduced on a communication stream while the backward pass still runs, the
         # clip-code gradient exchanged as B x (index, 32) rows, NCCL captured inside the step's CUDA graph; "serial" = one flat
         # all-reduce between two graphs (round-1 behaviour; also the fallback when NCCL cannot be captured on this stack)
-        self.comm_mode = os.environ.get("SDT_COMM", _DEFAULT_COMM) if self.world > 1 else "none"
         self._comm = torch.cuda.Stream(device=self.device) if self.world > 1 else None
         self._works = []
         self._aux = None
@@ -822,8 +843,11 @@ class Voice2PoseTrainer:
             ops.adam_flat(self.flat_p[sl], self.flat_g[sl], self.exp_avg[sl], self.exp_avg_sq[sl], self.adam_d, grad_scale=gs)
 
     def _allreduce(self):
-        """comm_mode "serial": ONE flat NCCL all-reduce of the whole gradient buffer between the two graphs + the scalars (C5)."""
-        if self.world > 1 and self.comm_mode != "overlap":
+        """comm_mode "serial": ONE flat NCCL all-reduce of the whole gradient buffer between the two graphs + the scalars (C5).
+        comm_mode "p2p": the same exchange through peer memory (parallel.PeerExchange / csrc/p2p.cu), no NCCL in the step."""
+        if self.world > 1 and self.comm_mode.startswith("p2p"):
+            self._px.allreduce(self._scal)
+        elif self.world > 1 and self.comm_mode != "overlap":
             parallel.allreduce_flat_(self.flat_g, self.pg)
             torch.distributed.all_reduce(self._scal, group=self.pg)
 
@@ -865,7 +889,7 @@ class Voice2PoseTrainer:
         # pile up behind it and run alone at the end.  SDT_MAIN_PRIORITY / SDT_WG_PRIORITY remain as tuning aids (default 0 = equal).
         side = torch.cuda.Stream(device=self.device, priority=int(os.environ.get("SDT_MAIN_PRIORITY", "0")))
         side.wait_stream(torch.cuda.current_stream())
-        if self.world == 1 or self.comm_mode == "overlap":
+        if self.world == 1 or self.comm_mode in ("overlap", "p2p"):       # p2p: barriers + the exchange kernel are plain launches
             try:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.stream(side):
@@ -876,8 +900,9 @@ class Voice2PoseTrainer:
                 if self.world == 1:
                     raise
                 import warnings
-                warnings.warn("capturing NCCL inside the step graph failed (%s: %s); falling back to SDT_COMM=serial" % (type(e).__name__, e))
-                self.comm_mode, self._works = "serial", []
+                warnings.warn("capturing the collectives inside the step graph failed (%s: %s); falling back to two graphs around an eager exchange"
+                              % (type(e).__name__, e))
+                self.comm_mode, self._works = ("p2p-2graphs" if self.comm_mode == "p2p" else "serial"), []
                 torch.cuda.synchronize()
         if self._graphs is None:
             g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
@@ -1025,7 +1050,9 @@ class Pose2PoseTrainer:
         params = [p for _, p in ae.named_parameters()]
         n = sum(p.numel() for p in params)
         self.flat_p = torch.zeros(n + ((-n) % 4), device=self.device)
-        self.flat_g = torch.zeros_like(self.flat_p)
+        self.comm_mode = os.environ.get("SDT_COMM", _DEFAULT_COMM) if self.world > 1 else "none"
+        self._px = _peer_exchange(self, self.flat_p.numel())
+        self.flat_g = self._px.flat if self._px is not None else torch.zeros_like(self.flat_p)
         self.exp_avg = torch.zeros_like(self.flat_p)
         self.exp_avg_sq = torch.zeros_like(self.flat_p)
         self.grads, off = {}, 0
@@ -1042,7 +1069,6 @@ class Pose2PoseTrainer:
         self._staging, self._graphs, self._warm = None, None, 0
         self.kernels_per_step = 0
         self.eps_override = None          # tests inject the N(0,1) draw here
-        self.comm_mode = os.environ.get("SDT_COMM", _DEFAULT_COMM) if self.world > 1 else "none"
         self._comm = torch.cuda.Stream(device=self.device) if self.world > 1 else None
         self._works, self._reduce_scalars = [], False
         self._scal = torch.zeros(len(self._SCALARS), device=self.device, dtype=torch.float64)
@@ -1135,8 +1161,16 @@ class Pose2PoseTrainer:
             self._works = []
             torch.cuda.current_stream().wait_stream(self._comm)
         elif self.world > 1:
-            parallel.allreduce_flat_(self.flat_g, self.pg)
+            self._allreduce()
         self._optim()
+
+    def _allreduce(self):
+        if self.comm_mode.startswith("p2p"):
+            self._scal.copy_(torch.cat([self.out[k].double().view(1) for k in self._SCALARS]))
+            self._reduce_scalars = True
+            self._px.allreduce(self._scal)
+        else:
+            parallel.allreduce_flat_(self.flat_g, self.pg)
 
     @_on_device
     def run_staged(self):
@@ -1147,7 +1181,7 @@ class Pose2PoseTrainer:
                 torch.cuda.synchronize()
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream())
-            if self.world == 1 or self.comm_mode == "overlap":
+            if self.world == 1 or self.comm_mode in ("overlap", "p2p"):       # p2p: barriers + the exchange kernel are plain launches
                 try:
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.stream(side):
@@ -1158,8 +1192,9 @@ class Pose2PoseTrainer:
                     if self.world == 1:
                         raise
                     import warnings
-                    warnings.warn("capturing NCCL inside the step graph failed (%s: %s); falling back to SDT_COMM=serial" % (type(e).__name__, e))
-                    self.comm_mode, self._works = "serial", []
+                    warnings.warn("capturing the collectives inside the step graph failed (%s: %s); falling back to two graphs around an eager exchange"
+                                  % (type(e).__name__, e))
+                    self.comm_mode, self._works = ("p2p-2graphs" if self.comm_mode == "p2p" else "serial"), []
                     torch.cuda.synchronize()
             if self._graphs is None:
                 g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
@@ -1175,7 +1210,7 @@ class Pose2PoseTrainer:
             self._graphs[0].replay()
             if len(self._graphs) == 2:
                 if self.world > 1:
-                    parallel.allreduce_flat_(self.flat_g, self.pg)
+                    self._allreduce()
                 self._graphs[1].replay()
         else:
             n0 = _lib.launch_count

@@ -391,3 +391,17 @@ def test_checkpoint_layout_loads_into_the_reference_classes_strictly(name):
     assert [n for n, _ in getattr(own, sub).named_parameters()] == [n for n, _ in getattr(ref, sub).named_parameters()]
     if name == "voice2pose_s2g":
         assert [n for n, _ in own.netD_pose.named_parameters()] == [n for n, _ in ref.netD_pose.named_parameters()]
+
+
+def test_p2p_allreduce_rejects_bad_arguments_without_launching():
+    """sdt_p2p_allreduce (csrc/p2p.cu) validates rank / world / alignment / element count before touching the device."""
+    _built()
+    from speechdrivestemplates_b200 import _lib
+    lib = _lib.load()
+    ptrs = (ctypes.c_uint64 * 2)(0x10000, 0x20000)
+    assert lib.sdt_p2p_allreduce(ptrs, 0, 2, 2, 1024, None, None, 0, None) != 0 and "rank" in _lib.last_error()
+    assert lib.sdt_p2p_allreduce(ptrs, 0, 0, 2, 1022, None, None, 0, None) != 0 and "multiple of 4" in _lib.last_error()
+    bad = (ctypes.c_uint64 * 2)(0x10000, 0x20004)
+    assert lib.sdt_p2p_allreduce(bad, 0, 0, 2, 1024, None, None, 0, None) != 0 and "aligned" in _lib.last_error()
+    assert lib.sdt_p2p_allreduce(ptrs, 0, 0, 2, 1024, None, None, 8, None) != 0 and "scalar" in _lib.last_error()
+    assert lib.sdt_p2p_allreduce(ptrs, 0, 0, 17, 1024, None, None, 0, None) != 0

@@ -433,3 +433,29 @@ def test_first_layer_rejects_non_invertible_activation(ops):
     act, sc, sh, mom = ops.first_layer_fwd(x, w, 0.0)
     with pytest.raises(SdtError):
         ops.first_layer_bwd(torch.zeros_like(act), act, x, w, mom, sc, sh, 0.0, torch.empty_like(w))
+
+
+@pytest.mark.parametrize("world,n", [(2, 4096), (4, 1000 * 4), (8, 8_126_464), (3, 52)])
+def test_p2p_allreduce_kernel_on_one_device(world, n):
+    """sdt_p2p_allreduce (csrc/p2p.cu) with the `peer` buffers all on this GPU, the ranks run one after the other (they touch disjoint
+    shards, so the order does not matter): every buffer ends up holding the fp32 sum in rank order, bit for bit; the scalar block of
+    every rank is summed into the caller's local output."""
+    import ctypes as C
+    from speechdrivestemplates_b200 import _lib
+    g = torch.Generator().manual_seed(world * 7 + n % 13)
+    bufs = [torch.randn(n, generator=g).cuda() for _ in range(world)]
+    scal = [torch.randn(12, generator=g, dtype=torch.float64).cuda() for _ in range(world)]
+    expect = bufs[0].clone()
+    for r in range(1, world):
+        expect = expect + bufs[r]                                          # rank order 0..W-1, fp32
+    expect_s = torch.stack(scal).sum(0)
+    ptrs = (C.c_uint64 * world)(*[b.data_ptr() for b in bufs])
+    sptrs = (C.c_uint64 * world)(*[s.data_ptr() for s in scal])
+    outs = [torch.zeros(12, dtype=torch.float64, device="cuda") for _ in range(world)]
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for r in range(world):
+        _lib.call("sdt_p2p_allreduce", ptrs, C.c_uint64(0), r, world, n, sptrs, C.c_void_p(outs[r].data_ptr()), 12, stream)
+    torch.cuda.synchronize()
+    for r in range(world):
+        assert torch.equal(bufs[r], expect), r
+        assert torch.allclose(outs[r], expect_s, rtol=0, atol=1e-12)

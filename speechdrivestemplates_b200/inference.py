@@ -25,6 +25,37 @@ MEL_PER_FRAME = 16000.0 / 15.0 / 160.0          # mel columns per video frame (h
 HALO = 64                                       # mel columns; > the encoder's receptive radius (42), multiple of its stride 8
 
 
+def plan_tiles(T, chunk_cols, halo=HALO):
+    """Time tiles of a T-column mel: [(a0, a1, hl, hr)] -- owned mel columns [a0, a1), loaded columns [a0 - hl, a1 + hr).  Every interior
+    boundary is a multiple of chunk_cols (itself a multiple of the encoder's total stride 8); the last tile takes a short rest."""
+    tiles, a0 = [], 0
+    while a0 < T:
+        a1 = min(T, a0 + chunk_cols)
+        if T - a1 < chunk_cols // 4:          # do not leave a sliver: the last tile takes the rest
+            a1 = T
+        tiles.append((a0, a1, halo if a0 > 0 else 0, halo if a1 < T else 0))
+        a0 = a1
+    return tiles
+
+
+def base_window(tile, T, stride_base, width_base):
+    """Columns [c0, c1) of a stored level (cumulative stride stride_base, full width width_base; the mel: stride 1, width T) that a
+    tile loads: the level's image of the tile's loaded mel columns."""
+    a0, a1, hl, hr = tile
+    c0 = (a0 - hl) // stride_base
+    c1 = width_base if a1 + hr >= T else (a1 + hr) // stride_base
+    return c0, c1
+
+
+def owned_window(tile, T, stride_l, width_l):
+    """(o0, o1, off): the tile OWNS output columns [o0, o1) of a level with cumulative stride stride_l and full width width_l (its
+    statistics and its stored copy come from these only); off = global column of the tile's local column 0 at that level."""
+    a0, a1, hl, _hr = tile
+    o0 = min(a0 // stride_l, width_l)
+    o1 = width_l if a1 >= T else min(a1 // stride_l, width_l)
+    return o0, o1, (a0 - hl) // stride_l
+
+
 class StreamingGenerator:
     """cfg: a Voice2Pose config (generator with NORM='IN' for the tiled path).  ``netG`` may be passed in (e.g. a trained
     ``Voice2PoseModel.netG``); otherwise a freshly initialised generator is built under the caller's torch seed."""
@@ -60,6 +91,8 @@ class StreamingGenerator:
         mel = self.mel(audio)
         T = mel.shape[-1]
         chunk_cols = int(round(self.chunk_frames * MEL_PER_FRAME / 8.0)) * 8 if self.chunk_frames > 0 else 0
+        if 0 < chunk_cols < HALO:
+            chunk_cols = HALO                       # a tile never reaches further back than its left neighbour
         if chunk_cols <= 0 or chunk_cols + 2 * HALO >= T or self.netG.norm_kind != "IN":
             self.last_chunks = 1
             out = self.netG(mel, num_frames, code)
@@ -93,14 +126,7 @@ class StreamingGenerator:
         for g in geoms:
             s_acc *= g.sw
             stride.append(s_acc)                                  # cumulative stride of layer l's OUTPUT in mel columns
-        # tiles in mel columns: owned [a0, a1), input [a0 - hl, a1 + hr); every boundary is a multiple of the total stride 8
-        tiles, a0 = [], 0
-        while a0 < T:
-            a1 = min(T, a0 + chunk_cols)
-            if T - a1 < chunk_cols // 4:          # do not leave a sliver: the last tile takes the rest
-                a1 = T
-            tiles.append((a0, a1, HALO if a0 > 0 else 0, HALO if a1 < T else 0))
-            a0 = a1
+        tiles = plan_tiles(T, chunk_cols)
         self.last_chunks = len(tiles)
         stored = {}                               # level -> full-length RAW map (B, H, W, C); level -1 = the mel
         stats = []                                # per layer: (scale, shift), each (B, C)
@@ -118,14 +144,12 @@ class StreamingGenerator:
             for ti, (a0, a1, hl, hr) in enumerate(tiles):
                 # ---- the tile of the base level (mel columns, or the stored raw map of `base` normalised + activated)
                 if base < 0:
-                    c0, c1 = a0 - hl, a1 + hr
+                    c0, c1 = base_window(tiles[ti], T, 1, T)
                     src = self._buf("tile_mel", (B, 80, c1 - c0, 1))
                     src.copy_(mel[:, :, c0:c1].unsqueeze(-1))
                     H, W = 80, c1 - c0
                 else:
-                    sb = stride[base]
-                    c0 = (a0 - hl) // sb
-                    c1 = hw[base + 1][1] if a1 + hr >= T else (a1 + hr) // sb
+                    c0, c1 = base_window(tiles[ti], T, stride[base], hw[base + 1][1])
                     H, W = hw[base + 1][0], c1 - c0
                     src = self._buf("tile_base%d" % base, (B, H, W, ENC2D[base][1]))
                     src.copy_(stored[base][:, :, c0:c1])
@@ -143,10 +167,7 @@ class StreamingGenerator:
                         ops.scale_shift_act(raw, stats[j][0], stats[j][1], g.cout, slope, out=act, tf32=tf32)
                         src, H, W = act, oh_j, ow_j
                 # ---- layer l's statistics over the OWNED output columns (global [o0, o1)) + the stored copy
-                sl = stride[l]
-                o0 = min(a0 // sl, ow_full)
-                o1 = ow_full if a1 >= T else min(a1 // sl, ow_full)
-                off = (a0 - hl) // sl
+                o0, o1, off = owned_window(tiles[ti], T, stride[l], ow_full)
                 ops.chan_stats(raw, o0 - off, o1 - off, rows_per_part, partial[:, part_off:part_off + parts[ti]])
                 part_off += parts[ti]
                 if l in keep and o1 > o0:

@@ -834,7 +834,8 @@ def run_demo(args):
     alen, nf = data.parse_audio_length(seconds * 16000, 16000, 15)
     torch.manual_seed(0)
     store = tuple(int(x) for x in args.store_layers.split(",") if x != "")
-    gen = inference.StreamingGenerator(C.get_cfg("voice2pose_sdt_bp"), dev, conv_math=conv_math, chunk_frames=args.chunk_frames, store_layers=store)
+    gen = inference.StreamingGenerator(C.get_cfg("voice2pose_sdt_bp"), dev, conv_math=conv_math, chunk_frames=args.chunk_frames, store_layers=store,
+                                       graph=args.chunk_frames > 0 and not args.no_graph)
     audio = (0.1 * torch.randn(1, alen, generator=torch.Generator().manual_seed(8 + rank))).pin_memory()
     code = 0.1 * torch.randn(1, 32, generator=torch.Generator().manual_seed(9))
     K, W = args.steps, max(args.warmup, 3)
@@ -890,6 +891,7 @@ def run_demo(args):
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if conv_math == 0 else "tf32",
         "data": "synthetic", "config": config_dict("demo", 1, world),
         "impl_detail": {"chunk_frames": gen.chunk_frames, "chunks": gen.last_chunks, "store_layers": list(gen.store_layers),
+                        "cuda_graph": gen.use_graph,
                         "peak_mem_GB": torch.cuda.max_memory_allocated() / 1e9,
                         "x_realtime": seconds / (ms / K * 1e-3), "out_shape": list(out.shape)},
         "e2e": {"value": nf * world * K / (ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": alen * 4, "d2h_bytes_per_step": nf * 242 * 4,

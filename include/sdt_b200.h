@@ -236,6 +236,12 @@ int sdt_first_layer_units(int H, int W);
 int sdt_first_layer_fwd(const float* x, const float* w, int B, int H, int W, int C, float eps, float slope,
                         double* mom_partial, double* moments, float* scale, float* shift, float* act, int out_tf32,
                         void* stream);
+/* The two halves separately, for the time-tiled long-audio forward (trainer.py:459-484 runs the whole utterance at once):
+ * sdt_first_layer_fwd with act == NULL computes the statistics (moments, scale, shift) of the WHOLE image only -- they follow in
+ * closed form from the input, no pass over the 64-channel map -- and sdt_first_layer_act writes the activated map of any tile of
+ * the image (x = the tile, zero padding at its edges) with the given per-(image, channel) scale / shift. */
+int sdt_first_layer_act(const float* x, const float* w, const float* scale, const float* shift, int B, int H, int W, int C,
+                        float slope, float* act, int out_tf32, void* stream);
 /* Weight gradient of that block from g_act = dLoss/d act in ONE pass over g_act: the InstanceNorm + LeakyReLU backward is
  * folded into per-(image, channel) sums and combined in closed form (f64) with the forward's moments; the block's input needs
  * no gradient (it is the mel spectrogram).  The pre-activation is recomputed from x with the forward's arithmetic, so `act`

@@ -61,6 +61,7 @@ SIGNATURES = {
     "sdt_rownorm_act_bwd": [c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, f32, c_ptr, i32, c_ptr],
     "sdt_scale_shift_act": [c_ptr, c_ptr, c_ptr, i32, i32, i32, i32, f32, c_ptr, i32, c_ptr],
     "sdt_first_layer_units": [i32, i32],
+    "sdt_first_layer_act": [c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, i32, i32, f32, c_ptr, i32, c_ptr],
     "sdt_first_layer_fwd": [c_ptr, c_ptr, i32, i32, i32, i32, f32, f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, i32, c_ptr],
     "sdt_first_layer_bwd": [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, i32, i32, i32, i32, f32, c_ptr, c_ptr, c_ptr],
     "sdt_enc_to_seq_fwd": [c_ptr, c_ptr, c_ptr, i32, f32, i32, i32, i32, i32, c_ptr, i32, i32, c_ptr, i32, c_ptr],

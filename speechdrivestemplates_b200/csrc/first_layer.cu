@@ -304,7 +304,7 @@ extern "C" int sdt_first_layer_units(int H, int W) { return H * ((W + kChunk - 1
 extern "C" int sdt_first_layer_fwd(const float* x, const float* w, int B, int H, int W, int C, float eps, float slope,
                                    double* mom_partial, double* moments, float* scale, float* shift, float* act,
                                    int out_tf32, void* stream) {
-    SDT_REQUIRE(x && w && mom_partial && moments && scale && shift && act, "sdt_first_layer_fwd: null pointer");
+    SDT_REQUIRE(x && w && mom_partial && moments && scale && shift, "sdt_first_layer_fwd: null pointer");        // act == NULL: statistics only
     SDT_REQUIRE(C == kC, "sdt_first_layer_fwd: the block has %d output channels (got %d)", kC, C);
     SDT_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535, "sdt_first_layer_fwd: bad extents");
     const int units = sdt_first_layer_units(H, W);
@@ -313,7 +313,19 @@ extern "C" int sdt_first_layer_fwd(const float* x, const float* w, int B, int H,
     SDT_LAUNCH_OK("fl_moments_kernel");
     sdt::launch(fl_stats_kernel, dim3(B), dim3(128), 0, st, mom_partial, w, units, (double)H * W, eps, moments, scale, shift);
     SDT_LAUNCH_OK("fl_stats_kernel");
+    if (act == nullptr) return SDT_OK;
     sdt::launch(fl_act_kernel, dim3(units, B), dim3(256), 0, st, x, w, scale, shift, H, W, slope, act, out_tf32);
+    SDT_LAUNCH_OK("fl_act_kernel");
+    return SDT_OK;
+}
+
+extern "C" int sdt_first_layer_act(const float* x, const float* w, const float* scale, const float* shift, int B, int H, int W, int C,
+                                   float slope, float* act, int out_tf32, void* stream) {
+    SDT_REQUIRE(x && w && scale && shift && act, "sdt_first_layer_act: null pointer");
+    SDT_REQUIRE(C == kC, "sdt_first_layer_act: the block has %d output channels (got %d)", kC, C);
+    SDT_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535, "sdt_first_layer_act: bad extents");
+    sdt::launch(fl_act_kernel, dim3(sdt_first_layer_units(H, W), B), dim3(256), 0, sdt::as_stream(stream), x, w, scale, shift, H, W, slope, act,
+                out_tf32);
     SDT_LAUNCH_OK("fl_act_kernel");
     return SDT_OK;
 }

@@ -60,7 +60,7 @@ class StreamingGenerator:
     """cfg: a Voice2Pose config (generator with NORM='IN' for the tiled path).  ``netG`` may be passed in (e.g. a trained
     ``Voice2PoseModel.netG``); otherwise a freshly initialised generator is built under the caller's torch seed."""
 
-    def __init__(self, cfg, device, conv_math=None, chunk_frames=0, netG=None, mel=None, store_layers=(3, 5)):
+    def __init__(self, cfg, device, conv_math=None, chunk_frames=0, netG=None, mel=None, store_layers=(3, 5), graph=False):
         self.cfg = cfg
         self.device = torch.device(device)
         own = netG is None
@@ -71,6 +71,10 @@ class StreamingGenerator:
         self.math = ops.resolve_math(conv_math)
         self.chunk_frames = int(chunk_frames)
         self.store_layers = tuple(store_layers)
+        # graph=True: the time-tiled forward of a given utterance length is captured into a CUDA graph on first use and replayed
+        # afterwards (its ~1,100 small launches are host-bound when issued one by one); a new length costs one extra eager pass
+        self.use_graph = bool(graph)
+        self._graph_cache = {}
         self.last_chunks = 1
         self.launches_per_call = 0
         self._bufs = {}
@@ -96,10 +100,43 @@ class StreamingGenerator:
         if chunk_cols <= 0 or chunk_cols + 2 * HALO >= T or self.netG.norm_kind != "IN":
             self.last_chunks = 1
             out = self.netG(mel, num_frames, code)
+        elif self.use_graph:
+            out = self._tiled_graphed(audio, mel, num_frames, code, chunk_cols)
         else:
             out = self._tiled(mel, num_frames, code, chunk_cols)
-        self.launches_per_call = _lib.launch_count - n0
+        self.launches_per_call = max(_lib.launch_count - n0, getattr(self, "_graph_launches", 0))
         return out
+
+    def _tiled_graphed(self, audio, mel, num_frames, code, chunk_cols):
+        key = (tuple(audio.shape), int(num_frames), int(chunk_cols), code is not None, self.store_layers)
+        ent = self._graph_cache.get(key)
+        if ent is None:
+            a = audio.clone()
+            c = code.clone() if code is not None else None
+            mel_buf = torch.empty_like(mel)
+
+            def run():
+                return self._tiled(self.mel(a, out=mel_buf), num_frames, c, chunk_cols)
+            n0 = _lib.launch_count
+            run()                                   # eager pass: buffers, weight-operand tables
+            self._graph_launches = _lib.launch_count - n0
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g, stream=side):
+                    out = run()
+            torch.cuda.current_stream().wait_stream(side)
+            if len(self._graph_cache) >= 4:         # a handful of utterance lengths at most
+                self._graph_cache.pop(next(iter(self._graph_cache)))
+            ent = self._graph_cache[key] = (g, a, c, out)
+        g, a, c, out = ent
+        a.copy_(audio)
+        if c is not None:
+            c.copy_(code)
+        g.replay()
+        return out.clone()
 
     # ---- tiled 2-D encoder ----------------------------------------------------------------------------
     def _buf(self, name, shape, dtype=torch.float32):
@@ -130,9 +167,16 @@ class StreamingGenerator:
         self.last_chunks = len(tiles)
         stored = {}                               # level -> full-length RAW map (B, H, W, C); level -1 = the mel
         stats = []                                # per layer: (scale, shift), each (B, C)
-        keep = set(self.store_layers) | {7}
+        keep = (set(self.store_layers) | {7}) - {0}
         rows_per_part = 64
-        for l in range(8):
+        # first block (1 -> 64 channels, the largest map): its InstanceNorm statistics follow in closed form from the input (54 tap
+        # moments of the whole mel, csrc/first_layer.cu), so it needs no sweep, and a tile's activated map is ONE pass from the mel tile
+        w0 = params[ENC_PREFIX + ENC2D[0][0] + ".conv.weight"]
+        sc0, sh0, _m = ops.first_layer_stats(mel, w0, out=(self._buf("scale0", (B, 64)), self._buf("shift0", (B, 64)),
+                                                           self._buf("mom0", (B, 54), torch.float64)),
+                                             scratch=self._buf("mom_partial0", (B, ops.first_layer_units(80, T), 54), torch.float64))
+        stats.append((sc0, sh0))
+        for l in range(1, 8):
             co = ENC2D[l][1]
             oh, ow_full = hw[l + 1]
             base = max([s for s in stored if s < l], default=-1)
@@ -145,17 +189,20 @@ class StreamingGenerator:
                 # ---- the tile of the base level (mel columns, or the stored raw map of `base` normalised + activated)
                 if base < 0:
                     c0, c1 = base_window(tiles[ti], T, 1, T)
-                    src = self._buf("tile_mel", (B, 80, c1 - c0, 1))
-                    src.copy_(mel[:, :, c0:c1].unsqueeze(-1))
                     H, W = 80, c1 - c0
+                    mt = self._buf("tile_mel", (B, 80, W))
+                    mt.copy_(mel[:, :, c0:c1])
+                    src = ops.first_layer_act(mt, w0, sc0, sh0, slope, out=self._buf("act0", (B, 80, W, 64)), tf32=tf32)
+                    first = 1                           # layers first .. l run as convolutions on the tile
                 else:
                     c0, c1 = base_window(tiles[ti], T, stride[base], hw[base + 1][1])
                     H, W = hw[base + 1][0], c1 - c0
                     src = self._buf("tile_base%d" % base, (B, H, W, ENC2D[base][1]))
                     src.copy_(stored[base][:, :, c0:c1])
                     ops.scale_shift_act(src, stats[base][0], stats[base][1], ENC2D[base][1], slope, out=src, tf32=tf32)
-                # ---- layers base + 1 .. l on the tile
-                for j in range(base + 1, l + 1):
+                    first = base + 1
+                # ---- layers first .. l on the tile
+                for j in range(first, l + 1):
                     g = geoms[j]
                     name = ENC_PREFIX + ENC2D[j][0]
                     oh_j, ow_j = g.out_hw(H, W)

@@ -526,6 +526,28 @@ def first_layer_fwd(x, w, slope, eps=None, out=None, scratch=None, tf32=False):
     return act, sc, sh, mom
 
 
+def first_layer_stats(x, w, eps=None, out=None, scratch=None):
+    """Statistics half of first_layer_fwd: x (B,H,W), w (64,1,3,3) -> (scale (B,64) = rstd, shift (B,64) = -mean*rstd, moments (B,54) f64)."""
+    B, H, W = x.shape
+    Cc = w.shape[0]
+    units = first_layer_units(H, W)
+    sc, sh, mom = out if out is not None else (torch.empty(B, Cc, device=x.device), torch.empty(B, Cc, device=x.device),
+                                               torch.empty(B, 54, device=x.device, dtype=torch.float64))
+    part = scratch if scratch is not None else torch.empty(B, units, 54, device=x.device, dtype=torch.float64)
+    call("sdt_first_layer_fwd", _p(x), _p(w), B, H, W, Cc, EPS_NORM if eps is None else eps, 1.0, _p(part), _p(mom), _p(sc), _p(sh), None, 0, _stream())
+    _lib.launch_count -= 1                      # call() counted three kernels; the activation pass is skipped
+    return sc, sh, mom
+
+
+def first_layer_act(x, w, scale, shift, slope, out=None, tf32=False):
+    """Activation half: x (B,H,W) (a tile of the image), per-(image, channel) scale / shift -> act (B,H,W,64)."""
+    B, H, W = x.shape
+    Cc = w.shape[0]
+    act = out if out is not None else torch.empty(B, H, W, Cc, device=x.device)
+    call("sdt_first_layer_act", _p(x), _p(w), _p(scale), _p(shift), B, H, W, Cc, slope, _p(act), int(tf32), _stream())
+    return act
+
+
 def first_layer_bwd(g_act, act, x, w, mom, sc, sh, slope, dw, scratch=None):
     """Weight gradient of the first block from dLoss/d act (IN + LeakyReLU backward folded in); dw (64,1,3,3) overwritten."""
     B, H, W = x.shape

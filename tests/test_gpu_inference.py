@@ -99,3 +99,21 @@ def test_dropin_model_demo_branch_streams_long_audio(monkeypatch):
         out = model(batch, None, return_loss=False)["poses_pred_batch"]
     assert model._streaming.last_chunks >= 5 and out.shape == ref.shape == (1, nf, 2, 121)
     assert float((out - ref).abs().max() / ref.abs().max()) < 2e-4        # conftest pins the fp32 math mode
+
+
+def test_graphed_tiled_forward_equals_the_eager_one():
+    """graph=True: the tiled forward of a given utterance length is captured once and replayed; same stream, bit for bit, also for a
+    different utterance of the same length (the captured graph reads the static input buffers)."""
+    from speechdrivestemplates_b200 import config, data, inference
+    cfg = config.get_cfg("voice2pose_sdt_bp")
+    alen, nf = data.parse_audio_length(40 * 16000, 16000, 15)
+    code = 0.1 * torch.randn(1, 32, generator=torch.Generator().manual_seed(9))
+    torch.manual_seed(0)
+    eager = inference.StreamingGenerator(cfg, "cuda:0", conv_math=3, chunk_frames=96)
+    graphed = inference.StreamingGenerator(cfg, "cuda:0", conv_math=3, chunk_frames=96, netG=eager.netG, mel=eager.mel, graph=True)
+    for seed in (1, 2, 3):
+        audio = 0.1 * torch.randn(1, alen, generator=torch.Generator().manual_seed(seed))
+        ref = eager(audio, nf, code)
+        out = graphed(audio, nf, code)
+        assert torch.equal(out, ref), seed
+    assert len(graphed._graph_cache) == 1 and graphed.last_chunks >= 4

@@ -8,7 +8,8 @@ Reference: ``Trainer.demo`` (core/pipelines/trainer.py:459-484) loops ``Voice2Po
 FLOPs and nearly all of the memory -- runs in time tiles with receptive-field halos, and the InstanceNorm2d statistics, which span
 the whole utterance, are made exact by sweeping the layers: sweep l recomputes the layers below l on each tile with their
 already-final statistics and accumulates layer l's sums over the tile's OWNED columns (deterministic fixed-order partials, one
-``sdt_norm_finalize`` per layer).  A sweep starts from the nearest STORED level below l: the mel, or the full-length raw map of a
+``sdt_norm_finalize`` per layer).  The first block (1 -> 64 channels, the largest map) needs no sweep: its statistics follow in
+closed form from the mel (csrc/first_layer.cu), and a tile's activated map is one pass.  A sweep starts from the nearest STORED level below l: the mel, or the full-length raw map of a
 layer in ``store_layers`` (default 3 and 5: maps at 1/4 and 1/8 of the mel resolution, 0.26 + 0.13 MB per second of audio), which
 cuts the recomputation from 4.4x the one-shot FLOPs (``store_layers=()``: memory independent of the length apart from the mel and
 the final 1/8-resolution map) to 1.8x.  The last sweep writes the encoder's final map; the resize to ``num_frames`` and the 1-D

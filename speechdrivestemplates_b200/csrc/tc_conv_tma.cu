@@ -18,6 +18,7 @@
 //   warp 5  : MMA issuer: 4 x tcgen05.mma per stage, tcgen05.commit -> empty[s]; owns the TMEM allocation.
 // 3 stages of 32 KB (BN = 128) -> two CTAs per SM.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "tc_api.h"
 #include "tc_common.cuh"
@@ -39,7 +40,8 @@ struct TileGeom {
 // operand stage has landed, after the last MMA was issued, when the accumulator is complete, at the end of the epilogue, at CTA end
 __device__ long long* g_tma_timeline = nullptr;
 __device__ int g_tma_timeline_ctas = 0;
-__device__ int g_tma_dbg = 0;            // with a timeline only (results are wrong): 1 = one MMA per k-block instead of four, 2 = no MMAs
+__device__ int g_tma_dbg = 0;            // with a timeline only (results are wrong): 1 = one MMA per k-block instead of four, 2 = no MMAs, 3 = no MMAs + plain arrive
+                                         // instead of tcgen05.commit, 4 = as 3 and weight boxes only (one TMA operation per stage)
 __device__ __forceinline__ long long gtimer_ns() {
     long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -139,6 +141,7 @@ __global__ void __launch_bounds__(THREADS, DEEP ? 1 : 2) tc_conv_tma_kernel(cons
     if (warp == 4) {
         // ================= TMA producer =================
         const int taps = d.TH * d.TW;
+        const int pdbg = tl ? g_tma_dbg : 0;
         int s = 0, par = 1;
         // k-block order: channel chunk major, tap minor (consecutive taps hit the same L2 lines)
         for (int c0 = 0; c0 < d.C; c0 += BKF) {
@@ -148,9 +151,14 @@ __global__ void __launch_bounds__(THREADS, DEEP ? 1 : 2) tc_conv_tma_kernel(cons
                     const int wx = x0 * d.x_mul + d.x_off + txx * d.tx_mul;
                     mbar_wait_spin(empty_bar(s), (uint32_t)par);
                     if (elect_one()) {
-                        mbar_expect_tx(full_bar(s), Cfg::A_BYTES + Cfg::B_BYTES);
-                        tma_load_4d(smA + s * Cfg::A_BYTES, &tmA, c0, wx, wy, b, full_bar(s));
-                        tma_load_2d(smB + s * Cfg::B_BYTES, &tmB, (tyy * d.TW + txx) * d.C + c0, n0, full_bar(s));
+                        if (pdbg == 4) {                                   // diagnostics: weight boxes only
+                            mbar_expect_tx(full_bar(s), Cfg::B_BYTES);
+                            tma_load_2d(smB + s * Cfg::B_BYTES, &tmB, (tyy * d.TW + txx) * d.C + c0, n0, full_bar(s));
+                        } else {
+                            mbar_expect_tx(full_bar(s), Cfg::A_BYTES + Cfg::B_BYTES);
+                            tma_load_4d(smA + s * Cfg::A_BYTES, &tmA, c0, wx, wy, b, full_bar(s));
+                            tma_load_2d(smB + s * Cfg::B_BYTES, &tmB, (tyy * d.TW + txx) * d.C + c0, n0, full_bar(s));
+                        }
                     }
                     __syncwarp();
                     if (++s == STAGES) { s = 0; par ^= 1; }
@@ -174,7 +182,8 @@ __global__ void __launch_bounds__(THREADS, DEEP ? 1 : 2) tc_conv_tma_kernel(cons
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4)
                     if (dbg == 0 || (dbg == 1 && k4 == 0)) mma_tf32_lohi(tmem_base, a_lo + 2u * k4, b_lo + 2u * k4, HI, idesc, started | (uint32_t)k4);
-                mma_commit(empty_bar(s));
+                if (dbg >= 3) mbar_arrive(empty_bar(s));          // no MMAs and the stage handed back WITHOUT tcgen05.commit
+                else mma_commit(empty_bar(s));
             }
             __syncwarp();
             started = 1;
@@ -428,6 +437,7 @@ int sdt_tc_conv_tma_launch(const sdt_conv_desc* d, cudaStream_t st) {
     }
     int bn = d->N % 128 == 0 ? 128 : 64;
     if (bn == 128 && tiles * (d->N / 128) < 2 * 148) bn = 64;               // small problems: more CTAs
+    if (getenv("SDT_TMA_BN128") != nullptr && d->N % 128 == 0) bn = 128;    // tuning aid (tests/diag_conv1d_timeline.py)
     const bool deep = tiles * (d->N / bn) <= 148;
     if (bn == 128) return deep ? launch_tma<128, true>(d, tg, st) : launch_tma<128, false>(d, tg, st);
     return deep ? launch_tma<64, true>(d, tg, st) : launch_tma<64, false>(d, tg, st);

@@ -22,7 +22,7 @@ def main():
     ops.set_conv_math(3)
     ncta = 1024
     tlbuf = torch.zeros(ncta, 8, dtype=torch.int64, device=dev)
-    for (L, k, s, p) in [(64, 3, 1, 1), (64, 4, 2, 1), (32, 4, 2, 1), (8, 3, 1, 1), (2, 3, 1, 1)]:
+    for (L, k, s, p) in [(64, 3, 1, 1), (64, 4, 2, 1), (2, 3, 1, 1)]:
         g = ops.ConvGeom.conv1d(256, 256, k, s, p)
         x = torch.randn(B, L, 256, device=dev)
         w = torch.randn(256, 256, k, device=dev) / math.sqrt(256 * k)
@@ -41,7 +41,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 50
-        for flags in (0, 1, 2):
+        for flags in (0, 2, 3, 4):
             tlbuf.zero_()
             lib.sdt_debug_tma_flags(flags)
             lib.sdt_debug_tma_timeline(C.c_void_p(tlbuf.data_ptr()), ncta)
@@ -54,7 +54,7 @@ def main():
             base = t[:, 0].min()
             rel = (t[:, :7] - base) / 1e3
             names = ["start", "prologue", "1st stage", "MMAs issued", "acc done", "epilogue", "end"]
-            what = ["", " [1 of 4 MMAs per k-block]", " [no MMAs]"][flags]
+            what = ["", " [1 of 4 MMAs per k-block]", " [no MMAs]", " [no MMAs, stages released by a plain mbarrier arrive]", " [no MMAs, plain arrive, weight boxes only]"][flags]
             print("L %2d k %d s %d%s: %d CTAs, %.1f us back to back | mean us since the first CTA start: %s | span %.2f us" % (
                 L, k, s, what, t.shape[0], us, "  ".join("%s %.2f" % (n, rel[:, i].mean()) for i, n in enumerate(names)), float(rel[:, 6].max())), flush=True)
     ops.set_conv_math(0)

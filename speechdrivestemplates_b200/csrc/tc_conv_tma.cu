@@ -53,7 +53,12 @@ __device__ __forceinline__ long long gtimer_ns() {
 constexpr int RN_CL = 4;               // CTAs per cluster of the fused row-norm epilogue: the four 64-column quarters of N = 256
 template <int BN, bool DEEP>
 struct TmaCfg {
-    static constexpr int STAGES = DEEP ? (BN == 64 ? 8 : 6) : (BN == 64 ? 4 : 3);
+    static constexpr int STAGES = DEEP ? (BN == 64 ? 8 : 6) : (BN == 64 ? 4 : 3);      // ring slots of one k-block each
+    // k-blocks per barrier hand-over.  The k loop of the latency-bound (DEEP) launches is paced by the mbarrier hand-shake itself:
+    // ~150 ns per iteration whatever the box sizes, TMA operations, ring depth, producers, MMAs or commits
+    // (profiles/r2_ablation_fused_rownorm.txt).  Two k-blocks per full / empty barrier halve the iterations on both sides.
+    static constexpr int KPS = DEEP ? 2 : 1;
+    static constexpr int GROUPS = STAGES / KPS;
     static constexpr int A_BYTES = BM * 128;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int BAR_BYTES = 256;
@@ -140,54 +145,65 @@ __global__ void __launch_bounds__(THREADS, DEEP ? 1 : 2) tc_conv_tma_kernel(cons
     // their loops as whole warps and elect one lane per instruction (tc_common.cuh: elect_one), and have the highest warp ids.
     if (warp == 4) {
         // ================= TMA producer =================
-        const int taps = d.TH * d.TW;
         const int pdbg = tl ? g_tma_dbg : 0;
-        int s = 0, par = 1;
-        // k-block order: channel chunk major, tap minor (consecutive taps hit the same L2 lines)
-        for (int c0 = 0; c0 < d.C; c0 += BKF) {
-            for (int tyy = 0; tyy < d.TH; ++tyy) {
-                const int wy = y0 * d.y_mul + d.y_off + tyy * d.ty_mul;
-                for (int txx = 0; txx < d.TW; ++txx) {
+        constexpr int KPS = Cfg::KPS, GROUPS = Cfg::GROUPS;
+        int g = 0, par = 1;
+        int txx = 0, tyy = 0, c0 = 0;               // (tap, channel chunk) of the next k-block; order: chunk major, tap minor
+        for (int kb = 0; kb < KB; kb += KPS) {
+            const int nkb = KB - kb < KPS ? KB - kb : KPS;
+            mbar_wait_spin(empty_bar(g), (uint32_t)par);
+            const bool leader = elect_one();
+            if (leader) mbar_expect_tx(full_bar(g), (uint32_t)(nkb * (pdbg == 4 ? Cfg::B_BYTES : Cfg::A_BYTES + Cfg::B_BYTES)));
+#pragma unroll
+            for (int j = 0; j < KPS; ++j) {
+                if (j < nkb) {
+                    const int s = g * KPS + j;
+                    const int wy = y0 * d.y_mul + d.y_off + tyy * d.ty_mul;
                     const int wx = x0 * d.x_mul + d.x_off + txx * d.tx_mul;
-                    mbar_wait_spin(empty_bar(s), (uint32_t)par);
-                    if (elect_one()) {
-                        if (pdbg == 4) {                                   // diagnostics: weight boxes only
-                            mbar_expect_tx(full_bar(s), Cfg::B_BYTES);
-                            tma_load_2d(smB + s * Cfg::B_BYTES, &tmB, (tyy * d.TW + txx) * d.C + c0, n0, full_bar(s));
-                        } else {
-                            mbar_expect_tx(full_bar(s), Cfg::A_BYTES + Cfg::B_BYTES);
-                            tma_load_4d(smA + s * Cfg::A_BYTES, &tmA, c0, wx, wy, b, full_bar(s));
-                            tma_load_2d(smB + s * Cfg::B_BYTES, &tmB, (tyy * d.TW + txx) * d.C + c0, n0, full_bar(s));
-                        }
+                    if (leader) {
+                        if (pdbg != 4) tma_load_4d(smA + s * Cfg::A_BYTES, &tmA, c0, wx, wy, b, full_bar(g));
+                        tma_load_2d(smB + s * Cfg::B_BYTES, &tmB, (tyy * d.TW + txx) * d.C + c0, n0, full_bar(g));
                     }
-                    __syncwarp();
-                    if (++s == STAGES) { s = 0; par ^= 1; }
+                    if (++txx == d.TW) {
+                        txx = 0;
+                        if (++tyy == d.TH) { tyy = 0; c0 += BKF; }
+                    }
                 }
             }
+            __syncwarp();
+            if (++g == GROUPS) { g = 0; par ^= 1; }
         }
-        (void)taps;
     } else if (warp == 5) {
         // ================= MMA issuer =================
         const uint32_t idesc = make_idesc_tf32(BN, 0, 0);
         constexpr uint32_t HI = desc_hi(1024, kSwizzle128B);
-        int s = 0, par = 0;
+        constexpr int KPS = Cfg::KPS, GROUPS = Cfg::GROUPS;
+        int g = 0, par = 0;
         uint32_t started = 0;
         const int dbg = tl ? g_tma_dbg : 0;
-        for (int kb = 0; kb < KB; ++kb) {
-            mbar_wait_spin(full_bar(s), (uint32_t)par);
+        for (int kb = 0; kb < KB; kb += KPS) {
+            const int nkb = KB - kb < KPS ? KB - kb : KPS;
+            mbar_wait_spin(full_bar(g), (uint32_t)par);
             if (tl && kb == 0 && lane == 0) tl[2] = gtimer_ns();
             tc_fence_after();
-            const uint32_t a_lo = desc_lo(smA + s * Cfg::A_BYTES, 16), b_lo = desc_lo(smB + s * Cfg::B_BYTES, 16);
             if (elect_one()) {
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4)
-                    if (dbg == 0 || (dbg == 1 && k4 == 0)) mma_tf32_lohi(tmem_base, a_lo + 2u * k4, b_lo + 2u * k4, HI, idesc, started | (uint32_t)k4);
-                if (dbg >= 3) mbar_arrive(empty_bar(s));          // no MMAs and the stage handed back WITHOUT tcgen05.commit
-                else mma_commit(empty_bar(s));
+                for (int j = 0; j < KPS; ++j) {
+                    if (j < nkb) {
+                        const int s = g * KPS + j;
+                        const uint32_t a_lo = desc_lo(smA + s * Cfg::A_BYTES, 16), b_lo = desc_lo(smB + s * Cfg::B_BYTES, 16);
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4)
+                            if (dbg == 0 || (dbg == 1 && k4 == 0))
+                                mma_tf32_lohi(tmem_base, a_lo + 2u * k4, b_lo + 2u * k4, HI, idesc, (started | (uint32_t)(j | k4)) ? 1u : 0u);
+                    }
+                }
+                if (dbg >= 3) mbar_arrive(empty_bar(g));          // no MMAs and the stage handed back WITHOUT tcgen05.commit
+                else mma_commit(empty_bar(g));
             }
             __syncwarp();
             started = 1;
-            if (++s == STAGES) { s = 0; par ^= 1; }
+            if (++g == GROUPS) { g = 0; par ^= 1; }
         }
         if (elect_one()) mma_commit(tmem_full_bar);
         __syncwarp();

@@ -690,6 +690,7 @@ def run_train(args):
         "data": "synthetic", "config": config_dict(config, B, world),
         "impl_detail": {"cuda_graph": tr._graphs is not None or b128 is not None, "graphs_per_step": len(tr._graphs) if tr._graphs else (1 if b128 else 0),
                         "comm_mode": getattr(tr, "comm_mode", "none"),
+                        "p2p_nvls_multicast": (bool(getattr(getattr(tr, "_px", None), "multicast", 0)) if getattr(tr, "_px", None) is not None else None),
                         "conv_math": ["fp32 FFMA", "tcgen05 TF32 operands, fp32 accumulate (FFMA for ineligible layers)",
                                       "tcgen05 TF32, TMA-fed operands for forward/dgrad, fp32 accumulate (FFMA for ineligible layers)",
                                       "tcgen05 kind::tf32 (operands stored round-to-nearest TF32, fp32 accumulation in TMEM), TMA-fed operands reused "
